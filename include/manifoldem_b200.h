@@ -1,0 +1,133 @@
+/* manifoldem_b200.h — C ABI of the B200-native ManifoldEM hot path.
+ *
+ * The reference (evanseitz/ManifoldEM_Python) has no FFI layer: its boundary
+ * for this path is three Python callables.  This header is the
+ * native surface those callables bind through ctypes; every entry point cites
+ * the reference code it replaces.  Plain pointers and sizes only — no torch
+ * types.  All functions return 0 on success, non-zero on error (message from
+ * mem_last_error()).  "device" pointers are CUDA device pointers on the
+ * context's device; "host" pointers are ordinary (ideally pinned) host memory.
+ *
+ * Image layout: [nS][N][N] float32, row-major, picture orientation
+ * (row = first NumPy axis).  Spectra: cuFFT R2C layout [nS][N][N/2+1] complex64.
+ */
+#ifndef MANIFOLDEM_B200_H
+#define MANIFOLDEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mem_ctx mem_ctx;
+
+/* ---- lifecycle ------------------------------------------------------------------ */
+int         mem_version(void);
+const char* mem_last_error(void);
+int         mem_ctx_create(int device, mem_ctx** out);
+int         mem_ctx_destroy(mem_ctx* ctx);
+int         mem_ctx_sync(mem_ctx* ctx);
+/* kernels launched by this library on ctx since the last reset (bench.py gpu_launches) */
+int64_t     mem_ctx_launch_count(mem_ctx* ctx, int reset);
+/* pinned host memory for the host-buffer entry points */
+int         mem_host_alloc(void** out, size_t bytes);
+int         mem_host_free(void* p);
+/* plain device memory + copies (so a ctypes host needs nothing else to stage data) */
+int         mem_dev_alloc(void** out, size_t bytes);
+int         mem_dev_free(void* p);
+int         mem_copy_h2d(mem_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int         mem_copy_d2h(mem_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+
+/* ---- per-PD distance stage -------------------------------------------------------
+ * Replaces getDistanceCTF_local_Conj9combinedS2.op
+ * (modules/getDistanceCTF_local_Conj9combinedS2.py:216-420) from the point where
+ * the particle images of the PD have been gathered, up to (not including) the
+ * pickle dump. Host-side scalars (psi angles, PD) are computed by the Python host
+ * exactly as the reference does (q2Spider / least_squares). */
+typedef struct {
+  int32_t nS;            /* particles in this PD                                   (:223) */
+  int32_t N;             /* box size p.nPix                                        (:225) */
+  int32_t transposed;    /* 1: SPIDER raw layout, picture = raw^T                  (:254-258) */
+  int32_t relion_shift;  /* 1: apply shift(order=3,mode='wrap') by (shy-.5,shx-.5) (:263-264) */
+  int32_t filter_type;   /* 0 = 'Butter', 1 = 'Gauss'                              (:156-167) */
+  int32_t filter_order;  /* filterPar['N']                                                    */
+  double  filter_Qc;     /* filterPar['Qc']                                                   */
+  double  pix_size;      /* p.pix_size [A]                                         (:337) */
+  double  Cs;            /* p.Cs [mm]                                                        */
+  double  EkV;           /* p.EkV [kV]                                                       */
+  double  gaussEnv;      /* p.gaussEnv (inf => envelope 1)                                   */
+  double  AmpContrast;   /* p.AmpContrast                                                    */
+  double  psi_p_deg;     /* psi_ang(PD), degrees                                   (:313) */
+  int32_t avg_only;      /* options['avgOnly']: skip D                             (:376) */
+  int32_t contraction;   /* 0 = tcgen05 3xTF32 (product), 1 = SIMT fp64-accumulate checker kernel */
+  int32_t k_chunk_blocks;/* tcgen05: K blocks (of 32) accumulated in TMEM before promotion; 0 = default */
+  int32_t split_k;       /* tcgen05: K slices per tile; 0 = auto (fill 148 SMs)                  */
+} mem_pd_params;
+
+typedef struct {
+  /* inputs */
+  const float*   raw;        /* [nS][N*N] gathered particle images as stored on disk           */
+  const uint8_t* flip;       /* [nS] 1 = conjugate member (np.flipud after reading)  (:271-275) */
+  const double*  shift;      /* [nS][2] (shy-0.5, shx-0.5) per member, or NULL                 */
+  const double*  psi_deg;    /* [nS] first in-plane rotation angle, degrees = -(180/pi)*Psi (:326) */
+  const double*  df;         /* [nS] defocus [A]                                               */
+  const uint8_t* msk2;       /* [N][N] projected volume mask or NULL (msk2 = 1)      (:304-310) */
+  /* outputs, any may be NULL */
+  float*  D;                 /* [nS][nS] squared distances                           (:391-397) */
+  float*  imgAll;            /* [nS][N][N] aligned images                            (:349) */
+  float*  imgAllFlip;        /* [nS][N][N] phase-flipped images                      (:346-347) */
+  double* CTF;               /* [nS][N*N]  CTF, ifftshift-ed, float64                (:339) */
+  float*  imgAvg;            /* [N][N] Wiener-filtered average                       (:353-366) */
+  float*  imgAvgFlip;        /* [N][N] average of phase-flipped images               (:367) */
+  float*  imgAllIntensity;   /* [N][N] mean(imgAllFlip^2)                            (:400) */
+} mem_pd_io;
+
+/* all pointers in io are DEVICE pointers; work is enqueued on `stream` (a cudaStream_t, NULL = the
+ * context's stream); no host synchronisation. */
+int mem_pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* io, void* stream);
+/* all pointers in io are HOST pointers; stages H2D, runs, copies results back, synchronises. */
+int mem_pd_distance_host(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* io);
+/* CUDA-event timings (ms) of the last mem_pd_distance_* call on ctx:
+ * [0] ingest+lowpass  [1] align (2x prefilter+rotate)  [2] FFT+CTF+operands  [3] flip/averages
+ * [4] contraction     [5] total device                 [6] h2d   [7] d2h            */
+int mem_pd_last_timings(mem_ctx* ctx, float* ms, int n);
+
+/* ---- contraction alone (operands already on device) ------------------------------------
+ * D = 4 * ( S1 S2^T + S2 S1^T - S3 S3^T ) over rows of Z = [S1 | S2 | S3]   
+ * == |C|^2 (|F|^2)^T + its transpose - 2 Re(A A^H)  of :391-397. */
+typedef struct {
+  int32_t nS;        /* rows                                          */
+  int32_t n1_blocks; /* 32-column blocks in S1 (== blocks in S2)      */
+  int32_t n3_blocks; /* 32-column blocks in S3                        */
+  int64_t ldz;       /* row pitch of Zhi/Zlo in floats (multiple of 4) */
+} mem_contract_shape;
+int mem_contract_device(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, const float* Zlo,
+                        float* D, int32_t contraction, int32_t k_chunk_blocks, int32_t split_k, void* stream);
+/* operand layout for a box size (columns of Z): fills n1_blocks, n3_blocks, ldz */
+int mem_operand_shape(mem_ctx* ctx, int32_t N, mem_contract_shape* out);
+
+/* ---- diffusion-map front end (DMembeddingII.op, modules/DMembeddingII.py:86-185) ---------- */
+/* a15 kNN (DMembeddingII.initialize :43-57): for every column i of the symmetric matrix D (float64,
+ * device), the k smallest entries with the diagonal forced first; idx [nS][k] int32, val [nS][k] f64
+ * (val[i][0] = 0).  D is not modified. */
+int mem_knn_device(mem_ctx* ctx, const double* D, int32_t nS, int32_t k, int32_t* idx, double* val, void* stream);
+/* a16 OR-symmetrised kNN graph (DMembeddingII.op :113-140) in dense form: M [nS][nS] float64 device,
+ * M[i][j] = d^2 of the union graph, 0 for the 'zero' (self) entries, -1 where there is no edge. */
+int mem_graph_dense_device(mem_ctx* ctx, const int32_t* idx, const double* val, int32_t nS, int32_t k, double* M,
+                           void* stream);
+/* a17 Ferguson sweep (fergusonE.op :36-43): out[e] = log sum_{d2/(2 eps_e) < thr} exp(-d2/(2 eps_e)),
+ * d2 [n] float64 device (negative entries = no edge, skipped), logEps [nEps] float64 HOST,
+ * out [nEps] float64 HOST.  Synchronises. */
+int mem_ferguson_device(mem_ctx* ctx, const double* d2, int64_t n, const double* logEps, int32_t nEps,
+                        double thr, double* out);
+/* a18 dense Gaussian-kernel Laplacian (slaplacianonFly.op :57-78) for the k = nS graph:
+ * W = exp(-M/sigma^2) on the graph support (M >= 0 entries; negative = no edge), alpha = 1
+ * normalisation, symmetric normalisation, L = |L + L^T|/2.  M, L: [nS][nS] float64 device. */
+int mem_laplacian_dense_device(mem_ctx* ctx, const double* M, int32_t nS, double sigma, double* L, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MANIFOLDEM_B200_H */

@@ -1,0 +1,228 @@
+// capi.cu — extern "C" surface declared in include/manifoldem_b200.h.
+#include "common.cuh"
+
+#include <math.h>
+#include <algorithm>
+#include <set>
+
+namespace mem {
+const char* last_error();
+int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* io, cudaStream_t st);
+int knn_device(mem_ctx* ctx, const double* D, int nS, int k, int* idx, double* val, cudaStream_t st);
+int graph_dense_device(mem_ctx* ctx, const int* idx, const double* val, int nS, int k, double* M, cudaStream_t st);
+int ferguson_device(mem_ctx* ctx, const double* d2, int64_t n, const double* logEps, int nEps, double thr, double* out);
+int laplacian_dense_device(mem_ctx* ctx, const double* M, int nS, double sigma, double* L, cudaStream_t st);
+}  // namespace mem
+
+using namespace mem;
+
+static cudaStream_t pick(mem_ctx* ctx, void* stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
+
+extern "C" {
+
+int mem_version(void) { return 100; }
+const char* mem_last_error(void) { return mem::last_error(); }
+
+int mem_ctx_create(int device, mem_ctx** out) {
+  int n = 0;
+  MEM_CUDA(cudaGetDeviceCount(&n));
+  if (device < 0 || device >= n) {
+    set_error("no CUDA device %d (found %d)", device, n);
+    return 1;
+  }
+  MEM_CUDA(cudaSetDevice(device));
+  mem_ctx* ctx = new mem_ctx();
+  ctx->device = device;
+  MEM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  MEM_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+  for (auto& e : ctx->ev) MEM_CUDA(cudaEventCreate(&e));
+  *out = ctx;
+  return 0;
+}
+
+int mem_ctx_destroy(mem_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->plans) {
+    cufftDestroy(kv.second.r2c);
+    cufftDestroy(kv.second.c2r);
+  }
+  mem::DevBuf* bufs[] = {&ctx->fft_work, &ctx->raw, &ctx->flip, &ctx->shift, &ctx->psi, &ctx->df, &ctx->msk2, &ctx->rot_cs,
+                         &ctx->imgA, &ctx->imgB, &ctx->imgAll, &ctx->imgFlip, &ctx->spec, &ctx->spec2, &ctx->cbin, &ctx->zhi,
+                         &ctx->zlo, &ctx->part_cf, &ctx->part_c2, &ctx->part_fl, &ctx->part_int, &ctx->avgspec, &ctx->avgimg,
+                         &ctx->stats, &ctx->D, &ctx->ctf64, &ctx->small_out, &ctx->contract_ws, &ctx->scratch,
+                         &ctx->geom.Gtab, &ctx->geom.bin_of_pix, &ctx->geom.r2_of_bin, &ctx->geom.bin_start,
+                         &ctx->geom.bin_pix, &ctx->geom.s3_col, &ctx->geom.special_pix};
+  for (auto* b : bufs) b->release();
+  for (auto& e : ctx->ev) cudaEventDestroy(e);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return 0;
+}
+
+int mem_ctx_sync(mem_ctx* ctx) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  MEM_CUDA(cudaStreamSynchronize(ctx->stream));
+  MEM_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+
+int64_t mem_ctx_launch_count(mem_ctx* ctx, int reset) {
+  const int64_t v = ctx->launches;
+  if (reset) ctx->launches = 0;
+  return v;
+}
+
+int mem_host_alloc(void** out, size_t bytes) {
+  MEM_CUDA(cudaMallocHost(out, bytes));
+  return 0;
+}
+int mem_host_free(void* p) {
+  MEM_CUDA(cudaFreeHost(p));
+  return 0;
+}
+int mem_dev_alloc(void** out, size_t bytes) {
+  MEM_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+  return 0;
+}
+int mem_dev_free(void* p) {
+  MEM_CUDA(cudaFree(p));
+  return 0;
+}
+int mem_copy_h2d(mem_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  MEM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  MEM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int mem_copy_d2h(mem_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  MEM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  MEM_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int mem_pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* io, void* stream) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  return pd_distance_device(ctx, prm, io, pick(ctx, stream));
+}
+
+int mem_pd_distance_host(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* h) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t nS = prm->nS, NN = (size_t)prm->N * prm->N;
+  mem_pd_io d = {};
+  MEM_CHECK(ctx->raw.ensure(nS * NN * sizeof(float)));
+  MEM_CHECK(ctx->flip.ensure(nS));
+  MEM_CHECK(ctx->psi.ensure(nS * sizeof(double)));
+  MEM_CHECK(ctx->df.ensure(nS * sizeof(double)));
+  MEM_CUDA(cudaEventRecord(ctx->ev[6], st));
+  MEM_CUDA(cudaMemcpyAsync(ctx->raw.p, h->raw, nS * NN * sizeof(float), cudaMemcpyHostToDevice, st));
+  MEM_CUDA(cudaMemcpyAsync(ctx->flip.p, h->flip, nS, cudaMemcpyHostToDevice, st));
+  MEM_CUDA(cudaMemcpyAsync(ctx->psi.p, h->psi_deg, nS * sizeof(double), cudaMemcpyHostToDevice, st));
+  MEM_CUDA(cudaMemcpyAsync(ctx->df.p, h->df, nS * sizeof(double), cudaMemcpyHostToDevice, st));
+  d.raw = ctx->raw.as<float>();
+  d.flip = ctx->flip.as<uint8_t>();
+  d.psi_deg = ctx->psi.as<double>();
+  d.df = ctx->df.as<double>();
+  if (h->msk2) {
+    MEM_CHECK(ctx->msk2.ensure(NN));
+    MEM_CUDA(cudaMemcpyAsync(ctx->msk2.p, h->msk2, NN, cudaMemcpyHostToDevice, st));
+    d.msk2 = ctx->msk2.as<uint8_t>();
+  }
+  MEM_CUDA(cudaEventRecord(ctx->ev[7], st));
+  if (h->D && !prm->avg_only) {
+    MEM_CHECK(ctx->D.ensure(nS * nS * sizeof(float)));
+    d.D = ctx->D.as<float>();
+  }
+  if (h->imgAll) {
+    MEM_CHECK(ctx->imgAll.ensure(nS * NN * sizeof(float)));
+    d.imgAll = ctx->imgAll.as<float>();
+  }
+  if (h->imgAllFlip) {
+    MEM_CHECK(ctx->imgFlip.ensure(nS * NN * sizeof(float)));
+    d.imgAllFlip = ctx->imgFlip.as<float>();
+  }
+  if (h->CTF) {
+    MEM_CHECK(ctx->ctf64.ensure(nS * NN * sizeof(double)));
+    d.CTF = ctx->ctf64.as<double>();
+  }
+  MEM_CHECK(ctx->stats.ensure(3 * NN * sizeof(float)));
+  float* small = ctx->stats.as<float>();
+  if (h->imgAvg) d.imgAvg = small;
+  if (h->imgAvgFlip) d.imgAvgFlip = small + NN;
+  if (h->imgAllIntensity) d.imgAllIntensity = small + 2 * NN;
+  MEM_CHECK(pd_distance_device(ctx, prm, &d, st));
+  MEM_CUDA(cudaEventRecord(ctx->ev[8], st));
+  if (d.D) MEM_CUDA(cudaMemcpyAsync(h->D, d.D, nS * nS * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (d.imgAll) MEM_CUDA(cudaMemcpyAsync(h->imgAll, d.imgAll, nS * NN * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (d.imgAllFlip) MEM_CUDA(cudaMemcpyAsync(h->imgAllFlip, d.imgAllFlip, nS * NN * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (d.CTF) MEM_CUDA(cudaMemcpyAsync(h->CTF, d.CTF, nS * NN * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (d.imgAvg) MEM_CUDA(cudaMemcpyAsync(h->imgAvg, d.imgAvg, NN * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (d.imgAvgFlip) MEM_CUDA(cudaMemcpyAsync(h->imgAvgFlip, d.imgAvgFlip, NN * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (d.imgAllIntensity) MEM_CUDA(cudaMemcpyAsync(h->imgAllIntensity, d.imgAllIntensity, NN * sizeof(float), cudaMemcpyDeviceToHost, st));
+  MEM_CUDA(cudaEventRecord(ctx->ev[9], st));
+  MEM_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int mem_pd_last_timings(mem_ctx* ctx, float* ms, int n) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  MEM_CUDA(cudaStreamSynchronize(ctx->stream));
+  float t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&t[i], ctx->ev[i], ctx->ev[i + 1]);
+  cudaEventElapsedTime(&t[5], ctx->ev[0], ctx->ev[5]);
+  if (cudaEventElapsedTime(&t[6], ctx->ev[6], ctx->ev[7]) != cudaSuccess) t[6] = 0;
+  if (cudaEventElapsedTime(&t[7], ctx->ev[8], ctx->ev[9]) != cudaSuccess) t[7] = 0;
+  cudaGetLastError();
+  for (int i = 0; i < n && i < 8; ++i) ms[i] = t[i];
+  return 0;
+}
+
+int mem_contract_device(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, const float* Zlo, float* D,
+                        int32_t contraction, int32_t k_chunk_blocks, int32_t split_k, void* stream) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  return contract_run(ctx, shp, Zhi, Zlo, D, contraction, k_chunk_blocks, split_k, pick(ctx, stream));
+}
+
+int mem_operand_shape(mem_ctx* ctx, int32_t N, mem_contract_shape* out) {
+  (void)ctx;
+  if (N < 4) {
+    set_error("bad box size %d", N);
+    return 1;
+  }
+  const int Nh = N / 2 + 1;
+  std::set<int> r2;
+  for (int ky = 0; ky < N; ++ky) {
+    const int fy = ky < (N + 1) / 2 ? ky : ky - N;
+    for (int kx = 0; kx < Nh; ++kx) r2.insert(fy * fy + kx * kx);
+  }
+  const bool even = (N % 2 == 0);
+  const int n_special = even ? 4 : 1;
+  const int two_k3 = N * N - n_special;
+  out->nS = 0;
+  out->n1_blocks = ((int)r2.size() + n_special + 31) / 32;
+  out->n3_blocks = (two_k3 + 31) / 32;
+  out->ldz = 32LL * (2 * out->n1_blocks + out->n3_blocks);
+  return 0;
+}
+
+int mem_knn_device(mem_ctx* ctx, const double* D, int32_t nS, int32_t k, int32_t* idx, double* val, void* stream) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  return knn_device(ctx, D, nS, k, idx, val, pick(ctx, stream));
+}
+int mem_graph_dense_device(mem_ctx* ctx, const int32_t* idx, const double* val, int32_t nS, int32_t k, double* M,
+                           void* stream) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  return graph_dense_device(ctx, idx, val, nS, k, M, pick(ctx, stream));
+}
+int mem_ferguson_device(mem_ctx* ctx, const double* d2, int64_t n, const double* logEps, int32_t nEps, double thr,
+                        double* out) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  return ferguson_device(ctx, d2, n, logEps, nEps, thr, out);
+}
+int mem_laplacian_dense_device(mem_ctx* ctx, const double* M, int32_t nS, double sigma, double* L, void* stream) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  return laplacian_dense_device(ctx, M, nS, sigma, L, pick(ctx, stream));
+}
+
+}  // extern "C"

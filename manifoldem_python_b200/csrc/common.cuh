@@ -1,0 +1,113 @@
+// common.cuh — context, workspace arena and error plumbing shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <map>
+#include <vector>
+#include <string>
+
+#include "../../include/manifoldem_b200.h"
+
+namespace mem {
+
+void set_error(const char* fmt, ...);
+
+#define MEM_CUDA(x)                                                                          \
+  do {                                                                                       \
+    cudaError_t e_ = (x);                                                                    \
+    if (e_ != cudaSuccess) {                                                                 \
+      mem::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_));      \
+      return 1;                                                                              \
+    }                                                                                        \
+  } while (0)
+
+#define MEM_CUFFT(x)                                                                         \
+  do {                                                                                       \
+    cufftResult r_ = (x);                                                                    \
+    if (r_ != CUFFT_SUCCESS) {                                                               \
+      mem::set_error("%s:%d %s -> cufft error %d", __FILE__, __LINE__, #x, (int)r_);         \
+      return 1;                                                                              \
+    }                                                                                        \
+  } while (0)
+
+#define MEM_CHECK(x)            \
+  do {                          \
+    if ((x) != 0) return 1;     \
+  } while (0)
+
+// every kernel launch goes through this so bench.py can report gpu_launches
+#define MEM_LAUNCH(ctx, kernel, grid, block, smem, stream, ...)                              \
+  do {                                                                                       \
+    kernel<<<grid, block, smem, stream>>>(__VA_ARGS__);                                      \
+    (ctx)->launches++;                                                                       \
+    cudaError_t e_ = cudaGetLastError();                                                     \
+    if (e_ != cudaSuccess) {                                                                 \
+      mem::set_error("%s:%d launch %s -> %s", __FILE__, __LINE__, #kernel, cudaGetErrorString(e_)); \
+      return 1;                                                                              \
+    }                                                                                        \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes);
+  void release();
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Per-box-size tables (device), built once per context and N / filter.
+struct Geometry {
+  int N = 0, Nh = 0;          // box, half-spectrum width N/2+1
+  int Kh = 0;                 // N*Nh half-spectrum pixels
+  int Kr = 0;                 // distinct |k|^2 values (radial bins)
+  int n_special = 0;          // purely-real self-conjugate pixels (4 for even N, 1 for odd N)
+  int n1_blocks = 0;          // 32-column blocks in S1 (and S2): ceil((Kr+n_special)/32)
+  int K3 = 0;                 // complex entries in S3
+  int n3_blocks = 0;          // ceil(2*K3/32)
+  int64_t ldz = 0;            // Z row pitch (floats) = 32*(2*n1_blocks+n3_blocks)
+  int filter_type = -1, filter_order = 0;
+  double filter_Qc = 0;
+  DevBuf Gtab;                // [Kh] float  low-pass * 1/N^2
+  DevBuf bin_of_pix;          // [Kh] int32
+  DevBuf r2_of_bin;           // [Kr] int32
+  DevBuf bin_start;           // [Kr+1] int32
+  DevBuf bin_pix;             // [Kh] int32 pixels sorted by bin
+  DevBuf s3_col;              // [Kh] int32: column (in floats, relative to Z row) of the re part, or -1
+  DevBuf special_pix;         // [4] int32
+};
+
+struct FftPlan { cufftHandle r2c = 0, c2r = 0; };
+
+}  // namespace mem
+
+struct mem_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+  int sm_count = 148;
+  mem::Geometry geom;
+  std::map<long long, mem::FftPlan> plans;   // key = N * 2^20 + batch
+  mem::DevBuf fft_work;
+  // workspace for one PD
+  mem::DevBuf raw, flip, shift, psi, df, msk2, rot_cs;
+  mem::DevBuf imgA, imgB, imgAll, imgFlip, spec, spec2, cbin, zhi, zlo;
+  mem::DevBuf part_cf, part_c2, part_fl, part_int, avgspec, avgimg, stats;
+  mem::DevBuf D, ctf64, small_out;
+  mem::DevBuf contract_ws;   // split-K partial tiles
+  mem::DevBuf scratch;       // misc (ferguson partials, knn)
+  cudaEvent_t ev[10] = {};
+  float timings[8] = {};
+  void* tmap_encode = nullptr;   // cuTensorMapEncodeTiled entry point
+};
+
+namespace mem {
+int geometry_prepare(mem_ctx* ctx, int N, int filter_type, int filter_order, double Qc);
+int fft_get(mem_ctx* ctx, int N, int batch, FftPlan* out);
+int contract_run(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, const float* Zlo, float* D,
+                 int contraction, int k_chunk_blocks, int split_k, cudaStream_t st);
+int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, const float* Zlo, float* D,
+                int k_chunk_blocks, int split_k, cudaStream_t st);
+}  // namespace mem

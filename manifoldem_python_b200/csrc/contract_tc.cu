@@ -1,0 +1,352 @@
+// contract_tc.cu — the distance contraction (row a12) on the 5th-generation tensor cores.
+//
+//   D = 4 * ( S1 S2^T + S2 S1^T - S3 S3^T )            rows of Z = [S1 | S2 | S3], Z = Zhi + Zlo
+//
+// One GEMM-shaped pass over a K axis of 32-column blocks.  A k-block in S1 pairs A = S1 block with
+// B = the matching S2 block, a k-block in S2 pairs A = S2 with B = S1, and the S3 blocks pair with
+// themselves with the A operand negated in the instruction descriptor, so the whole of
+// |C|^2 (|F|^2)^T + transpose - 2 Re(A A^H)  (getDistanceCTF...py:391-397) accumulates in ONE
+// TMEM accumulator.  FP32 accuracy comes from 3xTF32: hi*hi + hi*lo + lo*hi per k-step, and from
+// promoting the TMEM accumulator into FP32 registers every `chunk` k-blocks (tensor-core
+// accumulation error grows with the number of accumulate steps; SURVEY §7 hard part 1).
+//
+// CTA = one (128 x 256 tile of D, K-slice) work item, upper triangle of tiles only.
+//   warp 0      TMA producer  (cp.async.bulk.tensor, 128B swizzle, 2 stages x 96 KB)
+//   warp 1      tcgen05.mma issuer (one lane), owns the TMEM allocation (512 columns = 2 accumulators)
+//   warps 2..9  epilogue: tcgen05.ld the finished chunk, add into registers, release the accumulator;
+//               after the last chunk store the partial tile to the split-K workspace
+// k_contract_finalize sums the K-slices in a fixed order, scales by 4 and mirrors to the lower triangle.
+#include "common.cuh"
+
+#include <cuda.h>
+#include <algorithm>
+#include <vector>
+
+namespace mem {
+
+constexpr int BM = 128, BN = 256, BK = 32;
+constexpr int STAGES = 2;
+constexpr int BOX_ROWS = 128;
+constexpr int BOX_BYTES = BOX_ROWS * BK * 4;            // 16 KB
+constexpr int STAGE_BYTES = 6 * BOX_BYTES;              // A_hi, A_lo, B_hi(2), B_lo(2) = 96 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 320;
+
+struct WorkItem { int row0, col0, kb0, kb1, slice, pad0, pad1, pad2; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a broken pipeline traps (kernel error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) asm volatile("trap;");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows at 128 B pitch, 8-row groups 1024 B apart (SBO), LBO unused (=1)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::tf32, fp32 accumulate, K-major A and B, M=128, N=256; bit 13 negates A
+__device__ __forceinline__ uint32_t make_idesc(bool negate_a) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((negate_a ? 1u : 0u) << 13) | ((uint32_t)(BN >> 3) << 17) |
+         ((uint32_t)(BM >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_contract_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+              const WorkItem* __restrict__ items, float* __restrict__ ws, int nS, int ldw, int n1, int chunk) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bars = base + STAGES * STAGE_BYTES;
+  // barrier slots (8 B each): full[0..1], empty[2..3], tmem_full[4..5], tmem_empty[6..7]; tmem base at +64
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * STAGE_BYTES + 64);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const WorkItem it = items[blockIdx.x];
+  const int nkb = it.kb1 - it.kb0;
+  const int nchunks = (nkb + chunk - 1) / chunk;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bars + 8 * s, 1);
+      mbar_init(bars + 8 * (2 + s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bars + 8 * (4 + b), 1);
+      mbar_init(bars + 8 * (6 + b), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = it.kb0; kb < it.kb1; ++kb) {
+        int ca, cb;
+        if (kb < n1) { ca = kb; cb = kb + n1; }
+        else if (kb < 2 * n1) { ca = kb; cb = kb - n1; }
+        else { ca = kb; cb = kb; }
+        mbar_wait(bars + 8 * (2 + stage), phase ^ 1);
+        const uint32_t full = bars + 8 * stage;
+        mbar_expect_tx(full, STAGE_BYTES);
+        const uint32_t s0 = base + stage * STAGE_BYTES;
+        tma_load_2d(s0 + 0 * BOX_BYTES, &map_hi, full, ca * BK, it.row0);
+        tma_load_2d(s0 + 1 * BOX_BYTES, &map_lo, full, ca * BK, it.row0);
+        tma_load_2d(s0 + 2 * BOX_BYTES, &map_hi, full, cb * BK, it.col0);
+        tma_load_2d(s0 + 3 * BOX_BYTES, &map_hi, full, cb * BK, it.col0 + BOX_ROWS);
+        tma_load_2d(s0 + 4 * BOX_BYTES, &map_lo, full, cb * BK, it.col0);
+        tma_load_2d(s0 + 5 * BOX_BYTES, &map_lo, full, cb * BK, it.col0 + BOX_ROWS);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      int stage = 0;
+      uint32_t phase = 0;
+      int kb = it.kb0;
+      for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        mbar_wait(bars + 8 * (6 + buf), (((uint32_t)(c >> 1)) & 1u) ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + buf * BN;
+        const int kend = min(it.kb1, kb + chunk);
+        bool first = true;
+        for (; kb < kend; ++kb) {
+          const uint32_t idesc = make_idesc(kb >= 2 * n1);
+          mbar_wait(bars + 8 * stage, phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t s0 = base + stage * STAGE_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            const uint64_t a_hi = make_smem_desc(s0 + 0 * BOX_BYTES + ks * 32);
+            const uint64_t a_lo = make_smem_desc(s0 + 1 * BOX_BYTES + ks * 32);
+            const uint64_t b_hi = make_smem_desc(s0 + 2 * BOX_BYTES + ks * 32);
+            const uint64_t b_lo = make_smem_desc(s0 + 4 * BOX_BYTES + ks * 32);
+            umma_tf32(tacc, a_lo, b_hi, idesc, first ? 0u : 1u);
+            umma_tf32(tacc, a_hi, b_lo, idesc, 1u);
+            umma_tf32(tacc, a_hi, b_hi, idesc, 1u);
+            first = false;
+          }
+          umma_commit(bars + 8 * (2 + stage));   // smem slot free when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bars + 8 * (4 + buf));       // accumulator `buf` holds a finished chunk
+      }
+    }
+  } else {
+    // ===== epilogue: 8 warps, lane quarter q = warp % 4, column half h =====
+    const int q = warp & 3, h = (warp - 2) >> 2;
+    float acc[128];
+#pragma unroll
+    for (int j = 0; j < 128; ++j) acc[j] = 0.0f;
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1;
+      mbar_wait(bars + 8 * (4 + buf), ((uint32_t)(c >> 1)) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + h * 128;
+#pragma unroll
+      for (int gI = 0; gI < 4; ++gI) {
+        uint32_t v[32];
+        tmem_ld32(taddr + gI * 32, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[gI * 32 + j] += __uint_as_float(v[j]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 8 * (6 + buf));
+    }
+    const int row = it.row0 + q * 32 + lane;
+    const int col0 = it.col0 + h * 128;
+    if (row < nS) {
+      float* dst = ws + ((size_t)it.slice * ldw + row) * ldw + col0;
+#pragma unroll
+      for (int j = 0; j < 128; j += 4) {
+        if (col0 + j < ldw)
+          *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// D[i][j] = D[j][i] = 4 * sum_s ws[s][i][j]  (i <= j), 32x32 tiles, coalesced both ways
+__global__ void __launch_bounds__(256) k_contract_finalize(const float* __restrict__ ws, float* __restrict__ D, int nS,
+                                                           int ldw, int nslices) {
+  __shared__ float t[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj < bi) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi * 32 + r, j = bj * 32 + tx;
+    float v = 0.0f;
+    if (i < nS && j < nS)
+      for (int s = 0; s < nslices; ++s) v += ws[((size_t)s * ldw + i) * ldw + j];
+    t[r][tx] = 4.0f * v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi * 32 + r, j = bj * 32 + tx;
+    if (i < nS && j < nS) {
+      if (bi != bj) D[(size_t)i * nS + j] = t[r][tx];
+      else D[(size_t)i * nS + j] = (r <= tx) ? t[r][tx] : t[tx][r];
+    }
+    if (bi != bj) {
+      const int i2 = bj * 32 + r, j2 = bi * 32 + tx;   // mirrored tile, row of the column block
+      if (i2 < nS && j2 < nS) D[(size_t)i2 * nS + j2] = t[tx][r];
+    }
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map(mem_ctx* ctx, CUtensorMap* map, const float* Z, int nS, int64_t ldz) {
+  if (!ctx->tmap_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    MEM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled not available from the driver");
+      return 1;
+    }
+    ctx->tmap_encode = fn;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)ldz, (cuuint64_t)nS};
+  cuuint64_t gstr[1] = {(cuuint64_t)ldz * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BOX_ROWS};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ((PFN_encodeTiled)ctx->tmap_encode)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)Z, gdim, gstr, box,
+                                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: %d", (int)r);
+    return 1;
+  }
+  return 0;
+}
+
+int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, const float* Zlo, float* D,
+                int k_chunk_blocks, int split_k, cudaStream_t st) {
+  const int nS = shp->nS, n1 = shp->n1_blocks, n3 = shp->n3_blocks;
+  const int nkb = 2 * n1 + n3;
+  if (((uintptr_t)Zhi & 15) || ((uintptr_t)Zlo & 15)) {
+    set_error("contraction operands must be 16-byte aligned");
+    return 1;
+  }
+  int dev_cc_major = 0;
+  MEM_CUDA(cudaDeviceGetAttribute(&dev_cc_major, cudaDevAttrComputeCapabilityMajor, ctx->device));
+  if (dev_cc_major != 10) {
+    set_error("tcgen05 contraction needs an sm_100a device (found compute capability major %d); there is no fallback", dev_cc_major);
+    return 1;
+  }
+  const int chunk = k_chunk_blocks > 0 ? k_chunk_blocks : 16;
+  // tiles of the upper triangle (any element with col >= row)
+  std::vector<std::pair<int, int>> tiles;
+  const int tm = (nS + BM - 1) / BM, tn = (nS + BN - 1) / BN;
+  for (int bj = 0; bj < tn; ++bj)
+    for (int bi = 0; bi < tm; ++bi)
+      if (bj * BN + BN - 1 >= bi * BM) tiles.push_back({bi, bj});
+  const int T = (int)tiles.size();
+  int split = split_k;
+  if (split <= 0) {
+    const int min_kb = 4 * chunk;
+    double best = -1;
+    split = 1;
+    for (int s = 1; s <= 32; ++s) {
+      if (s > 1 && nkb / s < min_kb) break;
+      const int items = T * s;
+      const int waves = (items + ctx->sm_count - 1) / ctx->sm_count;
+      const double eff = (double)items / ((double)waves * ctx->sm_count);
+      if (eff > best + 0.02) { best = eff; split = s; }
+    }
+  }
+  split = std::max(1, std::min(split, nkb));
+  const int ldw = ((nS + 3) / 4) * 4;
+  std::vector<WorkItem> items;
+  for (int s = 0; s < split; ++s) {
+    const int kb0 = (int)((long long)nkb * s / split), kb1 = (int)((long long)nkb * (s + 1) / split);
+    for (auto& t : tiles) items.push_back({t.first * BM, t.second * BN, kb0, kb1, s, 0, 0, 0});
+  }
+  MEM_CHECK(ctx->contract_ws.ensure((size_t)split * ldw * ldw * sizeof(float) + items.size() * sizeof(WorkItem) + 256));
+  float* ws = ctx->contract_ws.as<float>();
+  WorkItem* d_items = reinterpret_cast<WorkItem*>(reinterpret_cast<uint8_t*>(ws) + (((size_t)split * ldw * ldw * sizeof(float) + 255) & ~(size_t)255));
+  MEM_CUDA(cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, st));
+  MEM_CUDA(cudaStreamSynchronize(st));   // items is a host temporary
+  CUtensorMap map_hi, map_lo;
+  MEM_CHECK(make_map(ctx, &map_hi, Zhi, nS, shp->ldz));
+  MEM_CHECK(make_map(ctx, &map_lo, Zlo, nS, shp->ldz));
+  MEM_CUDA(cudaFuncSetAttribute(k_contract_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  MEM_LAUNCH(ctx, k_contract_tc, (int)items.size(), NUM_THREADS, SMEM_BYTES, st, map_hi, map_lo, d_items, ws, nS, ldw, n1, chunk);
+  dim3 fgrid((nS + 31) / 32, (nS + 31) / 32);
+  MEM_LAUNCH(ctx, k_contract_finalize, fgrid, 256, 0, st, ws, D, nS, ldw, split);
+  return 0;
+}
+
+}  // namespace mem

@@ -1,0 +1,231 @@
+// dm.cu — device side of the diffusion-map front end (DMembeddingII.op, rows a15-a18):
+// kNN lists, OR-symmetrised graph, Ferguson log-sum sweep, Gaussian-kernel Laplacian.
+// All HBM/L2-bound integer + fp64 work; no tensor cores.
+#include "common.cuh"
+
+#include <math.h>
+#include <algorithm>
+
+namespace mem {
+
+// ---------------------------------------------------------------------------------------------
+// a15  DMembeddingII.initialize :43-57 — per point the k smallest distances, self first.
+// One CTA per point; (key, index) pairs bitonic-sorted in shared memory, ties broken by index.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_knn_sort(const double* __restrict__ D, int nS, int P, int k,
+                                                   int* __restrict__ idx, double* __restrict__ val) {
+  extern __shared__ uint8_t sm_raw[];
+  double* key = reinterpret_cast<double*>(sm_raw);
+  int* id = reinterpret_cast<int*>(sm_raw + (size_t)P * sizeof(double));
+  const int i = blockIdx.x;
+  const double* row = D + (size_t)i * nS;   // D symmetric: column i == row i
+  for (int j = threadIdx.x; j < P; j += blockDim.x) {
+    double v = INFINITY;
+    if (j < nS) v = (j == i) ? -INFINITY : row[j];   // D[iS,iS] = -inf, :48
+    key[j] = v;
+    id[j] = j;
+  }
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const double a = key[lo], b = key[hi];
+        const int ia = id[lo], ib = id[hi];
+        const bool gt = (a > b) || (a == b && ia > ib);
+        if (gt == up) {
+          key[lo] = b; key[hi] = a;
+          id[lo] = ib; id[hi] = ia;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int a = threadIdx.x; a < k; a += blockDim.x) {
+    idx[(size_t)i * k + a] = id[a];
+    val[(size_t)i * k + a] = (a == 0) ? 0.0 : key[a];   // yVal1[0,iS] = 0, :54
+  }
+}
+
+int knn_device(mem_ctx* ctx, const double* D, int nS, int k, int* idx, double* val, cudaStream_t st) {
+  if (k < 1 || k > nS) {
+    set_error("knn: need 1 <= k <= nS (k=%d nS=%d)", k, nS);
+    return 1;
+  }
+  int P = 1;
+  while (P < nS) P <<= 1;
+  const size_t smem = (size_t)P * (sizeof(double) + sizeof(int));
+  if (smem > 200 * 1024) {
+    set_error("knn: nS=%d exceeds the in-shared-memory sort (max 16384 points)", nS);
+    return 1;
+  }
+  MEM_CUDA(cudaFuncSetAttribute(k_knn_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int threads = std::max(32, std::min(1024, P / 2));
+  MEM_LAUNCH(ctx, k_knn_sort, nS, threads, smem, st, D, nS, P, k, idx, val);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a16  DMembeddingII.op :113-140 — union kNN graph with value d^2, dense form, absent = -1.
+//   pass 1: Y[i][j] = d^2 for directed list entries (zeros: flag matrix Zf[i][j] = 1)
+//   pass 2: M[i][j] = a^2 + b^2 - a b, a = sqrt(Y[i][j]) or 0, b = sqrt(Y[j][i]) or 0;
+//           entries whose result is 0 are absent unless the zero flag is set (value 0).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_graph_scatter(const int* __restrict__ idx, const double* __restrict__ val, int nS, int k,
+                                double* __restrict__ Y, uint8_t* __restrict__ Zf) {
+  const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (e >= (size_t)nS * k) return;
+  const int i = (int)(e / k);
+  const int j = idx[e];
+  const double v = val[e];
+  if (v < 1e-6) Zf[(size_t)i * nS + j] = 1;
+  else Y[(size_t)i * nS + j] = v;
+}
+__global__ void k_graph_combine(const double* __restrict__ Y, const uint8_t* __restrict__ Zf, int nS,
+                                double* __restrict__ M) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= nS) return;
+  const double yij = Y[(size_t)i * nS + j], yji = Y[(size_t)j * nS + i];
+  const double a = yij > 0 ? sqrt(yij) : 0.0, b = yji > 0 ? sqrt(yji) : 0.0;
+  const double m = a * a + b * b - a * b;
+  double out = -1.0;
+  if (m != 0.0) out = m;
+  else if (Zf[(size_t)i * nS + j]) out = 0.0;
+  M[(size_t)i * nS + j] = out;
+}
+
+int graph_dense_device(mem_ctx* ctx, const int* idx, const double* val, int nS, int k, double* M, cudaStream_t st) {
+  const size_t nn = (size_t)nS * nS;
+  MEM_CHECK(ctx->scratch.ensure(nn * sizeof(double) + nn));
+  double* Y = ctx->scratch.as<double>();
+  uint8_t* Zf = reinterpret_cast<uint8_t*>(Y + nn);
+  MEM_CUDA(cudaMemsetAsync(Y, 0, nn * sizeof(double) + nn, st));
+  const size_t tot = (size_t)nS * k;
+  MEM_LAUNCH(ctx, k_graph_scatter, (unsigned)((tot + 255) / 256), 256, 0, st, idx, val, nS, k, Y, Zf);
+  MEM_LAUNCH(ctx, k_graph_combine, dim3((nS + 255) / 256, nS), 256, 0, st, Y, Zf, nS, M);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a17  fergusonE.op :36-43 — for every eps: sum over present entries with d2/(2 eps) < thr of
+// exp(-d2/(2 eps)).  Each thread keeps 8 distances in registers and sweeps all eps; per-eps block
+// sums go to partial[block][eps], reduced in a fixed order by k_ferguson_reduce (deterministic).
+// ---------------------------------------------------------------------------------------------
+constexpr int FG_V = 8, FG_THREADS = 256, FG_ET = 32;
+__global__ void __launch_bounds__(FG_THREADS) k_ferguson(const double* __restrict__ d2, size_t n,
+                                                         const double* __restrict__ inv2eps, int nEps, double thr,
+                                                         double* __restrict__ partial) {
+  __shared__ double wsum[FG_THREADS / 32][FG_ET];
+  double x[FG_V];
+  const size_t base = (size_t)blockIdx.x * FG_THREADS * FG_V;
+#pragma unroll
+  for (int v = 0; v < FG_V; ++v) {
+    const size_t j = base + (size_t)v * FG_THREADS + threadIdx.x;
+    x[v] = (j < n) ? d2[j] : -1.0;   // negative = absent
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int e0 = 0; e0 < nEps; e0 += FG_ET) {
+    for (int ee = 0; ee < FG_ET && e0 + ee < nEps; ++ee) {
+      const double s = inv2eps[e0 + ee];
+      double acc = 0;
+#pragma unroll
+      for (int v = 0; v < FG_V; ++v) {
+        const double d = x[v] * s;
+        if (x[v] >= 0.0 && d < thr) acc += exp(-d);
+      }
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) wsum[warp][ee] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x < FG_ET && e0 + threadIdx.x < nEps) {
+      double t = 0;
+      for (int w = 0; w < FG_THREADS / 32; ++w) t += wsum[w][threadIdx.x];
+      partial[(size_t)blockIdx.x * nEps + e0 + threadIdx.x] = t;
+    }
+    __syncthreads();
+  }
+}
+__global__ void k_ferguson_reduce(const double* __restrict__ partial, int nBlocks, int nEps, double* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nEps) return;
+  double t = 0;
+  for (int b = 0; b < nBlocks; ++b) t += partial[(size_t)b * nEps + e];
+  out[e] = t;
+}
+
+int ferguson_device(mem_ctx* ctx, const double* d2, int64_t n, const double* logEps, int nEps, double thr,
+                    double* out_host) {
+  cudaStream_t st = ctx->stream;
+  std::vector<double> inv(nEps);
+  for (int e = 0; e < nEps; ++e) inv[e] = 1.0 / (2.0 * exp(logEps[e]));
+  const int nBlocks = (int)((n + (size_t)FG_THREADS * FG_V - 1) / ((size_t)FG_THREADS * FG_V));
+  MEM_CHECK(ctx->small_out.ensure((size_t)(2 * nEps) * sizeof(double) + (size_t)nBlocks * nEps * sizeof(double)));
+  double* d_inv = ctx->small_out.as<double>();
+  double* d_out = d_inv + nEps;
+  double* d_part = d_out + nEps;
+  MEM_CUDA(cudaMemcpyAsync(d_inv, inv.data(), nEps * sizeof(double), cudaMemcpyHostToDevice, st));
+  MEM_LAUNCH(ctx, k_ferguson, nBlocks, FG_THREADS, 0, st, d2, (size_t)n, d_inv, nEps, thr, d_part);
+  MEM_LAUNCH(ctx, k_ferguson_reduce, (nEps + 127) / 128, 128, 0, st, d_part, nBlocks, nEps, d_out);
+  std::vector<double> sums(nEps);
+  MEM_CUDA(cudaMemcpyAsync(sums.data(), d_out, nEps * sizeof(double), cudaMemcpyDeviceToHost, st));
+  MEM_CUDA(cudaStreamSynchronize(st));
+  for (int e = 0; e < nEps; ++e) out_host[e] = log(sums[e]);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a18  slaplacianonFly.op :57-78, dense storage (absent entries stay 0):
+//   W = exp(-d2/sigma^2);  W /= d_i d_j (d = column sums);  W /= sqrt(d'_i) sqrt(d'_j);  L = |W + W^T| / 2
+// ---------------------------------------------------------------------------------------------
+__global__ void k_lap_weights(const double* __restrict__ M, double* __restrict__ W, size_t nn, double inv_s2) {
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < nn; e += (size_t)gridDim.x * blockDim.x) {
+    const double m = M[e];
+    W[e] = (m >= 0.0) ? exp(-m * inv_s2) : 0.0;
+  }
+}
+// column sums: thread per column, fixed row order
+__global__ void k_colsum(const double* __restrict__ W, int nS, double* __restrict__ d, int take_sqrt) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nS) return;
+  double t = 0;
+  for (int i = 0; i < nS; ++i) t += W[(size_t)i * nS + j];
+  d[j] = take_sqrt ? sqrt(t) : t;
+}
+__global__ void k_lap_scale(double* __restrict__ W, int nS, const double* __restrict__ d) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= nS) return;
+  W[(size_t)i * nS + j] /= (d[i] * d[j]);
+}
+__global__ void k_lap_sym(const double* __restrict__ W, double* __restrict__ L, int nS) {
+  __shared__ double t[32][33];
+  const int bi = blockIdx.y * 32, bj = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bj + r, j = bi + tx;   // transposed tile
+    t[r][tx] = (i < nS && j < nS) ? W[(size_t)i * nS + j] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi + r, j = bj + tx;
+    if (i < nS && j < nS) L[(size_t)i * nS + j] = fabs(W[(size_t)i * nS + j] + t[tx][r]) * 0.5;
+  }
+}
+
+int laplacian_dense_device(mem_ctx* ctx, const double* M, int nS, double sigma, double* L, cudaStream_t st) {
+  const size_t nn = (size_t)nS * nS;
+  MEM_CHECK(ctx->scratch.ensure(nn * sizeof(double) + (size_t)nS * sizeof(double)));
+  double* W = ctx->scratch.as<double>();
+  double* d = W + nn;
+  const int g1 = (int)std::min<size_t>((nn + 255) / 256, (size_t)ctx->sm_count * 32);
+  MEM_LAUNCH(ctx, k_lap_weights, g1, 256, 0, st, M, W, nn, 1.0 / (sigma * sigma));
+  MEM_LAUNCH(ctx, k_colsum, (nS + 127) / 128, 128, 0, st, W, nS, d, 0);
+  MEM_LAUNCH(ctx, k_lap_scale, dim3((nS + 255) / 256, nS), 256, 0, st, W, nS, d);
+  MEM_LAUNCH(ctx, k_colsum, (nS + 127) / 128, 128, 0, st, W, nS, d, 1);
+  MEM_LAUNCH(ctx, k_lap_scale, dim3((nS + 255) / 256, nS), 256, 0, st, W, nS, d);
+  MEM_LAUNCH(ctx, k_lap_sym, dim3((nS + 31) / 32, (nS + 31) / 32), 256, 0, st, W, L, nS);
+  return 0;
+}
+
+}  // namespace mem

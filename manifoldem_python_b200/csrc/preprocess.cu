@@ -1,0 +1,779 @@
+// preprocess.cu — everything of getDistanceCTF_local_Conj9combinedS2.op except the contraction:
+// ingest/normalise (a2,a3), low-pass (a5), in-plane alignment (a7), CTF (a8), FFT + phase flip (a10),
+// Wiener/flip averages (a11), intensity (a13) and the operand writer that feeds the contraction (a12).
+// All kernels are HBM-bound; reference lines are cited per kernel.
+#include "common.cuh"
+
+#include <math.h>
+#include <algorithm>
+#include <stdarg.h>
+
+namespace mem {
+
+// ------------------------------------------------------------------------------------------------
+// error string + arena
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+int DevBuf::ensure(size_t bytes) {
+  if (bytes <= cap) return 0;
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+  size_t want = bytes + (bytes >> 3) + 256;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    e = cudaMalloc(&p, bytes);
+    want = bytes;
+  }
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    p = nullptr;
+    return 1;
+  }
+  cap = want;
+  return 0;
+}
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// geometry tables (host build, once per N / filter)
+// ------------------------------------------------------------------------------------------------
+static inline int freq_of(int k, int N) { return k < (N + 1) / 2 ? k : k - N; }
+
+int geometry_prepare(mem_ctx* ctx, int N, int filter_type, int filter_order, double Qc) {
+  Geometry& g = ctx->geom;
+  if (g.N == N && g.filter_type == filter_type && g.filter_order == filter_order && g.filter_Qc == Qc) return 0;
+  const int Nh = N / 2 + 1, Kh = N * Nh;
+  std::vector<int> r2(Kh);
+  int r2max = 0;
+  for (int ky = 0; ky < N; ++ky)
+    for (int kx = 0; kx < Nh; ++kx) {
+      int fy = freq_of(ky, N), fx = kx;
+      int v = fy * fy + fx * fx;
+      r2[ky * Nh + kx] = v;
+      r2max = std::max(r2max, v);
+    }
+  std::vector<int> bin_id(r2max + 1, -1);
+  for (int p = 0; p < Kh; ++p) bin_id[r2[p]] = 0;
+  std::vector<int> r2_of_bin;
+  for (int v = 0; v <= r2max; ++v)
+    if (bin_id[v] == 0) {
+      bin_id[v] = (int)r2_of_bin.size();
+      r2_of_bin.push_back(v);
+    }
+  const int Kr = (int)r2_of_bin.size();
+  std::vector<int> bin_of_pix(Kh), bin_start(Kr + 1, 0), bin_pix(Kh);
+  for (int p = 0; p < Kh; ++p) {
+    bin_of_pix[p] = bin_id[r2[p]];
+    bin_start[bin_of_pix[p] + 1]++;
+  }
+  for (int b = 0; b < Kr; ++b) bin_start[b + 1] += bin_start[b];
+  {
+    std::vector<int> fill(bin_start.begin(), bin_start.end() - 1);
+    for (int p = 0; p < Kh; ++p) bin_pix[fill[bin_of_pix[p]]++] = p;
+  }
+  // low-pass table, getDistanceCTF...py:139-167 + :288 (ifftshift) with the 1/N^2 of the unnormalised inverse FFT
+  std::vector<float> G(Kh);
+  for (int p = 0; p < Kh; ++p) {
+    double Q = sqrt((double)r2[p]) / (N / 2.0);
+    double gv;
+    if (filter_type == 1)
+      gv = exp(-(log(2.0) / 2.0) * (Q / Qc) * (Q / Qc));
+    else
+      gv = sqrt(1.0 / (1.0 + pow(Q / Qc, 2.0 * filter_order)));
+    G[p] = (float)(gv / ((double)N * N));
+  }
+  // S3 membership: one representative of every conjugate pair, weight-2 entries only
+  const bool even = (N % 2 == 0);
+  std::vector<int> special;
+  std::vector<int> s3_col(Kh, -1);
+  int j = 0;
+  for (int ky = 0; ky < N; ++ky)
+    for (int kx = 0; kx < Nh; ++kx) {
+      const int p = ky * Nh + kx;
+      const bool selfcol = (kx == 0) || (even && kx == N / 2);
+      if (!selfcol) {
+        s3_col[p] = j++;
+      } else {
+        const bool selfrow = (ky == 0) || (even && ky == N / 2);
+        if (selfrow)
+          special.push_back(p);
+        else if (ky < (N + 1) / 2)
+          s3_col[p] = j++;
+      }
+    }
+  const int K3 = j;
+  const int n_special = (int)special.size();
+  const int n1_blocks = (Kr + n_special + 31) / 32;
+  const int n3_blocks = (2 * K3 + 31) / 32;
+  for (int p = 0; p < Kh; ++p)
+    if (s3_col[p] >= 0) s3_col[p] = 64 * n1_blocks + 2 * s3_col[p];
+  while (special.size() < 4) special.push_back(-1);
+
+  MEM_CHECK(g.Gtab.ensure(Kh * sizeof(float)));
+  MEM_CHECK(g.bin_of_pix.ensure(Kh * sizeof(int)));
+  MEM_CHECK(g.r2_of_bin.ensure(Kr * sizeof(int)));
+  MEM_CHECK(g.bin_start.ensure((Kr + 1) * sizeof(int)));
+  MEM_CHECK(g.bin_pix.ensure(Kh * sizeof(int)));
+  MEM_CHECK(g.s3_col.ensure(Kh * sizeof(int)));
+  MEM_CHECK(g.special_pix.ensure(4 * sizeof(int)));
+  MEM_CUDA(cudaMemcpy(g.Gtab.p, G.data(), Kh * sizeof(float), cudaMemcpyHostToDevice));
+  MEM_CUDA(cudaMemcpy(g.bin_of_pix.p, bin_of_pix.data(), Kh * sizeof(int), cudaMemcpyHostToDevice));
+  MEM_CUDA(cudaMemcpy(g.r2_of_bin.p, r2_of_bin.data(), Kr * sizeof(int), cudaMemcpyHostToDevice));
+  MEM_CUDA(cudaMemcpy(g.bin_start.p, bin_start.data(), (Kr + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  MEM_CUDA(cudaMemcpy(g.bin_pix.p, bin_pix.data(), Kh * sizeof(int), cudaMemcpyHostToDevice));
+  MEM_CUDA(cudaMemcpy(g.s3_col.p, s3_col.data(), Kh * sizeof(int), cudaMemcpyHostToDevice));
+  MEM_CUDA(cudaMemcpy(g.special_pix.p, special.data(), 4 * sizeof(int), cudaMemcpyHostToDevice));
+  g.N = N; g.Nh = Nh; g.Kh = Kh; g.Kr = Kr; g.n_special = n_special; g.n1_blocks = n1_blocks;
+  g.K3 = K3; g.n3_blocks = n3_blocks; g.ldz = 32LL * (2 * n1_blocks + n3_blocks);
+  g.filter_type = filter_type; g.filter_order = filter_order; g.filter_Qc = Qc;
+  return 0;
+}
+
+int fft_get(mem_ctx* ctx, int N, int batch, FftPlan* out) {
+  long long key = ((long long)N << 24) + batch;
+  auto it = ctx->plans.find(key);
+  if (it != ctx->plans.end()) {
+    *out = it->second;
+    return 0;
+  }
+  FftPlan pl;
+  int n[2] = {N, N};
+  size_t ws1 = 0, ws2 = 0;
+  MEM_CUFFT(cufftCreate(&pl.r2c));
+  MEM_CUFFT(cufftSetAutoAllocation(pl.r2c, 0));
+  MEM_CUFFT(cufftMakePlanMany(pl.r2c, 2, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, batch, &ws1));
+  MEM_CUFFT(cufftCreate(&pl.c2r));
+  MEM_CUFFT(cufftSetAutoAllocation(pl.c2r, 0));
+  MEM_CUFFT(cufftMakePlanMany(pl.c2r, 2, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_C2R, batch, &ws2));
+  MEM_CHECK(ctx->fft_work.ensure(std::max(ws1, ws2)));
+  // the work area may have moved: re-attach it to every plan
+  ctx->plans[key] = pl;
+  for (auto& kv : ctx->plans) {
+    MEM_CUFFT(cufftSetWorkArea(kv.second.r2c, ctx->fft_work.p));
+    MEM_CUFFT(cufftSetWorkArea(kv.second.c2r, ctx->fft_work.p));
+  }
+  *out = pl;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double t = 0;
+  for (int i = 0; i < nw; ++i) t += sh[i];
+  return t;
+}
+
+// a2+a3 (:246-283): picture = raw^T (SPIDER) or raw; conjugates flipped upside down; then
+// (x - mean(b))/std(b) with b = x*(1-msk) over all N^2 pixels (population std).
+// One CTA per particle; pass 1 = moments (fp64 accumulators), pass 2 = 32x32 tile transpose + scale.
+__global__ void __launch_bounds__(256) k_ingest(const float* __restrict__ raw, const uint8_t* __restrict__ flip,
+                                                float* __restrict__ out, int N, int transposed) {
+  __shared__ double red[8];
+  __shared__ float tile[32][33];
+  const int i = blockIdx.x;
+  const float* src = raw + (size_t)i * N * N;
+  float* dst = out + (size_t)i * N * N;
+  const bool fl = flip[i] != 0;
+  const float half = 0.5f * N, r2lim = half * half;
+  double s = 0, s2 = 0;
+  for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+    const int a = e / N, b = e - a * N;
+    int r = transposed ? b : a;
+    const int c = transposed ? a : b;
+    if (fl) r = N - 1 - r;
+    const float x = (float)r - half + 1.0f, y = (float)c - half;   // annularMask.py:24-30, centre (N/2-1, N/2)
+    const float v = src[e];
+    const float bg = (x * x + y * y < r2lim) ? 0.0f : v;
+    s += bg;
+    s2 += (double)bg * bg;
+  }
+  s = block_sum(s, red);
+  s2 = block_sum(s2, red);
+  const double n = (double)N * N;
+  const double mean = s / n;
+  const double var = s2 / n - mean * mean;
+  const float fm = (float)mean;
+  const float inv = (float)(1.0 / sqrt(var));
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const int nt = (N + 31) / 32;
+  for (int t = 0; t < nt * nt; ++t) {
+    const int tr = (t / nt) * 32, tc = (t % nt) * 32;   // output tile origin (rows r', cols c)
+    __syncthreads();
+    if (transposed) {
+      // raw index = c*N + r : read with r fastest
+      for (int k = ty; k < 32; k += 8) {
+        const int c = tc + k, rp = tr + tx;
+        if (c < N && rp < N) {
+          const int r = fl ? N - 1 - rp : rp;
+          tile[k][tx] = src[(size_t)c * N + r];
+        }
+      }
+      __syncthreads();
+      for (int k = ty; k < 32; k += 8) {
+        const int rp = tr + k, c = tc + tx;
+        if (rp < N && c < N) dst[(size_t)rp * N + c] = (tile[tx][k] - fm) * inv;
+      }
+    } else {
+      for (int k = ty; k < 32; k += 8) {
+        const int rp = tr + k, c = tc + tx;
+        if (rp < N && c < N) {
+          const int r = fl ? N - 1 - rp : rp;
+          dst[(size_t)rp * N + c] = (src[(size_t)r * N + c] - fm) * inv;
+        }
+      }
+    }
+  }
+}
+
+// a5 (:286-293): spectrum *= ifftshift(G)/N^2
+__global__ void k_specmul(float2* __restrict__ spec, const float* __restrict__ G, int Kh, size_t total) {
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const float g = G[e % Kh];
+    float2 v = spec[e];
+    v.x *= g;
+    v.y *= g;
+    spec[e] = v;
+  }
+}
+
+// Cubic B-spline prefilter, periodic boundary (what scipy.ndimage.rotate's spline_filter amounts to on
+// the 3x3-tiled image of rotatefill.py:21-25 away from the tile border; SURVEY §7 hard part 2).
+//   c+[k] = 6 s[k] + z c+[k-1],  c[k] = z (c[k+1] - c+[k]),  z = sqrt(3) - 2
+// with the periodic initial values summed to |z|^24 < 2e-14.
+#define SPL_Z (-0.26794919243112270647f)
+#define SPL_W 24
+
+// rows: CTA = 32 rows of one image staged in smem (pitch odd -> conflict-free), one lane per row.
+__global__ void __launch_bounds__(32) k_prefilter_rows(const float* __restrict__ in, float* __restrict__ out, int N,
+                                                       int apply_mask) {
+  extern __shared__ float sm[];
+  const int pitch = N | 1;
+  const int img = blockIdx.y, r0 = blockIdx.x * 32;
+  const float* src = in + (size_t)img * N * N;
+  float* dst = out + (size_t)img * N * N;
+  const int rows = min(32, N - r0);
+  const float half = 0.5f * N, r2lim = half * half;
+  for (int e = threadIdx.x; e < rows * N; e += 32) {
+    const int rr = e / N, c = e - rr * N;
+    float v = src[(size_t)(r0 + rr) * N + c];
+    if (apply_mask) {   // img * msk, :325
+      const float x = (float)(r0 + rr) - half + 1.0f, y = (float)c - half;
+      if (!(x * x + y * y < r2lim)) v = 0.0f;
+    }
+    sm[rr * pitch + c] = 6.0f * v;
+  }
+  __syncwarp();
+  if ((int)threadIdx.x < rows) {
+    float* row = sm + threadIdx.x * pitch;
+    const int W = SPL_W;
+    float cp = 0.0f, zk = 1.0f;
+    for (int j = 0; j < W; ++j) {   // c+[0] = sum_j z^j s[-j mod N]
+      cp += zk * row[(N - j % N) % N];
+      zk *= SPL_Z;
+    }
+    row[0] = cp;
+    for (int k = 1; k < N; ++k) {
+      cp = row[k] + SPL_Z * cp;
+      row[k] = cp;
+    }
+    float cm = 0.0f;
+    zk = SPL_Z;
+    for (int j = 0; j < W; ++j) {   // c[N-1] = -sum_j z^(j+1) c+[(N-1+j) mod N]
+      cm -= zk * row[(N - 1 + j) % N];
+      zk *= SPL_Z;
+    }
+    row[N - 1] = cm;
+    for (int k = N - 2; k >= 0; --k) {
+      cm = SPL_Z * (cm - row[k]);
+      row[k] = cm;
+    }
+  }
+  __syncwarp();
+  for (int e = threadIdx.x; e < rows * N; e += 32) {
+    const int rr = e / N, c = e - rr * N;
+    dst[(size_t)(r0 + rr) * N + c] = sm[rr * pitch + c];
+  }
+}
+
+// columns: CTA = 32 columns x all rows in smem, one lane per column (bank = lane).
+__global__ void __launch_bounds__(32) k_prefilter_cols(float* __restrict__ data, int N) {
+  extern __shared__ float sm[];
+  const int img = blockIdx.y, c0 = blockIdx.x * 32;
+  float* base = data + (size_t)img * N * N;
+  const int c = c0 + threadIdx.x;
+  const bool ok = c < N;
+  for (int r = 0; r < N; ++r) sm[r * 32 + threadIdx.x] = ok ? 6.0f * base[(size_t)r * N + c] : 0.0f;
+  float* col = sm + threadIdx.x;
+  const int W = SPL_W;
+  float cp = 0.0f, zk = 1.0f;
+  for (int j = 0; j < W; ++j) {
+    cp += zk * col[((N - j % N) % N) * 32];
+    zk *= SPL_Z;
+  }
+  col[0] = cp;
+  for (int k = 1; k < N; ++k) {
+    cp = col[k * 32] + SPL_Z * cp;
+    col[k * 32] = cp;
+  }
+  float cm = 0.0f;
+  zk = SPL_Z;
+  for (int j = 0; j < W; ++j) {
+    cm -= zk * col[((N - 1 + j) % N) * 32];
+    zk *= SPL_Z;
+  }
+  col[(N - 1) * 32] = cm;
+  for (int k = N - 2; k >= 0; --k) {
+    cm = SPL_Z * (cm - col[k * 32]);
+    col[k * 32] = cm;
+  }
+  if (ok)
+    for (int r = 0; r < N; ++r) base[(size_t)r * N + c] = sm[r * 32 + threadIdx.x];
+}
+
+// per-image rotation cos/sin in fp64 (ndimage.rotate: matrix [[c, s], [-s, c]], angle in degrees)
+__global__ void k_angles(const double* __restrict__ psi_deg, double psi_p_deg, double2* __restrict__ cs, int nS) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nS) return;
+  const double a = (i < nS ? psi_deg[i] : -psi_p_deg) * 0.017453292519943295769;   // second rotation is by -psi_p (:330)
+  double s, c;
+  sincos(a, &s, &c);
+  cs[i] = make_double2(c, s);
+}
+
+// a7 (rotatefill.py:21-41): out(o) = sum_{4x4} w * coef[(floor(x)-1+a) mod N], x = R (o - ctr) + ctr, ctr=(N-1)/2.
+// Coordinates in fp64, weights in fp32.  If msk2 != NULL a second, masked copy is written (img*msk2, :344).
+__global__ void __launch_bounds__(256) k_rotate(const float* __restrict__ coef, float* __restrict__ out,
+                                                const double2* __restrict__ cs, int cs_stride, int N,
+                                                const uint8_t* __restrict__ msk2, float* __restrict__ out_masked) {
+  const int img = blockIdx.z;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int r = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (r >= N || c >= N) return;
+  const double2 a = cs[(size_t)img * cs_stride];
+  const double ctr = 0.5 * (N - 1);
+  const double dr = r - ctr, dc = c - ctr;
+  const double x0 = a.x * dr + a.y * dc + ctr;
+  const double x1 = -a.y * dr + a.x * dc + ctr;
+  const double f0 = floor(x0), f1 = floor(x1);
+  const float t0 = (float)(x0 - f0), t1 = (float)(x1 - f1);
+  int i0 = (int)f0 - 1, j0 = (int)f1 - 1;
+  i0 %= N; if (i0 < 0) i0 += N;
+  j0 %= N; if (j0 < 0) j0 += N;
+  float w0[4], w1[4];
+  {
+    const float t = t0, u = 1.0f - t;
+    w0[0] = u * u * u * (1.0f / 6.0f);
+    w0[1] = (4.0f - 6.0f * t * t + 3.0f * t * t * t) * (1.0f / 6.0f);
+    w0[2] = (4.0f - 6.0f * u * u + 3.0f * u * u * u) * (1.0f / 6.0f);
+    w0[3] = t * t * t * (1.0f / 6.0f);
+  }
+  {
+    const float t = t1, u = 1.0f - t;
+    w1[0] = u * u * u * (1.0f / 6.0f);
+    w1[1] = (4.0f - 6.0f * t * t + 3.0f * t * t * t) * (1.0f / 6.0f);
+    w1[2] = (4.0f - 6.0f * u * u + 3.0f * u * u * u) * (1.0f / 6.0f);
+    w1[3] = t * t * t * (1.0f / 6.0f);
+  }
+  const float* src = coef + (size_t)img * N * N;
+  int jj[4];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    int j = j0 + b;
+    if (j >= N) j -= N;
+    jj[b] = j;
+  }
+  float acc = 0.0f;
+#pragma unroll
+  for (int aI = 0; aI < 4; ++aI) {
+    int ii = i0 + aI;
+    if (ii >= N) ii -= N;
+    const float* row = src + (size_t)ii * N;
+    const float rsum = w1[0] * __ldg(row + jj[0]) + w1[1] * __ldg(row + jj[1]) + w1[2] * __ldg(row + jj[2]) +
+                       w1[3] * __ldg(row + jj[3]);
+    acc += w0[aI] * rsum;
+  }
+  const size_t o = (size_t)img * N * N + (size_t)r * N + c;
+  out[o] = acc;
+  if (out_masked) out_masked[o] = msk2[r * N + c] ? acc : 0.0f;
+}
+
+// a8 (ctemh_cryoFrank.py:24-44) at the distinct radii: C[i][b].
+// gamma in fp64, reduced mod 2 pi in fp64, sin/cos in fp32 on the reduced argument (|err| ~ 1e-7).
+struct CtfConst { double w1, w2_per_df, k2_scale, env_scale, ampc; };
+__device__ __forceinline__ float ctf_eval(const CtfConst& cc, double df, int r2) {
+  const double k2 = cc.k2_scale * (double)r2;
+  const double g = (0.5 * cc.w1 * k2 - cc.w2_per_df * df) * k2;
+  const double gr = g - 6.283185307179586476925 * rint(g * 0.15915494309189533576888);
+  float s, c;
+  sincosf((float)gr, &s, &c);
+  float v = s - (float)cc.ampc * c;
+  if (cc.env_scale != 0.0) v *= expf((float)(-k2 * cc.env_scale));
+  return v;
+}
+__global__ void k_ctf_bins(const double* __restrict__ df, const int* __restrict__ r2_of_bin, float* __restrict__ cbin,
+                           int Kr, CtfConst cc) {
+  const int i = blockIdx.y;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= Kr) return;
+  cbin[(size_t)i * Kr + b] = ctf_eval(cc, df[i], r2_of_bin[b]);
+}
+
+// full-precision CTF field for the output record (:339, stored ifftshift-ed, flattened by :393)
+__global__ void k_ctf_full(const double* __restrict__ df, double* __restrict__ out, int N, CtfConst cc) {
+  const int i = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N * N) return;
+  const int ky = e / N, kx = e - ky * N;
+  const int h = (N + 1) / 2;
+  const int fy = ky < h ? ky : ky - N, fx = kx < h ? kx : kx - N;
+  const double k2 = cc.k2_scale * (double)(fy * fy + fx * fx);
+  const double g = (0.5 * cc.w1 * k2 - cc.w2_per_df * df[i]) * k2;
+  double v = sin(g) - cc.ampc * cos(g);
+  if (cc.env_scale != 0.0) v *= exp(-k2 * cc.env_scale);
+  out[(size_t)i * N * N + e] = v;
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = tf32_rna(x);
+  lo = tf32_rna(x - hi);
+}
+
+// a12 operands, radial part: S1[i][b] = C_i(b)^2 / 4, S2[i][b] = P_i(b) = sum_{|k|^2 = r2(b)} |F_i(k)|^2
+// (full spectrum = half spectrum with weight 2 on the non-self-conjugate columns), summed in a fixed order.
+// Columns [Kr, Kr+n_special) carry the purely real self-conjugate pixels: S1 = -x/4, S2 = x, x = C*Re F.
+__global__ void k_operands_radial(const float2* __restrict__ spec, const float* __restrict__ cbin,
+                                  const int* __restrict__ bin_start, const int* __restrict__ bin_pix,
+                                  const int* __restrict__ bin_of_pix, const int* __restrict__ special_pix,
+                                  float* __restrict__ zhi, float* __restrict__ zlo, int N, int Nh, int Kh, int Kr,
+                                  int n_special, int n1_blocks, int64_t ldz) {
+  const int i = blockIdx.y;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int w1 = 32 * n1_blocks;
+  if (b >= w1) return;
+  const float2* F = spec + (size_t)i * Kh;
+  float s1 = 0.0f, s2 = 0.0f;
+  if (b < Kr) {
+    const float c = cbin[(size_t)i * Kr + b];
+    s1 = 0.25f * c * c;
+    float acc = 0.0f;
+    const bool even = (N & 1) == 0;
+    for (int q = bin_start[b]; q < bin_start[b + 1]; ++q) {
+      const int p = bin_pix[q];
+      const int kx = p % Nh;
+      const float2 f = F[p];
+      const float m = f.x * f.x + f.y * f.y;
+      acc += ((kx == 0) || (even && kx == N / 2)) ? m : 2.0f * m;
+    }
+    s2 = acc;
+  } else if (b < Kr + n_special) {
+    const int p = special_pix[b - Kr];
+    const float x = cbin[(size_t)i * Kr + bin_of_pix[p]] * F[p].x;
+    s1 = -0.25f * x;
+    s2 = x;
+  }
+  float h, l;
+  split_tf32(s1, h, l);
+  zhi[(size_t)i * ldz + b] = h;
+  zlo[(size_t)i * ldz + b] = l;
+  split_tf32(s2, h, l);
+  zhi[(size_t)i * ldz + w1 + b] = h;
+  zlo[(size_t)i * ldz + w1 + b] = l;
+}
+
+// a12 operands, S3 part + a10 phase flip + a11 partial sums.  Thread = one half-spectrum pixel, loops over
+// the images of its group (grid.y groups):  A = C*F -> Z (hi/lo), spec <- sign(C)*F in place,
+// partial sums of C*Fw, C^2 and sign(C)*F in fp64 (Fw = spectrum of the unmasked image when msk2 is used).
+__global__ void __launch_bounds__(256) k_operands_s3(float2* __restrict__ spec, const float2* __restrict__ specw,
+                                                     const float* __restrict__ cbin, const int* __restrict__ bin_of_pix,
+                                                     const int* __restrict__ s3_col, float* __restrict__ zhi,
+                                                     float* __restrict__ zlo, double2* __restrict__ part_cf,
+                                                     double* __restrict__ part_c2, double2* __restrict__ part_fl,
+                                                     int nS, int Kh, int Kr, int64_t ldz, int per_group, int write_z) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Kh) return;
+  const int g = blockIdx.y;
+  const int i0 = g * per_group, i1 = min(nS, i0 + per_group);
+  const int b = bin_of_pix[p];
+  const int col = s3_col[p];
+  double2 scf = make_double2(0, 0), sfl = make_double2(0, 0);
+  double sc2 = 0;
+  for (int i = i0; i < i1; ++i) {
+    const float c = cbin[(size_t)i * Kr + b];
+    const float2 f = spec[(size_t)i * Kh + p];
+    const float2 fw = specw ? specw[(size_t)i * Kh + p] : f;
+    const float sg = (c > 0.0f) ? 1.0f : ((c < 0.0f) ? -1.0f : 0.0f);
+    scf.x += (double)(c * fw.x);
+    scf.y += (double)(c * fw.y);
+    sc2 += (double)(c * c);
+    const float2 ff = make_float2(sg * f.x, sg * f.y);
+    sfl.x += ff.x;
+    sfl.y += ff.y;
+    spec[(size_t)i * Kh + p] = ff;
+    if (write_z && col >= 0) {
+      float2 h, l;
+      split_tf32(c * f.x, h.x, l.x);
+      split_tf32(c * f.y, h.y, l.y);
+      *reinterpret_cast<float2*>(zhi + (size_t)i * ldz + col) = h;
+      *reinterpret_cast<float2*>(zlo + (size_t)i * ldz + col) = l;
+    }
+  }
+  part_cf[(size_t)g * Kh + p] = scf;
+  part_c2[(size_t)g * Kh + p] = sc2;
+  part_fl[(size_t)g * Kh + p] = sfl;
+}
+
+// zero the K padding at the end of S3 (columns [64*n1 + 2*K3, ldz))
+__global__ void k_zero_tail(float* __restrict__ zhi, float* __restrict__ zlo, int nS, int64_t ldz, int from) {
+  const int i = blockIdx.x;
+  for (int c = from + threadIdx.x; c < ldz; c += blockDim.x) {
+    zhi[(size_t)i * ldz + c] = 0.0f;
+    zlo[(size_t)i * ldz + c] = 0.0f;
+  }
+}
+
+// a11 (:353-367, :422-430): avgspec[0] = sum_i C_i F_i / wd,  wd = -(sum_i C_i^2 + 1/5);  avgspec[1] = sum_i sign(C_i) F_i
+__global__ void k_avg_spectra(const double2* __restrict__ part_cf, const double* __restrict__ part_c2,
+                              const double2* __restrict__ part_fl, float2* __restrict__ avgspec, int Kh, int G) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Kh) return;
+  double2 cf = make_double2(0, 0), fl = make_double2(0, 0);
+  double c2 = 0;
+  for (int g = 0; g < G; ++g) {
+    const double2 a = part_cf[(size_t)g * Kh + p], b = part_fl[(size_t)g * Kh + p];
+    cf.x += a.x; cf.y += a.y; fl.x += b.x; fl.y += b.y;
+    c2 += part_c2[(size_t)g * Kh + p];
+  }
+  const double wd = -(c2 + 1.0 / 5.0);
+  avgspec[p] = make_float2((float)(cf.x / wd), (float)(cf.y / wd));
+  avgspec[Kh + p] = make_float2((float)fl.x, (float)fl.y);
+}
+
+// a10/a13: imgAllFlip = irfft(...)/N^2 (scale in place) and per-group partial sums of squares (:400)
+__global__ void __launch_bounds__(256) k_flip_scale_intensity(float* __restrict__ flipimg, double* __restrict__ part_int,
+                                                              int nS, int NN, int per_group, float scale) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= NN) return;
+  const int g = blockIdx.y;
+  const int i0 = g * per_group, i1 = min(nS, i0 + per_group);
+  double acc = 0;
+  for (int i = i0; i < i1; ++i) {
+    const float v = flipimg[(size_t)i * NN + e] * scale;
+    flipimg[(size_t)i * NN + e] = v;
+    acc += (double)v * v;
+  }
+  part_int[(size_t)g * NN + e] = acc;
+}
+
+// final small outputs: imgAvg, imgAvgFlip (x msk2 / (nS N^2)), imgAllIntensity
+__global__ void k_small_outputs(const float* __restrict__ avgimg, const double* __restrict__ part_int,
+                                const uint8_t* __restrict__ msk2, float* __restrict__ imgAvg,
+                                float* __restrict__ imgAvgFlip, float* __restrict__ intensity, int NN, int G, int nS) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= NN) return;
+  const float m = (msk2 ? (msk2[e] ? 1.0f : 0.0f) : 1.0f) / ((float)nS * (float)NN);
+  if (imgAvg) imgAvg[e] = avgimg[e] * m;
+  if (imgAvgFlip) imgAvgFlip[e] = avgimg[NN + e] * m;
+  if (intensity) {
+    double a = 0;
+    for (int g = 0; g < G; ++g) a += part_int[(size_t)g * NN + e];
+    intensity[e] = (float)(a / nS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host pipeline
+// ------------------------------------------------------------------------------------------------
+static int run_fft(mem_ctx* ctx, int N, int nS, bool forward, float* real, float2* cplx, cudaStream_t st) {
+  const int Kh = N * (N / 2 + 1);
+  const int BMAX = 1024;
+  for (int i0 = 0; i0 < nS; i0 += BMAX) {
+    const int b = std::min(BMAX, nS - i0);
+    FftPlan pl;
+    MEM_CHECK(fft_get(ctx, N, b, &pl));
+    if (forward) {
+      MEM_CUFFT(cufftSetStream(pl.r2c, st));
+      MEM_CUFFT(cufftExecR2C(pl.r2c, real + (size_t)i0 * N * N, reinterpret_cast<cufftComplex*>(cplx + (size_t)i0 * Kh)));
+    } else {
+      MEM_CUFFT(cufftSetStream(pl.c2r, st));
+      MEM_CUFFT(cufftExecC2R(pl.c2r, reinterpret_cast<cufftComplex*>(cplx + (size_t)i0 * Kh), real + (size_t)i0 * N * N));
+    }
+    ctx->launches += 1;   // library call, counted once
+  }
+  return 0;
+}
+
+static CtfConst make_ctf_const(const mem_pd_params* prm) {
+  CtfConst cc;
+  const double wav = 12.3986 / sqrt((2 * 511.0 + prm->EkV) * prm->EkV);
+  cc.w1 = M_PI * (prm->Cs * 1.0e7) * wav * wav * wav;
+  cc.w2_per_df = M_PI * wav;
+  const double half = prm->N / 2.0;
+  cc.k2_scale = 1.0 / (half * half) / (4.0 * prm->pix_size * prm->pix_size);   // k = Q / (2 pix), Q = r / (N/2)
+  if (isinf(prm->gaussEnv)) {
+    cc.env_scale = 0.0;
+  } else {
+    const double sig = prm->gaussEnv / sqrt(2 * log(2.0));
+    cc.env_scale = 1.0 / (2 * sig * sig);
+  }
+  cc.ampc = prm->AmpContrast;
+  return cc;
+}
+
+int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* io, cudaStream_t st) {
+  const int nS = prm->nS, N = prm->N;
+  if (nS <= 0 || N <= 3) {
+    set_error("bad shape nS=%d N=%d", nS, N);
+    return 1;
+  }
+  if (prm->relion_shift) {
+    set_error("relion_shift: the cubic 'wrap' shift is applied on the host side of this build; pass shifted images");
+    return 1;
+  }
+  MEM_CHECK(geometry_prepare(ctx, N, prm->filter_type, prm->filter_order, prm->filter_Qc));
+  const Geometry& g = ctx->geom;
+  const size_t NN = (size_t)N * N, Kh = g.Kh;
+  const size_t img_bytes = (size_t)nS * NN * sizeof(float);
+  const size_t spec_bytes = (size_t)nS * Kh * sizeof(float2);
+  MEM_CHECK(ctx->imgA.ensure(img_bytes));
+  MEM_CHECK(ctx->imgB.ensure(img_bytes));
+  MEM_CHECK(ctx->spec.ensure(spec_bytes));
+  MEM_CHECK(ctx->rot_cs.ensure((size_t)(nS + 1) * sizeof(double2)));
+  MEM_CHECK(ctx->cbin.ensure((size_t)nS * g.Kr * sizeof(float)));
+  float* imgAll = io->imgAll;
+  if (!imgAll) {
+    MEM_CHECK(ctx->imgAll.ensure(img_bytes));
+    imgAll = ctx->imgAll.as<float>();
+  }
+  float* imgFlip = io->imgAllFlip;
+  const bool need_flip = io->imgAllFlip || io->imgAllIntensity;
+  if (need_flip && !imgFlip) {
+    MEM_CHECK(ctx->imgFlip.ensure(img_bytes));
+    imgFlip = ctx->imgFlip.as<float>();
+  }
+  const bool want_D = (io->D != nullptr) && !prm->avg_only;
+  if (want_D) {
+    MEM_CHECK(ctx->zhi.ensure((size_t)nS * g.ldz * sizeof(float)));
+    MEM_CHECK(ctx->zlo.ensure((size_t)nS * g.ldz * sizeof(float)));
+  }
+  const int per_group = 64;
+  const int G = (nS + per_group - 1) / per_group;
+  MEM_CHECK(ctx->part_cf.ensure((size_t)G * Kh * sizeof(double2)));
+  MEM_CHECK(ctx->part_c2.ensure((size_t)G * Kh * sizeof(double)));
+  MEM_CHECK(ctx->part_fl.ensure((size_t)G * Kh * sizeof(double2)));
+  MEM_CHECK(ctx->part_int.ensure((size_t)G * NN * sizeof(double)));
+  MEM_CHECK(ctx->avgspec.ensure(2 * Kh * sizeof(float2)));
+  MEM_CHECK(ctx->avgimg.ensure(2 * NN * sizeof(float)));
+  if (io->msk2) MEM_CHECK(ctx->spec2.ensure(spec_bytes));
+
+  float* A = ctx->imgA.as<float>();
+  float* B = ctx->imgB.as<float>();
+  float2* spec = ctx->spec.as<float2>();
+  double2* cs = ctx->rot_cs.as<double2>();
+
+  MEM_CUDA(cudaEventRecord(ctx->ev[0], st));
+  // ---- a2/a3 ingest + normalise -> A
+  MEM_LAUNCH(ctx, k_ingest, nS, 256, 0, st, io->raw, io->flip, A, N, prm->transposed);
+  // ---- a5 low-pass: A -> spec -> *G -> B
+  MEM_CHECK(run_fft(ctx, N, nS, true, A, spec, st));
+  {
+    const size_t total = (size_t)nS * Kh;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 16);
+    MEM_LAUNCH(ctx, k_specmul, grid, 256, 0, st, spec, g.Gtab.as<float>(), (int)Kh, total);
+  }
+  MEM_CHECK(run_fft(ctx, N, nS, false, B, spec, st));
+  MEM_CUDA(cudaEventRecord(ctx->ev[1], st));
+  // ---- a7 alignment: two periodic cubic-spline rotations
+  MEM_LAUNCH(ctx, k_angles, (nS + 1 + 127) / 128, 128, 0, st, io->psi_deg, prm->psi_p_deg, cs, nS);
+  const dim3 gr_rows((N + 31) / 32, nS), gr_cols((N + 31) / 32, nS), gr_rot((N + 31) / 32, (N + 7) / 8, nS);
+  const size_t sm_rows = (size_t)32 * (N | 1) * sizeof(float), sm_cols = (size_t)32 * N * sizeof(float);
+  if (sm_rows > 48 * 1024) {
+    MEM_CUDA(cudaFuncSetAttribute(k_prefilter_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_rows));
+    MEM_CUDA(cudaFuncSetAttribute(k_prefilter_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cols));
+  }
+  MEM_LAUNCH(ctx, k_prefilter_rows, gr_rows, 32, sm_rows, st, B, A, N, 1);   // (img*msk) -> coef
+  MEM_LAUNCH(ctx, k_prefilter_cols, gr_cols, 32, sm_cols, st, A, N);
+  MEM_LAUNCH(ctx, k_rotate, gr_rot, 256, 0, st, A, B, cs, 1, N, (const uint8_t*)nullptr, (float*)nullptr);
+  MEM_LAUNCH(ctx, k_prefilter_rows, gr_rows, 32, sm_rows, st, B, A, N, 0);
+  MEM_LAUNCH(ctx, k_prefilter_cols, gr_cols, 32, sm_cols, st, A, N);
+  // second rotation by -psi_p (same for every image): cs[nS], stride 0; masked copy -> B when msk2 is given
+  MEM_LAUNCH(ctx, k_rotate, gr_rot, 256, 0, st, A, imgAll, cs + nS, 0, N, io->msk2, io->msk2 ? B : (float*)nullptr);
+  MEM_CUDA(cudaEventRecord(ctx->ev[2], st));
+  // ---- a10 FFT of img*msk2 (and of img for the Wiener average when they differ)
+  float2* specw = nullptr;
+  if (io->msk2) {
+    MEM_CHECK(run_fft(ctx, N, nS, true, B, spec, st));
+    specw = ctx->spec2.as<float2>();
+    MEM_CHECK(run_fft(ctx, N, nS, true, imgAll, specw, st));
+  } else {
+    MEM_CHECK(run_fft(ctx, N, nS, true, imgAll, spec, st));
+  }
+  // ---- a8 CTF at the distinct radii, a12 operands, a10 flip, a11 partial sums
+  const CtfConst cc = make_ctf_const(prm);
+  MEM_LAUNCH(ctx, k_ctf_bins, dim3((g.Kr + 255) / 256, nS), 256, 0, st, io->df, g.r2_of_bin.as<int>(),
+             ctx->cbin.as<float>(), g.Kr, cc);
+  float* zhi = ctx->zhi.as<float>();
+  float* zlo = ctx->zlo.as<float>();
+  if (want_D) {
+    MEM_LAUNCH(ctx, k_operands_radial, dim3((32 * g.n1_blocks + 255) / 256, nS), 256, 0, st, spec,
+               ctx->cbin.as<float>(), g.bin_start.as<int>(), g.bin_pix.as<int>(), g.bin_of_pix.as<int>(),
+               g.special_pix.as<int>(), zhi, zlo, N, g.Nh, g.Kh, g.Kr, g.n_special, g.n1_blocks, g.ldz);
+    const int from = 64 * g.n1_blocks + 2 * g.K3;
+    if (from < g.ldz) MEM_LAUNCH(ctx, k_zero_tail, nS, 64, 0, st, zhi, zlo, nS, g.ldz, from);
+  }
+  MEM_LAUNCH(ctx, k_operands_s3, dim3((g.Kh + 255) / 256, G), 256, 0, st, spec, specw, ctx->cbin.as<float>(),
+             g.bin_of_pix.as<int>(), g.s3_col.as<int>(), zhi, zlo, ctx->part_cf.as<double2>(),
+             ctx->part_c2.as<double>(), ctx->part_fl.as<double2>(), nS, g.Kh, g.Kr, g.ldz, per_group, want_D ? 1 : 0);
+  MEM_CUDA(cudaEventRecord(ctx->ev[3], st));
+  // ---- a10/a11/a13 phase-flipped images, averages, intensity
+  if (need_flip) {
+    MEM_CHECK(run_fft(ctx, N, nS, false, imgFlip, spec, st));
+    MEM_LAUNCH(ctx, k_flip_scale_intensity, dim3(((int)NN + 255) / 256, G), 256, 0, st, imgFlip,
+               ctx->part_int.as<double>(), nS, (int)NN, per_group, 1.0f / (float)NN);
+  }
+  if (io->imgAvg || io->imgAvgFlip || io->imgAllIntensity) {
+    MEM_LAUNCH(ctx, k_avg_spectra, (g.Kh + 255) / 256, 256, 0, st, ctx->part_cf.as<double2>(),
+               ctx->part_c2.as<double>(), ctx->part_fl.as<double2>(), ctx->avgspec.as<float2>(), g.Kh, G);
+    MEM_CHECK(run_fft(ctx, N, 2, false, ctx->avgimg.as<float>(), ctx->avgspec.as<float2>(), st));
+    MEM_LAUNCH(ctx, k_small_outputs, ((int)NN + 255) / 256, 256, 0, st, ctx->avgimg.as<float>(),
+               ctx->part_int.as<double>(), io->msk2, io->imgAvg, io->imgAvgFlip,
+               need_flip ? io->imgAllIntensity : (float*)nullptr, (int)NN, G, nS);
+  }
+  if (io->CTF)
+    MEM_LAUNCH(ctx, k_ctf_full, dim3(((int)NN + 255) / 256, nS), 256, 0, st, io->df, io->CTF, N, cc);
+  MEM_CUDA(cudaEventRecord(ctx->ev[4], st));
+  // ---- a12 contraction
+  if (want_D) {
+    mem_contract_shape shp;
+    shp.nS = nS; shp.n1_blocks = g.n1_blocks; shp.n3_blocks = g.n3_blocks; shp.ldz = g.ldz;
+    MEM_CHECK(contract_run(ctx, &shp, zhi, zlo, io->D, prm->contraction, prm->k_chunk_blocks, prm->split_k, st));
+  }
+  MEM_CUDA(cudaEventRecord(ctx->ev[5], st));
+  return 0;
+}
+
+}  // namespace mem

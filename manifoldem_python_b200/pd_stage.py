@@ -1,0 +1,142 @@
+"""Host side of one PD of the distance stage: scalar bookkeeping on the CPU exactly as the
+reference does it (a1, a6), image gather (a2), then ONE call through the C ABI for everything else.
+
+Reference: modules/getDistanceCTF_local_Conj9combinedS2.py:216-420.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from . import q2Spider
+
+VERSION = 'getDistanceCTF_local9, V 1.0'       # same tag the reference stores (:41)
+FILTERS = {'Butter': 0, 'Gauss': 1}
+
+
+# ----------------------------------------------------------------------------- a6 (host scalars)
+def calc_avg_pd(q):
+    """(:169-185) per-image projection directions, (3,nS)."""
+    if q.shape[0] <= 3:
+        raise AssertionError('quaternion has wrong dimensions')
+    return 2 * np.vstack((q[1] * q[3] - q[0] * q[2], q[0] * q[1] + q[2] * q[3], q[0] ** 2 + q[3] ** 2 - 0.5))
+
+
+def psi_ang(PD):
+    """(:206-213) in-plane angle of the PD itself in degrees, via q2Spider."""
+    Qr = np.array([1 + PD[2], PD[1], -PD[0], 0.0])
+    Qr = Qr / np.sqrt(np.sum(Qr ** 2))
+    _, _, psi = q2Spider.op(Qr)
+    return np.mod(psi, 2 * np.pi) * (180 / np.pi)
+
+
+def host_angles(q):
+    """PDs, PD, psi_p [deg], Psi [rad], s (Nom), c (Dnom) — (:297-323)."""
+    PDs = calc_avg_pd(q)
+    PD = np.sum(PDs, 1)
+    PD = PD / np.linalg.norm(PD)
+    psi_p = psi_ang(PD)
+    s = -(1 + PD[2]) * q[3] - PD[0] * q[1] - PD[1] * q[2]
+    c = (1 + PD[2]) * q[0] + PD[1] * q[1] - PD[0] * q[2]
+    with np.errstate(divide='ignore', invalid='ignore'):
+        Psi = 2 * np.arctan(s / c)
+    Psi = np.where(np.isnan(Psi), 0.0, Psi)
+    return PDs, PD, psi_p, Psi, s, c
+
+
+# ----------------------------------------------------------------------------- a2 (gather)
+def gather(stack, ind, nStot, N, out=None):
+    """Member images in PD order as stored on disk + conjugate flags (:246-262).
+    `stack`: flat float32 array / np.memmap (SPIDER raw) or (n,N,N) array (MRC stack data)."""
+    ind = np.asarray(ind)
+    nS = ind.shape[0]
+    half = nStot / 2
+    conj = ~(ind < half)
+    base = np.where(conj, ind - half, ind).astype(np.int64)
+    if out is None:
+        out = np.empty((nS, N * N), dtype=np.float32)
+    flat = stack.reshape(-1, N * N) if stack.ndim != 2 else stack
+    order = np.argsort(base, kind='stable')            # read the file front to back
+    out[order] = flat[base[order]]
+    return out, conj.astype(np.uint8), base
+
+
+def open_stack(imgFileName, N, relion):
+    """SPIDER: raw float32, image i at byte 4*N*N*i (:254-256).  RELION .mrcs: MRC2014 header
+    (1024 bytes + NSYMBT extended header), mode 2 float32, (n,N,N) (:259-262)."""
+    if not relion:
+        return np.memmap(imgFileName, dtype='float32', mode='r')
+    hdr = np.fromfile(imgFileName, dtype='<i4', count=256)
+    nx, ny, nz, mode, nsymbt = int(hdr[0]), int(hdr[1]), int(hdr[2]), int(hdr[3]), int(hdr[23])
+    if mode != 2 or nx != N or ny != N:
+        raise ValueError('unsupported MRC stack: mode %d, %dx%d (need float32 %dx%d)' % (mode, nx, ny, N, N))
+    return np.memmap(imgFileName, dtype='<f4', mode='r', offset=1024 + nsymbt, shape=(nz, ny, nx))
+
+
+# ----------------------------------------------------------------------------- the C-ABI call
+def run_pd(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast, gaussEnv=np.inf, filterPar=None,
+           msk2=None, relion=False, sh=None, avg_only=False, ctx=None, fields=('D', 'imgAll', 'imgAllFlip', 'CTF'),
+           contraction=0, k_chunk_blocks=0, split_k=0, float64=True):
+    """Returns the dict the reference pickles (same keys / shapes; float64 unless float64=False).
+    `fields` selects which of the heavy per-image outputs are materialised."""
+    lib = _lib.load()
+    ctx = ctx or _lib.default_context()
+    if filterPar is None:
+        filterPar = dict(type='Butter', Qc=0.5, N=8)
+    if filterPar['type'] not in FILTERS:
+        raise ValueError('%s filter is unsupported' % filterPar['type'])
+    ind = np.asarray(ind)
+    q = np.asarray(q, dtype=np.float64)
+    df = np.ascontiguousarray(df, dtype=np.float64)
+    nS = ind.shape[0]
+    PDs, PD, psi_p, Psi, s, c = host_angles(q)
+    raw, flip, base = gather(stack, ind, nStot, N)
+    if relion:
+        raise NotImplementedError('RELION cubic wrap shift: device kernel pending (row a2)')
+    psi_deg = np.ascontiguousarray(-(180 / math.pi) * Psi, dtype=np.float64)
+
+    prm = _lib.PdParams(nS=nS, N=N, transposed=0 if relion else 1, relion_shift=0,
+                        filter_type=FILTERS[filterPar['type']], filter_order=int(filterPar['N']),
+                        filter_Qc=float(filterPar['Qc']), pix_size=float(pix_size), Cs=float(Cs), EkV=float(EkV),
+                        gaussEnv=float(gaussEnv), AmpContrast=float(AmpContrast), psi_p_deg=float(psi_p),
+                        avg_only=1 if avg_only else 0, contraction=int(contraction),
+                        k_chunk_blocks=int(k_chunk_blocks), split_k=int(split_k))
+    outs = {}
+
+    def want(name, shape, dtype):
+        a = np.empty(shape, dtype=dtype)
+        outs[name] = a
+        return a.ctypes.data
+
+    io = _lib.PdIO()
+    io.raw, io.flip, io.psi_deg, io.df = raw.ctypes.data, flip.ctypes.data, psi_deg.ctypes.data, df.ctypes.data
+    m2 = None
+    if msk2 is not None and not np.isscalar(msk2):
+        m2 = np.ascontiguousarray(np.asarray(msk2) != 0, dtype=np.uint8)
+        io.msk2 = m2.ctypes.data
+    if 'D' in fields and not avg_only:
+        io.D = want('D', (nS, nS), np.float32)
+    if 'imgAll' in fields:
+        io.imgAll = want('imgAll', (nS, N, N), np.float32)
+    if 'imgAllFlip' in fields:
+        io.imgAllFlip = want('imgAllFlip', (nS, N, N), np.float32)
+    if 'CTF' in fields:
+        io.CTF = want('CTF', (nS, N * N), np.float64)
+    io.imgAvg = want('imgAvg', (N, N), np.float32)
+    io.imgAvgFlip = want('imgAvgFlip', (N, N), np.float32)
+    if 'imgAllFlip' in fields:
+        io.imgAllIntensity = want('imgAllIntensity', (N, N), np.float32)
+    _lib.check(lib.mem_pd_distance_host(ctx.handle, C.byref(prm), C.byref(io)))
+
+    cast = (lambda a: a.astype(np.float64)) if float64 else (lambda a: a)
+    res = dict(D=cast(outs['D']) if 'D' in outs else np.zeros((nS, nS)), ind=ind, q=q, df=df,
+               CTF=outs.get('CTF'), imgAll=cast(outs['imgAll']) if 'imgAll' in outs else None,
+               msk2=1 if m2 is None else (m2 != 0), PD=PD, PDs=PDs, Psis=Psi.reshape(nS, 1),
+               imgAvg=cast(outs['imgAvg']), imgAvgFlip=cast(outs['imgAvgFlip']),
+               imgAllFlip=cast(outs['imgAllFlip']) if 'imgAllFlip' in outs else None,
+               imgLabels=np.where(flip != 0, -1, 1).astype(int), Dnom=c.reshape(nS, 1), Nom=s.reshape(nS, 1),
+               imgAllIntensity=cast(outs['imgAllIntensity']) if 'imgAllIntensity' in outs else None,
+               version=VERSION)
+    res['_psi_p'] = psi_p
+    return res

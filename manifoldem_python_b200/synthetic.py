@@ -71,6 +71,12 @@ def make_pd(nS, N, seed=0, snr=0.1, conj_frac=1.0 / 3, n_blobs=20, tilt_sigma=0.
     theta = pd_theta + tilt_sigma * rng.standard_normal(nS)
     q = euler_to_quat(phi, theta, psi)
     df = rng.uniform(10000.0, 30000.0, nS)
+    # in-plane angle the alignment will undo (getDistanceCTF...py:187-202): Psi = 2 atan(s/c) w.r.t. the mean PD
+    PDs = 2 * np.vstack((q[1] * q[3] - q[0] * q[2], q[0] * q[1] + q[2] * q[3], q[0] ** 2 + q[3] ** 2 - 0.5))
+    PD = PDs.sum(1) / np.linalg.norm(PDs.sum(1))
+    sn = -(1 + PD[2]) * q[3] - PD[0] * q[1] - PD[1] * q[2]
+    cn = (1 + PD[2]) * q[0] + PD[1] * q[1] - PD[0] * q[2]
+    Psi = 2 * np.arctan(sn / cn)
 
     # template: blobs inside radius 0.35 N; blob 0 moves/widens with tau
     r = 0.35 * N * np.sqrt(rng.random(n_blobs))
@@ -85,8 +91,9 @@ def make_pd(nS, N, seed=0, snr=0.1, conj_frac=1.0 / 3, n_blobs=20, tilt_sigma=0.
         cx, cy, s = bx.copy(), by.copy(), bs.copy()
         cx[0] += 0.25 * N * (tau[i] - 0.5)
         s[0] *= 1.0 + 0.5 * tau[i]
-        ca, sa = np.cos(psi[i]), np.sin(psi[i])
-        rx, ry = ca * cx - sa * cy, sa * cx + ca * cy
+        # ndimage.rotate(img, -Psi) must give back the template: blob (row,col) -> R(-Psi) (row,col)
+        ca, sa = np.cos(Psi[i]), np.sin(Psi[i])
+        ry, rx = ca * cy - sa * cx, sa * cy + ca * cx
         U = np.exp(-(grid[:, None] - ry[None, :]) ** 2 / (2 * s ** 2))      # (N, blobs) rows
         V = np.exp(-(grid[:, None] - rx[None, :]) ** 2 / (2 * s ** 2))      # (N, blobs) cols
         img = (U * amp) @ V.T
