@@ -31,6 +31,13 @@ int         mem_ctx_destroy(mem_ctx* ctx);
 int         mem_ctx_sync(mem_ctx* ctx);
 /* kernels launched by this library on ctx since the last reset (bench.py gpu_launches) */
 int64_t     mem_ctx_launch_count(mem_ctx* ctx, int reset);
+/* CUDA-event stopwatch on the context's stream (bench.py times its steps on the launching stream) */
+int         mem_ctx_timer_start(mem_ctx* ctx);
+int         mem_ctx_timer_stop(mem_ctx* ctx, float* ms);
+/* summed CUDA-event duration of every tcgen05 contraction launch since the last reset, their count, and
+ * the work-item count / K blocks of the last one (executed-flop accounting for the roofline) */
+int         mem_ctx_kernel_time(mem_ctx* ctx, int reset, double* total_ms, int64_t* launches, int32_t* items,
+                                int32_t* k_blocks);
 /* pinned host memory for the host-buffer entry points */
 int         mem_host_alloc(void** out, size_t bytes);
 int         mem_host_free(void* p);

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libmanifoldem_b200.so')
 
 SYMBOLS = [
     'mem_version', 'mem_last_error', 'mem_ctx_create', 'mem_ctx_destroy', 'mem_ctx_sync', 'mem_ctx_launch_count',
-    'mem_host_alloc', 'mem_host_free', 'mem_dev_alloc', 'mem_dev_free', 'mem_copy_h2d', 'mem_copy_d2h',
+    'mem_ctx_timer_start', 'mem_ctx_timer_stop', 'mem_ctx_kernel_time', 'mem_host_alloc', 'mem_host_free', 'mem_dev_alloc', 'mem_dev_free', 'mem_copy_h2d', 'mem_copy_d2h',
     'mem_pd_distance_device', 'mem_pd_distance_host', 'mem_pd_last_timings', 'mem_contract_device',
     'mem_operand_shape', 'mem_knn_device', 'mem_graph_dense_device', 'mem_ferguson_device',
     'mem_laplacian_dense_device',
@@ -62,6 +62,10 @@ def load():
         lib.mem_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         lib.mem_ctx_destroy.argtypes = [C.c_void_p]
         lib.mem_ctx_sync.argtypes = [C.c_void_p]
+        lib.mem_ctx_timer_start.argtypes = [C.c_void_p]
+        lib.mem_ctx_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        lib.mem_ctx_kernel_time.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64),
+                                            C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         lib.mem_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
         lib.mem_host_free.argtypes = [C.c_void_p]
         lib.mem_dev_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
@@ -174,6 +178,21 @@ class Context:
         check(self.lib.mem_pd_last_timings(self.handle, t, 8))
         keys = ['ingest_lowpass', 'align', 'fft_ctf_operands', 'flip_avg', 'contraction', 'device_total', 'h2d', 'd2h']
         return dict(zip(keys, [float(x) for x in t]))
+
+    def timer_start(self):
+        check(self.lib.mem_ctx_timer_start(self.handle))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(self.lib.mem_ctx_timer_stop(self.handle, C.byref(ms)))
+        return float(ms.value)
+
+    def kernel_time(self, reset=True):
+        """(total ms, launches, work items, K blocks) of the tcgen05 contraction launches since the last reset."""
+        tot, n, items, kb = C.c_double(), C.c_int64(), C.c_int32(), C.c_int32()
+        check(self.lib.mem_ctx_kernel_time(self.handle, 1 if reset else 0, C.byref(tot), C.byref(n), C.byref(items),
+                                           C.byref(kb)))
+        return float(tot.value), int(n.value), int(items.value), int(kb.value)
 
     def close(self):
         if self.handle:

@@ -36,6 +36,7 @@ int mem_ctx_create(int device, mem_ctx** out) {
   MEM_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   MEM_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
   for (auto& e : ctx->ev) MEM_CUDA(cudaEventCreate(&e));
+  for (auto& e : ctx->timer) MEM_CUDA(cudaEventCreate(&e));
   *out = ctx;
   return 0;
 }
@@ -50,12 +51,14 @@ int mem_ctx_destroy(mem_ctx* ctx) {
   }
   mem::DevBuf* bufs[] = {&ctx->fft_work, &ctx->raw, &ctx->flip, &ctx->shift, &ctx->psi, &ctx->df, &ctx->msk2, &ctx->rot_cs,
                          &ctx->imgA, &ctx->imgB, &ctx->imgAll, &ctx->imgFlip, &ctx->spec, &ctx->spec2, &ctx->cbin, &ctx->zhi,
-                         &ctx->zlo, &ctx->part_cf, &ctx->part_c2, &ctx->part_fl, &ctx->part_int, &ctx->avgspec, &ctx->avgimg,
-                         &ctx->stats, &ctx->D, &ctx->ctf64, &ctx->small_out, &ctx->contract_ws, &ctx->scratch,
+                         &ctx->zlo, &ctx->part_cf, &ctx->part_cfw, &ctx->part_c2, &ctx->part_fl, &ctx->part_int, &ctx->avgspec, &ctx->avgimg,
+                         &ctx->stats, &ctx->D, &ctx->ctf64, &ctx->small_out, &ctx->contract_ws, &ctx->contract_items, &ctx->scratch,
                          &ctx->geom.Gtab, &ctx->geom.bin_of_pix, &ctx->geom.r2_of_bin, &ctx->geom.bin_start,
                          &ctx->geom.bin_pix, &ctx->geom.s3_col, &ctx->geom.special_pix};
   for (auto* b : bufs) b->release();
   for (auto& e : ctx->ev) cudaEventDestroy(e);
+  for (auto& e : ctx->timer) cudaEventDestroy(e);
+  for (auto& e : ctx->kev) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return 0;
@@ -72,6 +75,35 @@ int64_t mem_ctx_launch_count(mem_ctx* ctx, int reset) {
   const int64_t v = ctx->launches;
   if (reset) ctx->launches = 0;
   return v;
+}
+
+int mem_ctx_timer_start(mem_ctx* ctx) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  MEM_CUDA(cudaEventRecord(ctx->timer[0], ctx->stream));
+  return 0;
+}
+int mem_ctx_timer_stop(mem_ctx* ctx, float* ms) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  MEM_CUDA(cudaEventRecord(ctx->timer[1], ctx->stream));
+  MEM_CUDA(cudaEventSynchronize(ctx->timer[1]));
+  MEM_CUDA(cudaEventElapsedTime(ms, ctx->timer[0], ctx->timer[1]));
+  return 0;
+}
+int mem_ctx_kernel_time(mem_ctx* ctx, int reset, double* total_ms, int64_t* launches, int32_t* items, int32_t* k_blocks) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  MEM_CUDA(cudaStreamSynchronize(ctx->stream));
+  double tot = 0;
+  for (size_t i = 0; i + 1 < ctx->kev_used; i += 2) {
+    float ms = 0;
+    MEM_CUDA(cudaEventElapsedTime(&ms, ctx->kev[i], ctx->kev[i + 1]));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = (int64_t)(ctx->kev_used / 2);
+  if (items) *items = ctx->last_tc_items;
+  if (k_blocks) *k_blocks = ctx->last_tc_nkb;
+  if (reset) ctx->kev_used = 0;
+  return 0;
 }
 
 int mem_host_alloc(void** out, size_t bytes) {

@@ -94,11 +94,17 @@ struct mem_ctx {
   // workspace for one PD
   mem::DevBuf raw, flip, shift, psi, df, msk2, rot_cs;
   mem::DevBuf imgA, imgB, imgAll, imgFlip, spec, spec2, cbin, zhi, zlo;
-  mem::DevBuf part_cf, part_c2, part_fl, part_int, avgspec, avgimg, stats;
+  mem::DevBuf part_cf, part_cfw, part_c2, part_fl, part_int, avgspec, avgimg, stats;
   mem::DevBuf D, ctf64, small_out;
   mem::DevBuf contract_ws;   // split-K partial tiles
+  mem::DevBuf contract_items;   // work-item table of the last contraction shape
+  long long items_key[4] = {-1, -1, -1, -1};   // nS, nkb, split, count
   mem::DevBuf scratch;       // misc (ferguson partials, knn)
   cudaEvent_t ev[10] = {};
+  cudaEvent_t timer[2] = {};
+  std::vector<cudaEvent_t> kev;   // event pairs around every contraction launch since the last reset
+  size_t kev_used = 0;
+  int last_tc_items = 0, last_tc_nkb = 0;   // geometry of the last tcgen05 launch (executed-flop accounting)
   float timings[8] = {};
   void* tmap_encode = nullptr;   // cuTensorMapEncodeTiled entry point
 };

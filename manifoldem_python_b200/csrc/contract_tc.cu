@@ -306,7 +306,7 @@ int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, c
     set_error("tcgen05 contraction needs an sm_100a device (found compute capability major %d); there is no fallback", dev_cc_major);
     return 1;
   }
-  const int chunk = k_chunk_blocks > 0 ? k_chunk_blocks : 16;
+  const int chunk = k_chunk_blocks > 0 ? k_chunk_blocks : 4;
   // tiles of the upper triangle (any element with col >= row)
   std::vector<std::pair<int, int>> tiles;
   const int tm = (nS + BM - 1) / BM, tn = (nS + BN - 1) / BN;
@@ -334,16 +334,34 @@ int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, c
     const int kb0 = (int)((long long)nkb * s / split), kb1 = (int)((long long)nkb * (s + 1) / split);
     for (auto& t : tiles) items.push_back({t.first * BM, t.second * BN, kb0, kb1, s, 0, 0, 0});
   }
-  MEM_CHECK(ctx->contract_ws.ensure((size_t)split * ldw * ldw * sizeof(float) + items.size() * sizeof(WorkItem) + 256));
+  MEM_CHECK(ctx->contract_ws.ensure((size_t)split * ldw * ldw * sizeof(float)));
   float* ws = ctx->contract_ws.as<float>();
-  WorkItem* d_items = reinterpret_cast<WorkItem*>(reinterpret_cast<uint8_t*>(ws) + (((size_t)split * ldw * ldw * sizeof(float) + 255) & ~(size_t)255));
-  MEM_CUDA(cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, st));
-  MEM_CUDA(cudaStreamSynchronize(st));   // items is a host temporary
+  if (ctx->items_key[0] != nS || ctx->items_key[1] != nkb || ctx->items_key[2] != split ||
+      ctx->items_key[3] != (long long)items.size()) {
+    MEM_CHECK(ctx->contract_items.ensure(items.size() * sizeof(WorkItem)));
+    MEM_CUDA(cudaMemcpyAsync(ctx->contract_items.p, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, st));
+    MEM_CUDA(cudaStreamSynchronize(st));   // items is a host temporary; cached per shape afterwards
+    ctx->items_key[0] = nS; ctx->items_key[1] = nkb; ctx->items_key[2] = split; ctx->items_key[3] = (long long)items.size();
+  }
+  WorkItem* d_items = ctx->contract_items.as<WorkItem>();
   CUtensorMap map_hi, map_lo;
   MEM_CHECK(make_map(ctx, &map_hi, Zhi, nS, shp->ldz));
   MEM_CHECK(make_map(ctx, &map_lo, Zlo, nS, shp->ldz));
   MEM_CUDA(cudaFuncSetAttribute(k_contract_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  // per-launch device timing (read back by mem_ctx_kernel_time; bench.py roofline)
+  if (ctx->kev_used + 2 > ctx->kev.size()) {
+    for (int i = 0; i < 64; ++i) {
+      cudaEvent_t e;
+      MEM_CUDA(cudaEventCreate(&e));
+      ctx->kev.push_back(e);
+    }
+  }
+  MEM_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used], st));
   MEM_LAUNCH(ctx, k_contract_tc, (int)items.size(), NUM_THREADS, SMEM_BYTES, st, map_hi, map_lo, d_items, ws, nS, ldw, n1, chunk);
+  MEM_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used + 1], st));
+  ctx->kev_used += 2;
+  ctx->last_tc_items = (int)items.size();
+  ctx->last_tc_nkb = nkb;
   dim3 fgrid((nS + 31) / 32, (nS + 31) / 32);
   MEM_LAUNCH(ctx, k_contract_finalize, fgrid, 256, 0, st, ws, D, nS, ldw, split);
   return 0;

@@ -466,7 +466,8 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 // a12 operands, radial part: S1[i][b] = C_i(b)^2 / 4, S2[i][b] = P_i(b) = sum_{|k|^2 = r2(b)} |F_i(k)|^2
 // (full spectrum = half spectrum with weight 2 on the non-self-conjugate columns), summed in a fixed order.
 // Columns [Kr, Kr+n_special) carry the purely real self-conjugate pixels: S1 = -x/4, S2 = x, x = C*Re F.
-__global__ void k_operands_radial(const float2* __restrict__ spec, const float* __restrict__ cbin,
+__global__ void k_operands_radial(const float2* __restrict__ spec, const float2* __restrict__ Mspec,
+                                  const float* __restrict__ cbin,
                                   const int* __restrict__ bin_start, const int* __restrict__ bin_pix,
                                   const int* __restrict__ bin_of_pix, const int* __restrict__ special_pix,
                                   float* __restrict__ zhi, float* __restrict__ zlo, int N, int Nh, int Kh, int Kr,
@@ -485,14 +486,16 @@ __global__ void k_operands_radial(const float2* __restrict__ spec, const float* 
     for (int q = bin_start[b]; q < bin_start[b + 1]; ++q) {
       const int p = bin_pix[q];
       const int kx = p % Nh;
-      const float2 f = F[p];
-      const float m = f.x * f.x + f.y * f.y;
+      const float2 f = F[p], mm = Mspec[p];
+      const float gx = fmaf(-c, mm.x, f.x), gy = fmaf(-c, mm.y, f.y);   // residual after removing C_i * M
+      const float m = gx * gx + gy * gy;
       acc += ((kx == 0) || (even && kx == N / 2)) ? m : 2.0f * m;
     }
     s2 = acc;
   } else if (b < Kr + n_special) {
     const int p = special_pix[b - Kr];
-    const float x = cbin[(size_t)i * Kr + bin_of_pix[p]] * F[p].x;
+    const float cs = cbin[(size_t)i * Kr + bin_of_pix[p]];
+    const float x = cs * fmaf(-cs, Mspec[p].x, F[p].x);
     s1 = -0.25f * x;
     s2 = x;
   }
@@ -505,46 +508,74 @@ __global__ void k_operands_radial(const float2* __restrict__ spec, const float* 
   zlo[(size_t)i * ldz + w1 + b] = l;
 }
 
-// a12 operands, S3 part + a10 phase flip + a11 partial sums.  Thread = one half-spectrum pixel, loops over
-// the images of its group (grid.y groups):  A = C*F -> Z (hi/lo), spec <- sign(C)*F in place,
-// partial sums of C*Fw, C^2 and sign(C)*F in fp64 (Fw = spectrum of the unmasked image when msk2 is used).
-__global__ void __launch_bounds__(256) k_operands_s3(float2* __restrict__ spec, const float2* __restrict__ specw,
+// a11 partial sums (pass 1 over the spectra).  Thread = one half-spectrum pixel, loops over the images of
+// its group (grid.y groups): sum C*F (for the common component M), sum C*Fw (Wiener numerator; Fw = spectrum
+// of the unmasked image when msk2 is used), sum C^2, sum sign(C)*F — all in fp64.
+__global__ void __launch_bounds__(256) k_spec_sums(const float2* __restrict__ spec, const float2* __restrict__ specw,
+                                                   const float* __restrict__ cbin, const int* __restrict__ bin_of_pix,
+                                                   double2* __restrict__ part_cf, double2* __restrict__ part_cfw,
+                                                   double* __restrict__ part_c2, double2* __restrict__ part_fl,
+                                                   int nS, int Kh, int Kr, int per_group) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Kh) return;
+  const int g = blockIdx.y;
+  const int i0 = g * per_group, i1 = min(nS, i0 + per_group);
+  const int b = bin_of_pix[p];
+  double2 scf = make_double2(0, 0), scw = make_double2(0, 0), sfl = make_double2(0, 0);
+  double sc2 = 0;
+  for (int i = i0; i < i1; ++i) {
+    const float c = cbin[(size_t)i * Kr + b];
+    const float2 f = spec[(size_t)i * Kh + p];
+    const float sg = (c > 0.0f) ? 1.0f : ((c < 0.0f) ? -1.0f : 0.0f);
+    scf.x += (double)(c * f.x);
+    scf.y += (double)(c * f.y);
+    if (specw) {
+      const float2 fw = specw[(size_t)i * Kh + p];
+      scw.x += (double)(c * fw.x);
+      scw.y += (double)(c * fw.y);
+    }
+    sc2 += (double)(c * c);
+    sfl.x += (double)(sg * f.x);
+    sfl.y += (double)(sg * f.y);
+  }
+  part_cf[(size_t)g * Kh + p] = scf;
+  if (specw) part_cfw[(size_t)g * Kh + p] = scw;
+  part_c2[(size_t)g * Kh + p] = sc2;
+  part_fl[(size_t)g * Kh + p] = sfl;
+}
+
+// a12 operands, S3 part (pass 2) + a10 phase flip.  The distance is invariant under F_i -> F_i - C_i M for
+// ANY common M (C_j (C_i M) - C_i (C_j M) = 0); with M = sum C F / sum C^2 the residuals carry only noise and
+// conformational signal, which removes the catastrophic cancellation in a + b - 2c for similar images
+// (DESIGN.md §3).  A = C * (F - C M) -> Z (hi/lo);  spec <- sign(C) * F in place for the C2R of :346-347.
+__global__ void __launch_bounds__(256) k_operands_s3(float2* __restrict__ spec, const float2* __restrict__ Mspec,
                                                      const float* __restrict__ cbin, const int* __restrict__ bin_of_pix,
                                                      const int* __restrict__ s3_col, float* __restrict__ zhi,
-                                                     float* __restrict__ zlo, double2* __restrict__ part_cf,
-                                                     double* __restrict__ part_c2, double2* __restrict__ part_fl,
-                                                     int nS, int Kh, int Kr, int64_t ldz, int per_group, int write_z) {
+                                                     float* __restrict__ zlo, int nS, int Kh, int Kr, int64_t ldz,
+                                                     int per_group, int write_z, int flip) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= Kh) return;
   const int g = blockIdx.y;
   const int i0 = g * per_group, i1 = min(nS, i0 + per_group);
   const int b = bin_of_pix[p];
   const int col = s3_col[p];
-  double2 scf = make_double2(0, 0), sfl = make_double2(0, 0);
-  double sc2 = 0;
+  const float2 m = Mspec[p];
   for (int i = i0; i < i1; ++i) {
     const float c = cbin[(size_t)i * Kr + b];
     const float2 f = spec[(size_t)i * Kh + p];
-    const float2 fw = specw ? specw[(size_t)i * Kh + p] : f;
-    const float sg = (c > 0.0f) ? 1.0f : ((c < 0.0f) ? -1.0f : 0.0f);
-    scf.x += (double)(c * fw.x);
-    scf.y += (double)(c * fw.y);
-    sc2 += (double)(c * c);
-    const float2 ff = make_float2(sg * f.x, sg * f.y);
-    sfl.x += ff.x;
-    sfl.y += ff.y;
-    spec[(size_t)i * Kh + p] = ff;
+    if (flip) {
+      const float sg = (c > 0.0f) ? 1.0f : ((c < 0.0f) ? -1.0f : 0.0f);
+      spec[(size_t)i * Kh + p] = make_float2(sg * f.x, sg * f.y);
+    }
     if (write_z && col >= 0) {
+      const float gx = fmaf(-c, m.x, f.x), gy = fmaf(-c, m.y, f.y);
       float2 h, l;
-      split_tf32(c * f.x, h.x, l.x);
-      split_tf32(c * f.y, h.y, l.y);
+      split_tf32(c * gx, h.x, l.x);
+      split_tf32(c * gy, h.y, l.y);
       *reinterpret_cast<float2*>(zhi + (size_t)i * ldz + col) = h;
       *reinterpret_cast<float2*>(zlo + (size_t)i * ldz + col) = l;
     }
   }
-  part_cf[(size_t)g * Kh + p] = scf;
-  part_c2[(size_t)g * Kh + p] = sc2;
-  part_fl[(size_t)g * Kh + p] = sfl;
 }
 
 // zero the K padding at the end of S3 (columns [64*n1 + 2*K3, ldz))
@@ -556,21 +587,29 @@ __global__ void k_zero_tail(float* __restrict__ zhi, float* __restrict__ zlo, in
   }
 }
 
-// a11 (:353-367, :422-430): avgspec[0] = sum_i C_i F_i / wd,  wd = -(sum_i C_i^2 + 1/5);  avgspec[1] = sum_i sign(C_i) F_i
-__global__ void k_avg_spectra(const double2* __restrict__ part_cf, const double* __restrict__ part_c2,
-                              const double2* __restrict__ part_fl, float2* __restrict__ avgspec, int Kh, int G) {
+// a11 (:353-367, :422-430): avgspec[0] = sum_i C_i Fw_i / wd,  wd = -(sum_i C_i^2 + 1/5);  avgspec[1] = sum_i sign(C_i) F_i;
+// Mspec = sum_i C_i F_i / sum_i C_i^2  (the common component removed from the contraction operands)
+__global__ void k_avg_spectra(const double2* __restrict__ part_cf, const double2* __restrict__ part_cfw,
+                              const double* __restrict__ part_c2, const double2* __restrict__ part_fl,
+                              float2* __restrict__ avgspec, float2* __restrict__ Mspec, int Kh, int G) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= Kh) return;
-  double2 cf = make_double2(0, 0), fl = make_double2(0, 0);
+  double2 cf = make_double2(0, 0), cw = make_double2(0, 0), fl = make_double2(0, 0);
   double c2 = 0;
   for (int g = 0; g < G; ++g) {
     const double2 a = part_cf[(size_t)g * Kh + p], b = part_fl[(size_t)g * Kh + p];
     cf.x += a.x; cf.y += a.y; fl.x += b.x; fl.y += b.y;
+    if (part_cfw) {
+      const double2 w = part_cfw[(size_t)g * Kh + p];
+      cw.x += w.x; cw.y += w.y;
+    }
     c2 += part_c2[(size_t)g * Kh + p];
   }
+  if (!part_cfw) cw = cf;
   const double wd = -(c2 + 1.0 / 5.0);
-  avgspec[p] = make_float2((float)(cf.x / wd), (float)(cf.y / wd));
+  avgspec[p] = make_float2((float)(cw.x / wd), (float)(cw.y / wd));
   avgspec[Kh + p] = make_float2((float)fl.x, (float)fl.y);
+  Mspec[p] = (c2 > 1e-30) ? make_float2((float)(cf.x / c2), (float)(cf.y / c2)) : make_float2(0.0f, 0.0f);
 }
 
 // a10/a13: imgAllFlip = irfft(...)/N^2 (scale in place) and per-group partial sums of squares (:400)
@@ -686,9 +725,12 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
   MEM_CHECK(ctx->part_c2.ensure((size_t)G * Kh * sizeof(double)));
   MEM_CHECK(ctx->part_fl.ensure((size_t)G * Kh * sizeof(double2)));
   MEM_CHECK(ctx->part_int.ensure((size_t)G * NN * sizeof(double)));
-  MEM_CHECK(ctx->avgspec.ensure(2 * Kh * sizeof(float2)));
+  MEM_CHECK(ctx->avgspec.ensure(3 * Kh * sizeof(float2)));
   MEM_CHECK(ctx->avgimg.ensure(2 * NN * sizeof(float)));
-  if (io->msk2) MEM_CHECK(ctx->spec2.ensure(spec_bytes));
+  if (io->msk2) {
+    MEM_CHECK(ctx->spec2.ensure(spec_bytes));
+    MEM_CHECK(ctx->part_cfw.ensure((size_t)G * Kh * sizeof(double2)));
+  }
 
   float* A = ctx->imgA.as<float>();
   float* B = ctx->imgB.as<float>();
@@ -738,16 +780,24 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
              ctx->cbin.as<float>(), g.Kr, cc);
   float* zhi = ctx->zhi.as<float>();
   float* zlo = ctx->zlo.as<float>();
+  double2* part_cfw = specw ? ctx->part_cfw.as<double2>() : (double2*)nullptr;
+  float2* Mspec = ctx->avgspec.as<float2>() + 2 * Kh;
+  MEM_LAUNCH(ctx, k_spec_sums, dim3((g.Kh + 255) / 256, G), 256, 0, st, spec, specw, ctx->cbin.as<float>(),
+             g.bin_of_pix.as<int>(), ctx->part_cf.as<double2>(), part_cfw, ctx->part_c2.as<double>(),
+             ctx->part_fl.as<double2>(), nS, g.Kh, g.Kr, per_group);
+  MEM_LAUNCH(ctx, k_avg_spectra, (g.Kh + 255) / 256, 256, 0, st, ctx->part_cf.as<double2>(), part_cfw,
+             ctx->part_c2.as<double>(), ctx->part_fl.as<double2>(), ctx->avgspec.as<float2>(), Mspec, g.Kh, G);
   if (want_D) {
-    MEM_LAUNCH(ctx, k_operands_radial, dim3((32 * g.n1_blocks + 255) / 256, nS), 256, 0, st, spec,
+    MEM_LAUNCH(ctx, k_operands_radial, dim3((32 * g.n1_blocks + 255) / 256, nS), 256, 0, st, spec, Mspec,
                ctx->cbin.as<float>(), g.bin_start.as<int>(), g.bin_pix.as<int>(), g.bin_of_pix.as<int>(),
                g.special_pix.as<int>(), zhi, zlo, N, g.Nh, g.Kh, g.Kr, g.n_special, g.n1_blocks, g.ldz);
     const int from = 64 * g.n1_blocks + 2 * g.K3;
     if (from < g.ldz) MEM_LAUNCH(ctx, k_zero_tail, nS, 64, 0, st, zhi, zlo, nS, g.ldz, from);
   }
-  MEM_LAUNCH(ctx, k_operands_s3, dim3((g.Kh + 255) / 256, G), 256, 0, st, spec, specw, ctx->cbin.as<float>(),
-             g.bin_of_pix.as<int>(), g.s3_col.as<int>(), zhi, zlo, ctx->part_cf.as<double2>(),
-             ctx->part_c2.as<double>(), ctx->part_fl.as<double2>(), nS, g.Kh, g.Kr, g.ldz, per_group, want_D ? 1 : 0);
+  if (want_D || need_flip)
+    MEM_LAUNCH(ctx, k_operands_s3, dim3((g.Kh + 255) / 256, G), 256, 0, st, spec, Mspec, ctx->cbin.as<float>(),
+               g.bin_of_pix.as<int>(), g.s3_col.as<int>(), zhi, zlo, nS, g.Kh, g.Kr, g.ldz, per_group,
+               want_D ? 1 : 0, need_flip ? 1 : 0);
   MEM_CUDA(cudaEventRecord(ctx->ev[3], st));
   // ---- a10/a11/a13 phase-flipped images, averages, intensity
   if (need_flip) {
@@ -756,8 +806,6 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
                ctx->part_int.as<double>(), nS, (int)NN, per_group, 1.0f / (float)NN);
   }
   if (io->imgAvg || io->imgAvgFlip || io->imgAllIntensity) {
-    MEM_LAUNCH(ctx, k_avg_spectra, (g.Kh + 255) / 256, 256, 0, st, ctx->part_cf.as<double2>(),
-               ctx->part_c2.as<double>(), ctx->part_fl.as<double2>(), ctx->avgspec.as<float2>(), g.Kh, G);
     MEM_CHECK(run_fft(ctx, N, 2, false, ctx->avgimg.as<float>(), ctx->avgspec.as<float2>(), st));
     MEM_LAUNCH(ctx, k_small_outputs, ((int)NN + 255) / 256, 256, 0, st, ctx->avgimg.as<float>(),
                ctx->part_int.as<double>(), io->msk2, io->imgAvg, io->imgAvgFlip,

@@ -1,0 +1,183 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same seeded inputs,
+against the committed golden vectors, and through size-independent properties at larger sizes.
+
+Tolerances (north_star): off-diagonal D within 1e-5 relative of the float64 reference; diagonal
+|D_ii| <= 1e-5 * max D; images / averages within 2e-6 of their max (fp32 pipeline)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+D_RTOL = 1e-5
+IMG_TOL = 2e-6
+
+
+@pytest.fixture(scope='module')
+def env():
+    from manifoldem_python_b200 import _lib, pd_stage, synthetic
+    return _lib, pd_stage, synthetic
+
+
+def _oracle(pd, N, **kw):
+    from oracle import pd_distance as opd
+    em = pd['em']
+    return opd.pd_distance(pd['ind'], pd['q'], pd['df'], pd['stack'], pd['nStot'], N, em['pix_size'], em['Cs'],
+                           em['EkV'], em['AmpContrast'], **kw)
+
+
+def _gpu(pd_stage, pd, N, **kw):
+    em = pd['em']
+    return pd_stage.run_pd(pd['ind'], pd['q'], pd['df'], pd['stack'], pd['nStot'], N, em['pix_size'], em['Cs'],
+                           em['EkV'], em['AmpContrast'], **kw)
+
+
+def _check_D(D, Dr, rtol=D_RTOL):
+    n = D.shape[0]
+    off = ~np.eye(n, dtype=bool)
+    rel = np.abs(D - Dr)[off] / Dr[off]
+    assert rel.max() <= rtol, 'max rel err %.3e' % rel.max()
+    assert np.abs(np.diag(D) - np.diag(Dr)).max() <= 1e-5 * Dr.max()
+    assert np.array_equal(D, D.T)
+
+
+def _check_fields(res, ref, tol=IMG_TOL):
+    for k in ('imgAll', 'imgAllFlip', 'imgAvg', 'imgAvgFlip', 'imgAllIntensity'):
+        a, b = res[k].reshape(ref[k].shape), ref[k]
+        assert np.abs(a - b).max() <= tol * np.abs(b).max(), (k, np.abs(a - b).max() / np.abs(b).max())
+    assert np.abs(res['CTF'].reshape(ref['CTF'].shape) - ref['CTF']).max() < 1e-11
+    for k in ('PD', 'PDs', 'Psis', 'Dnom', 'Nom', 'imgLabels'):
+        assert np.array_equal(np.asarray(res[k]), np.asarray(ref[k])), k
+
+
+@pytest.mark.parametrize('name', ['pd_spider_N32.npz', 'pd_spider_N25_lownoise.npz'])
+def test_golden_reference_vectors(env, golden_dir, name):
+    """CUDA path vs outputs of the reference itself (fixtures from tests/golden/make_golden.py)."""
+    _lib, pd_stage, _ = env
+    g = np.load(os.path.join(golden_dir, name))
+    N = int(g['N'])
+    res = pd_stage.run_pd(g['ind'], g['q'], g['df'], g['stack'], int(g['nStot']), N, float(g['em_pix_size']),
+                          float(g['em_Cs']), float(g['em_EkV']), float(g['em_AmpContrast']))
+    ref = {k[4:]: g[k] for k in g.files if k.startswith('ref_')}
+    # N<=32: the reference's 3x3-tile rotate still feels its mirror border at 0.268^(0.79N) ~ 1e-9..4e-12
+    _check_D(res['D'], ref['D'])
+    _check_fields(res, ref)
+
+
+def test_golden_volmask(env, golden_dir):
+    _lib, pd_stage, _ = env
+    g = np.load(os.path.join(golden_dir, 'pd_volmask_N24.npz'))
+    N = int(g['N'])
+    res = pd_stage.run_pd(g['ind'], g['q'], g['df'], g['stack'], int(g['nStot']), N, float(g['em_pix_size']),
+                          float(g['em_Cs']), float(g['em_EkV']), float(g['em_AmpContrast']), msk2=g['ref_msk2'])
+    ref = {k[4:]: g[k] for k in g.files if k.startswith('ref_')}
+    _check_D(res['D'], ref['D'])
+    _check_fields(res, ref)
+    assert np.array_equal(res['msk2'], g['ref_msk2'])
+
+
+@pytest.mark.parametrize('nS,N,snr,seed', [(150, 64, 0.1, 2), (257, 64, 10.0, 5), (300, 128, 10.0, 3), (129, 96, 0.5, 7)])
+def test_oracle_parity_tc(env, nS, N, snr, seed):
+    """tcgen05 3xTF32 product path vs the float64 oracle, noisy and low-noise (worst cancellation)."""
+    _lib, pd_stage, synthetic = env
+    pd = synthetic.make_pd(nS, N, seed=seed, snr=snr)
+    res = _gpu(pd_stage, pd, N)
+    ref = _oracle(pd, N, rotate_impl='periodic')
+    _check_D(res['D'], ref['D'])
+    _check_fields(res, ref)
+
+
+def test_oracle_parity_simt_checker(env):
+    """The fp64-accumulate SIMT kernel isolates operand error from tensor-core accumulation error."""
+    _lib, pd_stage, synthetic = env
+    pd = synthetic.make_pd(100, 64, seed=9, snr=10.0)
+    res = _gpu(pd_stage, pd, 64, contraction=1)
+    ref = _oracle(pd, 64, rotate_impl='periodic')
+    _check_D(res['D'], ref['D'], rtol=3e-6)
+
+
+def test_gauss_filter_and_avg_only(env):
+    _lib, pd_stage, synthetic = env
+    pd = synthetic.make_pd(40, 48, seed=4, snr=0.3)
+    fp = dict(type='Gauss', Qc=0.4, N=8)
+    res = _gpu(pd_stage, pd, 48, filterPar=fp)
+    ref = _oracle(pd, 48, rotate_impl='periodic', filterPar=fp)
+    _check_D(res['D'], ref['D'])
+    _check_fields(res, ref)
+    res = _gpu(pd_stage, pd, 48, avg_only=True)
+    assert not res['D'].any()
+    with pytest.raises(ValueError):
+        _gpu(pd_stage, pd, 48, filterPar=dict(type='Box', Qc=0.4, N=8))
+
+
+def test_split_and_chunk_invariance(env):
+    """K-slicing and chunking change the summation order only: results agree to fp32 round-off."""
+    _lib, pd_stage, synthetic = env
+    pd = synthetic.make_pd(260, 64, seed=12, snr=0.2)
+    base = _gpu(pd_stage, pd, 64, fields=('D',))['D']
+    for chunk, split in ((2, 1), (4, 3), (8, 0)):
+        other = _gpu(pd_stage, pd, 64, fields=('D',), k_chunk_blocks=chunk, split_k=split)['D']
+        off = ~np.eye(260, dtype=bool)
+        assert (np.abs(other - base)[off] / base[off]).max() < 5e-6
+
+
+def test_invariances_full_size(env):
+    """Size-independent properties at BASELINE config-2 size (1000 x 128^2), no oracle needed:
+    symmetry, ~zero diagonal, permutation equivariance, and D(i,j)=0 for duplicated particles."""
+    _lib, pd_stage, synthetic = env
+    nS, N = 1000, 128
+    rng = np.random.default_rng(0)
+    stack = rng.standard_normal((nS, N, N)).astype(np.float32)
+    stack[1] = stack[0]                                   # duplicate particle
+    ind = np.arange(nS)
+    pd0 = synthetic.make_pd(4, 16, seed=0)                # only for the EM constants
+    em = pd0['em']
+    q = synthetic.euler_to_quat(0.7 + 0.03 * rng.standard_normal(nS), 1.1 + 0.03 * rng.standard_normal(nS),
+                                rng.uniform(0, 2 * np.pi, nS))
+    df = rng.uniform(10000, 30000, nS)
+    q[:, 1], df[1] = q[:, 0], df[0]
+    run = lambda idx: pd_stage.run_pd(idx, q[:, idx], df[idx], stack.reshape(-1), 2 * nS, N, em['pix_size'], em['Cs'],
+                                      em['EkV'], em['AmpContrast'], fields=('D',))['D']
+    D = run(ind)
+    assert np.array_equal(D, D.T)
+    assert np.abs(np.diag(D)).max() <= 1e-5 * D.max()
+    assert abs(D[0, 1]) <= 1e-5 * D.max()
+    assert (D[~np.eye(nS, dtype=bool)] > -1e-5 * D.max()).all()
+    # permuting the members permutes D.  (PD and psi_p are means over the same set -> unchanged to round-off.)
+    perm = rng.permutation(nS)
+    Dp = run(ind[perm])
+    ref = D[np.ix_(perm, perm)]
+    off = ~np.eye(nS, dtype=bool)
+    big = ref[off] > 1e-3 * D.max()
+    assert (np.abs(Dp - ref)[off][big] / ref[off][big]).max() < 2e-5
+
+
+def test_contraction_kernel_vs_fp64(env):
+    """mem_contract_device alone: random operands, tcgen05 vs numpy float64 on the same hi+lo values."""
+    _lib, _, _ = env
+    lib = _lib.load()
+    ctx = _lib.default_context()
+    rng = np.random.default_rng(3)
+    nS, n1, n3 = 300, 5, 37
+    K = 32 * (2 * n1 + n3)
+    Z = rng.standard_normal((nS, K)).astype(np.float32)
+    Z[:, :64 * n1] = np.abs(Z[:, :64 * n1])
+    hi = (Z.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+    lo = ((Z - hi).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+    z = (hi.astype(np.float64) + lo.astype(np.float64))
+    S1, S2, S3 = z[:, :32 * n1], z[:, 32 * n1:64 * n1], z[:, 64 * n1:]
+    exact = 4 * (S1 @ S2.T + S2 @ S1.T - S3 @ S3.T)
+    zhi = _lib.DeviceArray(ctx, Z.shape, np.float32, hi)
+    zlo = _lib.DeviceArray(ctx, Z.shape, np.float32, lo)
+    Dd = _lib.DeviceArray(ctx, (nS, nS), np.float32)
+    shp = _lib.ContractShape(nS=nS, n1_blocks=n1, n3_blocks=n3, ldz=K)
+    scale = 4 * (np.abs(S1) @ np.abs(S2).T + np.abs(S2) @ np.abs(S1).T + np.abs(S3) @ np.abs(S3).T)
+    for kind, tol in ((1, 2e-7), (0, 2e-6)):
+        _lib.check(lib.mem_contract_device(ctx.handle, C.byref(shp), zhi.ptr, zlo.ptr, Dd.ptr, kind, 0, 0, None))
+        ctx.sync()
+        D = Dd.download().astype(np.float64)
+        iu = np.triu_indices(nS)
+        assert (np.abs(D - exact)[iu] / scale[iu]).max() < tol, kind
+        assert np.array_equal(D, D.T)
