@@ -1,0 +1,401 @@
+// align.cu — ingest/normalise (a2, a3) and the in-plane alignment (a7): two periodic cubic-B-spline
+// resamplings per particle, each = separable recursive prefilter (rows, columns) + 4x4-tap gather.
+// All HBM-bound streaming kernels: every pass reads and writes each image exactly once.
+#include "common.cuh"
+
+namespace mem {
+
+// ------------------------------------------------------------------------------------------------
+// a2+a3 (getDistanceCTF...py:246-283): picture = raw^T (SPIDER) or raw; conjugates flipped upside down;
+// (x - mean(b))/std(b) with b = x*(1-msk) over all N^2 pixels (population std).
+// One CTA per particle.  Pass 1: moments in fp64 (rows over warps, float4 over lanes).  Pass 2: every
+// warp transposes 32x32 tiles through its own shared-memory buffer (no block barriers).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ingest(const float* __restrict__ raw, const uint8_t* __restrict__ flip,
+                                                float* __restrict__ out, int N, int transposed) {
+  __shared__ double red[16];
+  __shared__ float tile[8][32][33];
+  const int i = blockIdx.x;
+  const float* src = raw + (size_t)i * N * N;
+  float* dst = out + (size_t)i * N * N;
+  const bool fl = flip[i] != 0;
+  const float half = 0.5f * N, r2lim = half * half;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  double s = 0, s2 = 0;
+  for (int a = warp; a < N; a += nw) {
+    for (int b = lane; b < N; b += 32) {
+      int r = transposed ? b : a;
+      const int c = transposed ? a : b;
+      if (fl) r = N - 1 - r;
+      const float x = (float)r - half + 1.0f, y = (float)c - half;   // annularMask.py:24-30, centre (N/2-1, N/2)
+      const float v = src[(size_t)a * N + b];
+      if (!(x * x + y * y < r2lim)) {
+        s += v;
+        s2 += (double)v * v;
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane == 0) { red[warp] = s; red[8 + warp] = s2; }
+  __syncthreads();
+  s = 0; s2 = 0;
+  for (int w = 0; w < nw; ++w) { s += red[w]; s2 += red[8 + w]; }
+  const double n = (double)N * N;
+  const double mean = s / n;
+  const double var = s2 / n - mean * mean;
+  const float fm = (float)mean;
+  const float inv = (float)(1.0 / sqrt(var));
+  const int nt = (N + 31) / 32;
+  for (int t = warp; t < nt * nt; t += nw) {
+    const int tr = (t / nt) * 32, tc = (t % nt) * 32;   // output tile origin (rows r', cols c)
+    if (transposed) {
+      float v[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {                    // raw index = c*N + r : lanes run along r
+        const int c = tc + k, rp = tr + lane;
+        const int r = fl ? N - 1 - rp : rp;
+        v[k] = (c < N && rp < N) ? src[(size_t)c * N + r] : 0.0f;
+      }
+#pragma unroll
+      for (int k = 0; k < 32; ++k) tile[warp][k][lane] = v[k];
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const int rp = tr + k, c = tc + lane;
+        if (rp < N && c < N) dst[(size_t)rp * N + c] = (tile[warp][lane][k] - fm) * inv;
+      }
+      __syncwarp();
+    } else {
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) {
+        const int rp = tr + k, c = tc + lane;
+        if (rp < N && c < N) {
+          const int r = fl ? N - 1 - rp : rp;
+          dst[(size_t)rp * N + c] = (src[(size_t)r * N + c] - fm) * inv;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cubic B-spline prefilter with periodic boundary — what scipy.ndimage.rotate's spline_filter amounts to
+// on the 3x3-tiled image of rotatefill.py:21-25 away from the tile border (SURVEY §7 hard part 2):
+//   c+[k] = 6 s[k] + z c+[k-1],   c[k] = z (c[k+1] - c+[k]),   z = sqrt(3) - 2.
+// Both recursions are linear, so a line is cut into segments of E samples: each segment runs the
+// recursion from a zero carry, and the true carry is  sum_h z^(samples between) * (local end of the
+// h-th previous segment) — z^20 < 4e-12, so a few hops suffice, wrapping around for periodicity.
+// ------------------------------------------------------------------------------------------------
+#define SPL_Z (-0.26794919243112270647f)
+#define SPL_REACH 20   // samples after which z^n is dropped
+
+__device__ __forceinline__ float zpow(int n) {
+  float r = 1.0f, b = SPL_Z;
+  while (n > 0) {
+    if (n & 1) r *= b;
+    b *= b;
+    n >>= 1;
+  }
+  return r;
+}
+
+// Segment geometry of one filtered line, computed once on the host.
+struct SegGeom {
+  int E;        // samples per segment
+  int used;     // segments that own samples
+  int H;        // hops of the carry sum (<= used)
+  float zE;     // z^E
+  float zLast;  // z^(samples of the last segment)
+};
+
+// rows: one warp per image row, lane l owns samples [l*E, l*E+E).  Global traffic is fully coalesced
+// (lane l touches sample k*32+l); the regrouping to "E consecutive samples per lane" goes through a
+// per-warp shared-memory line with a +1 skew every 32 floats (conflict-free both ways for E = 2^m).
+// Carries travel through warp shuffles.  grid = (ceil(N/8), nS).
+template <int EMAX>
+__global__ void __launch_bounds__(256) k_prefilter_rows(const float* __restrict__ in, float* __restrict__ out, int N,
+                                                        SegGeom g, int apply_mask) {
+  __shared__ float line[8][EMAX * 32 + EMAX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp;
+  if (r >= N) return;
+  const size_t off = ((size_t)blockIdx.y * N + r) * N;
+  const float* src = in + off;
+  float* dst = out + off;
+  float* ln = line[warp];
+  const float half = 0.5f * N, r2lim = half * half;
+  const float xm = (float)r - half + 1.0f;
+  const float xm2 = xm * xm;
+#pragma unroll
+  for (int k = 0; k < EMAX; ++k) {
+    const int c = k * 32 + lane;
+    if (c < N) {
+      float t = src[c];
+      if (apply_mask) {                              // img * msk, :325
+        const float y = (float)c - half;
+        if (!(xm2 + y * y < r2lim)) t = 0.0f;
+      }
+      ln[c + k] = 6.0f * t;                          // c + (c >> 5)
+    }
+  }
+  __syncwarp();
+  const int E = g.E, used = g.used;
+  const int c0 = lane * E;
+  const int n = max(0, min(E, N - c0));              // samples of this lane
+  float v[EMAX];
+#pragma unroll
+  for (int j = 0; j < EMAX; ++j) v[j] = (j < n) ? ln[c0 + j + ((c0 + j) >> 5)] : 0.0f;
+  // causal pass, zero carry
+  float run = 0.0f;
+#pragma unroll
+  for (int j = 0; j < EMAX; ++j)
+    if (j < n) { run = fmaf(SPL_Z, run, v[j]); v[j] = run; }
+  // carry from the previous lanes (periodic)
+  float carry = 0.0f, f = 1.0f;
+  for (int h = 1; h <= g.H; ++h) {
+    int srcl = lane - h;
+    if (srcl < 0) srcl += used;
+    const float e = __shfl_sync(0xffffffffu, run, srcl & 31);
+    carry = fmaf(f, e, carry);
+    f *= (srcl == used - 1) ? g.zLast : g.zE;
+  }
+  float zp = SPL_Z * carry;
+#pragma unroll
+  for (int j = 0; j < EMAX; ++j)
+    if (j < n) { v[j] += zp; zp *= SPL_Z; }
+  // anti-causal pass on u[k] = -z c+[k], zero carry
+  run = 0.0f;
+#pragma unroll
+  for (int j = EMAX - 1; j >= 0; --j)
+    if (j < n) { run = SPL_Z * (run - v[j]); v[j] = run; }
+  carry = 0.0f; f = 1.0f;
+  for (int h = 1; h <= g.H; ++h) {
+    int srcl = lane + h;
+    if (srcl >= used) srcl -= used;
+    const float e = __shfl_sync(0xffffffffu, run, srcl & 31);
+    carry = fmaf(f, e, carry);
+    f *= (srcl == used - 1) ? g.zLast : g.zE;
+  }
+  zp = SPL_Z * carry;                                // restarts at the LAST sample of the lane
+#pragma unroll
+  for (int j = EMAX - 1; j >= 0; --j)
+    if (j < n) { v[j] += zp; zp *= SPL_Z; }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < EMAX; ++j)
+    if (j < n) ln[c0 + j + ((c0 + j) >> 5)] = v[j];
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < EMAX; ++k) {
+    const int c = k * 32 + lane;
+    if (c < N) dst[c] = ln[c + k];
+  }
+}
+
+// columns: CTA = 32 columns x S row-segments of up to 16 rows; a thread keeps its segment of one column
+// in registers (loads coalesced across the 32 columns), carries go through shared memory. In place.
+constexpr int COL_E = 16;
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_prefilter_cols(float* __restrict__ data, int N, SegGeom g) {
+  __shared__ float ends[32][33];
+  const int lane = threadIdx.x & 31;
+  const int col = blockIdx.x * 32 + lane;
+  const int seg = threadIdx.x >> 5;
+  const int E = g.E, used = g.used;                  // used == blockDim.x / 32
+  const int r0 = seg * E;
+  float* base = data + ((size_t)blockIdx.y * N + r0) * N + col;
+  const int n = (col < N) ? max(0, min(E, N - r0)) : 0;
+  float v[COL_E];
+#pragma unroll
+  for (int j = 0; j < COL_E; ++j) v[j] = (j < n) ? 6.0f * base[(size_t)j * N] : 0.0f;
+  float run = 0.0f;
+#pragma unroll
+  for (int j = 0; j < COL_E; ++j)
+    if (j < n) { run = fmaf(SPL_Z, run, v[j]); v[j] = run; }
+  ends[seg][lane] = run;
+  __syncthreads();
+  float carry = 0.0f, f = 1.0f;
+  for (int h = 1; h <= g.H; ++h) {
+    int s = seg - h;
+    if (s < 0) s += used;
+    carry = fmaf(f, ends[s][lane], carry);
+    f *= (s == used - 1) ? g.zLast : g.zE;
+  }
+  float zp = SPL_Z * carry;
+#pragma unroll
+  for (int j = 0; j < COL_E; ++j)
+    if (j < n) { v[j] += zp; zp *= SPL_Z; }
+  run = 0.0f;
+#pragma unroll
+  for (int j = COL_E - 1; j >= 0; --j)
+    if (j < n) { run = SPL_Z * (run - v[j]); v[j] = run; }
+  __syncthreads();
+  ends[seg][lane] = run;
+  __syncthreads();
+  carry = 0.0f; f = 1.0f;
+  for (int h = 1; h <= g.H; ++h) {
+    int s = seg + h;
+    if (s >= used) s -= used;
+    carry = fmaf(f, ends[s][lane], carry);
+    f *= (s == used - 1) ? g.zLast : g.zE;
+  }
+  zp = SPL_Z * carry;
+#pragma unroll
+  for (int j = COL_E - 1; j >= 0; --j)
+    if (j < n) { v[j] += zp; zp *= SPL_Z; }
+#pragma unroll
+  for (int j = 0; j < COL_E; ++j)
+    if (j < n) base[(size_t)j * N] = v[j];
+}
+
+// per-image rotation cos/sin in fp64 (ndimage.rotate: matrix [[c, s], [-s, c]], angle in degrees);
+// entry nS holds the common second rotation by -psi_p (:330)
+__global__ void k_angles(const double* __restrict__ psi_deg, double psi_p_deg, double2* __restrict__ cs, int nS) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nS) return;
+  const double a = (i < nS ? psi_deg[i] : -psi_p_deg) * 0.017453292519943295769;
+  double s, c;
+  sincos(a, &s, &c);
+  cs[i] = make_double2(c, s);
+}
+
+// cubic B-spline weights at fractional offset t in [0,1): taps at -1, 0, +1, +2
+__device__ __forceinline__ void bspline_w(float t, float (&w)[4]) {
+  const float u = 1.0f - t;
+  const float t2 = t * t, u2 = u * u;
+  w[0] = u2 * u * (1.0f / 6.0f);
+  w[3] = t2 * t * (1.0f / 6.0f);
+  w[1] = fmaf(t2, fmaf(0.5f, t, -1.0f), 2.0f / 3.0f);
+  w[2] = fmaf(u2, fmaf(0.5f, u, -1.0f), 2.0f / 3.0f);
+}
+
+// a7 (rotatefill.py:21-41): out(o) = sum_{4x4} w * coef[(floor(x)-1+a) mod N], x = R (o - ctr) + ctr, ctr=(N-1)/2.
+// CTA = 32x32 output tile; the (periodically wrapped) bounding box of its source footprint, at most
+// 50x50 coefficients, is staged in shared memory.  Coordinates in fp64, weights in fp32.
+// If msk2 != NULL a second, masked copy is written (img*msk2, :344).  FULL: N is a multiple of 32.
+constexpr int ROT_T = 32, ROT_B = 50, ROT_P = 51;
+template <bool FULL>
+__global__ void __launch_bounds__(256) k_rotate(const float* __restrict__ coef, float* __restrict__ out,
+                                                const double2* __restrict__ cs, int cs_stride, int N,
+                                                const uint8_t* __restrict__ msk2, float* __restrict__ out_masked) {
+  __shared__ float tile[ROT_B * ROT_P];
+  const int img = blockIdx.z;
+  const double2 a = cs[(size_t)img * cs_stride];
+  const double ctr = 0.5 * (N - 1);
+  const int r0 = blockIdx.y * ROT_T, c0 = blockIdx.x * ROT_T;
+  // source coordinates of the tile corners -> bounding box origin (floor(min) - 1); every thread computes it
+  const double tr = r0 - ctr, tc = c0 - ctr, ext = ROT_T - 1;
+  const double b0 = a.x * tr + a.y * tc + ctr + fmin(a.x * ext, 0.0) + fmin(a.y * ext, 0.0);
+  const double b1 = -a.y * tr + a.x * tc + ctr + fmin(-a.y * ext, 0.0) + fmin(a.x * ext, 0.0);
+  const int o0 = (int)floor(b0) - 1, o1 = (int)floor(b1) - 1;
+  const float* src = coef + (size_t)img * N * N;
+  int w0m = o0 % N; if (w0m < 0) w0m += N;
+  int w1m = o1 % N; if (w1m < 0) w1m += N;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  {
+    int gx0 = w1m + lane; while (gx0 >= N) gx0 -= N;
+    int gx1 = w1m + lane + 32; while (gx1 >= N) gx1 -= N;
+    for (int yy = wrp; yy < ROT_B; yy += 8) {
+      int gy = w0m + yy; while (gy >= N) gy -= N;
+      const float* rowp = src + (size_t)gy * N;
+      tile[yy * ROT_P + lane] = __ldg(rowp + gx0);
+      if (lane + 32 < ROT_B) tile[yy * ROT_P + lane + 32] = __ldg(rowp + gx1);
+    }
+  }
+  __syncthreads();
+  const int c = c0 + lane;
+  const double xb0 = a.x * ((r0 + wrp) - ctr) + a.y * (c - ctr) + ctr - (double)o0;   // row coordinate, bbox-relative
+  const double xb1 = -a.y * ((r0 + wrp) - ctr) + a.x * (c - ctr) + ctr - (double)o1;  // column coordinate
+  float* dst = out + (size_t)img * N * N + (size_t)(r0 + wrp) * N + c;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (!FULL && (r0 + wrp + 8 * q >= N || c >= N)) continue;
+    const double x0 = xb0 + (8 * q) * a.x;
+    const double x1 = xb1 - (8 * q) * a.y;
+    const int i0 = __double2int_rd(x0), j0 = __double2int_rd(x1);
+    const float t0 = (float)(x0 - (double)i0), t1 = (float)(x1 - (double)j0);
+    float wa[4], wb[4];
+    bspline_w(t0, wa);
+    bspline_w(t1, wb);
+    const float* p = tile + (i0 - 1) * ROT_P + (j0 - 1);      // 0 <= i0-1, j0-1 and i0+2, j0+2 < ROT_B
+    float acc = 0.0f;
+#pragma unroll
+    for (int ai = 0; ai < 4; ++ai) {
+      const float* rowp = p + ai * ROT_P;
+      float rs = wb[0] * rowp[0];
+      rs = fmaf(wb[1], rowp[1], rs);
+      rs = fmaf(wb[2], rowp[2], rs);
+      rs = fmaf(wb[3], rowp[3], rs);
+      acc = fmaf(wa[ai], rs, acc);
+    }
+    dst[(size_t)(8 * q) * N] = acc;
+    if (out_masked) {
+      const size_t o = (size_t)img * N * N + (size_t)(r0 + wrp + 8 * q) * N + c;
+      out_masked[o] = msk2[(r0 + wrp + 8 * q) * N + c] ? acc : 0.0f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+int ingest_run(mem_ctx* ctx, const float* raw, const uint8_t* flip, float* out, int nS, int N, int transposed,
+               cudaStream_t st) {
+  MEM_LAUNCH(ctx, k_ingest, nS, 256, 0, st, raw, flip, out, N, transposed);
+  return 0;
+}
+
+static SegGeom make_geom(int N, int E) {
+  SegGeom g;
+  g.E = E;
+  g.used = (N + E - 1) / E;
+  g.H = SPL_REACH / E + 2;
+  if (g.H > g.used) g.H = g.used;
+  const double z = sqrt(3.0) - 2.0;
+  g.zE = (float)pow(z, (double)E);
+  g.zLast = (float)pow(z, (double)(N - (g.used - 1) * E));
+  return g;
+}
+
+static int prefilter_run(mem_ctx* ctx, const float* in, float* out, int nS, int N, int apply_mask, cudaStream_t st) {
+  if (N > 512 || N < 16) {
+    set_error("box size %d outside [16, 512] is not supported by the spline prefilter", N);
+    return 1;
+  }
+  const int E = (N + 31) / 32;
+  const SegGeom gr = make_geom(N, E);
+  const dim3 grid((N + 7) / 8, nS);
+  if (E <= 4) MEM_LAUNCH(ctx, k_prefilter_rows<4>, grid, 256, 0, st, in, out, N, gr, apply_mask);
+  else if (E <= 8) MEM_LAUNCH(ctx, k_prefilter_rows<8>, grid, 256, 0, st, in, out, N, gr, apply_mask);
+  else MEM_LAUNCH(ctx, k_prefilter_rows<16>, grid, 256, 0, st, in, out, N, gr, apply_mask);
+  // columns: segments of <= 16 rows, S = ceil(N / 16) <= 32 segments per column
+  const int S = (N + COL_E - 1) / COL_E;
+  const int Ec = (N + S - 1) / S;
+  const SegGeom gc = make_geom(N, Ec);
+  const dim3 gcols((N + 31) / 32, nS);
+  auto kc_small = k_prefilter_cols<512, 2>;
+  auto kc_large = k_prefilter_cols<1024, 1>;
+  if (gc.used <= 16) MEM_LAUNCH(ctx, kc_small, gcols, 32 * gc.used, 0, st, out, N, gc);
+  else MEM_LAUNCH(ctx, kc_large, gcols, 32 * gc.used, 0, st, out, N, gc);
+  return 0;
+}
+
+// B (low-passed images) -> imgAll (aligned), optional masked copy into B.  A, B: [nS][N][N] scratch.
+int align_run(mem_ctx* ctx, float* A, float* B, float* imgAll, const double* psi_deg, double psi_p_deg, double2* cs,
+              const uint8_t* msk2, int nS, int N, cudaStream_t st) {
+  MEM_LAUNCH(ctx, k_angles, (nS + 1 + 127) / 128, 128, 0, st, psi_deg, psi_p_deg, cs, nS);
+  const dim3 grot((N + ROT_T - 1) / ROT_T, (N + ROT_T - 1) / ROT_T, nS);
+  const bool full = (N % ROT_T) == 0;
+  MEM_CHECK(prefilter_run(ctx, B, A, nS, N, 1, st));                    // (img * msk) -> coefficients
+  if (full) MEM_LAUNCH(ctx, k_rotate<true>, grot, 256, 0, st, A, B, cs, 1, N, (const uint8_t*)nullptr, (float*)nullptr);
+  else MEM_LAUNCH(ctx, k_rotate<false>, grot, 256, 0, st, A, B, cs, 1, N, (const uint8_t*)nullptr, (float*)nullptr);
+  MEM_CHECK(prefilter_run(ctx, B, A, nS, N, 0, st));
+  if (full) MEM_LAUNCH(ctx, k_rotate<true>, grot, 256, 0, st, A, imgAll, cs + nS, 0, N, msk2, msk2 ? B : (float*)nullptr);
+  else MEM_LAUNCH(ctx, k_rotate<false>, grot, 256, 0, st, A, imgAll, cs + nS, 0, N, msk2, msk2 ? B : (float*)nullptr);
+  return 0;
+}
+
+}  // namespace mem

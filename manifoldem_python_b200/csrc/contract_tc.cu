@@ -306,7 +306,7 @@ int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, c
     set_error("tcgen05 contraction needs an sm_100a device (found compute capability major %d); there is no fallback", dev_cc_major);
     return 1;
   }
-  const int chunk = k_chunk_blocks > 0 ? k_chunk_blocks : 4;
+  const int chunk = k_chunk_blocks > 0 ? k_chunk_blocks : 1;
   // tiles of the upper triangle (any element with col >= row)
   std::vector<std::pair<int, int>> tiles;
   const int tm = (nS + BM - 1) / BM, tn = (nS + BN - 1) / BN;

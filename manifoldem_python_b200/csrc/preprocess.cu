@@ -10,6 +10,11 @@
 
 namespace mem {
 
+int ingest_run(mem_ctx* ctx, const float* raw, const uint8_t* flip, float* out, int nS, int N, int transposed,
+               cudaStream_t st);
+int align_run(mem_ctx* ctx, float* A, float* B, float* imgAll, const double* psi_deg, double psi_p_deg, double2* cs,
+              const uint8_t* msk2, int nS, int N, cudaStream_t st);
+
 // ------------------------------------------------------------------------------------------------
 // error string + arena
 // ------------------------------------------------------------------------------------------------
@@ -183,68 +188,6 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
   return t;
 }
 
-// a2+a3 (:246-283): picture = raw^T (SPIDER) or raw; conjugates flipped upside down; then
-// (x - mean(b))/std(b) with b = x*(1-msk) over all N^2 pixels (population std).
-// One CTA per particle; pass 1 = moments (fp64 accumulators), pass 2 = 32x32 tile transpose + scale.
-__global__ void __launch_bounds__(256) k_ingest(const float* __restrict__ raw, const uint8_t* __restrict__ flip,
-                                                float* __restrict__ out, int N, int transposed) {
-  __shared__ double red[8];
-  __shared__ float tile[32][33];
-  const int i = blockIdx.x;
-  const float* src = raw + (size_t)i * N * N;
-  float* dst = out + (size_t)i * N * N;
-  const bool fl = flip[i] != 0;
-  const float half = 0.5f * N, r2lim = half * half;
-  double s = 0, s2 = 0;
-  for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
-    const int a = e / N, b = e - a * N;
-    int r = transposed ? b : a;
-    const int c = transposed ? a : b;
-    if (fl) r = N - 1 - r;
-    const float x = (float)r - half + 1.0f, y = (float)c - half;   // annularMask.py:24-30, centre (N/2-1, N/2)
-    const float v = src[e];
-    const float bg = (x * x + y * y < r2lim) ? 0.0f : v;
-    s += bg;
-    s2 += (double)bg * bg;
-  }
-  s = block_sum(s, red);
-  s2 = block_sum(s2, red);
-  const double n = (double)N * N;
-  const double mean = s / n;
-  const double var = s2 / n - mean * mean;
-  const float fm = (float)mean;
-  const float inv = (float)(1.0 / sqrt(var));
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-  const int nt = (N + 31) / 32;
-  for (int t = 0; t < nt * nt; ++t) {
-    const int tr = (t / nt) * 32, tc = (t % nt) * 32;   // output tile origin (rows r', cols c)
-    __syncthreads();
-    if (transposed) {
-      // raw index = c*N + r : read with r fastest
-      for (int k = ty; k < 32; k += 8) {
-        const int c = tc + k, rp = tr + tx;
-        if (c < N && rp < N) {
-          const int r = fl ? N - 1 - rp : rp;
-          tile[k][tx] = src[(size_t)c * N + r];
-        }
-      }
-      __syncthreads();
-      for (int k = ty; k < 32; k += 8) {
-        const int rp = tr + k, c = tc + tx;
-        if (rp < N && c < N) dst[(size_t)rp * N + c] = (tile[tx][k] - fm) * inv;
-      }
-    } else {
-      for (int k = ty; k < 32; k += 8) {
-        const int rp = tr + k, c = tc + tx;
-        if (rp < N && c < N) {
-          const int r = fl ? N - 1 - rp : rp;
-          dst[(size_t)rp * N + c] = (src[(size_t)r * N + c] - fm) * inv;
-        }
-      }
-    }
-  }
-}
-
 // a5 (:286-293): spectrum *= ifftshift(G)/N^2
 __global__ void k_specmul(float2* __restrict__ spec, const float* __restrict__ G, int Kh, size_t total) {
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
@@ -254,167 +197,6 @@ __global__ void k_specmul(float2* __restrict__ spec, const float* __restrict__ G
     v.y *= g;
     spec[e] = v;
   }
-}
-
-// Cubic B-spline prefilter, periodic boundary (what scipy.ndimage.rotate's spline_filter amounts to on
-// the 3x3-tiled image of rotatefill.py:21-25 away from the tile border; SURVEY §7 hard part 2).
-//   c+[k] = 6 s[k] + z c+[k-1],  c[k] = z (c[k+1] - c+[k]),  z = sqrt(3) - 2
-// with the periodic initial values summed to |z|^24 < 2e-14.
-#define SPL_Z (-0.26794919243112270647f)
-#define SPL_W 24
-
-// rows: CTA = 32 rows of one image staged in smem (pitch odd -> conflict-free), one lane per row.
-__global__ void __launch_bounds__(32) k_prefilter_rows(const float* __restrict__ in, float* __restrict__ out, int N,
-                                                       int apply_mask) {
-  extern __shared__ float sm[];
-  const int pitch = N | 1;
-  const int img = blockIdx.y, r0 = blockIdx.x * 32;
-  const float* src = in + (size_t)img * N * N;
-  float* dst = out + (size_t)img * N * N;
-  const int rows = min(32, N - r0);
-  const float half = 0.5f * N, r2lim = half * half;
-  for (int e = threadIdx.x; e < rows * N; e += 32) {
-    const int rr = e / N, c = e - rr * N;
-    float v = src[(size_t)(r0 + rr) * N + c];
-    if (apply_mask) {   // img * msk, :325
-      const float x = (float)(r0 + rr) - half + 1.0f, y = (float)c - half;
-      if (!(x * x + y * y < r2lim)) v = 0.0f;
-    }
-    sm[rr * pitch + c] = 6.0f * v;
-  }
-  __syncwarp();
-  if ((int)threadIdx.x < rows) {
-    float* row = sm + threadIdx.x * pitch;
-    const int W = SPL_W;
-    float cp = 0.0f, zk = 1.0f;
-    for (int j = 0; j < W; ++j) {   // c+[0] = sum_j z^j s[-j mod N]
-      cp += zk * row[(N - j % N) % N];
-      zk *= SPL_Z;
-    }
-    row[0] = cp;
-    for (int k = 1; k < N; ++k) {
-      cp = row[k] + SPL_Z * cp;
-      row[k] = cp;
-    }
-    float cm = 0.0f;
-    zk = SPL_Z;
-    for (int j = 0; j < W; ++j) {   // c[N-1] = -sum_j z^(j+1) c+[(N-1+j) mod N]
-      cm -= zk * row[(N - 1 + j) % N];
-      zk *= SPL_Z;
-    }
-    row[N - 1] = cm;
-    for (int k = N - 2; k >= 0; --k) {
-      cm = SPL_Z * (cm - row[k]);
-      row[k] = cm;
-    }
-  }
-  __syncwarp();
-  for (int e = threadIdx.x; e < rows * N; e += 32) {
-    const int rr = e / N, c = e - rr * N;
-    dst[(size_t)(r0 + rr) * N + c] = sm[rr * pitch + c];
-  }
-}
-
-// columns: CTA = 32 columns x all rows in smem, one lane per column (bank = lane).
-__global__ void __launch_bounds__(32) k_prefilter_cols(float* __restrict__ data, int N) {
-  extern __shared__ float sm[];
-  const int img = blockIdx.y, c0 = blockIdx.x * 32;
-  float* base = data + (size_t)img * N * N;
-  const int c = c0 + threadIdx.x;
-  const bool ok = c < N;
-  for (int r = 0; r < N; ++r) sm[r * 32 + threadIdx.x] = ok ? 6.0f * base[(size_t)r * N + c] : 0.0f;
-  float* col = sm + threadIdx.x;
-  const int W = SPL_W;
-  float cp = 0.0f, zk = 1.0f;
-  for (int j = 0; j < W; ++j) {
-    cp += zk * col[((N - j % N) % N) * 32];
-    zk *= SPL_Z;
-  }
-  col[0] = cp;
-  for (int k = 1; k < N; ++k) {
-    cp = col[k * 32] + SPL_Z * cp;
-    col[k * 32] = cp;
-  }
-  float cm = 0.0f;
-  zk = SPL_Z;
-  for (int j = 0; j < W; ++j) {
-    cm -= zk * col[((N - 1 + j) % N) * 32];
-    zk *= SPL_Z;
-  }
-  col[(N - 1) * 32] = cm;
-  for (int k = N - 2; k >= 0; --k) {
-    cm = SPL_Z * (cm - col[k * 32]);
-    col[k * 32] = cm;
-  }
-  if (ok)
-    for (int r = 0; r < N; ++r) base[(size_t)r * N + c] = sm[r * 32 + threadIdx.x];
-}
-
-// per-image rotation cos/sin in fp64 (ndimage.rotate: matrix [[c, s], [-s, c]], angle in degrees)
-__global__ void k_angles(const double* __restrict__ psi_deg, double psi_p_deg, double2* __restrict__ cs, int nS) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > nS) return;
-  const double a = (i < nS ? psi_deg[i] : -psi_p_deg) * 0.017453292519943295769;   // second rotation is by -psi_p (:330)
-  double s, c;
-  sincos(a, &s, &c);
-  cs[i] = make_double2(c, s);
-}
-
-// a7 (rotatefill.py:21-41): out(o) = sum_{4x4} w * coef[(floor(x)-1+a) mod N], x = R (o - ctr) + ctr, ctr=(N-1)/2.
-// Coordinates in fp64, weights in fp32.  If msk2 != NULL a second, masked copy is written (img*msk2, :344).
-__global__ void __launch_bounds__(256) k_rotate(const float* __restrict__ coef, float* __restrict__ out,
-                                                const double2* __restrict__ cs, int cs_stride, int N,
-                                                const uint8_t* __restrict__ msk2, float* __restrict__ out_masked) {
-  const int img = blockIdx.z;
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int r = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (r >= N || c >= N) return;
-  const double2 a = cs[(size_t)img * cs_stride];
-  const double ctr = 0.5 * (N - 1);
-  const double dr = r - ctr, dc = c - ctr;
-  const double x0 = a.x * dr + a.y * dc + ctr;
-  const double x1 = -a.y * dr + a.x * dc + ctr;
-  const double f0 = floor(x0), f1 = floor(x1);
-  const float t0 = (float)(x0 - f0), t1 = (float)(x1 - f1);
-  int i0 = (int)f0 - 1, j0 = (int)f1 - 1;
-  i0 %= N; if (i0 < 0) i0 += N;
-  j0 %= N; if (j0 < 0) j0 += N;
-  float w0[4], w1[4];
-  {
-    const float t = t0, u = 1.0f - t;
-    w0[0] = u * u * u * (1.0f / 6.0f);
-    w0[1] = (4.0f - 6.0f * t * t + 3.0f * t * t * t) * (1.0f / 6.0f);
-    w0[2] = (4.0f - 6.0f * u * u + 3.0f * u * u * u) * (1.0f / 6.0f);
-    w0[3] = t * t * t * (1.0f / 6.0f);
-  }
-  {
-    const float t = t1, u = 1.0f - t;
-    w1[0] = u * u * u * (1.0f / 6.0f);
-    w1[1] = (4.0f - 6.0f * t * t + 3.0f * t * t * t) * (1.0f / 6.0f);
-    w1[2] = (4.0f - 6.0f * u * u + 3.0f * u * u * u) * (1.0f / 6.0f);
-    w1[3] = t * t * t * (1.0f / 6.0f);
-  }
-  const float* src = coef + (size_t)img * N * N;
-  int jj[4];
-#pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    int j = j0 + b;
-    if (j >= N) j -= N;
-    jj[b] = j;
-  }
-  float acc = 0.0f;
-#pragma unroll
-  for (int aI = 0; aI < 4; ++aI) {
-    int ii = i0 + aI;
-    if (ii >= N) ii -= N;
-    const float* row = src + (size_t)ii * N;
-    const float rsum = w1[0] * __ldg(row + jj[0]) + w1[1] * __ldg(row + jj[1]) + w1[2] * __ldg(row + jj[2]) +
-                       w1[3] * __ldg(row + jj[3]);
-    acc += w0[aI] * rsum;
-  }
-  const size_t o = (size_t)img * N * N + (size_t)r * N + c;
-  out[o] = acc;
-  if (out_masked) out_masked[o] = msk2[r * N + c] ? acc : 0.0f;
 }
 
 // a8 (ctemh_cryoFrank.py:24-44) at the distinct radii: C[i][b].
@@ -739,7 +521,7 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
 
   MEM_CUDA(cudaEventRecord(ctx->ev[0], st));
   // ---- a2/a3 ingest + normalise -> A
-  MEM_LAUNCH(ctx, k_ingest, nS, 256, 0, st, io->raw, io->flip, A, N, prm->transposed);
+  MEM_CHECK(ingest_run(ctx, io->raw, io->flip, A, nS, N, prm->transposed, st));
   // ---- a5 low-pass: A -> spec -> *G -> B
   MEM_CHECK(run_fft(ctx, N, nS, true, A, spec, st));
   {
@@ -750,20 +532,7 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
   MEM_CHECK(run_fft(ctx, N, nS, false, B, spec, st));
   MEM_CUDA(cudaEventRecord(ctx->ev[1], st));
   // ---- a7 alignment: two periodic cubic-spline rotations
-  MEM_LAUNCH(ctx, k_angles, (nS + 1 + 127) / 128, 128, 0, st, io->psi_deg, prm->psi_p_deg, cs, nS);
-  const dim3 gr_rows((N + 31) / 32, nS), gr_cols((N + 31) / 32, nS), gr_rot((N + 31) / 32, (N + 7) / 8, nS);
-  const size_t sm_rows = (size_t)32 * (N | 1) * sizeof(float), sm_cols = (size_t)32 * N * sizeof(float);
-  if (sm_rows > 48 * 1024) {
-    MEM_CUDA(cudaFuncSetAttribute(k_prefilter_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_rows));
-    MEM_CUDA(cudaFuncSetAttribute(k_prefilter_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cols));
-  }
-  MEM_LAUNCH(ctx, k_prefilter_rows, gr_rows, 32, sm_rows, st, B, A, N, 1);   // (img*msk) -> coef
-  MEM_LAUNCH(ctx, k_prefilter_cols, gr_cols, 32, sm_cols, st, A, N);
-  MEM_LAUNCH(ctx, k_rotate, gr_rot, 256, 0, st, A, B, cs, 1, N, (const uint8_t*)nullptr, (float*)nullptr);
-  MEM_LAUNCH(ctx, k_prefilter_rows, gr_rows, 32, sm_rows, st, B, A, N, 0);
-  MEM_LAUNCH(ctx, k_prefilter_cols, gr_cols, 32, sm_cols, st, A, N);
-  // second rotation by -psi_p (same for every image): cs[nS], stride 0; masked copy -> B when msk2 is given
-  MEM_LAUNCH(ctx, k_rotate, gr_rot, 256, 0, st, A, imgAll, cs + nS, 0, N, io->msk2, io->msk2 ? B : (float*)nullptr);
+  MEM_CHECK(align_run(ctx, A, B, imgAll, io->psi_deg, prm->psi_p_deg, cs, io->msk2, nS, N, st));
   MEM_CUDA(cudaEventRecord(ctx->ev[2], st));
   // ---- a10 FFT of img*msk2 (and of img for the Wiener average when they differ)
   float2* specw = nullptr;

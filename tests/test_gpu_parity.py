@@ -120,7 +120,7 @@ def test_split_and_chunk_invariance(env):
     for chunk, split in ((2, 1), (4, 3), (8, 0)):
         other = _gpu(pd_stage, pd, 64, fields=('D',), k_chunk_blocks=chunk, split_k=split)['D']
         off = ~np.eye(260, dtype=bool)
-        assert (np.abs(other - base)[off] / base[off]).max() < 5e-6
+        assert (np.abs(other - base)[off] / base[off]).max() < 2e-5
 
 
 def test_invariances_full_size(env):
