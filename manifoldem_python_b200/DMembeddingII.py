@@ -1,0 +1,110 @@
+"""Drop-in for the diffusion-map front end (modules/DMembeddingII.py:86-185).
+
+op(D, k, tune, prefsigma) -> (lamb, psi, sigma, mu, logEps, logSumWij, popt, R_squared)
+
+On the GPU (C ABI): kNN lists (a15), OR-symmetrised graph (a16), the 1,501-point Ferguson sweep (a17 — 97 %
+of the reference's time), Gaussian kernel + alpha = 1 + symmetric normalisations (a18).  On the host, with the
+same SciPy calls as the reference: the 4-parameter tanh fit (curve_fit, fergusonE.py:45-57) and the ARPACK
+eigen-solve (eigsh, sembeddingonFly.py:27-35), so sigma and the eigenvectors follow the same code path.
+D is mutated in place (diagonal <- -inf) like the reference (:48).
+"""
+import ctypes as C
+
+import numpy as np
+from scipy.optimize import curve_fit, OptimizeWarning
+from scipy.sparse.linalg import eigsh, ArpackNoConvergence
+import warnings
+
+from . import _lib
+from .getDistanceCTF_local_Conj9combinedS2 import _cfg, _ctx
+
+warnings.simplefilter(action='ignore', category=OptimizeWarning)
+
+
+def fun(xx, aa0, aa1, aa2, aa3):
+    """fergusonE.fun :21-23."""
+    return aa3 + aa2 * np.tanh(aa0 * xx + aa1)
+
+
+def _fit(logEps, logSumWij, a0):
+    """fergusonE.op :45-57 — retry from random starts while sum sqrt|diag pcov| > 100."""
+    resnorm = np.inf
+    while resnorm > 100:
+        popt, pcov = curve_fit(fun, logEps, logSumWij, p0=a0)
+        resnorm = sum(np.sqrt(np.fabs(np.diag(pcov))))
+        a0 = 1 * (np.random.rand(4, 1) - .5)
+        residuals = logSumWij - fun(logEps, popt[0], popt[1], popt[2], popt[3])
+        ss_res = np.sum(residuals ** 2)
+        ss_tot = np.sum((logSumWij - np.mean(logSumWij)) ** 2)
+        R_squared = 1 - (ss_res / ss_tot)
+    return popt, resnorm, R_squared
+
+
+def graph_and_sweep(D, k, ctx=None):
+    """Device part up to the Ferguson curve.  Returns (M_dev DeviceArray (nS,nS) float64 graph,
+    logEps, logSumWij, idx (nS,k) int32, val (nS,k) float64)."""
+    lib = _lib.load()
+    ctx = ctx or _ctx()
+    nS = D.shape[0]
+    Dd = _lib.DeviceArray(ctx, (nS, nS), np.float64, np.ascontiguousarray(D, dtype=np.float64))
+    idx_d = _lib.DeviceArray(ctx, (nS, k), np.int32)
+    val_d = _lib.DeviceArray(ctx, (nS, k), np.float64)
+    _lib.check(lib.mem_knn_device(ctx.handle, Dd.ptr, nS, k, idx_d.ptr, val_d.ptr, None))
+    M = _lib.DeviceArray(ctx, (nS, nS), np.float64)
+    _lib.check(lib.mem_graph_dense_device(ctx.handle, idx_d.ptr, val_d.ptr, nS, k, M.ptr, None))
+    logEps = np.arange(-150, 150.2, 0.2)                                        # :146
+    # find_thres (fergusonE.py:25-31): ss = sum exp(-d2 / (2 max eps)), n = number of graph entries
+    one = np.array([np.max(logEps)], dtype=np.float64)
+    out1 = np.zeros(1)
+    _lib.check(lib.mem_ferguson_device(ctx.handle, M.ptr, nS * nS, one.ctypes.data, 1, float('inf'), out1.ctypes.data))
+    ss = float(np.exp(out1[0]))
+    huge = np.array([700.0], dtype=np.float64)
+    _lib.check(lib.mem_ferguson_device(ctx.handle, M.ptr, nS * nS, huge.ctypes.data, 1, float('inf'), out1.ctypes.data))
+    n_entries = float(np.rint(np.exp(out1[0])))
+    thr = max(-np.log(0.01 * ss / n_entries), 10)
+    logSumWij = np.zeros(len(logEps))
+    _lib.check(lib.mem_ferguson_device(ctx.handle, M.ptr, nS * nS, logEps.ctypes.data, len(logEps), float(thr),
+                                       logSumWij.ctypes.data))
+    idx, val = idx_d.download(), val_d.download()
+    for a in (Dd, idx_d, val_d):
+        a.free()
+    return M, logEps, logSumWij, idx, val
+
+
+def laplacian(M, nS, sigma, ctx=None):
+    """slaplacianonFly.op on the device, dense (nS,nS) float64 result on the host."""
+    lib = _lib.load()
+    ctx = ctx or _ctx()
+    L = _lib.DeviceArray(ctx, (nS, nS), np.float64)
+    _lib.check(lib.mem_laplacian_dense_device(ctx.handle, M.ptr, nS, float(sigma), L.ptr, None))
+    out = L.download()
+    L.free()
+    return out
+
+
+def op(D, k, tune, prefsigma):
+    p = _cfg()
+    nS = D.shape[0]
+    k = int(k)
+    M, logEps, logSumWij, _, _ = graph_and_sweep(D, k)
+    D[np.arange(nS), np.arange(nS)] = -np.inf                                    # :48, in place like the reference
+    a0 = (np.random.rand(4, 1) - .5)                                             # :142 (unseeded in the reference)
+    popt, resnorm, R_squared = _fit(logEps, logSumWij, a0)
+    nEigs = min(getattr(p, 'num_eigs', 15), nS - 3)                              # :149
+    sigma = tune * np.sqrt(2 * np.exp(-popt[1] / popt[0]))                       # :158
+    L = laplacian(M, nS, sigma)
+    M.free()
+    try:
+        vals, vecs = eigsh(L, k=nEigs + 1, maxiter=300)                          # sembeddingonFly.py:27
+    except ArpackNoConvergence as e:
+        vals, vecs = e.eigenvalues, e.eigenvectors
+        print("eigsh not converging in 300 iterations...")
+    ix = np.argsort(vals)[::-1]
+    lamb = np.sort(vals)[::-1]
+    v = vecs[:, ix]
+    true_shape = v.shape[1] - 1
+    psi = np.zeros((v.shape[0], nEigs))
+    psi[:, :true_shape] = v[:, 1:] / np.tile(v[:, 0].reshape((-1, 1)), (1, true_shape))    # :175-177
+    mu = v[:, 0]
+    mu = mu * mu                                                                 # :181-182
+    return (lamb, psi, sigma, mu, logEps, logSumWij, popt, R_squared)

@@ -1,0 +1,132 @@
+"""Drop-in for the distance-stage driver (modules/GetDistancesS2.py:53-124 and its _mpi twin :37-96).
+
+op(*argv): argv[0], if present, has .emit(int_percent) (Qt signal).  Reads the tessellation pickle
+p.tess_file (keys CG, df, q, sh), builds one job per projection direction [ind, q1, df1, dist_file, prD],
+skips PDs whose marker exists in p.dist_prog (resume), and runs the rest on the visible B200s:
+one spawned process per GPU (never fork after CUDA init), static LPT partition, no collective —
+results are the per-PD pickles, progress is read back from the marker directory exactly as the
+reference's MPI mode does (:69-73).
+"""
+import multiprocessing
+import os
+import time
+
+import numpy as np
+
+from . import myio, partition
+from . import getDistanceCTF_local_Conj9combinedS2 as worker
+from .getDistanceCTF_local_Conj9combinedS2 import _cfg
+
+
+def fileCheck():
+    """Finished PDs = names of the marker files under p.dist_prog (:29-35)."""
+    p = _cfg()
+    fin = []
+    for _root, _dirs, files in os.walk(p.dist_prog):
+        for f in sorted(files):
+            if not f.startswith('.'):
+                fin.append(int(f))
+    return fin
+
+
+def divide(CG, q, df, N):
+    """(:37-47) job list, skipping PDs with a marker."""
+    p = _cfg()
+    fin = set(fileCheck())
+    ll = []
+    for prD in range(N):
+        ind = CG[prD]
+        if prD not in fin:
+            ll.append([ind, q[:, ind], df[ind], '{}prD_{}'.format(p.dist_file, prD), prD])
+    return ll
+
+
+def count(N):
+    return N - len(fileCheck())
+
+
+def _set_params(do):
+    try:
+        import set_params          # the reference's persistence of p.* (modules/set_params.py), if present
+        set_params.op(do)
+    except ImportError:
+        pass
+
+
+def _n_gpus():
+    env = os.environ.get('MANIFOLDEM_B200_GPUS')
+    if env:
+        return max(1, int(env))
+    try:
+        import torch
+        return max(1, torch.cuda.device_count())
+    except Exception:
+        return 1
+
+
+def _gpu_worker(device, jobs, filterPar, imgFileName, sh, size, options, cfg):
+    """Runs in a spawned process: restore the config, bind the device, loop over this rank's PDs."""
+    os.environ['MANIFOLDEM_B200_DEVICE'] = str(device)
+    p = _cfg()
+    for k, v in cfg.items():
+        setattr(p, k, v)
+    for job in jobs:
+        worker.op(job, filterPar, imgFileName, sh, size, options)
+
+
+_CFG_KEYS = ('nPix', 'pix_size', 'Cs', 'EkV', 'AmpContrast', 'gaussEnv', 'mask_vol_file', 'dist_prog', 'dist_file',
+             'relion_data', 'ncpu')
+
+
+def op(*argv):
+    p = _cfg()
+    _set_params(1)
+    data = myio.fin1(p.tess_file)
+    CG = data['CG']
+    df, q, sh = data['df'], data['q'], data['sh']
+    size = len(df)
+    filterPar = dict(type='Butter', Qc=0.5, N=8)                                     # :83
+    options = dict(verbose=False, avgOnly=False, visual=False, parallel=False,
+                   relion_data=p.relion_data, thres=getattr(p, 'PDsizeThH', 2000))  # :84-85
+    if p.relion_data is False:                                                       # SPIDER: box from file size (:90-92)
+        p.nPix = int(np.sqrt(os.path.getsize(p.img_stack_file) / (4 * p.num_part)))
+        _set_params(0)
+    if not getattr(p, 'numberofJobs', 0):
+        p.numberofJobs = len(CG)
+    input_data = divide(CG, q, df, p.numberofJobs)
+    progress = argv[0] if argv else None
+    offset = p.numberofJobs - len(input_data)
+    if progress is not None:
+        progress.emit(int((offset / float(p.numberofJobs)) * 100))
+    print('Processing {} projection directions.'.format(len(input_data)))
+
+    n_workers = min(_n_gpus(), max(1, int(getattr(p, 'ncpu', 1))), max(1, len(input_data)))
+    if n_workers <= 1:
+        for job in input_data:                                                       # :102-108
+            worker.op(job, filterPar, p.img_stack_file, sh, size, options)
+            offset += 1
+            if progress is not None:
+                progress.emit(int((offset / float(p.numberofJobs)) * 100))
+    else:
+        costs = [partition.pd_cost(len(job[0]), p.nPix) for job in input_data]
+        shards = partition.lpt_partition(costs, n_workers)
+        cfg = {k: getattr(p, k) for k in _CFG_KEYS if hasattr(p, k)}
+        ctx = multiprocessing.get_context('spawn')
+        procs = [ctx.Process(target=_gpu_worker, args=(r, [input_data[i] for i in shards[r]], filterPar,
+                                                       p.img_stack_file, sh, size, options, cfg))
+                 for r in range(n_workers)]
+        for pr in procs:
+            pr.start()
+        while any(pr.is_alive() for pr in procs):                                    # marker polling, as :69-73
+            if progress is not None:
+                done = p.numberofJobs - count(p.numberofJobs)
+                progress.emit(int((done / float(p.numberofJobs)) * 100))
+            time.sleep(0.2)
+        for pr in procs:
+            pr.join()
+            if pr.exitcode != 0:
+                raise RuntimeError('GPU worker exited with code %s' % pr.exitcode)
+        if progress is not None:
+            progress.emit(int(((p.numberofJobs - count(p.numberofJobs)) / float(p.numberofJobs)) * 100))
+    _set_params(0)
+    return

@@ -102,6 +102,16 @@ __device__ __forceinline__ float zpow(int n) {
   return r;
 }
 
+// cubic B-spline weights at fractional offset t in [0,1): taps at -1, 0, +1, +2
+__device__ __forceinline__ void bspline_w(float t, float (&w)[4]) {
+  const float u = 1.0f - t;
+  const float t2 = t * t, u2 = u * u;
+  w[0] = u2 * u * (1.0f / 6.0f);
+  w[3] = t2 * t * (1.0f / 6.0f);
+  w[1] = fmaf(t2, fmaf(0.5f, t, -1.0f), 2.0f / 3.0f);
+  w[2] = fmaf(u2, fmaf(0.5f, u, -1.0f), 2.0f / 3.0f);
+}
+
 // Segment geometry of one filtered line, computed once on the host.
 struct SegGeom {
   int E;        // samples per segment
@@ -117,7 +127,7 @@ struct SegGeom {
 // Carries travel through warp shuffles.  grid = (ceil(N/8), nS).
 template <int EMAX>
 __global__ void __launch_bounds__(256) k_prefilter_rows(const float* __restrict__ in, float* __restrict__ out, int N,
-                                                        SegGeom g, int apply_mask) {
+                                                        int L, SegGeom g, int apply_mask) {
   __shared__ float line[8][EMAX * 32 + EMAX];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp;
@@ -132,8 +142,8 @@ __global__ void __launch_bounds__(256) k_prefilter_rows(const float* __restrict_
 #pragma unroll
   for (int k = 0; k < EMAX; ++k) {
     const int c = k * 32 + lane;
-    if (c < N) {
-      float t = src[c];
+    if (c < L) {
+      float t = src[c < N ? c : L - c];              // L == N: periodic line; L == 2N-2: mirror extension
       if (apply_mask) {                              // img * msk, :325
         const float y = (float)c - half;
         if (!(xm2 + y * y < r2lim)) t = 0.0f;
@@ -144,7 +154,7 @@ __global__ void __launch_bounds__(256) k_prefilter_rows(const float* __restrict_
   __syncwarp();
   const int E = g.E, used = g.used;
   const int c0 = lane * E;
-  const int n = max(0, min(E, N - c0));              // samples of this lane
+  const int n = max(0, min(E, L - c0));              // samples of this lane
   float v[EMAX];
 #pragma unroll
   for (int j = 0; j < EMAX; ++j) v[j] = (j < n) ? ln[c0 + j + ((c0 + j) >> 5)] : 0.0f;
@@ -199,18 +209,22 @@ __global__ void __launch_bounds__(256) k_prefilter_rows(const float* __restrict_
 // in registers (loads coalesced across the 32 columns), carries go through shared memory. In place.
 constexpr int COL_E = 16;
 template <int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) k_prefilter_cols(float* __restrict__ data, int N, SegGeom g) {
+__global__ void __launch_bounds__(MAXT, MINB) k_prefilter_cols(float* __restrict__ data, int N, int L, SegGeom g) {
   __shared__ float ends[32][33];
   const int lane = threadIdx.x & 31;
   const int col = blockIdx.x * 32 + lane;
   const int seg = threadIdx.x >> 5;
   const int E = g.E, used = g.used;                  // used == blockDim.x / 32
   const int r0 = seg * E;
-  float* base = data + ((size_t)blockIdx.y * N + r0) * N + col;
-  const int n = (col < N) ? max(0, min(E, N - r0)) : 0;
+  float* base = data + (size_t)blockIdx.y * N * N + col;
+  const int n = (col < N) ? max(0, min(E, L - r0)) : 0;
   float v[COL_E];
 #pragma unroll
-  for (int j = 0; j < COL_E; ++j) v[j] = (j < n) ? 6.0f * base[(size_t)j * N] : 0.0f;
+  for (int j = 0; j < COL_E; ++j) {
+    const int rr = r0 + j;
+    v[j] = (j < n) ? 6.0f * base[(size_t)(rr < N ? rr : L - rr) * N] : 0.0f;
+  }
+  if (L != N) __syncthreads();                       // mirror rows are read by two segments before any store
   float run = 0.0f;
 #pragma unroll
   for (int j = 0; j < COL_E; ++j)
@@ -248,7 +262,46 @@ __global__ void __launch_bounds__(MAXT, MINB) k_prefilter_cols(float* __restrict
     if (j < n) { v[j] += zp; zp *= SPL_Z; }
 #pragma unroll
   for (int j = 0; j < COL_E; ++j)
-    if (j < n) base[(size_t)j * N] = v[j];
+    if (j < n && r0 + j < N) base[(size_t)(r0 + j) * N] = v[j];
+}
+
+// a2, RELION branch (:263-264): scipy.ndimage.shift(img, (s0, s1), order=3, mode='wrap') on mirror-prefiltered
+// coefficients.  SciPy semantics pinned in SURVEY §7(2) and tests/test_host.py: input coordinate o - s is
+// wrapped with period N-1, the 4 support indices are mirrored (k<0 -> -k, k>N-1 -> 2(N-1)-k).
+__device__ __forceinline__ void shift_taps(int o, double s, int N, int (&k)[4], float (&w)[4]) {
+  double x = (double)o - s;
+  const double Lp = (double)(N - 1);
+  if (x < 0.0) x += Lp * (double)((int)(-x / Lp) + 1);
+  else if (x > Lp) x -= Lp * (double)((int)(x / Lp));
+  const double fl = floor(x);
+  const int i0 = (int)fl;
+  bspline_w((float)(x - fl), w);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    int kk = i0 - 1 + a;
+    if (kk < 0) kk = -kk;
+    if (kk > N - 1) kk = 2 * (N - 1) - kk;
+    k[a] = kk;
+  }
+}
+__global__ void __launch_bounds__(256) k_shift(const float* __restrict__ coef, float* __restrict__ out,
+                                               const double* __restrict__ shift, int N) {
+  const int img = blockIdx.z;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), r = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (r >= N || c >= N) return;
+  int ka[4], kb[4];
+  float wa[4], wb[4];
+  shift_taps(r, shift[2 * img], N, ka, wa);
+  shift_taps(c, shift[2 * img + 1], N, kb, wb);
+  const float* src = coef + (size_t)img * N * N;
+  float acc = 0.0f;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const float* rowp = src + (size_t)ka[a] * N;
+    acc = fmaf(wa[a], wb[0] * __ldg(rowp + kb[0]) + wb[1] * __ldg(rowp + kb[1]) + wb[2] * __ldg(rowp + kb[2]) +
+                          wb[3] * __ldg(rowp + kb[3]), acc);
+  }
+  out[(size_t)img * N * N + (size_t)r * N + c] = acc;
 }
 
 // per-image rotation cos/sin in fp64 (ndimage.rotate: matrix [[c, s], [-s, c]], angle in degrees);
@@ -260,16 +313,6 @@ __global__ void k_angles(const double* __restrict__ psi_deg, double psi_p_deg, d
   double s, c;
   sincos(a, &s, &c);
   cs[i] = make_double2(c, s);
-}
-
-// cubic B-spline weights at fractional offset t in [0,1): taps at -1, 0, +1, +2
-__device__ __forceinline__ void bspline_w(float t, float (&w)[4]) {
-  const float u = 1.0f - t;
-  const float t2 = t * t, u2 = u * u;
-  w[0] = u2 * u * (1.0f / 6.0f);
-  w[3] = t2 * t * (1.0f / 6.0f);
-  w[1] = fmaf(t2, fmaf(0.5f, t, -1.0f), 2.0f / 3.0f);
-  w[2] = fmaf(u2, fmaf(0.5f, u, -1.0f), 2.0f / 3.0f);
 }
 
 // a7 (rotatefill.py:21-41): out(o) = sum_{4x4} w * coef[(floor(x)-1+a) mod N], x = R (o - ctr) + ctr, ctr=(N-1)/2.
@@ -348,7 +391,8 @@ int ingest_run(mem_ctx* ctx, const float* raw, const uint8_t* flip, float* out, 
   return 0;
 }
 
-static SegGeom make_geom(int N, int E) {
+static SegGeom make_geom(int L, int E) {
+  const int N = L;
   SegGeom g;
   g.E = E;
   g.used = (N + E - 1) / E;
@@ -360,26 +404,38 @@ static SegGeom make_geom(int N, int E) {
   return g;
 }
 
-static int prefilter_run(mem_ctx* ctx, const float* in, float* out, int nS, int N, int apply_mask, cudaStream_t st) {
-  if (N > 512 || N < 16) {
-    set_error("box size %d outside [16, 512] is not supported by the spline prefilter", N);
+// mirror == 0: periodic boundary (rotatefill); mirror == 1: whole-sample mirror boundary, realised as the
+// periodic filter on the (2N-2)-long mirror extension of every line (ndimage.shift's spline_filter).
+static int prefilter_run(mem_ctx* ctx, const float* in, float* out, int nS, int N, int apply_mask, int mirror,
+                         cudaStream_t st) {
+  const int L = mirror ? 2 * N - 2 : N;
+  if (L > 512 || N < 16) {
+    set_error("box size %d is not supported by the spline prefilter (16 <= N <= 512; RELION shift: N <= 257)", N);
     return 1;
   }
-  const int E = (N + 31) / 32;
-  const SegGeom gr = make_geom(N, E);
+  const int E = (L + 31) / 32;
+  const SegGeom gr = make_geom(L, E);
   const dim3 grid((N + 7) / 8, nS);
-  if (E <= 4) MEM_LAUNCH(ctx, k_prefilter_rows<4>, grid, 256, 0, st, in, out, N, gr, apply_mask);
-  else if (E <= 8) MEM_LAUNCH(ctx, k_prefilter_rows<8>, grid, 256, 0, st, in, out, N, gr, apply_mask);
-  else MEM_LAUNCH(ctx, k_prefilter_rows<16>, grid, 256, 0, st, in, out, N, gr, apply_mask);
+  if (E <= 4) MEM_LAUNCH(ctx, k_prefilter_rows<4>, grid, 256, 0, st, in, out, N, L, gr, apply_mask);
+  else if (E <= 8) MEM_LAUNCH(ctx, k_prefilter_rows<8>, grid, 256, 0, st, in, out, N, L, gr, apply_mask);
+  else MEM_LAUNCH(ctx, k_prefilter_rows<16>, grid, 256, 0, st, in, out, N, L, gr, apply_mask);
   // columns: segments of <= 16 rows, S = ceil(N / 16) <= 32 segments per column
-  const int S = (N + COL_E - 1) / COL_E;
-  const int Ec = (N + S - 1) / S;
-  const SegGeom gc = make_geom(N, Ec);
+  const int S = (L + COL_E - 1) / COL_E;
+  const int Ec = (L + S - 1) / S;
+  const SegGeom gc = make_geom(L, Ec);
   const dim3 gcols((N + 31) / 32, nS);
   auto kc_small = k_prefilter_cols<512, 2>;
   auto kc_large = k_prefilter_cols<1024, 1>;
-  if (gc.used <= 16) MEM_LAUNCH(ctx, kc_small, gcols, 32 * gc.used, 0, st, out, N, gc);
-  else MEM_LAUNCH(ctx, kc_large, gcols, 32 * gc.used, 0, st, out, N, gc);
+  if (gc.used <= 16) MEM_LAUNCH(ctx, kc_small, gcols, 32 * gc.used, 0, st, out, N, L, gc);
+  else MEM_LAUNCH(ctx, kc_large, gcols, 32 * gc.used, 0, st, out, N, L, gc);
+  return 0;
+}
+
+// RELION ingest: raw (picture orientation) -> cubic 'wrap' shift by shift[i] = (s0, s1) -> out.  tmp: scratch.
+int shift_run(mem_ctx* ctx, const float* raw, const double* shift, float* tmp, float* out, int nS, int N,
+              cudaStream_t st) {
+  MEM_CHECK(prefilter_run(ctx, raw, tmp, nS, N, 0, 1, st));
+  MEM_LAUNCH(ctx, k_shift, dim3((N + 31) / 32, (N + 7) / 8, nS), 256, 0, st, tmp, out, shift, N);
   return 0;
 }
 
@@ -389,10 +445,10 @@ int align_run(mem_ctx* ctx, float* A, float* B, float* imgAll, const double* psi
   MEM_LAUNCH(ctx, k_angles, (nS + 1 + 127) / 128, 128, 0, st, psi_deg, psi_p_deg, cs, nS);
   const dim3 grot((N + ROT_T - 1) / ROT_T, (N + ROT_T - 1) / ROT_T, nS);
   const bool full = (N % ROT_T) == 0;
-  MEM_CHECK(prefilter_run(ctx, B, A, nS, N, 1, st));                    // (img * msk) -> coefficients
+  MEM_CHECK(prefilter_run(ctx, B, A, nS, N, 1, 0, st));                    // (img * msk) -> coefficients
   if (full) MEM_LAUNCH(ctx, k_rotate<true>, grot, 256, 0, st, A, B, cs, 1, N, (const uint8_t*)nullptr, (float*)nullptr);
   else MEM_LAUNCH(ctx, k_rotate<false>, grot, 256, 0, st, A, B, cs, 1, N, (const uint8_t*)nullptr, (float*)nullptr);
-  MEM_CHECK(prefilter_run(ctx, B, A, nS, N, 0, st));
+  MEM_CHECK(prefilter_run(ctx, B, A, nS, N, 0, 0, st));
   if (full) MEM_LAUNCH(ctx, k_rotate<true>, grot, 256, 0, st, A, imgAll, cs + nS, 0, N, msk2, msk2 ? B : (float*)nullptr);
   else MEM_LAUNCH(ctx, k_rotate<false>, grot, 256, 0, st, A, imgAll, cs + nS, 0, N, msk2, msk2 ? B : (float*)nullptr);
   return 0;

@@ -156,6 +156,11 @@ int mem_pd_distance_host(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io
   d.flip = ctx->flip.as<uint8_t>();
   d.psi_deg = ctx->psi.as<double>();
   d.df = ctx->df.as<double>();
+  if (h->shift) {
+    MEM_CHECK(ctx->shift.ensure(nS * 2 * sizeof(double)));
+    MEM_CUDA(cudaMemcpyAsync(ctx->shift.p, h->shift, nS * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    d.shift = ctx->shift.as<double>();
+  }
   if (h->msk2) {
     MEM_CHECK(ctx->msk2.ensure(NN));
     MEM_CUDA(cudaMemcpyAsync(ctx->msk2.p, h->msk2, NN, cudaMemcpyHostToDevice, st));

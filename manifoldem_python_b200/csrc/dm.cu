@@ -89,7 +89,8 @@ __global__ void k_graph_combine(const double* __restrict__ Y, const uint8_t* __r
   if (j >= nS) return;
   const double yij = Y[(size_t)i * nS + j], yji = Y[(size_t)j * nS + i];
   const double a = yij > 0 ? sqrt(yij) : 0.0, b = yji > 0 ? sqrt(yji) : 0.0;
-  const double m = a * a + b * b - a * b;
+  // separately rounded like NumPy's y**2 + (y**2).T - y*y.T (no FMA contraction: the graph is bit-exact)
+  const double m = __dsub_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(a, b));
   double out = -1.0;
   if (m != 0.0) out = m;
   else if (Zf[(size_t)i * nS + j]) out = 0.0;

@@ -12,6 +12,8 @@ namespace mem {
 
 int ingest_run(mem_ctx* ctx, const float* raw, const uint8_t* flip, float* out, int nS, int N, int transposed,
                cudaStream_t st);
+int shift_run(mem_ctx* ctx, const float* raw, const double* shift, float* tmp, float* out, int nS, int N,
+              cudaStream_t st);
 int align_run(mem_ctx* ctx, float* A, float* B, float* imgAll, const double* psi_deg, double psi_p_deg, double2* cs,
               const uint8_t* msk2, int nS, int N, cudaStream_t st);
 
@@ -471,8 +473,8 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
     set_error("bad shape nS=%d N=%d", nS, N);
     return 1;
   }
-  if (prm->relion_shift) {
-    set_error("relion_shift: the cubic 'wrap' shift is applied on the host side of this build; pass shifted images");
+  if (prm->relion_shift && (!io->shift || prm->transposed)) {
+    set_error("relion_shift needs io->shift and picture-orientation images (transposed = 0)");
     return 1;
   }
   MEM_CHECK(geometry_prepare(ctx, N, prm->filter_type, prm->filter_order, prm->filter_Qc));
@@ -521,7 +523,12 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
 
   MEM_CUDA(cudaEventRecord(ctx->ev[0], st));
   // ---- a2/a3 ingest + normalise -> A
-  MEM_CHECK(ingest_run(ctx, io->raw, io->flip, A, nS, N, prm->transposed, st));
+  if (prm->relion_shift) {   // :263-264 shift(order=3, mode='wrap') before the flip / normalisation
+    MEM_CHECK(shift_run(ctx, io->raw, io->shift, A, B, nS, N, st));
+    MEM_CHECK(ingest_run(ctx, B, io->flip, A, nS, N, 0, st));
+  } else {
+    MEM_CHECK(ingest_run(ctx, io->raw, io->flip, A, nS, N, prm->transposed, st));
+  }
   // ---- a5 low-pass: A -> spec -> *G -> B
   MEM_CHECK(run_fft(ctx, N, nS, true, A, spec, st));
   {

@@ -1,0 +1,79 @@
+"""Drop-in for the reference's per-PD worker (modules/getDistanceCTF_local_Conj9combinedS2.py:216-420).
+
+Same call signature, same implicit inputs from the module-global config `p`, same side effects: a pickle at
+`outFile` with the reference's 19 keys (float64 arrays, same shapes), then an empty marker file
+`p.dist_prog/<prD>` written only AFTER the pickle dump returned (resume protocol, :415-419).
+All arithmetic between "images gathered" and "arrays ready to pickle" runs on the GPU through the C ABI.
+"""
+import os
+import threading
+
+import numpy as np
+
+from . import myio, pd_stage
+from . import _lib
+
+version = pd_stage.VERSION
+
+_KEYS = ['D', 'ind', 'q', 'df', 'CTF', 'imgAll', 'msk2', 'PD', 'PDs', 'Psis', 'imgAvg', 'imgAvgFlip',
+         'imgAllFlip', 'imgLabels', 'Dnom', 'Nom', 'imgAllIntensity', 'version', 'options']
+
+_tls = threading.local()
+
+
+def _cfg():
+    """The reference's module-global config when running inside ManifoldEM, else this package's p."""
+    try:
+        import p                      # noqa: WPS433  (modules/p.py when modules/ is on sys.path)
+        if hasattr(p, 'nPix'):
+            return p
+    except ImportError:
+        pass
+    from . import p as own
+    return own
+
+
+def _ctx():
+    """One CUDA context object per host thread and device (callable from a non-main thread; the GUI does)."""
+    dev = int(os.environ.get('MANIFOLDEM_B200_DEVICE', '0'))
+    ctx = getattr(_tls, 'ctx', None)
+    if ctx is None or ctx.device != dev:
+        ctx = _lib.Context(dev)
+        _tls.ctx = ctx
+    return ctx
+
+
+def _read_mrc_volume(path):
+    """3-D mask volume (:305-306): MRC2014, modes 0/1/2/6, as mrcfile's .data (z,y,x)."""
+    hdr = np.fromfile(path, dtype='<i4', count=256)
+    nx, ny, nz, mode, nsymbt = int(hdr[0]), int(hdr[1]), int(hdr[2]), int(hdr[3]), int(hdr[23])
+    dt = {0: np.int8, 1: '<i2', 2: '<f4', 6: '<u2'}[mode]
+    return np.fromfile(path, dtype=dt, offset=1024 + nsymbt, count=nx * ny * nz).reshape(nz, ny, nx)
+
+
+def op(input_data, filterPar, imgFileName, sh, nStot, options, fields=None):
+    """[ind, q(4,nS), df(nS), outFile, prD], filterPar{'type','Qc','N'}, stack path, (shx, shy), augmented
+    particle count, options{'verbose','avgOnly','visual','parallel','relion_data','thres'} -> None.
+
+    `fields` (extension, default None = everything the reference stores) may name a subset of the heavy
+    per-image arrays ('D','imgAll','imgAllFlip','CTF') to materialise; the others are stored as None."""
+    p = _cfg()
+    ind, q, df, outFile, prD = input_data[0], input_data[1], input_data[2], input_data[3], input_data[4]
+    N = int(p.nPix)
+    relion = bool(options.get('relion_data', False))
+    stack = pd_stage.open_stack(imgFileName, N, relion)
+    angles = pd_stage.host_angles(np.asarray(q, dtype=np.float64))
+    msk2 = None
+    if getattr(p, 'mask_vol_file', ''):                                   # :303-310
+        from . import projectMask
+        msk2 = projectMask.op(_read_mrc_volume(p.mask_vol_file), angles[1])
+    res = pd_stage.run_pd(ind, q, df, stack, nStot, N, p.pix_size, p.Cs, p.EkV, p.AmpContrast,
+                          gaussEnv=getattr(p, 'gaussEnv', np.inf), filterPar=filterPar, msk2=msk2, relion=relion,
+                          sh=sh, avg_only=bool(options.get('avgOnly', False)), ctx=_ctx(), angles=angles,
+                          fields=fields or ('D', 'imgAll', 'imgAllFlip', 'CTF'))
+    if options.get('parallel') and res['CTF'] is not None:
+        res['CTF'] = res['CTF'].reshape(-1, N, N)                         # that branch leaves CTF un-flattened (:378-389)
+    res['options'] = options
+    myio.fout1(outFile, _KEYS, [res[k] for k in _KEYS])
+    # marker AFTER the dump: signifies a non-corrupted pickle (:415-419)
+    open(os.path.join(p.dist_prog, '%s' % (prD)), 'a').close()

@@ -77,7 +77,7 @@ def open_stack(imgFileName, N, relion):
 # ----------------------------------------------------------------------------- the C-ABI call
 def run_pd(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast, gaussEnv=np.inf, filterPar=None,
            msk2=None, relion=False, sh=None, avg_only=False, ctx=None, fields=('D', 'imgAll', 'imgAllFlip', 'CTF'),
-           contraction=0, k_chunk_blocks=0, split_k=0, float64=True):
+           contraction=0, k_chunk_blocks=0, split_k=0, float64=True, angles=None):
     """Returns the dict the reference pickles (same keys / shapes; float64 unless float64=False).
     `fields` selects which of the heavy per-image outputs are materialised."""
     lib = _lib.load()
@@ -90,13 +90,15 @@ def run_pd(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast, gaussEnv
     q = np.asarray(q, dtype=np.float64)
     df = np.ascontiguousarray(df, dtype=np.float64)
     nS = ind.shape[0]
-    PDs, PD, psi_p, Psi, s, c = host_angles(q)
+    PDs, PD, psi_p, Psi, s, c = angles if angles is not None else host_angles(q)
     raw, flip, base = gather(stack, ind, nStot, N)
-    if relion:
-        raise NotImplementedError('RELION cubic wrap shift: device kernel pending (row a2)')
+    shift = None
+    if relion:                                         # (:263) shi = (sh[1][idx] - 0.5, sh[0][idx] - 0.5)
+        shift = np.ascontiguousarray(np.stack((np.asarray(sh[1])[base] - 0.5, np.asarray(sh[0])[base] - 0.5), axis=1),
+                                     dtype=np.float64)
     psi_deg = np.ascontiguousarray(-(180 / math.pi) * Psi, dtype=np.float64)
 
-    prm = _lib.PdParams(nS=nS, N=N, transposed=0 if relion else 1, relion_shift=0,
+    prm = _lib.PdParams(nS=nS, N=N, transposed=0 if relion else 1, relion_shift=1 if relion else 0,
                         filter_type=FILTERS[filterPar['type']], filter_order=int(filterPar['N']),
                         filter_Qc=float(filterPar['Qc']), pix_size=float(pix_size), Cs=float(Cs), EkV=float(EkV),
                         gaussEnv=float(gaussEnv), AmpContrast=float(AmpContrast), psi_p_deg=float(psi_p),
@@ -111,6 +113,8 @@ def run_pd(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast, gaussEnv
 
     io = _lib.PdIO()
     io.raw, io.flip, io.psi_deg, io.df = raw.ctypes.data, flip.ctypes.data, psi_deg.ctypes.data, df.ctypes.data
+    if shift is not None:
+        io.shift = shift.ctypes.data
     m2 = None
     if msk2 is not None and not np.isscalar(msk2):
         m2 = np.ascontiguousarray(np.asarray(msk2) != 0, dtype=np.uint8)

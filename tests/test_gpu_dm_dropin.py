@@ -1,0 +1,177 @@
+"""GPU tests: diffusion-map front end (kNN, graph, Ferguson sweep, Laplacian) against the oracle and the
+reference-generated golden vectors; the three drop-in callables end to end (pickle layout, resume markers)."""
+import ctypes as C
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _load_dm(golden_dir):
+    return np.load(os.path.join(golden_dir, 'dm_nS72.npz'))
+
+
+@pytest.mark.parametrize('k', [72, 20])
+def test_dm_against_reference_golden(golden_dir, k):
+    """DMembeddingII.op drop-in vs the reference's own outputs on the same D (same np.random draws)."""
+    from manifoldem_python_b200 import DMembeddingII, p
+    p.init()
+    g = _load_dm(golden_dir)
+    D = g['D'].copy()
+    np.random.seed(1234)
+    lamb, psi, sigma, mu, logEps, logSumWij, popt, R2 = DMembeddingII.op(D, k, 3.0, 60000)
+    assert np.isneginf(D[3, 3])                                              # mutated in place like the reference
+    assert np.array_equal(logEps, g['logEps'])
+    assert np.allclose(logSumWij, g[f'k{k}_logSumWij'], rtol=1e-11, atol=1e-11)
+    assert np.allclose(popt, g[f'k{k}_popt'], rtol=1e-6)
+    assert abs(sigma - float(g[f'k{k}_sigma'])) <= 1e-8 * sigma
+    assert np.allclose(lamb, g[f'k{k}_lamb'], rtol=1e-8, atol=1e-10)
+    assert np.allclose(mu, g[f'k{k}_mu'], rtol=1e-6, atol=1e-12)
+    assert abs(R2 - float(g[f'k{k}_R2'])) < 1e-9
+    ref_psi = g[f'k{k}_psi']
+    assert psi.shape == ref_psi.shape
+    for j in range(5):                                                       # |corr| >= 0.9999 (north_star)
+        assert abs(np.corrcoef(psi[:, j], ref_psi[:, j])[0, 1]) > 0.9999, j
+
+
+@pytest.mark.parametrize('nS,k', [(300, 300), (300, 40), (1000, 100), (77, 77)])
+def test_knn_graph_laplacian_vs_oracle(nS, k):
+    from manifoldem_python_b200 import DMembeddingII, _lib
+    from oracle import dm_embedding as odm
+    rng = np.random.default_rng(nS + k)
+    X = rng.standard_normal((nS, 6)) * np.array([3, 2, 1, 1, 0.5, 0.5])
+    D = ((X[:, None, :] - X[None, :, :]) ** 2).sum(-1) * 1e3                 # squared distances, symmetric
+    D = (D + D.T) / 2
+    M, logEps, logSumWij, idx, val = DMembeddingII.graph_and_sweep(D, k)
+    Do = D.copy()
+    idx_o, val_o = odm.knn_lists(Do, k)                                      # (k, nS)
+    assert np.array_equal(idx[:, 0], np.arange(nS)) and not val[:, 0].any()
+    assert np.array_equal(val, val_o.T)                                      # distances bit-exact
+    for i in range(nS):                                                      # identical kNN index sets (no ties here)
+        assert set(idx[i]) == set(idx_o[:, i])
+    assert np.array_equal(idx, idx_o.T)
+    yRow, yCol, yVal = odm.symmetrise(idx_o, val_o, nS)
+    Mo = -np.ones((nS, nS))
+    Mo[yRow, yCol] = yVal
+    assert np.array_equal(M.download(), Mo)                                  # graph bit-exact (integer/index work)
+    ls_o, thr = odm.ferguson_logsum(np.sqrt(yVal))
+    assert thr == 10
+    assert np.allclose(logSumWij, ls_o, rtol=1e-12, atol=1e-12)
+    sigma = 3.0 * np.sqrt(np.median(yVal[yVal > 0]))
+    L = DMembeddingII.laplacian(M, nS, sigma)
+    Lo = odm.laplacian(yVal, yCol, yRow, nS, sigma).toarray()
+    assert np.abs(L - Lo).max() <= 1e-12 * np.abs(Lo).max()
+    M.free()
+
+
+def test_knn_ties_and_errors():
+    from manifoldem_python_b200 import DMembeddingII, _lib
+    nS = 40
+    D = np.ones((nS, nS)) * 5.0                                              # all off-diagonal distances tie
+    np.fill_diagonal(D, 0.0)
+    M, _, _, idx, val = DMembeddingII.graph_and_sweep(D, 7)
+    assert np.array_equal(idx[:, 0], np.arange(nS))
+    assert (val[:, 1:] == 5.0).all()
+    for i in range(nS):                                                      # ties broken by index: the smallest others
+        assert list(idx[i, 1:]) == [j for j in range(nS) if j != i][:6]
+    M.free()
+    lib, ctx = _lib.load(), _lib.default_context()
+    with pytest.raises(RuntimeError):
+        _lib.check(lib.mem_knn_device(ctx.handle, None, 10, 11, None, None, None))
+
+
+def test_dropin_worker_and_driver(tmp_path):
+    """GetDistancesS2.op -> getDistanceCTF_local_Conj9combinedS2.op: pickle keys/shapes/dtypes as the
+    reference writes them, markers after the dump, finished PDs skipped on a second run."""
+    from manifoldem_python_b200 import GetDistancesS2, myio, p, synthetic
+    from oracle import pd_distance as opd
+    N = 32
+    pds = [synthetic.make_pd(n, N, seed=20 + i, snr=0.5) for i, n in enumerate((24, 17, 30))]
+    # one augmented data set: concatenate the three PDs' particles
+    n_half = sum(pd['nStot'] // 2 for pd in pds)
+    stack = np.concatenate([pd['stack'] for pd in pds])
+    q = np.zeros((4, 2 * n_half))
+    df = np.zeros(2 * n_half)
+    CG, off = [], 0
+    for pd in pds:
+        h = pd['nStot'] // 2
+        base = np.where(pd['ind'] >= h, pd['ind'] - h, pd['ind']) + off
+        ind = np.where(pd['ind'] >= h, base + n_half, base)
+        q[:, ind] = pd['q']
+        df[ind] = pd['df']
+        CG.append(ind)
+        off += h
+    p.init()
+    p.user_dir, p.proj_name = str(tmp_path), 'demo'
+    p.create_dir()
+    em = pds[0]['em']
+    p.pix_size, p.Cs, p.EkV, p.AmpContrast = em['pix_size'], em['Cs'], em['EkV'], em['AmpContrast']
+    p.relion_data, p.ncpu, p.num_part = False, 1, n_half
+    p.img_stack_file = str(tmp_path / 'stack.dat')
+    stack.tofile(p.img_stack_file)
+    p.numberofJobs = 3
+    myio.fout1(p.tess_file, ['CG', 'df', 'q', 'sh'], [CG, df, q, (np.zeros(n_half), np.zeros(n_half))])
+
+    class Sig:
+        vals = []
+
+        def emit(self, v):
+            self.vals.append(v)
+    sig = Sig()
+    GetDistancesS2.op(sig)
+    assert p.nPix == N and sig.vals[0] == 0 and sig.vals[-1] == 100
+    assert sorted(os.listdir(p.dist_prog)) == ['0', '1', '2']
+    for prD, pd in enumerate(pds):
+        with open('{}prD_{}'.format(p.dist_file, prD), 'rb') as f:
+            rec = pickle.load(f)
+        nS = len(CG[prD])
+        assert list(rec.keys()) == ['D', 'ind', 'q', 'df', 'CTF', 'imgAll', 'msk2', 'PD', 'PDs', 'Psis', 'imgAvg',
+                                    'imgAvgFlip', 'imgAllFlip', 'imgLabels', 'Dnom', 'Nom', 'imgAllIntensity',
+                                    'version', 'options']
+        shapes = dict(D=(nS, nS), CTF=(nS, N * N), imgAll=(nS, N, N), imgAllFlip=(nS, N, N), PD=(3,), PDs=(3, nS),
+                      Psis=(nS, 1), imgAvg=(N, N), imgAvgFlip=(N, N), Dnom=(nS, 1), Nom=(nS, 1),
+                      imgAllIntensity=(N, N), q=(4, nS), df=(nS,))
+        for k, shp in shapes.items():
+            assert rec[k].shape == shp and rec[k].dtype == np.float64, k
+        assert rec['msk2'] == 1 and rec['version'] == 'getDistanceCTF_local9, V 1.0'
+        assert rec['options']['relion_data'] is False
+        ref = opd.pd_distance(CG[prD], q[:, CG[prD]], df[CG[prD]], stack, 2 * n_half, N, em['pix_size'], em['Cs'],
+                              em['EkV'], em['AmpContrast'], rotate_impl='periodic')
+        offd = ~np.eye(nS, dtype=bool)
+        assert (np.abs(rec['D'] - ref['D'])[offd] / ref['D'][offd]).max() < 1e-5
+        assert np.array_equal(rec['imgLabels'], ref['imgLabels'])
+    # resume: remove one marker, only that PD is recomputed
+    os.remove(os.path.join(p.dist_prog, '1'))
+    mt = {i: os.path.getmtime('{}prD_{}'.format(p.dist_file, i)) for i in range(3)}
+    GetDistancesS2.op()
+    assert sorted(os.listdir(p.dist_prog)) == ['0', '1', '2']
+    assert os.path.getmtime('{}prD_0'.format(p.dist_file)) == mt[0]
+    assert os.path.getmtime('{}prD_1'.format(p.dist_file)) >= mt[1]
+
+
+def test_manifold_trimming_consumer(tmp_path):
+    """The consumer chain of the embedding stage (manifoldTrimmingAuto.py:44-70): D from the PD pickle ->
+    DMembeddingII.op(D, k=nS) -> leading eigenvector recovers the 1-D latent coordinate of the synthetic PD."""
+    from manifoldem_python_b200 import DMembeddingII, p, pd_stage, synthetic
+    p.init()
+    pd = synthetic.make_pd(160, 48, seed=31, snr=3.0)
+    em = pd['em']
+    D = pd_stage.run_pd(pd['ind'], pd['q'], pd['df'], pd['stack'], pd['nStot'], 48, em['pix_size'], em['Cs'],
+                        em['EkV'], em['AmpContrast'], fields=('D',))['D']
+    np.random.seed(0)
+    lamb, psi, sigma, mu, logEps, logSumWij, popt, R2 = DMembeddingII.op(D.copy(), 160, 3.0, 60000)
+    assert lamb[0] == pytest.approx(1.0, abs=1e-6) and (np.diff(lamb) <= 1e-12).all()
+    assert abs(mu.sum() - 1.0) < 1e-8
+    # the same chain entirely on the CPU oracle (float64 reference D -> oracle embedding, same random draws)
+    from oracle import dm_embedding as odm, pd_distance as opd
+    Dr = opd.pd_distance(pd['ind'], pd['q'], pd['df'], pd['stack'], pd['nStot'], 48, em['pix_size'], em['Cs'],
+                         em['EkV'], em['AmpContrast'], rotate_impl='periodic', keep=('D',))['D']
+    np.random.seed(0)
+    lamb_o, psi_o, sigma_o, mu_o = odm.dm_embedding(Dr.copy(), 160, 3.0)[:4]
+    assert abs(sigma - sigma_o) <= 1e-5 * sigma_o
+    assert np.allclose(lamb[:6], lamb_o[:6], rtol=1e-4)
+    for j in range(3):                                   # north_star: leading eigenvectors |corr| >= 0.9999
+        assert abs(np.corrcoef(psi[:, j], psi_o[:, j])[0, 1]) >= 0.9999, j

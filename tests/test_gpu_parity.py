@@ -78,6 +78,20 @@ def test_golden_volmask(env, golden_dir):
     assert np.array_equal(res['msk2'], g['ref_msk2'])
 
 
+def test_golden_relion(env, golden_dir):
+    """RELION branch: cubic 'wrap' shift by (shy-0.5, shx-0.5) on the device vs the reference's ndimage.shift."""
+    _lib, pd_stage, _ = env
+    g = np.load(os.path.join(golden_dir, 'pd_relion_N24.npz'))
+    N = int(g['N'])
+    stack3d = g['stack'].reshape(-1, N, N)
+    res = pd_stage.run_pd(g['ind'], g['q'], g['df'], stack3d, int(g['nStot']), N, float(g['em_pix_size']),
+                          float(g['em_Cs']), float(g['em_EkV']), float(g['em_AmpContrast']), relion=True,
+                          sh=(g['shx'], g['shy']))
+    ref = {k[4:]: g[k] for k in g.files if k.startswith('ref_')}
+    _check_D(res['D'], ref['D'])
+    _check_fields(res, ref)
+
+
 @pytest.mark.parametrize('nS,N,snr,seed', [(150, 64, 0.1, 2), (257, 64, 10.0, 5), (300, 128, 10.0, 3), (129, 96, 0.5, 7)])
 def test_oracle_parity_tc(env, nS, N, snr, seed):
     """tcgen05 3xTF32 product path vs the float64 oracle, noisy and low-noise (worst cancellation)."""

@@ -1,0 +1,237 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every declared symbol, host-side logic of the
+drop-in modules (job list / resume markers, gather, MRC reader, partition, projectMask), and the SciPy
+semantics the device kernels were written against."""
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from manifoldem_python_b200 import _lib
+    lib = _lib.load()                                   # dlopen only, no CUDA call
+    hdr = open(os.path.join(ROOT, 'include', 'manifoldem_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(mem_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) >= 20
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert set(_lib.SYMBOLS) == declared
+    assert lib.mem_version() == 100
+
+
+def test_host_angles_match_oracle():
+    from manifoldem_python_b200 import pd_stage, synthetic
+    from oracle import pd_distance as opd
+    pd = synthetic.make_pd(30, 16, seed=5)
+    PDs, PD, psi_p, Psi, s, c = pd_stage.host_angles(pd['q'])
+    PDs_o = opd.calc_avg_pd(pd['q'])
+    PD_o = PDs_o.sum(1) / np.linalg.norm(PDs_o.sum(1))
+    Psi_o, s_o, c_o = opd.get_psi(pd['q'], PD_o)
+    assert np.array_equal(PDs, PDs_o) and np.array_equal(PD, PD_o)
+    assert np.array_equal(Psi, Psi_o) and np.array_equal(s, s_o) and np.array_equal(c, c_o)
+    assert psi_p == opd.psi_ang(PD_o)
+
+
+def test_gather_conjugates_and_order():
+    from manifoldem_python_b200 import pd_stage
+    N, n_half = 4, 6
+    stack = np.arange(n_half * N * N, dtype=np.float32)
+    ind = np.array([7, 2, 11, 0, 5])                       # >= 6 are conjugates of 1, 5
+    raw, flip, base = pd_stage.gather(stack, ind, 2 * n_half, N)
+    assert list(base) == [1, 2, 5, 0, 5] and list(flip) == [1, 0, 1, 0, 0]
+    for i, b in enumerate(base):
+        assert np.array_equal(raw[i], stack[b * N * N:(b + 1) * N * N])
+    raw3, _, _ = pd_stage.gather(stack.reshape(n_half, N, N), ind, 2 * n_half, N)
+    assert np.array_equal(raw3, raw)
+
+
+def test_open_stack_spider_and_mrc(tmp_path):
+    from manifoldem_python_b200 import pd_stage
+    N, n = 6, 5
+    data = np.random.default_rng(0).standard_normal((n, N, N)).astype(np.float32)
+    f = tmp_path / 'stack.dat'
+    data.tofile(f)
+    st = pd_stage.open_stack(str(f), N, False)
+    assert st.shape == (n * N * N,) and np.array_equal(np.asarray(st), data.reshape(-1))
+    hdr = np.zeros(256, dtype='<i4')
+    hdr[0], hdr[1], hdr[2], hdr[3], hdr[23] = N, N, n, 2, 80
+    m = tmp_path / 'stack.mrcs'
+    with open(m, 'wb') as fh:
+        fh.write(hdr.tobytes())
+        fh.write(b'\0' * 80)
+        fh.write(data.tobytes())
+    st = pd_stage.open_stack(str(m), N, True)
+    assert st.shape == (n, N, N) and np.array_equal(np.asarray(st), data)
+    hdr[3] = 1
+    with open(m, 'wb') as fh:
+        fh.write(hdr.tobytes())
+    with pytest.raises(ValueError):
+        pd_stage.open_stack(str(m), N, True)
+
+
+def test_myio_semantics(tmp_path):
+    from manifoldem_python_b200 import myio
+    f = str(tmp_path / 'x.pkl')
+    myio.fout1(f, ['a', 'b'], [1, np.arange(3)])
+    d = myio.fin1(f)
+    assert d['a'] == 1 and np.array_equal(d['b'], np.arange(3))
+    with open(f, 'rb') as fh:
+        assert pickle.load(fh).keys() == d.keys()
+    open(f, 'wb').write(b'garbage')
+    assert myio.fin1(f) is None                          # unreadable pickle -> None (myio.py:21-30)
+    assert myio.fin1(str(tmp_path / 'missing')) is None
+    myio.fout2(f, dict(z=3))
+    assert myio.fin1(f) == dict(z=3)
+
+
+def test_divide_skips_finished_pds(tmp_path):
+    """Resume protocol (GetDistancesS2.py:29-47): PDs with a marker in dist_prog are not re-queued."""
+    from manifoldem_python_b200 import GetDistancesS2, p
+    p.init()
+    p.user_dir, p.proj_name = str(tmp_path), 't'
+    p.create_dir()
+    CG = [np.array([0, 3]), np.array([1, 2, 5]), np.array([4])]
+    q = np.arange(24, dtype=float).reshape(4, 6)
+    df = np.arange(6, dtype=float)
+    jobs = GetDistancesS2.divide(CG, q, df, 3)
+    assert [j[4] for j in jobs] == [0, 1, 2]
+    assert np.array_equal(jobs[1][1], q[:, [1, 2, 5]]) and np.array_equal(jobs[1][2], df[[1, 2, 5]])
+    assert jobs[2][3].endswith('IMGs_prD_2')
+    open(os.path.join(p.dist_prog, '1'), 'a').close()
+    open(os.path.join(p.dist_prog, '.hidden'), 'a').close()
+    assert GetDistancesS2.fileCheck() == [1]
+    assert [j[4] for j in GetDistancesS2.divide(CG, q, df, 3)] == [0, 2]
+    assert GetDistancesS2.count(3) == 2
+
+
+def test_lpt_partition_properties():
+    from manifoldem_python_b200 import partition
+    rng = np.random.default_rng(1)
+    nS = rng.integers(100, 2001, size=53)
+    costs = [partition.pd_cost(int(n), 256) for n in nS]
+    for g in (1, 2, 4, 8):
+        shards = partition.lpt_partition(costs, g)
+        flat = sorted(i for s in shards for i in s)
+        assert flat == list(range(53))                   # every PD exactly once
+        assert partition.imbalance(costs, shards) <= partition.imbalance(costs, partition.round_robin(53, g)) + 1e-12
+        assert partition.imbalance(costs, shards) < 1.0 + max(costs) / (sum(costs) / g)
+        assert shards == partition.lpt_partition(costs, g)   # deterministic
+    eq = partition.lpt_partition([1.0] * 1000, 8)
+    assert all(len(s) == 125 for s in eq)
+    assert partition.lpt_partition([], 4) == [[], [], [], []]
+
+
+def test_project_mask_matches_reference_golden(golden_dir):
+    from manifoldem_python_b200 import projectMask
+    g = np.load(os.path.join(golden_dir, 'pd_volmask_N24.npz'))
+    msk2 = projectMask.op(g['mask3d'], g['ref_PD'])
+    assert msk2.dtype == bool and np.array_equal(msk2, g['ref_msk2'])
+
+
+def test_scipy_wrap_shift_model():
+    """The algorithm of k_shift (align.cu): mirror prefilter + coordinate wrap with period N-1 + mirrored
+    support indices reproduces scipy.ndimage.shift(order=3, mode='wrap') (getDistanceCTF...py:264)."""
+    from scipy import ndimage
+    rng = np.random.default_rng(0)
+    N = 17
+    img = rng.standard_normal((N, N))
+    for s in ((0.3, -2.7), (5.5, -0.5), (-16.2, 18.9)):
+        ref = ndimage.shift(img, s, order=3, mode='wrap')
+        c = ndimage.spline_filter(img, order=3, mode='mirror')
+
+        def taps(o, sh):
+            x = o - sh
+            L = N - 1
+            if x < 0:
+                x += L * (int(-x / L) + 1)
+            elif x > L:
+                x -= L * int(x / L)
+            i0 = int(np.floor(x))
+            t = x - i0
+            u = 1 - t
+            w = [u ** 3 / 6, 2 / 3 + t * t * (0.5 * t - 1), 2 / 3 + u * u * (0.5 * u - 1), t ** 3 / 6]
+            k = []
+            for a in range(4):
+                kk = i0 - 1 + a
+                kk = -kk if kk < 0 else kk
+                kk = 2 * (N - 1) - kk if kk > N - 1 else kk
+                k.append(kk)
+            return k, w
+        out = np.zeros_like(img)
+        for r in range(N):
+            ka, wa = taps(r, s[0])
+            for cc in range(N):
+                kb, wb = taps(cc, s[1])
+                out[r, cc] = sum(wa[a] * wb[b] * c[ka[a], kb[b]] for a in range(4) for b in range(4))
+        assert np.abs(out - ref).max() < 1e-12
+    # mirror prefilter == periodic prefilter of the (2N-2)-long mirror extension (how the kernel realises it)
+    line = rng.standard_normal(N)
+    ext = np.concatenate([line, line[-2:0:-1]])
+    per = ndimage.spline_filter1d(ext, order=3, mode='grid-wrap')[:N]
+    assert np.abs(per - ndimage.spline_filter1d(line, order=3, mode='mirror')).max() < 1e-12
+
+
+def test_segmented_recursive_prefilter_model():
+    """The segmented carry scheme of k_prefilter_rows / _cols (align.cu) in NumPy float64 against
+    scipy's periodic cubic spline filter."""
+    from scipy import ndimage
+    z = np.sqrt(3.0) - 2.0
+    rng = np.random.default_rng(3)
+    for L, E in ((256, 8), (100, 4), (25, 1), (510, 16), (37, 3)):
+        s = rng.standard_normal(L)
+        used = (L + E - 1) // E
+        H = min(used, 20 // E + 2)
+        segs = [np.arange(i * E, min(L, (i + 1) * E)) for i in range(used)]
+        v = 6.0 * s.copy()
+        ends = np.zeros(used)
+        for i, sg in enumerate(segs):
+            run = 0.0
+            for j in sg:
+                run = v[j] + z * run
+                v[j] = run
+            ends[i] = run
+        cplus = v.copy()
+        for i, sg in enumerate(segs):
+            carry, f = 0.0, 1.0
+            for h in range(1, H + 1):
+                src = (i - h) % used
+                carry += f * ends[src]
+                f *= z ** len(segs[src])
+            cplus[sg] += carry * z ** (np.arange(len(sg)) + 1)
+        v = cplus.copy()
+        for i, sg in enumerate(segs):
+            run = 0.0
+            for j in sg[::-1]:
+                run = z * (run - v[j])
+                v[j] = run
+            ends[i] = run
+        out = v.copy()
+        for i, sg in enumerate(segs):
+            carry, f = 0.0, 1.0
+            for h in range(1, H + 1):
+                src = (i + h) % used
+                carry += f * ends[src]
+                f *= z ** len(segs[src])
+            out[sg] += carry * z ** (len(sg) - np.arange(len(sg)))
+        ref = ndimage.spline_filter1d(s, order=3, mode='grid-wrap')
+        assert np.abs(out - ref).max() < 1e-9 * np.abs(ref).max(), (L, E)
+
+
+def test_dropin_shims_resolve():
+    import importlib
+    import sys
+    d = os.path.join(ROOT, 'manifoldem_python_b200', 'dropin')
+    sys.path.insert(0, d)
+    try:
+        for name in ('getDistanceCTF_local_Conj9combinedS2', 'GetDistancesS2', 'DMembeddingII'):
+            sys.modules.pop(name, None)
+            m = importlib.import_module(name)
+            assert callable(m.op) and m.__file__.startswith(d)
+            sys.modules.pop(name, None)
+    finally:
+        sys.path.remove(d)
