@@ -157,11 +157,18 @@ def cpu_reference_sample(nS, N, n_img, cores, contraction_rows):
     K = N * N
     CTF = rng.standard_normal((rows, K))
     fy = rng.standard_normal((rows, K)) + 1j * rng.standard_normal((rows, K))
+    try:                                  # torchrun exports OMP_NUM_THREADS=1: give the GEMMs every core back
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=cores)
+    except Exception:
+        limiter = None
     t0 = time.perf_counter()
     CTFfy = CTF.conj() * fy
     D = np.dot(np.abs(CTF) ** 2, (np.abs(fy) ** 2).T)
     D = D + D.T - 2 * np.real(np.dot(CTFfy, CTFfy.conj().T))
     t_gemm = time.perf_counter() - t0
+    if limiter is not None:
+        limiter.restore_original_limits()
     # rows x rows block measured; the full matrix has (nS/rows)^2 such blocks
     t_pd = (nS / n_done) * t_img + (nS / rows) ** 2 * t_gemm
     detail = dict(images=n_done, t_images_s=round(t_img, 3), gemm_rows=rows, t_gemm_s=round(t_gemm, 3),
@@ -205,7 +212,17 @@ def run_b200(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1:
         torch.cuda.set_device(local)
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        # NCCL prints its version banner on stdout at the first collective: keep stdout = the one JSON line
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     lib = _lib.load()
     nS, N, P = args.nS, args.N, args.pds
     ctx = _lib.Context(local)
@@ -310,7 +327,7 @@ def run_b200(args):
     if rank == 0:
         peaks, peak_src = load_peaks()
         # executed TF32 tensor flops of one contraction launch: items x (128x256 tile) x K x 2 x 3 passes
-        flops_launch = float(k_items) * 128 * 256 * 2 * 3 * 32.0 * _avg_kb(k_items, k_kb, nS)
+        flops_launch = float(k_items) * 128 * 256 * 2 * 3 * 32.0 * k_kb      # CTAs x tile x K per CTA x 3 passes
         k_avg_ms = k_ms / max(1, k_n)
         achieved = flops_launch / (k_avg_ms * 1e-3) / 1e12 if k_n else None
         # TF32 dense runs at half the bf16 rate; the contraction launches are ~1.4 ms bursts between HBM-bound
@@ -345,18 +362,6 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-
-
-def _avg_kb(items, nkb, nS):
-    """K blocks per work item: every K slice covers nkb/split blocks, items = tiles x split."""
-    tiles = 0
-    tm, tn = (nS + 127) // 128, (nS + 255) // 256
-    for bj in range(tn):
-        for bi in range(tm):
-            if bj * 256 + 255 >= bi * 128:
-                tiles += 1
-    split = max(1, items // max(1, tiles))
-    return nkb / split
 
 
 if __name__ == '__main__':

@@ -35,7 +35,8 @@ int64_t     mem_ctx_launch_count(mem_ctx* ctx, int reset);
 int         mem_ctx_timer_start(mem_ctx* ctx);
 int         mem_ctx_timer_stop(mem_ctx* ctx, float* ms);
 /* summed CUDA-event duration of every tcgen05 contraction launch since the last reset, their count, and
- * the work-item count / K blocks of the last one (executed-flop accounting for the roofline) */
+ * the CTA count (each CTA = one 128x256 tile of one K slice) and K blocks per CTA of the last one
+ * (executed-flop accounting for the roofline) */
 int         mem_ctx_kernel_time(mem_ctx* ctx, int reset, double* total_ms, int64_t* launches, int32_t* items,
                                 int32_t* k_blocks);
 /* pinned host memory for the host-buffer entry points */
@@ -68,7 +69,7 @@ typedef struct {
   double  AmpContrast;   /* p.AmpContrast                                                    */
   double  psi_p_deg;     /* psi_ang(PD), degrees                                   (:313) */
   int32_t avg_only;      /* options['avgOnly']: skip D                             (:376) */
-  int32_t contraction;   /* 0 = tcgen05 3xTF32 (product), 1 = SIMT fp64-accumulate checker kernel */
+  int32_t contraction;   /* 0 = tcgen05 3xTF32, CTA-pair tiles (product); 1 = SIMT fp64-accumulate checker; 2 = tcgen05 single-CTA tiles */
   int32_t k_chunk_blocks;/* tcgen05: K blocks (of 32) accumulated in TMEM before promotion; 0 = default */
   int32_t split_k;       /* tcgen05: K slices per tile; 0 = auto (fill 148 SMs)                  */
 } mem_pd_params;

@@ -115,5 +115,5 @@ int fft_get(mem_ctx* ctx, int N, int batch, FftPlan* out);
 int contract_run(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, const float* Zlo, float* D,
                  int contraction, int k_chunk_blocks, int split_k, cudaStream_t st);
 int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, const float* Zlo, float* D,
-                int k_chunk_blocks, int split_k, cudaStream_t st);
+                int k_chunk_blocks, int split_k, cudaStream_t st, int two_cta);
 }  // namespace mem

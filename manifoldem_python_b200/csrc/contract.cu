@@ -59,11 +59,12 @@ int contract_run(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, 
     MEM_LAUNCH(ctx, k_contract_simt, grid, 256, 0, st, Zhi, Zlo, D, shp->nS, shp->n1_blocks, shp->n3_blocks, shp->ldz);
     return 0;
   }
-  if (contraction != 0) {
+  if (contraction != 0 && contraction != 2) {
     set_error("unknown contraction kind %d", contraction);
     return 1;
   }
-  return contract_tc(ctx, shp, Zhi, Zlo, D, k_chunk_blocks, split_k, st);
+  // 0: product path, CTA-pair tiles (cta_group::2);  2: single-CTA tiles (kept for comparison and tests)
+  return contract_tc(ctx, shp, Zhi, Zlo, D, k_chunk_blocks, split_k, st, contraction == 0 ? 1 : 0);
 }
 
 }  // namespace mem

@@ -235,6 +235,202 @@ k_contract_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// 2-CTA variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 tile.  CTA r holds rows
+// [128 r, 128 r + 128) of the A operand and rows [128 r, +128) of the B operand (the N side) in its own shared
+// memory, so every SM reads only 4 KB + 4 KB per 256x256x8 MMA instead of 4 + 8 KB: the 1-CTA kernel is
+// bound by shared-memory bandwidth (operand reads + TMA fill ~ 156 B/clk/SM), this one needs ~ 106 B/clk/SM.
+//   stage (per CTA) = A_hi, A_lo, B_hi, B_lo boxes of 128 rows x 32 columns = 64 KB, 3 stages
+//   full[s]        leader's barrier; both CTAs' TMA complete_tx on it (peer bit of the address cleared)
+//   empty[s]       each CTA's own barrier, released by the leader's tcgen05.commit multicast
+//   tmem_full[b]   each CTA's own barrier (commit multicast); tmem_empty[b] leader's, 32 arrivals (16 warps x 2 CTAs)
+// 16 epilogue warps per CTA (lane quarter x 64-column group) keep the per-chunk TMEM drain to two
+// tcgen05.ld round trips, so the accumulator turns around well inside one chunk of MMAs.
+// ------------------------------------------------------------------------------------------------
+constexpr int STAGES2 = 3;
+constexpr int STAGE2_BYTES = 4 * BOX_BYTES;             // 64 KB per CTA
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+constexpr int EPI_WARPS2 = 16;
+constexpr int NUM_THREADS2 = 64 + 32 * EPI_WARPS2;      // TMA warp, MMA warp, 16 epilogue warps
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta0(uint32_t bar) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(bar));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// M = 256 (two CTAs x 128), N = 256
+__device__ __forceinline__ uint32_t make_idesc2(bool negate_a) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((negate_a ? 1u : 0u) << 13) | ((uint32_t)(256 >> 3) << 17) |
+         ((uint32_t)(256 >> 4) << 24);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
+k_contract_tc2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+               const WorkItem* __restrict__ items, float* __restrict__ ws, int nS, int ldw, int n1, int chunk) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bars = base + STAGES2 * STAGE2_BYTES;
+  // 8-byte slots: full[0..2], empty[3..5], tmem_full[6..7], tmem_empty[8..9]; tmem base at +96
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES2 * STAGE2_BYTES + 96);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const WorkItem it = items[blockIdx.x >> 1];
+  const int nkb = it.kb1 - it.kb0;
+  const int nchunks = (nkb + chunk - 1) / chunk;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(bars + 8 * s, 1);
+      mbar_init(bars + 8 * (3 + s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bars + 8 * (6 + b), 1);
+      mbar_init(bars + 8 * (8 + b), 2 * EPI_WARPS2);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs; each loads its own halves, transaction bytes land on the leader's barrier) =====
+      int stage = 0;
+      uint32_t phase = 0;
+      const int arow = it.row0 + (int)rank * BOX_ROWS, brow = it.col0 + (int)rank * BOX_ROWS;
+      for (int kb = it.kb0; kb < it.kb1; ++kb) {
+        int ca, cb;
+        if (kb < n1) { ca = kb; cb = kb + n1; }
+        else if (kb < 2 * n1) { ca = kb; cb = kb - n1; }
+        else { ca = kb; cb = kb; }
+        mbar_wait(bars + 8 * (3 + stage), phase ^ 1);
+        const uint32_t full = bars + 8 * stage;
+        if (rank == 0) mbar_expect_tx(full, 2 * STAGE2_BYTES);
+        const uint32_t s0 = base + stage * STAGE2_BYTES;
+        tma_load_2d_2sm(s0 + 0 * BOX_BYTES, &map_hi, full, ca * BK, arow);
+        tma_load_2d_2sm(s0 + 1 * BOX_BYTES, &map_lo, full, ca * BK, arow);
+        tma_load_2d_2sm(s0 + 2 * BOX_BYTES, &map_hi, full, cb * BK, brow);
+        tma_load_2d_2sm(s0 + 3 * BOX_BYTES, &map_lo, full, cb * BK, brow);
+        if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ===== MMA issuer (leader CTA only) =====
+      int stage = 0;
+      uint32_t phase = 0;
+      int kb = it.kb0;
+      for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        mbar_wait(bars + 8 * (8 + buf), (((uint32_t)(c >> 1)) & 1u) ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + buf * BN;
+        const int kend = min(it.kb1, kb + chunk);
+        bool first = true;
+        for (; kb < kend; ++kb) {
+          const uint32_t idesc = make_idesc2(kb >= 2 * n1);
+          mbar_wait(bars + 8 * stage, phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t s0 = base + stage * STAGE2_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            const uint64_t a_hi = make_smem_desc(s0 + 0 * BOX_BYTES + ks * 32);
+            const uint64_t a_lo = make_smem_desc(s0 + 1 * BOX_BYTES + ks * 32);
+            const uint64_t b_hi = make_smem_desc(s0 + 2 * BOX_BYTES + ks * 32);
+            const uint64_t b_lo = make_smem_desc(s0 + 3 * BOX_BYTES + ks * 32);
+            umma_tf32_2sm(tacc, a_lo, b_hi, idesc, first ? 0u : 1u);
+            umma_tf32_2sm(tacc, a_hi, b_lo, idesc, 1u);
+            umma_tf32_2sm(tacc, a_hi, b_hi, idesc, 1u);
+            first = false;
+          }
+          umma_commit_2sm(bars + 8 * (3 + stage));   // both CTAs' smem slots free when these MMAs retire
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(bars + 8 * (6 + buf));       // accumulator `buf` (both CTAs' halves) holds a finished chunk
+      }
+    }
+  } else {
+    // ===== epilogue: 16 warps per CTA on this CTA's 128 accumulator rows; warp = (lane quarter q, 64-column group) =====
+    const int q = warp & 3, cg = (warp - 2) >> 2;
+    float acc[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) acc[j] = 0.0f;
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1;
+      mbar_wait(bars + 8 * (6 + buf), ((uint32_t)(c >> 1)) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + cg * 64;
+#pragma unroll
+      for (int gI = 0; gI < 2; ++gI) {
+        uint32_t v[32];
+        tmem_ld32(taddr + gI * 32, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (gI == 1) {                       // all TMEM reads of this chunk are done: release the accumulator first
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cta0(bars + 8 * (8 + buf));
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[gI * 32 + j] += __uint_as_float(v[j]);
+      }
+    }
+    const int row = it.row0 + (int)rank * BOX_ROWS + q * 32 + lane;
+    const int col0 = it.col0 + cg * 64;
+    if (row < nS) {
+      float* dst = ws + ((size_t)it.slice * ldw + row) * ldw + col0;
+#pragma unroll
+      for (int j = 0; j < 64; j += 4) {
+        if (col0 + j < ldw)
+          *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();     // the peer may still be reading its TMEM half / arriving on the leader's barriers
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 // D[i][j] = D[j][i] = 4 * sum_s ws[s][i][j]  (i <= j), 32x32 tiles, coalesced both ways
 __global__ void __launch_bounds__(256) k_contract_finalize(const float* __restrict__ ws, float* __restrict__ D, int nS,
                                                            int ldw, int nslices) {
@@ -293,7 +489,7 @@ static int make_map(mem_ctx* ctx, CUtensorMap* map, const float* Z, int nS, int6
 }
 
 int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, const float* Zlo, float* D,
-                int k_chunk_blocks, int split_k, cudaStream_t st) {
+                int k_chunk_blocks, int split_k, cudaStream_t st, int two_cta) {
   const int nS = shp->nS, n1 = shp->n1_blocks, n3 = shp->n3_blocks;
   const int nkb = 2 * n1 + n3;
   if (((uintptr_t)Zhi & 15) || ((uintptr_t)Zlo & 15)) {
@@ -309,10 +505,12 @@ int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, c
   const int chunk = k_chunk_blocks > 0 ? k_chunk_blocks : 1;
   // tiles of the upper triangle (any element with col >= row)
   std::vector<std::pair<int, int>> tiles;
-  const int tm = (nS + BM - 1) / BM, tn = (nS + BN - 1) / BN;
+  const int TM = two_cta ? 2 * BM : BM;                  // tile rows: a CTA pair covers 256
+  const int units = two_cta ? ctx->sm_count / 2 : ctx->sm_count;
+  const int tm = (nS + TM - 1) / TM, tn = (nS + BN - 1) / BN;
   for (int bj = 0; bj < tn; ++bj)
     for (int bi = 0; bi < tm; ++bi)
-      if (bj * BN + BN - 1 >= bi * BM) tiles.push_back({bi, bj});
+      if (bj * BN + BN - 1 >= bi * TM) tiles.push_back({bi, bj});
   const int T = (int)tiles.size();
   int split = split_k;
   if (split <= 0) {
@@ -322,8 +520,8 @@ int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, c
     for (int s = 1; s <= 32; ++s) {
       if (s > 1 && nkb / s < min_kb) break;
       const int items = T * s;
-      const int waves = (items + ctx->sm_count - 1) / ctx->sm_count;
-      const double eff = (double)items / ((double)waves * ctx->sm_count);
+      const int waves = (items + units - 1) / units;
+      const double eff = (double)items / ((double)waves * units);
       if (eff > best + 0.02) { best = eff; split = s; }
     }
   }
@@ -332,22 +530,23 @@ int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, c
   std::vector<WorkItem> items;
   for (int s = 0; s < split; ++s) {
     const int kb0 = (int)((long long)nkb * s / split), kb1 = (int)((long long)nkb * (s + 1) / split);
-    for (auto& t : tiles) items.push_back({t.first * BM, t.second * BN, kb0, kb1, s, 0, 0, 0});
+    for (auto& t : tiles) items.push_back({t.first * TM, t.second * BN, kb0, kb1, s, 0, 0, 0});
   }
   MEM_CHECK(ctx->contract_ws.ensure((size_t)split * ldw * ldw * sizeof(float)));
   float* ws = ctx->contract_ws.as<float>();
-  if (ctx->items_key[0] != nS || ctx->items_key[1] != nkb || ctx->items_key[2] != split ||
-      ctx->items_key[3] != (long long)items.size()) {
+  const long long key3 = (long long)items.size() * 2 + two_cta;
+  if (ctx->items_key[0] != nS || ctx->items_key[1] != nkb || ctx->items_key[2] != split || ctx->items_key[3] != key3) {
     MEM_CHECK(ctx->contract_items.ensure(items.size() * sizeof(WorkItem)));
     MEM_CUDA(cudaMemcpyAsync(ctx->contract_items.p, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, st));
     MEM_CUDA(cudaStreamSynchronize(st));   // items is a host temporary; cached per shape afterwards
-    ctx->items_key[0] = nS; ctx->items_key[1] = nkb; ctx->items_key[2] = split; ctx->items_key[3] = (long long)items.size();
+    ctx->items_key[0] = nS; ctx->items_key[1] = nkb; ctx->items_key[2] = split; ctx->items_key[3] = key3;
   }
   WorkItem* d_items = ctx->contract_items.as<WorkItem>();
   CUtensorMap map_hi, map_lo;
   MEM_CHECK(make_map(ctx, &map_hi, Zhi, nS, shp->ldz));
   MEM_CHECK(make_map(ctx, &map_lo, Zlo, nS, shp->ldz));
   MEM_CUDA(cudaFuncSetAttribute(k_contract_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  MEM_CUDA(cudaFuncSetAttribute(k_contract_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
   // per-launch device timing (read back by mem_ctx_kernel_time; bench.py roofline)
   if (ctx->kev_used + 2 > ctx->kev.size()) {
     for (int i = 0; i < 64; ++i) {
@@ -357,11 +556,14 @@ int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, c
     }
   }
   MEM_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used], st));
-  MEM_LAUNCH(ctx, k_contract_tc, (int)items.size(), NUM_THREADS, SMEM_BYTES, st, map_hi, map_lo, d_items, ws, nS, ldw, n1, chunk);
+  if (two_cta)
+    MEM_LAUNCH(ctx, k_contract_tc2, 2 * (int)items.size(), NUM_THREADS2, SMEM2_BYTES, st, map_hi, map_lo, d_items, ws, nS, ldw, n1, chunk);
+  else
+    MEM_LAUNCH(ctx, k_contract_tc, (int)items.size(), NUM_THREADS, SMEM_BYTES, st, map_hi, map_lo, d_items, ws, nS, ldw, n1, chunk);
   MEM_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used + 1], st));
   ctx->kev_used += 2;
-  ctx->last_tc_items = (int)items.size();
-  ctx->last_tc_nkb = nkb;
+  ctx->last_tc_items = (two_cta ? 2 : 1) * (int)items.size();   // CTAs, each computing a 128 x 256 tile of its slice
+  ctx->last_tc_nkb = (nkb + split - 1) / split;                   // K blocks per CTA
   dim3 fgrid((nS + 31) / 32, (nS + 31) / 32);
   MEM_LAUNCH(ctx, k_contract_finalize, fgrid, 256, 0, st, ws, D, nS, ldw, split);
   return 0;

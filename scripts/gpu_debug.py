@@ -71,21 +71,33 @@ def contraction_timing(nS, N, reps=5):
     zhi = _lib.DeviceArray(ctx, Z.shape, np.float32, hi)
     zlo = _lib.DeviceArray(ctx, Z.shape, np.float32, lo)
     Dd = _lib.DeviceArray(ctx, (nS, nS), np.float32)
-    for chunk in (1, 2, 4, 16):
-        for _ in range(2):
-            _lib.check(lib.mem_contract_device(ctx.handle, C.byref(shp), zhi.ptr, zlo.ptr, Dd.ptr, 0, chunk, 0, None))
-        ctx.sync()
-        t0 = time.time()
-        for _ in range(reps):
-            _lib.check(lib.mem_contract_device(ctx.handle, C.byref(shp), zhi.ptr, zlo.ptr, Dd.ptr, 0, chunk, 0, None))
-        ctx.sync()
-        dt = (time.time() - t0) / reps
-        print('contraction nS=%d N=%d K=%d chunk=%d: %.3f ms  %.3f Gpairs/s' % (nS, N, K, chunk, dt * 1e3, nS * nS / dt / 1e9))
+    for kind in (0, 2):
+        for chunk in (1, 4):
+            for _ in range(2):
+                _lib.check(lib.mem_contract_device(ctx.handle, C.byref(shp), zhi.ptr, zlo.ptr, Dd.ptr, kind, chunk, 0, None))
+            ctx.sync()
+            t0 = time.time()
+            for _ in range(reps):
+                _lib.check(lib.mem_contract_device(ctx.handle, C.byref(shp), zhi.ptr, zlo.ptr, Dd.ptr, kind, chunk, 0, None))
+            ctx.sync()
+            dt = (time.time() - t0) / reps
+            print('contraction kind=%d nS=%d N=%d K=%d chunk=%d: %.3f ms  %.3f Gpairs/s' %
+                  (kind, nS, N, K, chunk, dt * 1e3, nS * nS / dt / 1e9))
     for a in (zhi, zlo, Dd):
         a.free()
 
 
 if __name__ == '__main__':
+    if 'tc2' in sys.argv:
+        report_pd(40, 32, 0, 0.1, contraction=2, impl='tile', fields=False)
+        report_pd(40, 32, 0, 0.1, contraction=0, impl='tile', fields=False)
+        report_pd(300, 128, 3, 10.0, contraction=2, fields=False)
+        report_pd(300, 128, 3, 10.0, contraction=0, fields=False)
+        report_pd(300, 128, 3, 10.0, contraction=0, fields=False, split=1)
+        report_pd(300, 128, 3, 10.0, contraction=0, fields=False, split=3, chunk=2)
+        contraction_timing(1000, 128)
+        contraction_timing(2000, 256)
+        sys.exit(0)
     report_pd(40, 32, 0, 0.1, contraction=1, impl='tile')
     report_pd(40, 32, 0, 0.1, contraction=0, impl='tile')
     report_pd(37, 25, 1, 10.0, contraction=0, impl='tile')
