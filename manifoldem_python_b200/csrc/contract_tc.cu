@@ -502,7 +502,9 @@ int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, c
     set_error("tcgen05 contraction needs an sm_100a device (found compute capability major %d); there is no fallback", dev_cc_major);
     return 1;
   }
-  const int chunk = k_chunk_blocks > 0 ? k_chunk_blocks : 1;
+  // default promotion period: 1 k-block for single-CTA tiles; 2 for CTA pairs, whose accumulator hand-over crosses
+  // the cluster twice per chunk (commit multicast + remote arrive ~ 650 clk) and needs the longer chunk to hide it
+  const int chunk = k_chunk_blocks > 0 ? k_chunk_blocks : (two_cta ? 2 : 1);
   // tiles of the upper triangle (any element with col >= row)
   std::vector<std::pair<int, int>> tiles;
   const int TM = two_cta ? 2 * BM : BM;                  // tile rows: a CTA pair covers 256

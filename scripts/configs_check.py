@@ -1,0 +1,84 @@
+"""BASELINE.json configs beyond the bench shape, on one B200 (timings + property checks, no oracle):
+  C2  single PD 1,000 x 128^2, full D
+  C3  single PD 5,000 x 256^2, kNN k=100 + Ferguson sweep + Laplacian from the resident D
+  C5' large box 6,000 x 320^2 (N = 320 path: E = 10 prefilter segments, 102,400-pixel spectra)
+  demo-like  53 PDs with the occupancies of the RyR1 demo (117..450, median 206) at N = 128 and 256
+python scripts/configs_check.py [c2] [c3] [c5] [demo]
+"""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from manifoldem_python_b200 import _lib, DMembeddingII   # noqa: E402
+import bench                                              # noqa: E402
+
+lib = _lib.load()
+ctx = _lib.Context(0)
+
+
+def run_shape(nS, N, reps=3, keepD=False):
+    pds, rng = bench.make_inputs(nS, N, 1, seed=nS + N)
+    pd = pds[0]
+    raw = _lib.DeviceArray(ctx, (nS, N * N), np.float32, rng.standard_normal((nS, N * N), dtype=np.float32))
+    flip = _lib.DeviceArray(ctx, (nS,), np.uint8, pd['flip'])
+    psi = _lib.DeviceArray(ctx, (nS,), np.float64, pd['psi_deg'])
+    df = _lib.DeviceArray(ctx, (nS,), np.float64, pd['df'])
+    D = _lib.DeviceArray(ctx, (nS, nS), np.float32)
+    prm = bench.pd_params(_lib, nS, N, pd['psi_p'])
+    io = _lib.PdIO()
+    io.raw, io.flip, io.psi_deg, io.df, io.D = raw.ptr, flip.ptr, psi.ptr, df.ptr, D.ptr
+    t = []
+    for r in range(reps + 1):
+        ctx.timer_start()
+        _lib.check(lib.mem_pd_distance_device(ctx.handle, C.byref(prm), C.byref(io), None))
+        t.append(ctx.timer_stop())
+    stage = ctx.timings()
+    for a in (raw, flip, psi, df):
+        a.free()
+    ms = float(np.median(t[1:]))
+    print('PD %5d x %d^2: %.3f ms  -> %.3f Gpairs/s   stages %s' %
+          (nS, N, ms, nS * nS / ms / 1e6, {k: round(v, 2) for k, v in stage.items() if v > 0}))
+    if keepD:
+        return D, ms
+    D.free()
+    return None, ms
+
+
+if 'c2' in sys.argv:
+    run_shape(1000, 128)
+
+if 'c3' in sys.argv:
+    nS, k = 5000, 100
+    Dd, ms = run_shape(nS, 256, reps=2, keepD=True)
+    D = Dd.download().astype(np.float64)
+    Dd.free()
+    assert np.array_equal(D, D.T) and np.abs(np.diag(D)).max() < 1e-5 * D.max()
+    t0 = time.time()
+    M, logEps, logSumWij, idx, val = DMembeddingII.graph_and_sweep(D, k)
+    t1 = time.time()
+    # kNN property checks: sorted ascending, self first, every listed neighbour no farther than the k-th
+    assert np.array_equal(idx[:, 0], np.arange(nS)) and (np.diff(val[:, 1:], axis=1) >= 0).all()
+    rows = np.random.default_rng(0).integers(0, nS, 50)
+    for i in rows:
+        d = D[i].copy()
+        d[i] = -np.inf
+        assert set(np.argsort(d, kind='stable')[:k]) == set(idx[i])
+    L = DMembeddingII.laplacian(M, nS, 3.0 * np.sqrt(np.median(val[:, 1:])))
+    t2 = time.time()
+    M.free()
+    assert np.allclose(L, L.T) and np.isfinite(L).all()
+    print('C3 kNN(k=%d)+graph+Ferguson sweep: %.1f ms, Laplacian+D2H: %.1f ms (incl. 200 MB H2D of D)' %
+          (k, (t1 - t0) * 1e3, (t2 - t1) * 1e3))
+
+if 'c5' in sys.argv:
+    run_shape(6000, 320, reps=1)
+
+if 'demo' in sys.argv:
+    for N in (128, 256):
+        for nS in (117, 206, 450):      # min / median / max occupancy of the demo's 53 PDs
+            run_shape(nS, N, reps=5)

@@ -72,7 +72,7 @@ def contraction_timing(nS, N, reps=5):
     zlo = _lib.DeviceArray(ctx, Z.shape, np.float32, lo)
     Dd = _lib.DeviceArray(ctx, (nS, nS), np.float32)
     for kind in (0, 2):
-        for chunk in (1, 4):
+        for chunk in (1, 2, 3, 4, 8):
             for _ in range(2):
                 _lib.check(lib.mem_contract_device(ctx.handle, C.byref(shp), zhi.ptr, zlo.ptr, Dd.ptr, kind, chunk, 0, None))
             ctx.sync()
