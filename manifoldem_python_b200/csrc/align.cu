@@ -265,6 +265,112 @@ __global__ void __launch_bounds__(MAXT, MINB) k_prefilter_cols(float* __restrict
     if (j < n && r0 + j < N) base[(size_t)(r0 + j) * N] = v[j];
 }
 
+// Exact-fit specialisations for the common box sizes (periodic boundary): N == 32*E for the row pass and
+// N == 16*S for the column pass, so every lane / segment owns a full segment, all guards fold away and the hop
+// count is a compile-time constant (the generic kernels above are issue-bound on their predication).
+template <int E, bool MASK>
+__global__ void __launch_bounds__(256) k_prefilter_rows_x(const float* __restrict__ in, float* __restrict__ out, float zE) {
+  constexpr int N = 32 * E;
+  constexpr int H = SPL_REACH / E + 2;
+  __shared__ float line[8][N + E];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp;
+  const size_t off = ((size_t)blockIdx.y * N + r) * N;
+  const float* src = in + off;
+  float* dst = out + off;
+  float* ln = line[warp];
+  constexpr float half = 0.5f * N, r2lim = half * half;
+  const float xm = (float)r - half + 1.0f;
+  const float lim = r2lim - xm * xm;                  // keep the pixel iff y*y < lim
+#pragma unroll
+  for (int k = 0; k < E; ++k) {
+    const int c = k * 32 + lane;
+    float t = src[c];
+    if (MASK) {                                        // img * msk, :325
+      const float y = (float)c - half;
+      if (!(y * y < lim)) t = 0.0f;
+    }
+    ln[c + k] = 6.0f * t;
+  }
+  __syncwarp();
+  const int c0 = lane * E;
+  float v[E];
+#pragma unroll
+  for (int j = 0; j < E; ++j) v[j] = ln[c0 + j + ((c0 + j) >> 5)];
+  float run = 0.0f;
+#pragma unroll
+  for (int j = 0; j < E; ++j) { run = fmaf(SPL_Z, run, v[j]); v[j] = run; }
+  float carry = 0.0f, f = 1.0f;
+#pragma unroll
+  for (int h = 1; h <= H; ++h) {
+    carry = fmaf(f, __shfl_sync(0xffffffffu, run, (lane - h) & 31), carry);
+    f *= zE;
+  }
+  float zp = SPL_Z * carry;
+#pragma unroll
+  for (int j = 0; j < E; ++j) { v[j] += zp; zp *= SPL_Z; }
+  run = 0.0f;
+#pragma unroll
+  for (int j = E - 1; j >= 0; --j) { run = SPL_Z * (run - v[j]); v[j] = run; }
+  carry = 0.0f; f = 1.0f;
+#pragma unroll
+  for (int h = 1; h <= H; ++h) {
+    carry = fmaf(f, __shfl_sync(0xffffffffu, run, (lane + h) & 31), carry);
+    f *= zE;
+  }
+  zp = SPL_Z * carry;
+#pragma unroll
+  for (int j = E - 1; j >= 0; --j) { v[j] += zp; zp *= SPL_Z; }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < E; ++j) ln[c0 + j + ((c0 + j) >> 5)] = v[j];
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < E; ++k) dst[k * 32 + lane] = ln[k * 32 + lane + k];
+}
+
+template <int S>
+__global__ void __launch_bounds__(32 * S, (S <= 16 ? 2 : 1)) k_prefilter_cols_x(float* __restrict__ data, float zE) {
+  constexpr int N = 16 * S, E = 16, H = SPL_REACH / E + 2;
+  __shared__ float ends[S][33];
+  const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  float* base = data + ((size_t)blockIdx.y * N + seg * E) * N + blockIdx.x * 32 + lane;
+  float v[E];
+#pragma unroll
+  for (int j = 0; j < E; ++j) v[j] = 6.0f * base[(size_t)j * N];
+  float run = 0.0f;
+#pragma unroll
+  for (int j = 0; j < E; ++j) { run = fmaf(SPL_Z, run, v[j]); v[j] = run; }
+  ends[seg][lane] = run;
+  __syncthreads();
+  float carry = 0.0f, f = 1.0f;
+#pragma unroll
+  for (int h = 1; h <= H; ++h) {
+    carry = fmaf(f, ends[(seg - h + S) % S][lane], carry);
+    f *= zE;
+  }
+  float zp = SPL_Z * carry;
+#pragma unroll
+  for (int j = 0; j < E; ++j) { v[j] += zp; zp *= SPL_Z; }
+  run = 0.0f;
+#pragma unroll
+  for (int j = E - 1; j >= 0; --j) { run = SPL_Z * (run - v[j]); v[j] = run; }
+  __syncthreads();
+  ends[seg][lane] = run;
+  __syncthreads();
+  carry = 0.0f; f = 1.0f;
+#pragma unroll
+  for (int h = 1; h <= H; ++h) {
+    carry = fmaf(f, ends[(seg + h) % S][lane], carry);
+    f *= zE;
+  }
+  zp = SPL_Z * carry;
+#pragma unroll
+  for (int j = E - 1; j >= 0; --j) { v[j] += zp; zp *= SPL_Z; }
+#pragma unroll
+  for (int j = 0; j < E; ++j) base[(size_t)j * N] = v[j];
+}
+
 // a2, RELION branch (:263-264): scipy.ndimage.shift(img, (s0, s1), order=3, mode='wrap') on mirror-prefiltered
 // coefficients.  SciPy semantics pinned in SURVEY §7(2) and tests/test_host.py: input coordinate o - s is
 // wrapped with period N-1, the 4 support indices are mirrored (k<0 -> -k, k>N-1 -> 2(N-1)-k).
@@ -319,15 +425,17 @@ __global__ void k_angles(const double* __restrict__ psi_deg, double psi_p_deg, d
 // CTA = 32x32 output tile; the (periodically wrapped) bounding box of its source footprint, at most
 // 50x50 coefficients, is staged in shared memory.  Coordinates in fp64, weights in fp32.
 // If msk2 != NULL a second, masked copy is written (img*msk2, :344).  FULL: N is a multiple of 32.
-// pitch 51 (odd): measured 1.64 ms per PD pair of rotations vs 2.00 ms with the unpadded pitch 50
-constexpr int ROT_T = 32, ROT_B = 50, ROT_P = 51;
+// Bank = (i*P + j) mod 32 with lanes stepping by (sin, cos) per output column: P = 65 gives bank = i + j, which
+// advances by |sin + cos| >= 1 per lane when sin*cos >= 0; P = 63 gives j - i for the other two quadrants.
+constexpr int ROT_T = 32, ROT_B = 50, ROT_PMAX = 65;
 template <bool FULL>
 __global__ void __launch_bounds__(256) k_rotate(const float* __restrict__ coef, float* __restrict__ out,
                                                 const double2* __restrict__ cs, int cs_stride, int N,
                                                 const uint8_t* __restrict__ msk2, float* __restrict__ out_masked) {
-  __shared__ float tile[ROT_B * ROT_P];
+  __shared__ float tile[ROT_B * ROT_PMAX];
   const int img = blockIdx.z;
   const double2 a = cs[(size_t)img * cs_stride];
+  const int ROT_P = (a.x * a.y >= 0.0) ? 65 : 63;
   const double ctr = 0.5 * (N - 1);
   const int r0 = blockIdx.y * ROT_T, c0 = blockIdx.x * ROT_T;
   // source coordinates of the tile corners -> bounding box origin (floor(min) - 1); every thread computes it
@@ -417,7 +525,19 @@ static int prefilter_run(mem_ctx* ctx, const float* in, float* out, int nS, int 
   const int E = (L + 31) / 32;
   const SegGeom gr = make_geom(L, E);
   const dim3 grid((N + 7) / 8, nS);
-  if (E <= 4) MEM_LAUNCH(ctx, k_prefilter_rows<4>, grid, 256, 0, st, in, out, N, L, gr, apply_mask);
+  const bool rows_exact = !mirror && (N == 64 || N == 128 || N == 256);
+  if (rows_exact) {
+    if (N == 64) {
+      if (apply_mask) MEM_LAUNCH(ctx, (k_prefilter_rows_x<2, true>), grid, 256, 0, st, in, out, gr.zE);
+      else MEM_LAUNCH(ctx, (k_prefilter_rows_x<2, false>), grid, 256, 0, st, in, out, gr.zE);
+    } else if (N == 128) {
+      if (apply_mask) MEM_LAUNCH(ctx, (k_prefilter_rows_x<4, true>), grid, 256, 0, st, in, out, gr.zE);
+      else MEM_LAUNCH(ctx, (k_prefilter_rows_x<4, false>), grid, 256, 0, st, in, out, gr.zE);
+    } else {
+      if (apply_mask) MEM_LAUNCH(ctx, (k_prefilter_rows_x<8, true>), grid, 256, 0, st, in, out, gr.zE);
+      else MEM_LAUNCH(ctx, (k_prefilter_rows_x<8, false>), grid, 256, 0, st, in, out, gr.zE);
+    }
+  } else if (E <= 4) MEM_LAUNCH(ctx, k_prefilter_rows<4>, grid, 256, 0, st, in, out, N, L, gr, apply_mask);
   else if (E <= 8) MEM_LAUNCH(ctx, k_prefilter_rows<8>, grid, 256, 0, st, in, out, N, L, gr, apply_mask);
   else MEM_LAUNCH(ctx, k_prefilter_rows<16>, grid, 256, 0, st, in, out, N, L, gr, apply_mask);
   // columns: segments of <= 16 rows, S = ceil(N / 16) <= 32 segments per column
@@ -425,6 +545,11 @@ static int prefilter_run(mem_ctx* ctx, const float* in, float* out, int nS, int 
   const int Ec = (L + S - 1) / S;
   const SegGeom gc = make_geom(L, Ec);
   const dim3 gcols((N + 31) / 32, nS);
+  if (!mirror && (N == 128 || N == 256)) {
+    if (N == 128) MEM_LAUNCH(ctx, k_prefilter_cols_x<8>, gcols, 256, 0, st, out, gc.zE);
+    else MEM_LAUNCH(ctx, k_prefilter_cols_x<16>, gcols, 512, 0, st, out, gc.zE);
+    return 0;
+  }
   auto kc_small = k_prefilter_cols<512, 2>;
   auto kc_large = k_prefilter_cols<1024, 1>;
   if (gc.used <= 16) MEM_LAUNCH(ctx, kc_small, gcols, 32 * gc.used, 0, st, out, N, L, gc);

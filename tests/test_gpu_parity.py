@@ -204,3 +204,36 @@ def test_contraction_kernel_vs_fp64(env):
         iu = np.triu_indices(nS)
         assert (np.abs(D - exact)[iu] / scale[iu]).max() < tol, kind
         assert np.array_equal(D, D.T)
+
+
+@pytest.mark.parametrize('nS', [1, 2, 5])
+def test_tiny_pds(env, nS):
+    """Edge cases: PDs far smaller than one 256 x 256 tile (TMA zero-fills the missing rows)."""
+    _lib, pd_stage, synthetic = env
+    pd = synthetic.make_pd(nS, 32, seed=40 + nS, snr=1.0)
+    res = _gpu(pd_stage, pd, 32)
+    ref = _oracle(pd, 32, rotate_impl='periodic')
+    assert res['D'].shape == (nS, nS)
+    if nS > 1:
+        _check_D(res['D'], ref['D'])
+    else:
+        assert abs(res['D'][0, 0]) <= 1e-5 * max(1.0, np.abs(ref['imgAll']).max() ** 2 * 32 * 32)
+    _check_fields(res, ref)
+
+
+def test_bad_inputs_fail_loudly(env):
+    """No silent fallback: unsupported shapes and parameters surface as errors."""
+    _lib, pd_stage, synthetic = env
+    lib, ctx = _lib.load(), _lib.default_context()
+    prm = _lib.PdParams(nS=0, N=64, transposed=1, filter_order=8, filter_Qc=0.5, pix_size=1.0, Cs=2.0, EkV=300.0,
+                        gaussEnv=float('inf'), AmpContrast=0.1)
+    io = _lib.PdIO()
+    assert lib.mem_pd_distance_host(ctx.handle, C.byref(prm), C.byref(io)) != 0        # empty PD
+    assert b'bad shape' in lib.mem_last_error()
+    pd = synthetic.make_pd(4, 8, seed=1)
+    with pytest.raises(RuntimeError):                                                   # N < 16
+        _gpu(pd_stage, pd, 8)
+    shp = _lib.ContractShape(nS=4, n1_blocks=1, n3_blocks=1, ldz=32)                    # ldz too small
+    assert lib.mem_contract_device(ctx.handle, C.byref(shp), None, None, None, 0, 0, 0, None) != 0
+    shp = _lib.ContractShape(nS=4, n1_blocks=1, n3_blocks=1, ldz=96)
+    assert lib.mem_contract_device(ctx.handle, C.byref(shp), None, None, None, 7, 0, 0, None) != 0   # unknown kind
