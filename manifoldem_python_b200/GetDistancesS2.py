@@ -102,11 +102,17 @@ def op(*argv):
 
     n_workers = min(_n_gpus(), max(1, int(getattr(p, 'ncpu', 1))), max(1, len(input_data)))
     if n_workers <= 1:
-        for job in input_data:                                                       # :102-108
-            worker.op(job, filterPar, p.img_stack_file, sh, size, options)
-            offset += 1
-            if progress is not None:
-                progress.emit(int((offset / float(p.numberofJobs)) * 100))
+        # :102-108, with two PDs in flight on the one GPU: the float64 conversion + pickle dump of PD k (host,
+        # GIL released in NumPy / file I/O) overlaps the device work of PD k+1; each host thread owns its context
+        inflight = max(1, int(os.environ.get('MANIFOLDEM_B200_INFLIGHT', '2')))
+        from concurrent.futures import ThreadPoolExecutor, as_completed
+        with ThreadPoolExecutor(max_workers=inflight) as pool:
+            futs = [pool.submit(worker.op, job, filterPar, p.img_stack_file, sh, size, options) for job in input_data]
+            for fut in as_completed(futs):
+                fut.result()                                                         # re-raise worker errors
+                offset += 1
+                if progress is not None:
+                    progress.emit(int((offset / float(p.numberofJobs)) * 100))
     else:
         costs = [partition.pd_cost(len(job[0]), p.nPix) for job in input_data]
         shards = partition.lpt_partition(costs, n_workers)

@@ -442,52 +442,73 @@ __global__ void __launch_bounds__(256) k_rotate(const float* __restrict__ coef, 
   const double tr = r0 - ctr, tc = c0 - ctr, ext = ROT_T - 1;
   const double b0 = a.x * tr + a.y * tc + ctr + fmin(a.x * ext, 0.0) + fmin(a.y * ext, 0.0);
   const double b1 = -a.y * tr + a.x * tc + ctr + fmin(-a.y * ext, 0.0) + fmin(a.x * ext, 0.0);
-  const int o0 = (int)floor(b0) - 1, o1 = (int)floor(b1) - 1;
+  const int o0 = __double2int_rd(b0) - 1, o1 = __double2int_rd(b1) - 1;
   const float* src = coef + (size_t)img * N * N;
-  int w0m = o0 % N; if (w0m < 0) w0m += N;
-  int w1m = o1 % N; if (w1m < 0) w1m += N;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   {
-    int gx0 = w1m + lane; while (gx0 >= N) gx0 -= N;
-    int gx1 = w1m + lane + 32; while (gx1 >= N) gx1 -= N;
-    for (int yy = wrp; yy < ROT_B; yy += 8) {
-      int gy = w0m + yy; while (gy >= N) gy -= N;
-      const float* rowp = src + (size_t)gy * N;
-      tile[yy * ROT_P + lane] = __ldg(rowp + gx0);
-      if (lane + 32 < ROT_B) tile[yy * ROT_P + lane + 32] = __ldg(rowp + gx1);
+    // periodic wrap of the box origin: |o| < 2N for every box size >= 32, smaller boxes take the loop
+    int w0m = o0, w1m = o1;
+    while (w0m < 0) w0m += N;
+    while (w1m < 0) w1m += N;
+    int gx0 = w1m + lane;
+    while (gx0 >= N) gx0 -= N;
+    int gx1 = gx0 + 32;
+    while (gx1 >= N) gx1 -= N;
+    int gy = w0m + wrp;
+    while (gy >= N) gy -= N;
+    const int step = 8 % N;
+    int ti = wrp * ROT_P + lane;
+    const bool second = lane + 32 < ROT_B;
+#pragma unroll
+    for (int it = 0; it < (ROT_B + 7) / 8; ++it) {
+      if (it * 8 + wrp < ROT_B) {                      // warp-uniform
+        const int rowoff = gy * N;
+        tile[ti] = __ldg(src + rowoff + gx0);
+        if (second) tile[ti + 32] = __ldg(src + rowoff + gx1);
+      }
+      gy += step;
+      if (gy >= N) gy -= N;
+      ti += 8 * ROT_P;
     }
   }
   __syncthreads();
   const int c = c0 + lane;
   const double xb0 = a.x * ((r0 + wrp) - ctr) + a.y * (c - ctr) + ctr - (double)o0;   // row coordinate, bbox-relative
   const double xb1 = -a.y * ((r0 + wrp) - ctr) + a.x * (c - ctr) + ctr - (double)o1;  // column coordinate
-  float* dst = out + (size_t)img * N * N + (size_t)(r0 + wrp) * N + c;
+  // 32.32 fixed point from here on (coordinates are in [1, 48)): integer part = tap origin, low word = fraction.
+  // The 4 outputs of a thread are 8 rows apart: one 64-bit add per axis instead of fp64 floor/convert chains.
+  long long x0 = __double2ll_rn(xb0 * 4294967296.0), x1 = __double2ll_rn(xb1 * 4294967296.0);
+  const long long DX0 = __double2ll_rn(8.0 * a.x * 4294967296.0), DX1 = __double2ll_rn(-8.0 * a.y * 4294967296.0);
+  const int oidx = (r0 + wrp) * N + c;                  // pixel index inside the image (N*N < 2^31)
+  float* dst = out + (size_t)img * N * N + oidx;
+  float* dstm = out_masked ? out_masked + (size_t)img * N * N + oidx : nullptr;
+  const uint8_t* mk = msk2 ? msk2 + oidx : nullptr;
+  const int rstep = 8 * N;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    if (!FULL && (r0 + wrp + 8 * q >= N || c >= N)) continue;
-    const double x0 = xb0 + (8 * q) * a.x;
-    const double x1 = xb1 - (8 * q) * a.y;
-    const int i0 = __double2int_rd(x0), j0 = __double2int_rd(x1);
-    const float t0 = (float)(x0 - (double)i0), t1 = (float)(x1 - (double)j0);
-    float wa[4], wb[4];
-    bspline_w(t0, wa);
-    bspline_w(t1, wb);
-    const float* p = tile + (i0 - 1) * ROT_P + (j0 - 1);      // 0 <= i0-1, j0-1 and i0+2, j0+2 < ROT_B
-    float acc = 0.0f;
+    if (FULL || (r0 + wrp + 8 * q < N && c < N)) {
+      const int i0 = (int)(x0 >> 32), j0 = (int)(x1 >> 32);
+      const float t0 = (float)(unsigned int)(x0 & 0xffffffffLL) * 2.3283064365386963e-10f;
+      const float t1 = (float)(unsigned int)(x1 & 0xffffffffLL) * 2.3283064365386963e-10f;
+      float wa[4], wb[4];
+      bspline_w(t0, wa);
+      bspline_w(t1, wb);
+      const float* p = tile + ((i0 - 1) * ROT_P + (j0 - 1));   // 0 <= i0-1, j0-1 and i0+2, j0+2 < ROT_B
+      float acc = 0.0f;
 #pragma unroll
-    for (int ai = 0; ai < 4; ++ai) {
-      const float* rowp = p + ai * ROT_P;
-      float rs = wb[0] * rowp[0];
-      rs = fmaf(wb[1], rowp[1], rs);
-      rs = fmaf(wb[2], rowp[2], rs);
-      rs = fmaf(wb[3], rowp[3], rs);
-      acc = fmaf(wa[ai], rs, acc);
+      for (int ai = 0; ai < 4; ++ai) {
+        float rs = wb[0] * p[0];
+        rs = fmaf(wb[1], p[1], rs);
+        rs = fmaf(wb[2], p[2], rs);
+        rs = fmaf(wb[3], p[3], rs);
+        acc = fmaf(wa[ai], rs, acc);
+        p += ROT_P;
+      }
+      dst[q * rstep] = acc;
+      if (dstm) dstm[q * rstep] = mk[q * rstep] ? acc : 0.0f;
     }
-    dst[(size_t)(8 * q) * N] = acc;
-    if (out_masked) {
-      const size_t o = (size_t)img * N * N + (size_t)(r0 + wrp + 8 * q) * N + c;
-      out_masked[o] = msk2[(r0 + wrp + 8 * q) * N + c] ? acc : 0.0f;
-    }
+    x0 += DX0;
+    x1 += DX1;
   }
 }
 
