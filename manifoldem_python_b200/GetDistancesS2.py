@@ -104,7 +104,9 @@ def op(*argv):
     if n_workers <= 1:
         # :102-108, with two PDs in flight on the one GPU: the float64 conversion + pickle dump of PD k (host,
         # GIL released in NumPy / file I/O) overlaps the device work of PD k+1; each host thread owns its context
-        inflight = max(1, int(os.environ.get('MANIFOLDEM_B200_INFLIGHT', '2')))
+        # small PDs are launch/latency-bound: 4 streams double the throughput at nS ~ 200 (scripts/overlap_test.py)
+        work = float(np.median([len(j[0]) for j in input_data])) * p.nPix * p.nPix if input_data else 0.0
+        inflight = max(1, int(os.environ.get('MANIFOLDEM_B200_INFLIGHT', '4' if work < 3e7 else '2')))
         from concurrent.futures import ThreadPoolExecutor, as_completed
         with ThreadPoolExecutor(max_workers=inflight) as pool:
             futs = [pool.submit(worker.op, job, filterPar, p.img_stack_file, sh, size, options) for job in input_data]

@@ -176,6 +176,8 @@ k_contract_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
           mbar_wait(bars + 8 * stage, phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t s0 = base + stage * STAGE_BYTES;
+          // the small cross terms (2^-11 of the products) first: on the first block of a chunk they accumulate from
+          // zero, where the truncating accumulator loses nothing that matters; then the four hi*hi steps
 #pragma unroll
           for (int ks = 0; ks < BK / 8; ++ks) {
             const uint64_t a_hi = make_smem_desc(s0 + 0 * BOX_BYTES + ks * 32);
@@ -184,8 +186,13 @@ k_contract_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
             const uint64_t b_lo = make_smem_desc(s0 + 4 * BOX_BYTES + ks * 32);
             umma_tf32(tacc, a_lo, b_hi, idesc, first ? 0u : 1u);
             umma_tf32(tacc, a_hi, b_lo, idesc, 1u);
-            umma_tf32(tacc, a_hi, b_hi, idesc, 1u);
             first = false;
+          }
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            const uint64_t a_hi = make_smem_desc(s0 + 0 * BOX_BYTES + ks * 32);
+            const uint64_t b_hi = make_smem_desc(s0 + 2 * BOX_BYTES + ks * 32);
+            umma_tf32(tacc, a_hi, b_hi, idesc, 1u);
           }
           umma_commit(bars + 8 * (2 + stage));   // smem slot free when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -370,15 +377,20 @@ k_contract_tc2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t s0 = base + stage * STAGE2_BYTES;
 #pragma unroll
-          for (int ks = 0; ks < BK / 8; ++ks) {
+          for (int ks = 0; ks < BK / 8; ++ks) {          // cross terms first (see the single-CTA kernel)
             const uint64_t a_hi = make_smem_desc(s0 + 0 * BOX_BYTES + ks * 32);
             const uint64_t a_lo = make_smem_desc(s0 + 1 * BOX_BYTES + ks * 32);
             const uint64_t b_hi = make_smem_desc(s0 + 2 * BOX_BYTES + ks * 32);
             const uint64_t b_lo = make_smem_desc(s0 + 3 * BOX_BYTES + ks * 32);
             umma_tf32_2sm(tacc, a_lo, b_hi, idesc, first ? 0u : 1u);
             umma_tf32_2sm(tacc, a_hi, b_lo, idesc, 1u);
-            umma_tf32_2sm(tacc, a_hi, b_hi, idesc, 1u);
             first = false;
+          }
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            const uint64_t a_hi = make_smem_desc(s0 + 0 * BOX_BYTES + ks * 32);
+            const uint64_t b_hi = make_smem_desc(s0 + 2 * BOX_BYTES + ks * 32);
+            umma_tf32_2sm(tacc, a_hi, b_hi, idesc, 1u);
           }
           umma_commit_2sm(bars + 8 * (3 + stage));   // both CTAs' smem slots free when these MMAs retire
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
