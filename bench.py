@@ -344,9 +344,12 @@ def run_b200(args):
                                 l2='inputs larger than L2: %d distinct 524 MB stacks cycled' % POOL,
                                 per_pd_ms=ms / args.steps / P, stage_ms_last_pd=stage),
                     clocks=clocks, gpu_launches=launches, e2e=e2e,
-                    roofline=dict(bound='tensor', kernel='k_contract_tc (tcgen05 kind::tf32, 3 passes)',
+                    roofline=dict(bound='tensor', kernel='k_contract_tc2 (tcgen05 cta_group::2 kind::tf32, 3 passes)',
                                   achieved=achieved, peak=peak, unit='TFLOP/s', frac=(achieved / peak) if achieved else None,
                                   traffic=traffic, avg_launch_ms=k_avg_ms, launches=k_n,
+                                  # hardware ceiling at the clock sampled during the run: 148 SMs x 2048 TF32 MAC/clk x 2
+                                  frac_of_hw_rate_at_sampled_clock=(achieved / (148 * 2048 * 2 * clocks['sm_mhz'] * 1e6 / 1e12))
+                                  if (achieved and clocks and clocks.get('sm_mhz')) else None,
                                   ncu_tensor_pipe_active_pct=75.9 if traffic else None,
                                   executed_flops_per_launch=flops_launch,
                                   algorithmic_tflops=alg / (k_avg_ms * 1e-3) / 1e12 if k_n else None,
