@@ -121,10 +121,15 @@ int mem_operand_shape(mem_ctx* ctx, int32_t N, mem_contract_shape* out);
  * device), the k smallest entries with the diagonal forced first; idx [nS][k] int32, val [nS][k] f64
  * (val[i][0] = 0).  D is not modified. */
 int mem_knn_device(mem_ctx* ctx, const double* D, int32_t nS, int32_t k, int32_t* idx, double* val, void* stream);
+/* a15 on the float32 D that mem_pd_distance_device leaves on the device (D never visits the host) */
+int mem_knn_device_f32(mem_ctx* ctx, const float* D, int32_t nS, int32_t k, int32_t* idx, double* val, void* stream);
 /* a16 OR-symmetrised kNN graph (DMembeddingII.op :113-140) in dense form: M [nS][nS] float64 device,
  * M[i][j] = d^2 of the union graph, 0 for the 'zero' (self) entries, -1 where there is no edge. */
 int mem_graph_dense_device(mem_ctx* ctx, const int32_t* idx, const double* val, int32_t nS, int32_t k, double* M,
                            void* stream);
+/* row-major compaction of the graph entries (M >= 0) into out[*count] (device, capacity >= number of edges;
+ * nS*nS always suffices): lets the Ferguson sweep run over the edges only when k < nS.  Synchronises. */
+int mem_graph_compact_device(mem_ctx* ctx, const double* M, int32_t nS, double* out, int64_t* count);
 /* a17 Ferguson sweep (fergusonE.op :36-43): out[e] = log sum_{d2/(2 eps_e) < thr} exp(-d2/(2 eps_e)),
  * d2 [n] float64 device (negative entries = no edge, skipped), logEps [nEps] float64 HOST,
  * out [nEps] float64 HOST.  Synchronises. */

@@ -40,34 +40,53 @@ def _fit(logEps, logSumWij, a0):
     return popt, resnorm, R_squared
 
 
-def graph_and_sweep(D, k, ctx=None):
-    """Device part up to the Ferguson curve.  Returns (M_dev DeviceArray (nS,nS) float64 graph,
-    logEps, logSumWij, idx (nS,k) int32, val (nS,k) float64)."""
+def graph_and_sweep(D, k, ctx=None, nS=None):
+    """Device part up to the Ferguson curve.  `D`: host (nS,nS) array, or a `_lib.DeviceArray` holding the
+    float32 D that the distance stage left on the device (then D never visits the host).
+    Returns (M_dev DeviceArray (nS,nS) float64 graph, logEps, logSumWij, idx (nS,k) int32, val (nS,k) float64)."""
     lib = _lib.load()
     ctx = ctx or _ctx()
+    resident = isinstance(D, _lib.DeviceArray)
     nS = D.shape[0]
-    Dd = _lib.DeviceArray(ctx, (nS, nS), np.float64, np.ascontiguousarray(D, dtype=np.float64))
     idx_d = _lib.DeviceArray(ctx, (nS, k), np.int32)
     val_d = _lib.DeviceArray(ctx, (nS, k), np.float64)
-    _lib.check(lib.mem_knn_device(ctx.handle, Dd.ptr, nS, k, idx_d.ptr, val_d.ptr, None))
+    if resident:
+        if D.dtype != np.float32:
+            raise TypeError('resident D must be float32')
+        _lib.check(lib.mem_knn_device_f32(ctx.handle, D.ptr, nS, k, idx_d.ptr, val_d.ptr, None))
+        Dd = None
+    else:
+        Dd = _lib.DeviceArray(ctx, (nS, nS), np.float64, np.ascontiguousarray(D, dtype=np.float64))
+        _lib.check(lib.mem_knn_device(ctx.handle, Dd.ptr, nS, k, idx_d.ptr, val_d.ptr, None))
     M = _lib.DeviceArray(ctx, (nS, nS), np.float64)
     _lib.check(lib.mem_graph_dense_device(ctx.handle, idx_d.ptr, val_d.ptr, nS, k, M.ptr, None))
+    # k < nS: sweep over the edges only (row-major compaction), not over the nS^2 slots of the dense graph
+    vals, n_vals, compact = M, nS * nS, None
+    if k < nS:
+        compact = _lib.DeviceArray(ctx, (min(nS * nS, 2 * nS * k),), np.float64)
+        cnt = C.c_int64()
+        _lib.check(lib.mem_graph_compact_device(ctx.handle, M.ptr, nS, compact.ptr, C.byref(cnt)))
+        vals, n_vals = compact, int(cnt.value)
     logEps = np.arange(-150, 150.2, 0.2)                                        # :146
     # find_thres (fergusonE.py:25-31): ss = sum exp(-d2 / (2 max eps)), n = number of graph entries
     one = np.array([np.max(logEps)], dtype=np.float64)
     out1 = np.zeros(1)
-    _lib.check(lib.mem_ferguson_device(ctx.handle, M.ptr, nS * nS, one.ctypes.data, 1, float('inf'), out1.ctypes.data))
+    _lib.check(lib.mem_ferguson_device(ctx.handle, vals.ptr, n_vals, one.ctypes.data, 1, float('inf'), out1.ctypes.data))
     ss = float(np.exp(out1[0]))
-    huge = np.array([700.0], dtype=np.float64)
-    _lib.check(lib.mem_ferguson_device(ctx.handle, M.ptr, nS * nS, huge.ctypes.data, 1, float('inf'), out1.ctypes.data))
-    n_entries = float(np.rint(np.exp(out1[0])))
+    if compact is not None:
+        n_entries = float(n_vals)
+    else:
+        huge = np.array([700.0], dtype=np.float64)
+        _lib.check(lib.mem_ferguson_device(ctx.handle, vals.ptr, n_vals, huge.ctypes.data, 1, float('inf'), out1.ctypes.data))
+        n_entries = float(np.rint(np.exp(out1[0])))
     thr = max(-np.log(0.01 * ss / n_entries), 10)
     logSumWij = np.zeros(len(logEps))
-    _lib.check(lib.mem_ferguson_device(ctx.handle, M.ptr, nS * nS, logEps.ctypes.data, len(logEps), float(thr),
+    _lib.check(lib.mem_ferguson_device(ctx.handle, vals.ptr, n_vals, logEps.ctypes.data, len(logEps), float(thr),
                                        logSumWij.ctypes.data))
     idx, val = idx_d.download(), val_d.download()
-    for a in (Dd, idx_d, val_d):
-        a.free()
+    for a in (Dd, idx_d, val_d, compact):
+        if a is not None:
+            a.free()
     return M, logEps, logSumWij, idx, val
 
 

@@ -15,7 +15,7 @@ SYMBOLS = [
     'mem_version', 'mem_last_error', 'mem_ctx_create', 'mem_ctx_destroy', 'mem_ctx_sync', 'mem_ctx_launch_count',
     'mem_ctx_timer_start', 'mem_ctx_timer_stop', 'mem_ctx_kernel_time', 'mem_host_alloc', 'mem_host_free', 'mem_dev_alloc', 'mem_dev_free', 'mem_copy_h2d', 'mem_copy_d2h',
     'mem_pd_distance_device', 'mem_pd_distance_host', 'mem_pd_last_timings', 'mem_contract_device',
-    'mem_operand_shape', 'mem_knn_device', 'mem_graph_dense_device', 'mem_ferguson_device',
+    'mem_operand_shape', 'mem_knn_device', 'mem_knn_device_f32', 'mem_graph_dense_device', 'mem_graph_compact_device', 'mem_ferguson_device',
     'mem_laplacian_dense_device',
 ]
 
@@ -79,6 +79,8 @@ def load():
                                             C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
         lib.mem_operand_shape.argtypes = [C.c_void_p, C.c_int32, C.POINTER(ContractShape)]
         lib.mem_knn_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.mem_knn_device_f32.argtypes = lib.mem_knn_device.argtypes
+        lib.mem_graph_compact_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int64)]
         lib.mem_graph_dense_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                                C.c_void_p]
         lib.mem_ferguson_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_double,

@@ -9,6 +9,8 @@ namespace mem {
 const char* last_error();
 int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* io, cudaStream_t st);
 int knn_device(mem_ctx* ctx, const double* D, int nS, int k, int* idx, double* val, cudaStream_t st);
+int knn_device_f32(mem_ctx* ctx, const float* D, int nS, int k, int* idx, double* val, cudaStream_t st);
+int graph_compact_device(mem_ctx* ctx, const double* M, int nS, double* out, long long* count);
 int graph_dense_device(mem_ctx* ctx, const int* idx, const double* val, int nS, int k, double* M, cudaStream_t st);
 int ferguson_device(mem_ctx* ctx, const double* d2, int64_t n, const double* logEps, int nEps, double thr, double* out);
 int laplacian_dense_device(mem_ctx* ctx, const double* M, int nS, double sigma, double* L, cudaStream_t st);
@@ -246,6 +248,17 @@ int mem_operand_shape(mem_ctx* ctx, int32_t N, mem_contract_shape* out) {
 int mem_knn_device(mem_ctx* ctx, const double* D, int32_t nS, int32_t k, int32_t* idx, double* val, void* stream) {
   MEM_CUDA(cudaSetDevice(ctx->device));
   return knn_device(ctx, D, nS, k, idx, val, pick(ctx, stream));
+}
+int mem_knn_device_f32(mem_ctx* ctx, const float* D, int32_t nS, int32_t k, int32_t* idx, double* val, void* stream) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  return knn_device_f32(ctx, D, nS, k, idx, val, pick(ctx, stream));
+}
+int mem_graph_compact_device(mem_ctx* ctx, const double* M, int32_t nS, double* out, int64_t* count) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  long long c = 0;
+  MEM_CHECK(graph_compact_device(ctx, M, nS, out, &c));
+  *count = c;
+  return 0;
 }
 int mem_graph_dense_device(mem_ctx* ctx, const int32_t* idx, const double* val, int32_t nS, int32_t k, double* M,
                            void* stream) {

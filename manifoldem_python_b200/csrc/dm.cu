@@ -5,6 +5,7 @@
 
 #include <math.h>
 #include <algorithm>
+#include <vector>
 
 namespace mem {
 
@@ -12,16 +13,17 @@ namespace mem {
 // a15  DMembeddingII.initialize :43-57 — per point the k smallest distances, self first.
 // One CTA per point; (key, index) pairs bitonic-sorted in shared memory, ties broken by index.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_knn_sort(const double* __restrict__ D, int nS, int P, int k,
+template <class T>
+__global__ void __launch_bounds__(1024) k_knn_sort(const T* __restrict__ D, int nS, int P, int k,
                                                    int* __restrict__ idx, double* __restrict__ val) {
   extern __shared__ uint8_t sm_raw[];
   double* key = reinterpret_cast<double*>(sm_raw);
   int* id = reinterpret_cast<int*>(sm_raw + (size_t)P * sizeof(double));
   const int i = blockIdx.x;
-  const double* row = D + (size_t)i * nS;   // D symmetric: column i == row i
+  const T* row = D + (size_t)i * nS;        // D symmetric: column i == row i
   for (int j = threadIdx.x; j < P; j += blockDim.x) {
     double v = INFINITY;
-    if (j < nS) v = (j == i) ? -INFINITY : row[j];   // D[iS,iS] = -inf, :48
+    if (j < nS) v = (j == i) ? -INFINITY : (double)row[j];   // D[iS,iS] = -inf, :48
     key[j] = v;
     id[j] = j;
   }
@@ -49,7 +51,8 @@ __global__ void __launch_bounds__(1024) k_knn_sort(const double* __restrict__ D,
   }
 }
 
-int knn_device(mem_ctx* ctx, const double* D, int nS, int k, int* idx, double* val, cudaStream_t st) {
+template <class T>
+static int knn_device_t(mem_ctx* ctx, const T* D, int nS, int k, int* idx, double* val, cudaStream_t st) {
   if (k < 1 || k > nS) {
     set_error("knn: need 1 <= k <= nS (k=%d nS=%d)", k, nS);
     return 1;
@@ -61,10 +64,17 @@ int knn_device(mem_ctx* ctx, const double* D, int nS, int k, int* idx, double* v
     set_error("knn: nS=%d exceeds the in-shared-memory sort (max 16384 points)", nS);
     return 1;
   }
-  MEM_CUDA(cudaFuncSetAttribute(k_knn_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MEM_CUDA(cudaFuncSetAttribute(k_knn_sort<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int threads = std::max(32, std::min(1024, P / 2));
-  MEM_LAUNCH(ctx, k_knn_sort, nS, threads, smem, st, D, nS, P, k, idx, val);
+  MEM_LAUNCH(ctx, k_knn_sort<T>, nS, threads, smem, st, D, nS, P, k, idx, val);
   return 0;
+}
+int knn_device(mem_ctx* ctx, const double* D, int nS, int k, int* idx, double* val, cudaStream_t st) {
+  return knn_device_t<double>(ctx, D, nS, k, idx, val, st);
+}
+// same on the float32 D the distance stage leaves on the device (no host round trip of the N x N matrix)
+int knn_device_f32(mem_ctx* ctx, const float* D, int nS, int k, int* idx, double* val, cudaStream_t st) {
+  return knn_device_t<float>(ctx, D, nS, k, idx, val, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -106,6 +116,64 @@ int graph_dense_device(mem_ctx* ctx, const int* idx, const double* val, int nS, 
   const size_t tot = (size_t)nS * k;
   MEM_LAUNCH(ctx, k_graph_scatter, (unsigned)((tot + 255) / 256), 256, 0, st, idx, val, nS, k, Y, Zf);
   MEM_LAUNCH(ctx, k_graph_combine, dim3((nS + 255) / 256, nS), 256, 0, st, Y, Zf, nS, M);
+  return 0;
+}
+
+// Row-major compaction of the graph entries (M >= 0) into a dense vector: for k < nS the Ferguson sweep then
+// touches nnz <= 2 nS k values instead of nS^2 slots.  Deterministic order (row, then column).
+__global__ void __launch_bounds__(256) k_row_counts(const double* __restrict__ M, int nS, int* __restrict__ counts) {
+  __shared__ int red[8];
+  const int i = blockIdx.x;
+  int c = 0;
+  for (int j = threadIdx.x; j < nS; j += 256) c += (M[(size_t)i * nS + j] >= 0.0);
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    counts[i] = t;
+  }
+}
+__global__ void __launch_bounds__(256) k_row_compact(const double* __restrict__ M, int nS, const long long* __restrict__ offs,
+                                                     double* __restrict__ out) {
+  __shared__ int wsum[8];
+  const int i = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long base = offs[i];
+  for (int j0 = 0; j0 < nS; j0 += 256) {
+    const int j = j0 + threadIdx.x;
+    const double v = (j < nS) ? M[(size_t)i * nS + j] : -1.0;
+    const bool keep = v >= 0.0;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) wsum[warp] = __popc(m);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < 8; ++w) {
+      if (w < warp) before += wsum[w];
+      total += wsum[w];
+    }
+    if (keep) out[base + before + __popc(m & ((1u << lane) - 1u))] = v;
+    base += total;
+    __syncthreads();
+  }
+}
+int graph_compact_device(mem_ctx* ctx, const double* M, int nS, double* out, long long* count) {
+  cudaStream_t st = ctx->stream;
+  const size_t off_bytes = ((size_t)nS * sizeof(int) + 15) & ~(size_t)15;
+  MEM_CHECK(ctx->small_out.ensure(off_bytes + (size_t)nS * sizeof(long long)));
+  int* d_counts = ctx->small_out.as<int>();
+  MEM_LAUNCH(ctx, k_row_counts, nS, 256, 0, st, M, nS, d_counts);
+  std::vector<int> counts(nS);
+  MEM_CUDA(cudaMemcpyAsync(counts.data(), d_counts, nS * sizeof(int), cudaMemcpyDeviceToHost, st));
+  MEM_CUDA(cudaStreamSynchronize(st));
+  std::vector<long long> offs(nS);
+  long long tot = 0;
+  for (int i = 0; i < nS; ++i) { offs[i] = tot; tot += counts[i]; }
+  long long* d_offs = reinterpret_cast<long long*>(ctx->small_out.as<uint8_t>() + off_bytes);
+  MEM_CUDA(cudaMemcpyAsync(d_offs, offs.data(), nS * sizeof(long long), cudaMemcpyHostToDevice, st));
+  MEM_LAUNCH(ctx, k_row_compact, nS, 256, 0, st, M, nS, d_offs, out);
+  MEM_CUDA(cudaStreamSynchronize(st));
+  *count = tot;
   return 0;
 }
 

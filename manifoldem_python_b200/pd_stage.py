@@ -144,3 +144,34 @@ def run_pd(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast, gaussEnv
                version=VERSION)
     res['_psi_p'] = psi_p
     return res
+
+
+def run_pd_resident(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast, gaussEnv=np.inf, filterPar=None,
+                    ctx=None, angles=None):
+    """Distance stage with the result kept ON THE DEVICE: returns a `_lib.DeviceArray` (nS,nS) float32 holding D,
+    for consumers that run there too (DMembeddingII.graph_and_sweep accepts it) — the N x N matrix never
+    round-trips through the host (BASELINE config 3: kNN / kernel construction only)."""
+    lib = _lib.load()
+    ctx = ctx or _lib.default_context()
+    if filterPar is None:
+        filterPar = dict(type='Butter', Qc=0.5, N=8)
+    ind = np.asarray(ind)
+    q = np.asarray(q, dtype=np.float64)
+    nS = ind.shape[0]
+    PDs, PD, psi_p, Psi, s, c = angles if angles is not None else host_angles(q)
+    raw, flip, base = gather(stack, ind, nStot, N)
+    bufs = [_lib.DeviceArray(ctx, raw.shape, np.float32, raw), _lib.DeviceArray(ctx, (nS,), np.uint8, flip),
+            _lib.DeviceArray(ctx, (nS,), np.float64, -(180 / math.pi) * Psi),
+            _lib.DeviceArray(ctx, (nS,), np.float64, np.ascontiguousarray(df, dtype=np.float64))]
+    D = _lib.DeviceArray(ctx, (nS, nS), np.float32)
+    prm = _lib.PdParams(nS=nS, N=N, transposed=1, relion_shift=0, filter_type=FILTERS[filterPar['type']],
+                        filter_order=int(filterPar['N']), filter_Qc=float(filterPar['Qc']), pix_size=float(pix_size),
+                        Cs=float(Cs), EkV=float(EkV), gaussEnv=float(gaussEnv), AmpContrast=float(AmpContrast),
+                        psi_p_deg=float(psi_p))
+    io = _lib.PdIO()
+    io.raw, io.flip, io.psi_deg, io.df, io.D = bufs[0].ptr, bufs[1].ptr, bufs[2].ptr, bufs[3].ptr, D.ptr
+    _lib.check(lib.mem_pd_distance_device(ctx.handle, C.byref(prm), C.byref(io), None))
+    ctx.sync()
+    for b in bufs:
+        b.free()
+    return D

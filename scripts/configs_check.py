@@ -56,11 +56,14 @@ if 'c3' in sys.argv:
     nS, k = 5000, 100
     Dd, ms = run_shape(nS, 256, reps=2, keepD=True)
     D = Dd.download().astype(np.float64)
-    Dd.free()
     assert np.array_equal(D, D.T) and np.abs(np.diag(D)).max() < 1e-5 * D.max()
-    t0 = time.time()
-    M, logEps, logSumWij, idx, val = DMembeddingII.graph_and_sweep(D, k)
-    t1 = time.time()
+    for _ in range(2):                      # second pass = warm
+        t0 = time.time()
+        M, logEps, logSumWij, idx, val = DMembeddingII.graph_and_sweep(Dd, k)    # D resident on the device
+        t1 = time.time()
+        if _ == 0:
+            M.free()
+    Dd.free()
     # kNN property checks: sorted ascending, self first, every listed neighbour no farther than the k-th
     assert np.array_equal(idx[:, 0], np.arange(nS)) and (np.diff(val[:, 1:], axis=1) >= 0).all()
     rows = np.random.default_rng(0).integers(0, nS, 50)
@@ -72,7 +75,7 @@ if 'c3' in sys.argv:
     t2 = time.time()
     M.free()
     assert np.allclose(L, L.T) and np.isfinite(L).all()
-    print('C3 kNN(k=%d)+graph+Ferguson sweep: %.1f ms, Laplacian+D2H: %.1f ms (incl. 200 MB H2D of D)' %
+    print('C3 kNN(k=%d)+graph+compaction+Ferguson sweep on the resident D: %.1f ms; Laplacian + 200 MB D2H of L: %.1f ms' %
           (k, (t1 - t0) * 1e3, (t2 - t1) * 1e3))
 
 if 'c5' in sys.argv:

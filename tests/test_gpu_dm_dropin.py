@@ -175,3 +175,29 @@ def test_manifold_trimming_consumer(tmp_path):
     assert np.allclose(lamb[:6], lamb_o[:6], rtol=1e-4)
     for j in range(3):                                   # north_star: leading eigenvectors |corr| >= 0.9999
         assert abs(np.corrcoef(psi[:, j], psi_o[:, j])[0, 1]) >= 0.9999, j
+
+
+def test_resident_chain_distance_to_knn():
+    """BASELINE config 3 shape of use: D stays on the device, kNN (k < nS) + Ferguson sweep over the compacted
+    edges; same lists / curve as the host-D path on the downloaded matrix."""
+    from manifoldem_python_b200 import DMembeddingII, pd_stage, synthetic
+    pd = synthetic.make_pd(333, 64, seed=77, snr=0.3)
+    em = pd['em']
+    Dd = pd_stage.run_pd_resident(pd['ind'], pd['q'], pd['df'], pd['stack'], pd['nStot'], 64, em['pix_size'], em['Cs'],
+                                  em['EkV'], em['AmpContrast'])
+    k = 25
+    M1, logEps, ls1, idx1, val1 = DMembeddingII.graph_and_sweep(Dd, k)
+    D = Dd.download().astype(np.float64)
+    M2, _, ls2, idx2, val2 = DMembeddingII.graph_and_sweep(D, k)
+    assert np.array_equal(idx1, idx2) and np.array_equal(val1, val2)
+    assert np.array_equal(M1.download(), M2.download())
+    assert np.array_equal(ls1, ls2)
+    # compacted sweep (k < nS) == dense sweep of the oracle
+    from oracle import dm_embedding as odm
+    Do = D.copy()
+    io, vo = odm.knn_lists(Do, k)
+    yRow, yCol, yVal = odm.symmetrise(io, vo, 333)
+    ls_o, _ = odm.ferguson_logsum(np.sqrt(yVal))
+    assert np.allclose(ls1, ls_o, rtol=1e-12, atol=1e-12)
+    for a in (Dd, M1, M2):
+        a.free()
