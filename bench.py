@@ -99,6 +99,24 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU, so that the pinned host
+    stacks of the e2e leg live on that socket (8 ranks otherwise share one socket's memory controllers)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        cpus = [c for c in cpus if c < os.cpu_count()]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def make_inputs(nS, N, pool, seed):
     """Synthetic PD stacks of the named shape: white-noise particles (timing does not depend on the
     pixel values), random defocus 1-3 um, orientations scattered 0.03 rad around one PD."""
@@ -225,6 +243,7 @@ def run_b200(args):
             os.close(saved)
     lib = _lib.load()
     nS, N, P = args.nS, args.N, args.pds
+    numa = bind_to_gpu_numa_node(local)       # pinned staging buffers are first-touched on the GPU's own socket
     ctx = _lib.Context(local)
     pds, rng = make_inputs(nS, N, POOL, seed=1000 + rank)
     NN = N * N
@@ -357,6 +376,10 @@ def run_b200(args):
                                   share_of_step=k_ms / ms if ms else None))
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
+            try:
+                os.sched_setaffinity(0, range(cores))       # the CPU arm gets every host core back
+            except Exception:
+                pass
             v, detail = cpu_reference_sample(nS, N, 4 * cores, cores, contraction_rows=min(nS, 500))
             line['cpu_baseline'] = dict(value=v, unit=UNIT, cores=cores, kind='port', detail=detail,
                                         sample='%d of %d particles through the per-image stages + a %dx%d block of the '

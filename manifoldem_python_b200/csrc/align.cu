@@ -207,8 +207,7 @@ __global__ void __launch_bounds__(256) k_prefilter_rows(const float* __restrict_
 
 // columns: CTA = 32 columns x S row-segments of up to 16 rows; a thread keeps its segment of one column
 // in registers (loads coalesced across the 32 columns), carries go through shared memory. In place.
-constexpr int COL_E = 16;
-template <int MAXT, int MINB>
+template <int MAXT, int MINB, int COL_E>
 __global__ void __launch_bounds__(MAXT, MINB) k_prefilter_cols(float* __restrict__ data, int N, int L, SegGeom g) {
   __shared__ float ends[32][33];
   const int lane = threadIdx.x & 31;
@@ -539,8 +538,8 @@ static SegGeom make_geom(int L, int E) {
 static int prefilter_run(mem_ctx* ctx, const float* in, float* out, int nS, int N, int apply_mask, int mirror,
                          cudaStream_t st) {
   const int L = mirror ? 2 * N - 2 : N;
-  if (L > 512 || N < 16) {
-    set_error("box size %d is not supported by the spline prefilter (16 <= N <= 512; RELION shift: N <= 257)", N);
+  if (L > 1024 || N > 512 || N < 16) {
+    set_error("box size %d is not supported by the spline prefilter (16 <= N <= 512)", N);
     return 1;
   }
   const int E = (L + 31) / 32;
@@ -560,9 +559,11 @@ static int prefilter_run(mem_ctx* ctx, const float* in, float* out, int nS, int 
     }
   } else if (E <= 4) MEM_LAUNCH(ctx, k_prefilter_rows<4>, grid, 256, 0, st, in, out, N, L, gr, apply_mask);
   else if (E <= 8) MEM_LAUNCH(ctx, k_prefilter_rows<8>, grid, 256, 0, st, in, out, N, L, gr, apply_mask);
-  else MEM_LAUNCH(ctx, k_prefilter_rows<16>, grid, 256, 0, st, in, out, N, L, gr, apply_mask);
-  // columns: segments of <= 16 rows, S = ceil(N / 16) <= 32 segments per column
-  const int S = (L + COL_E - 1) / COL_E;
+  else if (E <= 16) MEM_LAUNCH(ctx, k_prefilter_rows<16>, grid, 256, 0, st, in, out, N, L, gr, apply_mask);
+  else MEM_LAUNCH(ctx, k_prefilter_rows<32>, grid, 256, 0, st, in, out, N, L, gr, apply_mask);
+  // columns: segments of <= 16 rows (<= 32 rows for lines longer than 512), at most 32 segments per column
+  const int CE = L <= 512 ? 16 : 32;
+  const int S = (L + CE - 1) / CE;
   const int Ec = (L + S - 1) / S;
   const SegGeom gc = make_geom(L, Ec);
   const dim3 gcols((N + 31) / 32, nS);
@@ -571,9 +572,11 @@ static int prefilter_run(mem_ctx* ctx, const float* in, float* out, int nS, int 
     else MEM_LAUNCH(ctx, k_prefilter_cols_x<16>, gcols, 512, 0, st, out, gc.zE);
     return 0;
   }
-  auto kc_small = k_prefilter_cols<512, 2>;
-  auto kc_large = k_prefilter_cols<1024, 1>;
-  if (gc.used <= 16) MEM_LAUNCH(ctx, kc_small, gcols, 32 * gc.used, 0, st, out, N, L, gc);
+  auto kc_small = k_prefilter_cols<512, 2, 16>;
+  auto kc_large = k_prefilter_cols<1024, 1, 16>;
+  auto kc_long = k_prefilter_cols<1024, 1, 32>;
+  if (CE == 32) MEM_LAUNCH(ctx, kc_long, gcols, 32 * gc.used, 0, st, out, N, L, gc);
+  else if (gc.used <= 16) MEM_LAUNCH(ctx, kc_small, gcols, 32 * gc.used, 0, st, out, N, L, gc);
   else MEM_LAUNCH(ctx, kc_large, gcols, 32 * gc.used, 0, st, out, N, L, gc);
   return 0;
 }

@@ -92,6 +92,23 @@ def test_golden_relion(env, golden_dir):
     _check_fields(res, ref)
 
 
+@pytest.mark.parametrize('N', [100, 300])
+def test_relion_shift_large_boxes(env, N):
+    """RELION branch at box sizes whose mirror extension (2N-2) takes the long-line prefilter kernels."""
+    _lib, pd_stage, synthetic = env
+    nS = 6
+    pd = synthetic.make_pd(nS, N, seed=50 + N, snr=1.0)
+    rng = np.random.default_rng(N)
+    sh = (rng.uniform(-4, 4, nS), rng.uniform(-4, 4, nS))
+    stack3d = pd['stack'].reshape(nS, N, N)
+    em = pd['em']
+    res = pd_stage.run_pd(pd['ind'], pd['q'], pd['df'], stack3d, pd['nStot'], N, em['pix_size'], em['Cs'], em['EkV'],
+                          em['AmpContrast'], relion=True, sh=sh)
+    ref = _oracle(dict(pd, stack=stack3d), N, relion=True, sh=sh, rotate_impl='periodic')
+    _check_D(res['D'], ref['D'])
+    _check_fields(res, ref)
+
+
 @pytest.mark.parametrize('nS,N,snr,seed', [(150, 64, 0.1, 2), (257, 64, 10.0, 5), (300, 128, 10.0, 3), (129, 96, 0.5, 7)])
 def test_oracle_parity_tc(env, nS, N, snr, seed):
     """tcgen05 3xTF32 product path vs the float64 oracle, noisy and low-noise (worst cancellation)."""
