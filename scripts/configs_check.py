@@ -81,6 +81,35 @@ if 'c3' in sys.argv:
 if 'c5' in sys.argv:
     run_shape(6000, 320, reps=1)
 
+if 'c5full' in sys.argv:
+    # BASELINE config 5, one PD at full size: 20,000 particles x 320^2 (8.2 GB of raw particles, ~60 GB of workspace).
+    # The particle stack is generated on the device with torch (host RNG would take minutes); torch only allocates.
+    import torch
+    nS, N = 20000, 320
+    pds, rng = bench.make_inputs(nS, N, 1, seed=5)
+    pd = pds[0]
+    g = torch.Generator(device='cuda:0').manual_seed(5)
+    raw_t = torch.randn((nS, N * N), dtype=torch.float32, device='cuda:0', generator=g)
+    D_t = torch.empty((nS, nS), dtype=torch.float32, device='cuda:0')
+    torch.cuda.synchronize()
+    flip = _lib.DeviceArray(ctx, (nS,), np.uint8, pd['flip'])
+    psi = _lib.DeviceArray(ctx, (nS,), np.float64, pd['psi_deg'])
+    df = _lib.DeviceArray(ctx, (nS,), np.float64, pd['df'])
+    prm = bench.pd_params(_lib, nS, N, pd['psi_p'])
+    io = _lib.PdIO()
+    io.raw, io.flip, io.psi_deg, io.df, io.D = raw_t.data_ptr(), flip.ptr, psi.ptr, df.ptr, D_t.data_ptr()
+    for r in range(2):
+        ctx.timer_start()
+        _lib.check(lib.mem_pd_distance_device(ctx.handle, C.byref(prm), C.byref(io), None))
+        ms = ctx.timer_stop()
+    free, total = torch.cuda.mem_get_info(0)
+    sub = D_t[:2000, :2000]
+    assert torch.equal(sub, sub.T) and float(D_t.diagonal().abs().max()) < 1e-5 * float(D_t.max())
+    assert bool(torch.isfinite(D_t).all()) and float(D_t.min()) > -1e-5 * float(D_t.max())
+    print('C5 PD %d x %d^2: %.1f ms -> %.3f Gpairs/s; stages %s; device memory in use %.1f GB of %.1f GB' %
+          (nS, N, ms, nS * nS / ms / 1e6, {k: round(v, 1) for k, v in ctx.timings().items() if v > 0},
+           (total - free) / 1e9, total / 1e9))
+
 if 'demo' in sys.argv:
     for N in (128, 256):
         for nS in (117, 206, 450):      # min / median / max occupancy of the demo's 53 PDs

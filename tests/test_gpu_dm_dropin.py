@@ -201,3 +201,54 @@ def test_resident_chain_distance_to_knn():
     assert np.allclose(ls1, ls_o, rtol=1e-12, atol=1e-12)
     for a in (Dd, M1, M2):
         a.free()
+
+
+def test_manifold_trimming_dropin(tmp_path):
+    """manifoldTrimmingAuto.op drop-in (modules/manifoldTrimmingAuto.py:38-95) on a PD pickle written by the
+    distance worker: same trimming loop, psi pickle keys, marker and eig_spec file; the final embedding matches the
+    same loop run on the CPU oracle."""
+    from manifoldem_python_b200 import manifoldTrimmingAuto as mta, getDistanceCTF_local_Conj9combinedS2 as worker
+    from manifoldem_python_b200 import myio, p, synthetic
+    from oracle import dm_embedding as odm
+    N, nS = 32, 90
+    pd = synthetic.make_pd(nS, N, seed=61, snr=2.0)
+    p.init()
+    p.user_dir, p.proj_name = str(tmp_path), 'trim'
+    p.create_dir()
+    em = pd['em']
+    p.nPix, p.pix_size, p.Cs, p.EkV, p.AmpContrast = N, em['pix_size'], em['Cs'], em['EkV'], em['AmpContrast']
+    stack_file = str(tmp_path / 'stack.dat')
+    pd['stack'].tofile(stack_file)
+    dist_file = '{}prD_{}'.format(p.dist_file, 0)
+    worker.op([pd['ind'], pd['q'], pd['df'], dist_file, 0], dict(type='Butter', Qc=0.5, N=8), stack_file, pd['sh'],
+              pd['nStot'], dict(verbose=False, avgOnly=False, visual=False, parallel=False, relion_data=False, thres=2000),
+              fields=('D',))
+    psi_file = '{}prD_{}'.format(p.psi_file, 0)
+    eig_file = str(tmp_path / 'eig_spec.txt')
+    rad = 3.0                                                       # small enough to trigger the trimming loop (6 passes)
+    np.random.seed(5)
+    mta.op([dist_file, psi_file, eig_file, 0], 0, 3.0, rad, False, dict(outputFile='', Is=True))
+    rec = myio.fin1(psi_file)
+    assert list(rec.keys()) == ['lamb', 'psi', 'sigma', 'mu', 'posPath', 'ind', 'logEps', 'logSumWij', 'popt', 'R_squared']
+    assert os.path.exists(os.path.join(p.psi_prog, '0'))
+    n_keep = len(rec['posPath'])
+    assert 3 < n_keep <= nS and rec['psi'].shape[0] == n_keep and rec['mu'].shape == (n_keep,)
+    assert np.all(np.sqrt((rec['psi'][:, :3] ** 2).sum(1)) < rad)
+    lines = open(eig_file).read().strip().splitlines()
+    assert len(lines) == len(rec['lamb']) - 1 and lines[0].split()[0] == '1'
+    # the same loop on the oracle
+    D = myio.fin1(dist_file)['D']
+    np.random.seed(5)
+    pos = np.arange(nS)
+    out = odm.dm_embedding(D.copy(), nS, 3.0)
+    psi = out[1]
+    pos1 = mta.get_psiPath(psi, rad, 0)
+    n = nS
+    while len(pos1) < n:
+        n = len(pos1)
+        D1 = D[pos1][:, pos1]
+        out = odm.dm_embedding(D1.copy(), n, 3.0)
+        pos1 = pos1[mta.get_psiPath(out[1], rad, 0)]
+    assert np.array_equal(rec['posPath'], pos[pos1])
+    for j in range(3):
+        assert abs(np.corrcoef(rec['psi'][:, j], out[1][:, j])[0, 1]) >= 0.9999
