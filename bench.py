@@ -99,6 +99,34 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
+def measure_cublas_tf32(index):
+    """cuBLAS TF32 GEMM (8192^3, best of 5 after warm-up) measured in this run, next to the roofline's official
+    denominator (MEASURED_PEAKS.json has no TF32 entry): context for the reader, not the `peak` field."""
+    try:
+        import torch
+        dev = torch.device('cuda', index)
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn(8192, 8192, device=dev)
+        b = torch.randn(8192, 8192, device=dev)
+        for _ in range(2):
+            a @ b
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        torch.backends.cuda.matmul.allow_tf32 = old
+        del a, b
+        torch.cuda.empty_cache()
+        return 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+    except Exception:
+        return None
+
+
 def bind_to_gpu_numa_node(index):
     """Pin this rank's host threads to the CPUs NVML reports as local to its GPU, so that the pinned host
     stacks of the e2e leg live on that socket (8 ranks otherwise share one socket's memory controllers)."""
@@ -345,6 +373,7 @@ def run_b200(args):
 
     if rank == 0:
         peaks, peak_src = load_peaks()
+        tf32_cublas = measure_cublas_tf32(local)
         # executed TF32 tensor flops of one contraction launch: items x (128x256 tile) x K x 2 x 3 passes
         flops_launch = float(k_items) * 128 * 256 * 2 * 3 * 32.0 * k_kb      # CTAs x tile x K per CTA x 3 passes
         k_avg_ms = k_ms / max(1, k_n)
@@ -366,6 +395,7 @@ def run_b200(args):
                     roofline=dict(bound='tensor', kernel='k_contract_tc2 (tcgen05 cta_group::2 kind::tf32, 3 passes)',
                                   achieved=achieved, peak=peak, unit='TFLOP/s', frac=(achieved / peak) if achieved else None,
                                   traffic=traffic, avg_launch_ms=k_avg_ms, launches=k_n,
+                                  cublas_tf32_tflops_measured_in_run=tf32_cublas,
                                   # hardware ceiling at the clock sampled during the run: 148 SMs x 2048 TF32 MAC/clk x 2
                                   frac_of_hw_rate_at_sampled_clock=(achieved / (148 * 2048 * 2 * clocks['sm_mhz'] * 1e6 / 1e12))
                                   if (achieved and clocks and clocks.get('sm_mhz')) else None,
