@@ -139,6 +139,9 @@ int mem_ferguson_device(mem_ctx* ctx, const double* d2, int64_t n, const double*
  * W = exp(-M/sigma^2) on the graph support (M >= 0 entries; negative = no edge), alpha = 1
  * normalisation, symmetric normalisation, L = |L + L^T|/2.  M, L: [nS][nS] float64 device. */
 int mem_laplacian_dense_device(mem_ctx* ctx, const double* M, int32_t nS, double sigma, double* L, void* stream);
+/* a19 operator application for the host eigen-solver (sembeddingonFly.op :27, scipy ARPACK eigsh): y = L x with
+ * L [nS][nS] float64 on the device, x and y [nS] float64 on the HOST.  Synchronises. */
+int mem_symv_host(mem_ctx* ctx, const double* L, int32_t nS, const double* x, double* y);
 
 #ifdef __cplusplus
 }

@@ -90,15 +90,33 @@ def graph_and_sweep(D, k, ctx=None, nS=None):
     return M, logEps, logSumWij, idx, val
 
 
-def laplacian(M, nS, sigma, ctx=None):
-    """slaplacianonFly.op on the device, dense (nS,nS) float64 result on the host."""
+def laplacian(M, nS, sigma, ctx=None, resident=False):
+    """slaplacianonFly.op on the device: dense (nS,nS) float64 L, downloaded to the host or (resident=True)
+    left on the device as a `_lib.DeviceArray`."""
     lib = _lib.load()
     ctx = ctx or _ctx()
     L = _lib.DeviceArray(ctx, (nS, nS), np.float64)
     _lib.check(lib.mem_laplacian_dense_device(ctx.handle, M.ptr, nS, float(sigma), L.ptr, None))
+    if resident:
+        return L
     out = L.download()
     L.free()
     return out
+
+
+def device_operator(L_dev, nS, ctx=None):
+    """scipy LinearOperator whose matvec runs on the device (L never leaves it): ARPACK stays on the host and
+    follows the reference's own eigsh call, only the O(nS^2) operator application moves."""
+    from scipy.sparse.linalg import LinearOperator
+    lib = _lib.load()
+    ctx = ctx or _ctx()
+    y = np.empty(nS, dtype=np.float64)
+
+    def matvec(x):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        _lib.check(lib.mem_symv_host(ctx.handle, L_dev.ptr, nS, x.ctypes.data, y.ctypes.data))
+        return y.copy()
+    return LinearOperator((nS, nS), matvec=matvec, dtype=np.float64)
 
 
 def op(D, k, tune, prefsigma):
@@ -111,13 +129,15 @@ def op(D, k, tune, prefsigma):
     popt, resnorm, R_squared = _fit(logEps, logSumWij, a0)
     nEigs = min(getattr(p, 'num_eigs', 15), nS - 3)                              # :149
     sigma = tune * np.sqrt(2 * np.exp(-popt[1] / popt[0]))                       # :158
-    L = laplacian(M, nS, sigma)
+    L = laplacian(M, nS, sigma, resident=True)
     M.free()
     try:
-        vals, vecs = eigsh(L, k=nEigs + 1, maxiter=300)                          # sembeddingonFly.py:27
+        vals, vecs = eigsh(device_operator(L, nS), k=nEigs + 1, maxiter=300)     # sembeddingonFly.py:27
     except ArpackNoConvergence as e:
         vals, vecs = e.eigenvalues, e.eigenvectors
         print("eigsh not converging in 300 iterations...")
+    finally:
+        L.free()
     ix = np.argsort(vals)[::-1]
     lamb = np.sort(vals)[::-1]
     v = vecs[:, ix]

@@ -16,7 +16,7 @@ SYMBOLS = [
     'mem_ctx_timer_start', 'mem_ctx_timer_stop', 'mem_ctx_kernel_time', 'mem_host_alloc', 'mem_host_free', 'mem_dev_alloc', 'mem_dev_free', 'mem_copy_h2d', 'mem_copy_d2h',
     'mem_pd_distance_device', 'mem_pd_distance_host', 'mem_pd_last_timings', 'mem_contract_device',
     'mem_operand_shape', 'mem_knn_device', 'mem_knn_device_f32', 'mem_graph_dense_device', 'mem_graph_compact_device', 'mem_ferguson_device',
-    'mem_laplacian_dense_device',
+    'mem_laplacian_dense_device', 'mem_symv_host',
 ]
 
 
@@ -86,6 +86,7 @@ def load():
         lib.mem_ferguson_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_double,
                                             C.c_void_p]
         lib.mem_laplacian_dense_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]
+        lib.mem_symv_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         _lib = lib
         return lib
 

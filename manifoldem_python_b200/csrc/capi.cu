@@ -14,6 +14,7 @@ int graph_compact_device(mem_ctx* ctx, const double* M, int nS, double* out, lon
 int graph_dense_device(mem_ctx* ctx, const int* idx, const double* val, int nS, int k, double* M, cudaStream_t st);
 int ferguson_device(mem_ctx* ctx, const double* d2, int64_t n, const double* logEps, int nEps, double thr, double* out);
 int laplacian_dense_device(mem_ctx* ctx, const double* M, int nS, double sigma, double* L, cudaStream_t st);
+int symv_host(mem_ctx* ctx, const double* L, int nS, const double* x_host, double* y_host);
 }  // namespace mem
 
 using namespace mem;
@@ -273,6 +274,10 @@ int mem_ferguson_device(mem_ctx* ctx, const double* d2, int64_t n, const double*
 int mem_laplacian_dense_device(mem_ctx* ctx, const double* M, int32_t nS, double sigma, double* L, void* stream) {
   MEM_CUDA(cudaSetDevice(ctx->device));
   return laplacian_dense_device(ctx, M, nS, sigma, L, pick(ctx, stream));
+}
+int mem_symv_host(mem_ctx* ctx, const double* L, int32_t nS, const double* x, double* y) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  return symv_host(ctx, L, nS, x, y);
 }
 
 }  // extern "C"

@@ -297,4 +297,32 @@ int laplacian_dense_device(mem_ctx* ctx, const double* M, int nS, double sigma, 
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// a19 helper: y = L x for the dense symmetric L that stays on the device.  ARPACK (scipy eigsh,
+// sembeddingonFly.py:27) keeps running on the host exactly as in the reference, but its O(nS^2) operator
+// application happens here, one warp per row in a fixed summation order (deterministic).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_symv(const double* __restrict__ L, const double* __restrict__ x,
+                                              double* __restrict__ y, int nS) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= nS) return;
+  const double* r = L + (size_t)row * nS;
+  double acc = 0.0;
+  for (int j = lane; j < nS; j += 32) acc = fma(r[j], x[j], acc);
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) y[row] = acc;
+}
+
+int symv_host(mem_ctx* ctx, const double* L, int nS, const double* x_host, double* y_host) {
+  cudaStream_t st = ctx->stream;
+  MEM_CHECK(ctx->small_out.ensure((size_t)2 * nS * sizeof(double)));
+  double* dx = ctx->small_out.as<double>();
+  double* dy = dx + nS;
+  MEM_CUDA(cudaMemcpyAsync(dx, x_host, (size_t)nS * sizeof(double), cudaMemcpyHostToDevice, st));
+  MEM_LAUNCH(ctx, k_symv, (nS + 7) / 8, 256, 0, st, L, dx, dy, nS);
+  MEM_CUDA(cudaMemcpyAsync(y_host, dy, (size_t)nS * sizeof(double), cudaMemcpyDeviceToHost, st));
+  MEM_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 }  // namespace mem

@@ -72,13 +72,15 @@ int geometry_prepare(mem_ctx* ctx, int N, int filter_type, int filter_order, dou
       r2[ky * Nh + kx] = v;
       r2max = std::max(r2max, v);
     }
+  // bins numbered by the address of their first pixel (not by radius): consecutive threads of the radial
+  // operand kernel then start their gathers at neighbouring addresses; the column order of S1/S2 is arbitrary
+  // as long as both use the same one
   std::vector<int> bin_id(r2max + 1, -1);
-  for (int p = 0; p < Kh; ++p) bin_id[r2[p]] = 0;
   std::vector<int> r2_of_bin;
-  for (int v = 0; v <= r2max; ++v)
-    if (bin_id[v] == 0) {
-      bin_id[v] = (int)r2_of_bin.size();
-      r2_of_bin.push_back(v);
+  for (int p = 0; p < Kh; ++p)
+    if (bin_id[r2[p]] < 0) {
+      bin_id[r2[p]] = (int)r2_of_bin.size();
+      r2_of_bin.push_back(r2[p]);
     }
   const int Kr = (int)r2_of_bin.size();
   std::vector<int> bin_of_pix(Kh), bin_start(Kr + 1, 0), bin_pix(Kh);
