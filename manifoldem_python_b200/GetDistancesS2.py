@@ -70,8 +70,22 @@ def _gpu_worker(device, jobs, filterPar, imgFileName, sh, size, options, cfg):
     p = _cfg()
     for k, v in cfg.items():
         setattr(p, k, v)
-    for job in jobs:
-        worker.op(job, filterPar, imgFileName, sh, size, options)
+    _run_jobs(jobs, filterPar, imgFileName, sh, size, options, p.nPix, None)
+
+
+def _run_jobs(jobs, filterPar, imgFileName, sh, size, options, nPix, on_done):
+    """The PDs of one GPU, a few in flight: the float64 conversion + pickle dump of PD k (host; NumPy and file I/O
+    release the GIL) overlaps the device work of PD k+1.  Every host thread owns its context (stream + workspace).
+    Small PDs are launch/latency-bound: 4 streams double the throughput at nS ~ 200 (scripts/overlap_test.py)."""
+    from concurrent.futures import ThreadPoolExecutor, as_completed
+    work = float(np.median([len(j[0]) for j in jobs])) * nPix * nPix if jobs else 0.0
+    inflight = max(1, int(os.environ.get('MANIFOLDEM_B200_INFLIGHT', '4' if work < 3e7 else '2')))
+    with ThreadPoolExecutor(max_workers=inflight) as pool:
+        futs = [pool.submit(worker.op, job, filterPar, imgFileName, sh, size, options) for job in jobs]
+        for fut in as_completed(futs):
+            fut.result()                                                             # re-raise worker errors
+            if on_done is not None:
+                on_done()
 
 
 _CFG_KEYS = ('nPix', 'pix_size', 'Cs', 'EkV', 'AmpContrast', 'gaussEnv', 'mask_vol_file', 'dist_prog', 'dist_file',
@@ -102,19 +116,13 @@ def op(*argv):
 
     n_workers = min(_n_gpus(), max(1, int(getattr(p, 'ncpu', 1))), max(1, len(input_data)))
     if n_workers <= 1:
-        # :102-108, with two PDs in flight on the one GPU: the float64 conversion + pickle dump of PD k (host,
-        # GIL released in NumPy / file I/O) overlaps the device work of PD k+1; each host thread owns its context
-        # small PDs are launch/latency-bound: 4 streams double the throughput at nS ~ 200 (scripts/overlap_test.py)
-        work = float(np.median([len(j[0]) for j in input_data])) * p.nPix * p.nPix if input_data else 0.0
-        inflight = max(1, int(os.environ.get('MANIFOLDEM_B200_INFLIGHT', '4' if work < 3e7 else '2')))
-        from concurrent.futures import ThreadPoolExecutor, as_completed
-        with ThreadPoolExecutor(max_workers=inflight) as pool:
-            futs = [pool.submit(worker.op, job, filterPar, p.img_stack_file, sh, size, options) for job in input_data]
-            for fut in as_completed(futs):
-                fut.result()                                                         # re-raise worker errors
-                offset += 1
-                if progress is not None:
-                    progress.emit(int((offset / float(p.numberofJobs)) * 100))
+        state = {'offset': offset}                                                   # :102-108
+
+        def on_done():
+            state['offset'] += 1
+            if progress is not None:
+                progress.emit(int((state['offset'] / float(p.numberofJobs)) * 100))
+        _run_jobs(input_data, filterPar, p.img_stack_file, sh, size, options, p.nPix, on_done)
     else:
         costs = [partition.pd_cost(len(job[0]), p.nPix) for job in input_data]
         shards = partition.lpt_partition(costs, n_workers)

@@ -1,0 +1,66 @@
+"""GetDistancesS2.op on a box with several GPUs: p.ncpu caps the worker count, one spawned process per GPU,
+static LPT partition, markers as the only gather.  python scripts/multigpu_driver_check.py [n_gpus]"""
+import os
+import pickle
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    from manifoldem_python_b200 import GetDistancesS2, myio, p, synthetic
+    n_gpus = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+    N = 64
+    sizes = (150, 90, 200, 120, 60, 180, 75)
+    pds = [synthetic.make_pd(n, N, seed=30 + i, snr=0.5) for i, n in enumerate(sizes)]
+    n_half = sum(pd['nStot'] // 2 for pd in pds)
+    stack = np.concatenate([pd['stack'] for pd in pds])
+    q = np.zeros((4, 2 * n_half))
+    df = np.zeros(2 * n_half)
+    CG, off = [], 0
+    for pd in pds:
+        h = pd['nStot'] // 2
+        base = np.where(pd['ind'] >= h, pd['ind'] - h, pd['ind']) + off
+        ind = np.where(pd['ind'] >= h, base + n_half, base)
+        q[:, ind] = pd['q']
+        df[ind] = pd['df']
+        CG.append(ind)
+        off += h
+    with tempfile.TemporaryDirectory() as tmp:
+        p.init()
+        p.user_dir, p.proj_name = tmp, 'multi'
+        p.create_dir()
+        em = pds[0]['em']
+        p.pix_size, p.Cs, p.EkV, p.AmpContrast = em['pix_size'], em['Cs'], em['EkV'], em['AmpContrast']
+        p.relion_data, p.ncpu, p.num_part = False, n_gpus, n_half
+        p.img_stack_file = os.path.join(tmp, 'stack.dat')
+        stack.tofile(p.img_stack_file)
+        p.numberofJobs = len(CG)
+        myio.fout1(p.tess_file, ['CG', 'df', 'q', 'sh'], [CG, df, q, (np.zeros(n_half), np.zeros(n_half))])
+
+        class Sig:
+            vals = []
+
+            def emit(self, v):
+                self.vals.append(v)
+        t0 = time.time()
+        GetDistancesS2.op(Sig())
+        dt = time.time() - t0
+        assert sorted(int(f) for f in os.listdir(p.dist_prog)) == list(range(len(CG)))
+        assert Sig.vals[-1] == 100
+        for prD in range(len(CG)):
+            with open('{}prD_{}'.format(p.dist_file, prD), 'rb') as f:
+                rec = pickle.load(f)
+            nS = len(CG[prD])
+            assert rec['D'].shape == (nS, nS) and np.array_equal(rec['D'], rec['D'].T) and np.isfinite(rec['D']).all()
+        print('GetDistancesS2.op with p.ncpu=%d on %d visible GPUs: %d PDs in %.1f s (incl. worker spawn + CUDA init), '
+              'all markers present, progress %s' % (n_gpus, GetDistancesS2._n_gpus(), len(CG), dt, Sig.vals[-3:]))
+
+
+if __name__ == '__main__':
+    main()

@@ -109,7 +109,8 @@ def test_relion_shift_large_boxes(env, N):
     _check_fields(res, ref)
 
 
-@pytest.mark.parametrize('nS,N,snr,seed', [(150, 64, 0.1, 2), (257, 64, 10.0, 5), (300, 128, 10.0, 3), (129, 96, 0.5, 7)])
+@pytest.mark.parametrize('nS,N,snr,seed', [(150, 64, 0.1, 2), (257, 64, 10.0, 5), (300, 128, 10.0, 3), (129, 96, 0.5, 7),
+                                           (24, 320, 0.5, 8), (40, 256, 0.2, 9)])
 def test_oracle_parity_tc(env, nS, N, snr, seed):
     """tcgen05 3xTF32 product path vs the float64 oracle, noisy and low-noise (worst cancellation)."""
     _lib, pd_stage, synthetic = env
