@@ -70,7 +70,9 @@ typedef struct {
   double  psi_p_deg;     /* psi_ang(PD), degrees                                   (:313) */
   int32_t avg_only;      /* options['avgOnly']: skip D                             (:376) */
   int32_t contraction;   /* 0 = tcgen05 3xTF32, CTA-pair tiles (product); 1 = SIMT fp64-accumulate checker; 2 = tcgen05 single-CTA tiles */
-  int32_t k_chunk_blocks;/* tcgen05: K blocks (of 32) accumulated in TMEM before promotion; 0 = default */
+  int32_t k_chunk_blocks;/* tcgen05: K blocks (of 32) accumulated in TMEM before promotion to FP32 registers;
+                            low byte = period inside the S1/S2 columns, bits 8.. = period inside S3 (0 = same);
+                            0 = default (CTA pairs: 2 | 4 << 8, single CTA: 1) */
   int32_t split_k;       /* tcgen05: K slices per tile; 0 = auto (fill 148 SMs)                  */
 } mem_pd_params;
 

@@ -77,6 +77,11 @@ struct Geometry {
   DevBuf bin_pix;             // [Kh] int32 pixels sorted by bin
   DevBuf s3_col;              // [Kh] int32: column (in floats, relative to Z row) of the re part, or -1
   DevBuf special_pix;         // [4] int32
+  // rows ky and N-ky share |k|^2: the folded quadrant [Na][Nh], Na = N/2+1, is what the radial sums gather from
+  int Na = 0;
+  DevBuf fold_bin;            // [Na*Nh] int32 bin of the folded entry
+  DevBuf fold_start;          // [Kr+1] int32
+  DevBuf fold_ent;            // [Na*Nh] int32 folded entries sorted by bin
 };
 
 struct FftPlan { cufftHandle r2c = 0, c2r = 0; };

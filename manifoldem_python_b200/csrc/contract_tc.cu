@@ -110,8 +110,10 @@ k_contract_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * STAGE_BYTES + 64);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const WorkItem it = items[blockIdx.x];
-  const int nkb = it.kb1 - it.kb0;
-  const int nchunks = (nkb + chunk - 1) / chunk;
+  // promotion period: `chunk & 255` k-blocks inside the S1/S2 columns, `chunk >> 8` (if set) inside S3
+  const int c12 = chunk & 255, c3 = (chunk >> 8) ? (chunk >> 8) : c12;
+  const int kmid = min(max(2 * n1, it.kb0), it.kb1);
+  const int nchunks = (kmid - it.kb0 + c12 - 1) / c12 + (it.kb1 - kmid + c3 - 1) / c3;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
@@ -169,7 +171,7 @@ k_contract_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         mbar_wait(bars + 8 * (6 + buf), (((uint32_t)(c >> 1)) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tacc = tmem_base + buf * BN;
-        const int kend = min(it.kb1, kb + chunk);
+        const int kend = kb < kmid ? min(kmid, kb + c12) : min(it.kb1, kb + c3);
         bool first = true;
         for (; kb < kend; ++kb) {
           const uint32_t idesc = make_idesc(kb >= 2 * n1);
@@ -310,8 +312,10 @@ k_contract_tc2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const WorkItem it = items[blockIdx.x >> 1];
-  const int nkb = it.kb1 - it.kb0;
-  const int nchunks = (nkb + chunk - 1) / chunk;
+  // promotion period: `chunk & 255` k-blocks inside the S1/S2 columns, `chunk >> 8` (if set) inside S3
+  const int c12 = chunk & 255, c3 = (chunk >> 8) ? (chunk >> 8) : c12;
+  const int kmid = min(max(2 * n1, it.kb0), it.kb1);
+  const int nchunks = (kmid - it.kb0 + c12 - 1) / c12 + (it.kb1 - kmid + c3 - 1) / c3;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
@@ -369,7 +373,7 @@ k_contract_tc2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
         mbar_wait(bars + 8 * (8 + buf), (((uint32_t)(c >> 1)) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tacc = tmem_base + buf * BN;
-        const int kend = min(it.kb1, kb + chunk);
+        const int kend = kb < kmid ? min(kmid, kb + c12) : min(it.kb1, kb + c3);
         bool first = true;
         for (; kb < kend; ++kb) {
           const uint32_t idesc = make_idesc2(kb >= 2 * n1);
@@ -516,7 +520,9 @@ int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, c
   }
   // default promotion period: 1 k-block for single-CTA tiles; 2 for CTA pairs, whose accumulator hand-over crosses
   // the cluster twice per chunk (commit multicast + remote arrive ~ 650 clk) and needs the longer chunk to hide it
-  const int chunk = k_chunk_blocks > 0 ? k_chunk_blocks : (two_cta ? 2 : 1);
+  // The S3 columns (mixed-sign products, 78 % of K) tolerate 4 blocks per promotion at the same measured accuracy
+  // (scripts/gpu_debug.py chunk3): code = period(S1,S2) | period(S3) << 8.
+  const int chunk = k_chunk_blocks > 0 ? k_chunk_blocks : (two_cta ? (2 | 4 << 8) : 1);
   // tiles of the upper triangle (any element with col >= row)
   std::vector<std::pair<int, int>> tiles;
   const int TM = two_cta ? 2 * BM : BM;                  // tile rows: a CTA pair covers 256
@@ -528,7 +534,7 @@ int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, c
   const int T = (int)tiles.size();
   int split = split_k;
   if (split <= 0) {
-    const int min_kb = 4 * chunk;
+    const int min_kb = 4 * (chunk & 255);
     double best = -1;
     split = 1;
     for (int s = 1; s <= 32; ++s) {

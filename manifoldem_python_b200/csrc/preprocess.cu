@@ -131,6 +131,25 @@ int geometry_prepare(mem_ctx* ctx, int N, int filter_type, int filter_order, dou
     if (s3_col[p] >= 0) s3_col[p] = 64 * n1_blocks + 2 * s3_col[p];
   while (special.size() < 4) special.push_back(-1);
 
+  // folded quadrant (rows a and N-a share |k|^2): CSR of its entries by bin
+  const int Na = N / 2 + 1, Kq = Na * Nh;
+  std::vector<int> fold_bin(Kq), fold_start(Kr + 1, 0), fold_ent(Kq);
+  for (int e = 0; e < Kq; ++e) {
+    fold_bin[e] = bin_of_pix[e];          // row a <= N/2 of the half spectrum has |fy| = a
+    fold_start[fold_bin[e] + 1]++;
+  }
+  for (int b = 0; b < Kr; ++b) fold_start[b + 1] += fold_start[b];
+  {
+    std::vector<int> fill(fold_start.begin(), fold_start.end() - 1);
+    for (int e = 0; e < Kq; ++e) fold_ent[fill[fold_bin[e]]++] = e;
+  }
+  MEM_CHECK(g.fold_bin.ensure(Kq * sizeof(int)));
+  MEM_CHECK(g.fold_start.ensure((Kr + 1) * sizeof(int)));
+  MEM_CHECK(g.fold_ent.ensure(Kq * sizeof(int)));
+  MEM_CUDA(cudaMemcpy(g.fold_bin.p, fold_bin.data(), Kq * sizeof(int), cudaMemcpyHostToDevice));
+  MEM_CUDA(cudaMemcpy(g.fold_start.p, fold_start.data(), (Kr + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  MEM_CUDA(cudaMemcpy(g.fold_ent.p, fold_ent.data(), Kq * sizeof(int), cudaMemcpyHostToDevice));
+  g.Na = Na;
   MEM_CHECK(g.Gtab.ensure(Kh * sizeof(float)));
   MEM_CHECK(g.bin_of_pix.ensure(Kh * sizeof(int)));
   MEM_CHECK(g.r2_of_bin.ensure(Kr * sizeof(int)));
@@ -292,6 +311,92 @@ __global__ void k_operands_radial(const float2* __restrict__ spec, const float2*
   split_tf32(s2, h, l);
   zhi[(size_t)i * ldz + w1 + b] = h;
   zlo[(size_t)i * ldz + w1 + b] = l;
+}
+
+// Same operands, one block per image.  Pass 1 reads the spectrum coalesced, two rows (ky = a and N - a, which share
+// |k|^2 and therefore the CTF value) per folded row, and leaves w (|G(a,kx)|^2 + |G(N-a,kx)|^2), G = F - C M, in
+// shared memory: (N/2+1) x Nh floats, 66 KB at N = 256, so three blocks share an SM.  Pass 2 gathers every bin's
+// entries from shared memory in a fixed order.  The global gather of the kernel above uses a quarter of every
+// 32-byte sector and one CTF lookup per pixel; this one is bound by the spectrum read.
+constexpr int RADIAL_THREADS = 512;
+__global__ void __launch_bounds__(RADIAL_THREADS, 2)
+k_operands_radial_sm(const float2* __restrict__ spec, const float2* __restrict__ Mspec, const float* __restrict__ cbin,
+                     const int* __restrict__ fold_bin, const int* __restrict__ fold_start,
+                     const int* __restrict__ fold_ent, const int* __restrict__ bin_of_pix,
+                     const int* __restrict__ special_pix, float* __restrict__ zhi, float* __restrict__ zlo, int N,
+                     int Nh, int Na, int Kh, int Kr, int n_special, int n1_blocks, int64_t ldz) {
+  extern __shared__ float pw[];
+  const int i = blockIdx.x;
+  const int w1 = 32 * n1_blocks;
+  const float2* F = spec + (size_t)i * Kh;
+  const int Kq = Na * Nh;
+  float* cb = pw + Kq;                       // this image's CTF row, staged so the per-entry lookups stay on chip
+  for (int b = threadIdx.x; b < Kr; b += RADIAL_THREADS) cb[b] = cbin[(size_t)i * Kr + b];
+  __syncthreads();
+  const int nyq = (N & 1) ? -1 : N / 2;
+  const int step_x = RADIAL_THREADS % Nh, step_a = RADIAL_THREADS / Nh;
+  int a = threadIdx.x / Nh, kx = threadIdx.x % Nh;
+  // four entries per thread and trip, every load issued before the first use (the kernel is latency-bound otherwise)
+  constexpr int U = 4;
+  for (int e0 = threadIdx.x; e0 < Kq; e0 += U * RADIAL_THREADS) {
+    float2 f[U], f2[U], mm[U], m2[U];
+    int bn[U];
+    float wself[U], wpart[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = e0 + u * RADIAL_THREADS;
+      const bool valid = e < Kq;
+      const int ec = valid ? e : 0;
+      const bool part = valid && a != 0 && 2 * a != N;
+      const int e2 = part ? (N - a) * Nh + kx : ec;     // no partner row: re-read the entry itself with weight 0
+      const float w = (kx == 0 || kx == nyq) ? 1.0f : 2.0f;
+      wself[u] = w;
+      wpart[u] = part ? w : 0.0f;
+      bn[u] = fold_bin[ec];
+      f[u] = F[ec];
+      mm[u] = Mspec[ec];
+      f2[u] = F[e2];
+      m2[u] = Mspec[e2];
+      kx += step_x;
+      a += step_a;
+      if (kx >= Nh) { kx -= Nh; ++a; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = e0 + u * RADIAL_THREADS;
+      if (e < Kq) {
+        const float c = cb[bn[u]];
+        const float gx = fmaf(-c, mm[u].x, f[u].x), gy = fmaf(-c, mm[u].y, f[u].y);
+        const float hx = fmaf(-c, m2[u].x, f2[u].x), hy = fmaf(-c, m2[u].y, f2[u].y);
+        pw[e] = wself[u] * (gx * gx + gy * gy) + wpart[u] * (hx * hx + hy * hy);
+      }
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < w1; b += RADIAL_THREADS) {
+    float s1 = 0.0f, s2 = 0.0f;
+    if (b < Kr) {
+      const float c = cb[b];
+      s1 = 0.25f * c * c;
+      float acc = 0.0f;
+      const int q1 = fold_start[b + 1];
+      for (int q = fold_start[b]; q < q1; ++q) acc += pw[fold_ent[q]];
+      s2 = acc;
+    } else if (b < Kr + n_special) {
+      const int p = special_pix[b - Kr];
+      const float cs = cb[bin_of_pix[p]];
+      const float x = cs * fmaf(-cs, Mspec[p].x, F[p].x);
+      s1 = -0.25f * x;
+      s2 = x;
+    }
+    float h, l;
+    split_tf32(s1, h, l);
+    zhi[(size_t)i * ldz + b] = h;
+    zlo[(size_t)i * ldz + b] = l;
+    split_tf32(s2, h, l);
+    zhi[(size_t)i * ldz + w1 + b] = h;
+    zlo[(size_t)i * ldz + w1 + b] = l;
+  }
 }
 
 // a11 partial sums (pass 1 over the spectra).  Thread = one half-spectrum pixel, loops over the images of
@@ -566,9 +671,17 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
   MEM_LAUNCH(ctx, k_avg_spectra, (g.Kh + 255) / 256, 256, 0, st, ctx->part_cf.as<double2>(), part_cfw,
              ctx->part_c2.as<double>(), ctx->part_fl.as<double2>(), ctx->avgspec.as<float2>(), Mspec, g.Kh, G);
   if (want_D) {
-    MEM_LAUNCH(ctx, k_operands_radial, dim3((32 * g.n1_blocks + 255) / 256, nS), 256, 0, st, spec, Mspec,
-               ctx->cbin.as<float>(), g.bin_start.as<int>(), g.bin_pix.as<int>(), g.bin_of_pix.as<int>(),
-               g.special_pix.as<int>(), zhi, zlo, N, g.Nh, g.Kh, g.Kr, g.n_special, g.n1_blocks, g.ldz);
+    const size_t pw_bytes = ((size_t)g.Na * g.Nh + g.Kr) * sizeof(float);
+    if (pw_bytes <= 200 * 1024) {
+      MEM_CUDA(cudaFuncSetAttribute(k_operands_radial_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pw_bytes));
+      MEM_LAUNCH(ctx, k_operands_radial_sm, nS, RADIAL_THREADS, pw_bytes, st, spec, Mspec, ctx->cbin.as<float>(),
+                 g.fold_bin.as<int>(), g.fold_start.as<int>(), g.fold_ent.as<int>(), g.bin_of_pix.as<int>(),
+                 g.special_pix.as<int>(), zhi, zlo, N, g.Nh, g.Na, g.Kh, g.Kr, g.n_special, g.n1_blocks, g.ldz);
+    } else {   // boxes above ~ 450 px: the folded power map does not fit shared memory
+      MEM_LAUNCH(ctx, k_operands_radial, dim3((32 * g.n1_blocks + 255) / 256, nS), 256, 0, st, spec, Mspec,
+                 ctx->cbin.as<float>(), g.bin_start.as<int>(), g.bin_pix.as<int>(), g.bin_of_pix.as<int>(),
+                 g.special_pix.as<int>(), zhi, zlo, N, g.Nh, g.Kh, g.Kr, g.n_special, g.n1_blocks, g.ldz);
+    }
     const int from = 64 * g.n1_blocks + 2 * g.K3;
     if (from < g.ldz) MEM_LAUNCH(ctx, k_zero_tail, nS, 64, 0, st, zhi, zlo, nS, g.ldz, from);
   }

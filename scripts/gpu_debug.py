@@ -57,7 +57,7 @@ def report_pd(nS, N, seed, snr, contraction, chunk=0, split=0, msk=False, impl='
     return res, ref
 
 
-def contraction_timing(nS, N, reps=5):
+def contraction_timing(nS, N, reps=5, kinds=(0, 2), chunks=(1, 2, 3, 4, 8)):
     lib = _lib.load()
     ctx = _lib.default_context()
     shp = _lib.ContractShape()
@@ -71,8 +71,8 @@ def contraction_timing(nS, N, reps=5):
     zhi = _lib.DeviceArray(ctx, Z.shape, np.float32, hi)
     zlo = _lib.DeviceArray(ctx, Z.shape, np.float32, lo)
     Dd = _lib.DeviceArray(ctx, (nS, nS), np.float32)
-    for kind in (0, 2):
-        for chunk in (1, 2, 3, 4, 8):
+    for kind in kinds:
+        for chunk in chunks:
             for _ in range(2):
                 _lib.check(lib.mem_contract_device(ctx.handle, C.byref(shp), zhi.ptr, zlo.ptr, Dd.ptr, kind, chunk, 0, None))
             ctx.sync()
@@ -88,6 +88,13 @@ def contraction_timing(nS, N, reps=5):
 
 
 if __name__ == '__main__':
+    if 'chunk3' in sys.argv:      # promotion period per column group: code = c12 | c3 << 8
+        codes = (2, 2 | 4 << 8, 2 | 8 << 8, 2 | 16 << 8, 1 | 8 << 8, 1 | 16 << 8, 8)
+        for case in ((300, 128, 3, 10.0), (300, 128, 3, 0.1), (200, 256, 7, 10.0), (600, 64, 8, 100.0)):
+            for code in codes:
+                report_pd(*case, contraction=0, chunk=code, fields=False)
+        contraction_timing(2000, 256, kinds=(0,), chunks=codes)
+        sys.exit(0)
     if 'tc2' in sys.argv:
         report_pd(40, 32, 0, 0.1, contraction=2, impl='tile', fields=False)
         report_pd(40, 32, 0, 0.1, contraction=0, impl='tile', fields=False)
