@@ -57,7 +57,8 @@ int mem_ctx_destroy(mem_ctx* ctx) {
                          &ctx->zlo, &ctx->part_cf, &ctx->part_cfw, &ctx->part_c2, &ctx->part_fl, &ctx->part_int, &ctx->avgspec, &ctx->avgimg,
                          &ctx->stats, &ctx->D, &ctx->ctf64, &ctx->small_out, &ctx->contract_ws, &ctx->contract_items, &ctx->scratch,
                          &ctx->geom.Gtab, &ctx->geom.bin_of_pix, &ctx->geom.r2_of_bin, &ctx->geom.bin_start,
-                         &ctx->geom.bin_pix, &ctx->geom.s3_col, &ctx->geom.special_pix};
+                         &ctx->geom.bin_pix, &ctx->geom.s3_col, &ctx->geom.special_pix, &ctx->geom.fold_bin,
+                         &ctx->geom.fold_start, &ctx->geom.fold_ent, &ctx->knn_ws};
   for (auto* b : bufs) b->release();
   for (auto& e : ctx->ev) cudaEventDestroy(e);
   for (auto& e : ctx->timer) cudaEventDestroy(e);

@@ -105,6 +105,7 @@ struct mem_ctx {
   mem::DevBuf contract_items;   // work-item table of the last contraction shape
   long long items_key[4] = {-1, -1, -1, -1};   // nS, nkb, split, count
   mem::DevBuf scratch;       // misc (ferguson partials, knn)
+  mem::DevBuf knn_ws;        // (key, index) rows of the chunked sort, only for nS > 16,384
   cudaEvent_t ev[10] = {};
   cudaEvent_t timer[2] = {};
   std::vector<cudaEvent_t> kev;   // event pairs around every contraction launch since the last reset

@@ -51,6 +51,104 @@ __global__ void __launch_bounds__(1024) k_knn_sort(const T* __restrict__ D, int 
   }
 }
 
+// Rows longer than one shared-memory sort (nS > 16,384): the same bitonic network over P = 2^m padded entries, cut
+// into chunks of KNN_CH.  Every compare-exchange with stride < KNN_CH stays inside a chunk and runs in shared
+// memory; the log2(P / KNN_CH) levels above it take one pass per stride >= KNN_CH through the (key, index) rows in
+// global memory.  Same (value, index) order as k_knn_sort, so ties resolve identically.
+constexpr int KNN_CH = 16384;
+
+template <class T>
+__device__ __forceinline__ void knn_cmpx(T* key, int* id, int lo, int hi, bool up) {
+  const T a = key[lo], b = key[hi];
+  const int ia = id[lo], ib = id[hi];
+  const bool gt = (a > b) || (a == b && ia > ib);
+  if (gt == up) {
+    key[lo] = b; key[hi] = a;
+    id[lo] = ib; id[hi] = ia;
+  }
+}
+
+// grid (P / KNN_CH, nS).  first != 0: load the chunk from D and run every level up to KNN_CH; otherwise load it from
+// the workspace and finish level `size` (strides KNN_CH/2 .. 1).  last != 0: the chunk holding ranks < k writes idx/val.
+template <class T>
+__global__ void __launch_bounds__(1024) k_knn_chunk(const T* __restrict__ D, int nS, int P, int k, int size, int first,
+                                                    int last, T* __restrict__ wkey, int* __restrict__ wid,
+                                                    int* __restrict__ idx, double* __restrict__ val) {
+  extern __shared__ uint8_t sm_raw[];
+  T* key = reinterpret_cast<T*>(sm_raw);
+  int* id = reinterpret_cast<int*>(sm_raw + (size_t)KNN_CH * sizeof(T));
+  const int i = blockIdx.y, base = blockIdx.x * KNN_CH;
+  T* gk = wkey + (size_t)i * P + base;
+  int* gi = wid + (size_t)i * P + base;
+  if (first) {
+    const T* row = D + (size_t)i * nS;
+    for (int t = threadIdx.x; t < KNN_CH; t += blockDim.x) {
+      const int j = base + t;
+      T v = (T)INFINITY;
+      if (j < nS) v = (j == i) ? (T)(-INFINITY) : row[j];
+      key[t] = v;
+      id[t] = j;
+    }
+  } else {
+    for (int t = threadIdx.x; t < KNN_CH; t += blockDim.x) {
+      key[t] = gk[t];
+      id[t] = gi[t];
+    }
+  }
+  __syncthreads();
+  for (int sz = first ? 2 : size; sz <= (first ? KNN_CH : size); sz <<= 1) {
+    for (int stride = min(sz, KNN_CH) >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (KNN_CH >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));
+        knn_cmpx(key, id, lo, lo + stride, (((base + lo) & sz) == 0));
+      }
+      __syncthreads();
+    }
+  }
+  if (last) {
+    for (int t = threadIdx.x; t < KNN_CH; t += blockDim.x) {
+      const int a = base + t;
+      if (a < k) {
+        idx[(size_t)i * k + a] = id[t];
+        val[(size_t)i * k + a] = (a == 0) ? 0.0 : (double)key[t];
+      }
+    }
+  } else {
+    for (int t = threadIdx.x; t < KNN_CH; t += blockDim.x) {
+      gk[t] = key[t];
+      gi[t] = id[t];
+    }
+  }
+}
+
+// one compare-exchange pass of level `size` at a stride >= KNN_CH; grid (P / 2 / 256, nS)
+template <class T>
+__global__ void __launch_bounds__(256) k_knn_global_step(T* __restrict__ wkey, int* __restrict__ wid, int P, int size,
+                                                         int stride) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (P >> 1)) return;
+  const int lo = 2 * t - (t & (stride - 1));
+  knn_cmpx(wkey + (size_t)blockIdx.y * P, wid + (size_t)blockIdx.y * P, lo, lo + stride, ((lo & size) == 0));
+}
+
+template <class T>
+static int knn_chunked(mem_ctx* ctx, const T* D, int nS, int P, int k, int* idx, double* val, cudaStream_t st) {
+  const size_t rows = (size_t)nS * P;
+  MEM_CHECK(ctx->knn_ws.ensure(rows * (sizeof(T) + sizeof(int))));
+  T* wkey = ctx->knn_ws.as<T>();
+  int* wid = reinterpret_cast<int*>(wkey + rows);
+  const size_t smem = (size_t)KNN_CH * (sizeof(T) + sizeof(int));
+  MEM_CUDA(cudaFuncSetAttribute(k_knn_chunk<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const dim3 gc(P / KNN_CH, nS), gs((P / 2 + 255) / 256, nS);
+  MEM_LAUNCH(ctx, k_knn_chunk<T>, gc, 1024, smem, st, D, nS, P, k, 0, 1, 0, wkey, wid, idx, val);
+  for (int size = 2 * KNN_CH; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride >= KNN_CH; stride >>= 1)
+      MEM_LAUNCH(ctx, k_knn_global_step<T>, gs, 256, 0, st, wkey, wid, P, size, stride);
+    MEM_LAUNCH(ctx, k_knn_chunk<T>, gc, 1024, smem, st, D, nS, P, k, size, 0, size == P ? 1 : 0, wkey, wid, idx, val);
+  }
+  return 0;
+}
+
 template <class T>
 static int knn_device_t(mem_ctx* ctx, const T* D, int nS, int k, int* idx, double* val, cudaStream_t st) {
   if (k < 1 || k > nS) {
@@ -59,11 +157,8 @@ static int knn_device_t(mem_ctx* ctx, const T* D, int nS, int k, int* idx, doubl
   }
   int P = 1;
   while (P < nS) P <<= 1;
+  if (P > KNN_CH) return knn_chunked<T>(ctx, D, nS, P, k, idx, val, st);
   const size_t smem = (size_t)P * (sizeof(double) + sizeof(int));
-  if (smem > 200 * 1024) {
-    set_error("knn: nS=%d exceeds the in-shared-memory sort (max 16384 points)", nS);
-    return 1;
-  }
   MEM_CUDA(cudaFuncSetAttribute(k_knn_sort<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int threads = std::max(32, std::min(1024, P / 2));
   MEM_LAUNCH(ctx, k_knn_sort<T>, nS, threads, smem, st, D, nS, P, k, idx, val);

@@ -83,6 +83,34 @@ def test_knn_ties_and_errors():
         _lib.check(lib.mem_knn_device(ctx.handle, None, 10, 11, None, None, None))
 
 
+@pytest.mark.parametrize('nS,dtype', [(16500, np.float32), (20000, np.float32), (16390, np.float64)])
+def test_knn_rows_longer_than_one_smem_sort(nS, dtype):
+    """C5-sized PDs (nS = 20,000): the chunked bitonic network (shared-memory chunks + global strides) gives the
+    same (value, index) order as a host sort, duplicates included."""
+    from manifoldem_python_b200 import _lib
+    lib, ctx = _lib.load(), _lib.default_context()
+    rng = np.random.default_rng(nS)
+    D = rng.integers(0, 4000, size=(nS, nS)).astype(dtype)                    # many exact ties per row
+    D = np.maximum(D, D.T)
+    k = 257
+    Dd = _lib.DeviceArray(ctx, (nS, nS), dtype, D)
+    idx_d = _lib.DeviceArray(ctx, (nS, k), np.int32)
+    val_d = _lib.DeviceArray(ctx, (nS, k), np.float64)
+    fn = lib.mem_knn_device_f32 if dtype == np.float32 else lib.mem_knn_device
+    _lib.check(fn(ctx.handle, Dd.ptr, nS, k, idx_d.ptr, val_d.ptr, None))
+    idx, val = idx_d.download(), val_d.download()
+    for a in (Dd, idx_d, val_d):
+        a.free()
+    for i in list(range(0, nS, 1237)) + [nS - 1]:
+        row = D[i].astype(np.float64)
+        row[i] = -np.inf
+        order = np.lexsort((np.arange(nS), row))[:k]
+        assert np.array_equal(idx[i], order), i
+        expect = row[order]
+        expect[0] = 0.0
+        assert np.array_equal(val[i], expect), i
+
+
 def test_dropin_worker_and_driver(tmp_path):
     """GetDistancesS2.op -> getDistanceCTF_local_Conj9combinedS2.op: pickle keys/shapes/dtypes as the
     reference writes them, markers after the dump, finished PDs skipped on a second run."""
