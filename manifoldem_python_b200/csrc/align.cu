@@ -11,6 +11,7 @@ namespace mem {
 // One CTA per particle.  Pass 1: moments in fp64 (rows over warps, float4 over lanes).  Pass 2: every
 // warp transposes 32x32 tiles through its own shared-memory buffer (no block barriers).
 // ------------------------------------------------------------------------------------------------
+template <bool FULL>   // FULL: N is a multiple of 32 (no edge predicates, 32-bit offsets)
 __global__ void __launch_bounds__(256) k_ingest(const float* __restrict__ raw, const uint8_t* __restrict__ flip,
                                                 float* __restrict__ out, int N, int transposed) {
   __shared__ double red[16];
@@ -22,18 +23,22 @@ __global__ void __launch_bounds__(256) k_ingest(const float* __restrict__ raw, c
   const float half = 0.5f * N, r2lim = half * half;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   double s = 0, s2 = 0;
+  // Pixels inside the disc contribute 0.  Per warp row the fp32 partial sums of <= N values are promoted to fp64 once.
   for (int a = warp; a < N; a += nw) {
+    float rs = 0.0f, rs2 = 0.0f;
+    const float* rowp = src + a * N;
     for (int b = lane; b < N; b += 32) {
       int r = transposed ? b : a;
       const int c = transposed ? a : b;
       if (fl) r = N - 1 - r;
       const float x = (float)r - half + 1.0f, y = (float)c - half;   // annularMask.py:24-30, centre (N/2-1, N/2)
-      const float v = src[(size_t)a * N + b];
-      if (!(x * x + y * y < r2lim)) {
-        s += v;
-        s2 += (double)v * v;
-      }
+      const float v = rowp[b];
+      const float m = (x * x + y * y < r2lim) ? 0.0f : v;
+      rs += m;
+      rs2 = fmaf(m, m, rs2);
     }
+    s += (double)rs;
+    s2 += (double)rs2;
   }
   for (int o = 16; o > 0; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -53,20 +58,18 @@ __global__ void __launch_bounds__(256) k_ingest(const float* __restrict__ raw, c
     const int tr = (t / nt) * 32, tc = (t % nt) * 32;   // output tile origin (rows r', cols c)
     if (transposed) {
       float v[32];
+      const int rp0 = tr + lane;
+      const float* sp = src + tc * N + (fl ? N - 1 - rp0 : rp0);   // raw index = c*N + r : lanes run along r
 #pragma unroll
-      for (int k = 0; k < 32; ++k) {                    // raw index = c*N + r : lanes run along r
-        const int c = tc + k, rp = tr + lane;
-        const int r = fl ? N - 1 - rp : rp;
-        v[k] = (c < N && rp < N) ? src[(size_t)c * N + r] : 0.0f;
-      }
+      for (int k = 0; k < 32; ++k)
+        v[k] = (FULL || (tc + k < N && rp0 < N)) ? sp[k * N] : 0.0f;
 #pragma unroll
       for (int k = 0; k < 32; ++k) tile[warp][k][lane] = v[k];
       __syncwarp();
+      float* dp = dst + tr * N + tc + lane;
 #pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const int rp = tr + k, c = tc + lane;
-        if (rp < N && c < N) dst[(size_t)rp * N + c] = (tile[warp][lane][k] - fm) * inv;
-      }
+      for (int k = 0; k < 32; ++k)
+        if (FULL || (tr + k < N && tc + lane < N)) dp[k * N] = (tile[warp][lane][k] - fm) * inv;
       __syncwarp();
     } else {
 #pragma unroll 8
@@ -516,7 +519,8 @@ __global__ void __launch_bounds__(256) k_rotate(const float* __restrict__ coef, 
 // ------------------------------------------------------------------------------------------------
 int ingest_run(mem_ctx* ctx, const float* raw, const uint8_t* flip, float* out, int nS, int N, int transposed,
                cudaStream_t st) {
-  MEM_LAUNCH(ctx, k_ingest, nS, 256, 0, st, raw, flip, out, N, transposed);
+  if (N % 32 == 0) MEM_LAUNCH(ctx, k_ingest<true>, nS, 256, 0, st, raw, flip, out, N, transposed);
+  else MEM_LAUNCH(ctx, k_ingest<false>, nS, 256, 0, st, raw, flip, out, N, transposed);
   return 0;
 }
 
