@@ -430,14 +430,11 @@ __global__ void k_angles(const double* __restrict__ psi_deg, double psi_p_deg, d
 // Bank = (i*P + j) mod 32 with lanes stepping by (sin, cos) per output column: P = 65 gives bank = i + j, which
 // advances by |sin + cos| >= 1 per lane when sin*cos >= 0; P = 63 gives j - i for the other two quadrants.
 constexpr int ROT_T = 32, ROT_B = 50, ROT_PMAX = 65;
-template <bool FULL>
-__global__ void __launch_bounds__(256) k_rotate(const float* __restrict__ coef, float* __restrict__ out,
-                                                const double2* __restrict__ cs, int cs_stride, int N,
-                                                const uint8_t* __restrict__ msk2, float* __restrict__ out_masked) {
-  __shared__ float tile[ROT_B * ROT_PMAX];
+template <bool FULL, int ROT_P>   // the pitch is a compile-time constant so the 16 taps use immediate offsets
+__device__ __forceinline__ void rotate_tile(float* __restrict__ tile, const double2 a, const float* __restrict__ coef,
+                                            float* __restrict__ out, int N, const uint8_t* __restrict__ msk2,
+                                            float* __restrict__ out_masked) {
   const int img = blockIdx.z;
-  const double2 a = cs[(size_t)img * cs_stride];
-  const int ROT_P = (a.x * a.y >= 0.0) ? 65 : 63;
   const double ctr = 0.5 * (N - 1);
   const int r0 = blockIdx.y * ROT_T, c0 = blockIdx.x * ROT_T;
   // source coordinates of the tile corners -> bounding box origin (floor(min) - 1); every thread computes it
@@ -512,6 +509,16 @@ __global__ void __launch_bounds__(256) k_rotate(const float* __restrict__ coef, 
     x0 += DX0;
     x1 += DX1;
   }
+}
+
+template <bool FULL>
+__global__ void __launch_bounds__(256) k_rotate(const float* __restrict__ coef, float* __restrict__ out,
+                                                const double2* __restrict__ cs, int cs_stride, int N,
+                                                const uint8_t* __restrict__ msk2, float* __restrict__ out_masked) {
+  __shared__ float tile[ROT_B * ROT_PMAX];
+  const double2 a = cs[(size_t)blockIdx.z * cs_stride];
+  if (a.x * a.y >= 0.0) rotate_tile<FULL, 65>(tile, a, coef, out, N, msk2, out_masked);
+  else rotate_tile<FULL, 63>(tile, a, coef, out, N, msk2, out_masked);
 }
 
 // ------------------------------------------------------------------------------------------------

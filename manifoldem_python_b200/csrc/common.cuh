@@ -117,7 +117,11 @@ struct mem_ctx {
 
 namespace mem {
 int geometry_prepare(mem_ctx* ctx, int N, int filter_type, int filter_order, double Qc);
-int fft_get(mem_ctx* ctx, int N, int batch, FftPlan* out);
+int fft_get(mem_ctx* ctx, int N, int batch, FftPlan* out, bool rows_only = false);
+// column pass of the low-pass on the row-transformed half spectra: FFT along ky, * G, inverse FFT, in place.
+// Returns false when the box size has no specialised kernel (the caller keeps the 2-D cuFFT path).
+bool colfilter_supported(int N);
+int colfilter_run(mem_ctx* ctx, float2* spec, const float* G, int nS, int N, cudaStream_t st);
 int contract_run(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, const float* Zlo, float* D,
                  int contraction, int k_chunk_blocks, int split_k, cudaStream_t st);
 int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, const float* Zlo, float* D,

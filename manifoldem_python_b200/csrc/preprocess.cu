@@ -170,8 +170,9 @@ int geometry_prepare(mem_ctx* ctx, int N, int filter_type, int filter_order, dou
   return 0;
 }
 
-int fft_get(mem_ctx* ctx, int N, int batch, FftPlan* out) {
-  long long key = ((long long)N << 24) + batch;
+// rows_only: batch x N one-dimensional transforms of length N (the row pass of the fused low-pass, lowpass.cu)
+int fft_get(mem_ctx* ctx, int N, int batch, FftPlan* out, bool rows_only) {
+  long long key = ((long long)N << 24) + batch + (rows_only ? (1LL << 60) : 0);
   auto it = ctx->plans.find(key);
   if (it != ctx->plans.end()) {
     *out = it->second;
@@ -179,13 +180,14 @@ int fft_get(mem_ctx* ctx, int N, int batch, FftPlan* out) {
   }
   FftPlan pl;
   int n[2] = {N, N};
+  const int rank = rows_only ? 1 : 2, count = rows_only ? batch * N : batch;
   size_t ws1 = 0, ws2 = 0;
   MEM_CUFFT(cufftCreate(&pl.r2c));
   MEM_CUFFT(cufftSetAutoAllocation(pl.r2c, 0));
-  MEM_CUFFT(cufftMakePlanMany(pl.r2c, 2, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, batch, &ws1));
+  MEM_CUFFT(cufftMakePlanMany(pl.r2c, rank, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, count, &ws1));
   MEM_CUFFT(cufftCreate(&pl.c2r));
   MEM_CUFFT(cufftSetAutoAllocation(pl.c2r, 0));
-  MEM_CUFFT(cufftMakePlanMany(pl.c2r, 2, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_C2R, batch, &ws2));
+  MEM_CUFFT(cufftMakePlanMany(pl.c2r, rank, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_C2R, count, &ws2));
   MEM_CHECK(ctx->fft_work.ensure(std::max(ws1, ws2)));
   // the work area may have moved: re-attach it to every plan
   ctx->plans[key] = pl;
@@ -414,20 +416,34 @@ __global__ void __launch_bounds__(256) k_spec_sums(const float2* __restrict__ sp
   const int b = bin_of_pix[p];
   double2 scf = make_double2(0, 0), scw = make_double2(0, 0), sfl = make_double2(0, 0);
   double sc2 = 0;
-  for (int i = i0; i < i1; ++i) {
-    const float c = cbin[(size_t)i * Kr + b];
-    const float2 f = spec[(size_t)i * Kh + p];
-    const float sg = (c > 0.0f) ? 1.0f : ((c < 0.0f) ? -1.0f : 0.0f);
-    scf.x += (double)(c * f.x);
-    scf.y += (double)(c * f.y);
-    if (specw) {
-      const float2 fw = specw[(size_t)i * Kh + p];
-      scw.x += (double)(c * fw.x);
-      scw.y += (double)(c * fw.y);
+  constexpr int U = 4;                       // loads of four images in flight per thread (latency, not HBM, binds otherwise)
+  for (int ib = i0; ib < i1; ib += U) {
+    float cu[U];
+    float2 fu[U], fwu[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = min(ib + u, i1 - 1);
+      cu[u] = cbin[(size_t)i * Kr + b];
+      fu[u] = spec[(size_t)i * Kh + p];
+      if (specw) fwu[u] = specw[(size_t)i * Kh + p];
     }
-    sc2 += (double)(c * c);
-    sfl.x += (double)(sg * f.x);
-    sfl.y += (double)(sg * f.y);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (ib + u < i1) {
+        const float c = cu[u];
+        const float2 f = fu[u];
+        const float sg = (c > 0.0f) ? 1.0f : ((c < 0.0f) ? -1.0f : 0.0f);
+        scf.x += (double)(c * f.x);
+        scf.y += (double)(c * f.y);
+        if (specw) {
+          scw.x += (double)(c * fwu[u].x);
+          scw.y += (double)(c * fwu[u].y);
+        }
+        sc2 += (double)(c * c);
+        sfl.x += (double)(sg * f.x);
+        sfl.y += (double)(sg * f.y);
+      }
+    }
   }
   part_cf[(size_t)g * Kh + p] = scf;
   if (specw) part_cfw[(size_t)g * Kh + p] = scw;
@@ -451,20 +467,35 @@ __global__ void __launch_bounds__(256) k_operands_s3(float2* __restrict__ spec, 
   const int b = bin_of_pix[p];
   const int col = s3_col[p];
   const float2 m = Mspec[p];
-  for (int i = i0; i < i1; ++i) {
-    const float c = cbin[(size_t)i * Kr + b];
-    const float2 f = spec[(size_t)i * Kh + p];
-    if (flip) {
-      const float sg = (c > 0.0f) ? 1.0f : ((c < 0.0f) ? -1.0f : 0.0f);
-      spec[(size_t)i * Kh + p] = make_float2(sg * f.x, sg * f.y);
+  // four images per trip, all loads ahead of the (possibly aliasing, in-place) stores: with one image per trip the
+  // kernel is bound by load latency, not by HBM
+  constexpr int U = 4;
+  for (int ib = i0; ib < i1; ib += U) {
+    float c[U];
+    float2 f[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = min(ib + u, i1 - 1);
+      c[u] = cbin[(size_t)i * Kr + b];
+      f[u] = spec[(size_t)i * Kh + p];
     }
-    if (write_z && col >= 0) {
-      const float gx = fmaf(-c, m.x, f.x), gy = fmaf(-c, m.y, f.y);
-      float2 h, l;
-      split_tf32(c * gx, h.x, l.x);
-      split_tf32(c * gy, h.y, l.y);
-      *reinterpret_cast<float2*>(zhi + (size_t)i * ldz + col) = h;
-      *reinterpret_cast<float2*>(zlo + (size_t)i * ldz + col) = l;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = ib + u;
+      if (i < i1) {
+        if (flip) {
+          const float sg = (c[u] > 0.0f) ? 1.0f : ((c[u] < 0.0f) ? -1.0f : 0.0f);
+          spec[(size_t)i * Kh + p] = make_float2(sg * f[u].x, sg * f[u].y);
+        }
+        if (write_z && col >= 0) {
+          const float gx = fmaf(-c[u], m.x, f[u].x), gy = fmaf(-c[u], m.y, f[u].y);
+          float2 h, l;
+          split_tf32(c[u] * gx, h.x, l.x);
+          split_tf32(c[u] * gy, h.y, l.y);
+          *reinterpret_cast<float2*>(zhi + (size_t)i * ldz + col) = h;
+          *reinterpret_cast<float2*>(zlo + (size_t)i * ldz + col) = l;
+        }
+      }
     }
   }
 }
@@ -538,13 +569,14 @@ __global__ void k_small_outputs(const float* __restrict__ avgimg, const double* 
 // ------------------------------------------------------------------------------------------------
 // host pipeline
 // ------------------------------------------------------------------------------------------------
-static int run_fft(mem_ctx* ctx, int N, int nS, bool forward, float* real, float2* cplx, cudaStream_t st) {
+static int run_fft(mem_ctx* ctx, int N, int nS, bool forward, float* real, float2* cplx, cudaStream_t st,
+                   bool rows_only = false) {
   const int Kh = N * (N / 2 + 1);
   const int BMAX = 1024;
   for (int i0 = 0; i0 < nS; i0 += BMAX) {
     const int b = std::min(BMAX, nS - i0);
     FftPlan pl;
-    MEM_CHECK(fft_get(ctx, N, b, &pl));
+    MEM_CHECK(fft_get(ctx, N, b, &pl, rows_only));
     if (forward) {
       MEM_CUFFT(cufftSetStream(pl.r2c, st));
       MEM_CUFFT(cufftExecR2C(pl.r2c, real + (size_t)i0 * N * N, reinterpret_cast<cufftComplex*>(cplx + (size_t)i0 * Kh)));
@@ -637,13 +669,19 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
     MEM_CHECK(ingest_run(ctx, io->raw, io->flip, A, nS, N, prm->transposed, st));
   }
   // ---- a5 low-pass: A -> spec -> *G -> B
-  MEM_CHECK(run_fft(ctx, N, nS, true, A, spec, st));
-  {
+  if (colfilter_supported(N)) {
+    // rows by cuFFT (1-D R2C / C2R), the whole column pass — FFT, * G, inverse FFT — in one kernel of ours: the
+    // spectrum makes one round trip through HBM between the row passes instead of three
+    MEM_CHECK(run_fft(ctx, N, nS, true, A, spec, st, true));
+    MEM_CHECK(colfilter_run(ctx, spec, g.Gtab.as<float>(), nS, N, st));
+    MEM_CHECK(run_fft(ctx, N, nS, false, B, spec, st, true));
+  } else {
+    MEM_CHECK(run_fft(ctx, N, nS, true, A, spec, st));
     const size_t total = (size_t)nS * Kh;
     const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 16);
     MEM_LAUNCH(ctx, k_specmul, grid, 256, 0, st, spec, g.Gtab.as<float>(), (int)Kh, total);
+    MEM_CHECK(run_fft(ctx, N, nS, false, B, spec, st));
   }
-  MEM_CHECK(run_fft(ctx, N, nS, false, B, spec, st));
   MEM_CUDA(cudaEventRecord(ctx->ev[1], st));
   // ---- a7 alignment: two periodic cubic-spline rotations
   MEM_CHECK(align_run(ctx, A, B, imgAll, io->psi_deg, prm->psi_p_deg, cs, io->msk2, nS, N, st));
