@@ -445,39 +445,51 @@ __device__ __forceinline__ void rotate_tile(float* __restrict__ tile, const doub
   const float* src = coef + (size_t)img * N * N;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   {
-    // periodic wrap of the box origin: |o| < 2N for every box size >= 32, smaller boxes take the loop
+    // Periodic wrap of the box origin.  Source coordinates stay within ctr +- N/sqrt(2), so -N < o < 2N, and every
+    // index below exceeds N by less than 2N for N >= 16 (the smallest box the prefilter takes): conditional
+    // adds instead of modulo arithmetic, and two running row pointers instead of one 64-bit address per load.
     int w0m = o0, w1m = o1;
-    while (w0m < 0) w0m += N;
-    while (w1m < 0) w1m += N;
+    w0m += (w0m < 0) ? N : 0;
+    w0m -= (w0m >= N) ? N : 0;
+    w1m += (w1m < 0) ? N : 0;
+    w1m -= (w1m >= N) ? N : 0;
     int gx0 = w1m + lane;
-    while (gx0 >= N) gx0 -= N;
+    gx0 -= (gx0 >= N) ? N : 0;
+    gx0 -= (gx0 >= N) ? N : 0;
     int gx1 = gx0 + 32;
-    while (gx1 >= N) gx1 -= N;
+    gx1 -= (gx1 >= N) ? N : 0;
+    gx1 -= (gx1 >= N) ? N : 0;
     int gy = w0m + wrp;
-    while (gy >= N) gy -= N;
-    const int step = 8 % N;
-    int ti = wrp * ROT_P + lane;
+    gy -= (gy >= N) ? N : 0;
+    const float* p0 = src + (gy * N + gx0);
+    const float* p1 = src + (gy * N + gx1);
+    const int fwd = 8 * N, back = 8 * N - N * N;
+    float* tp = tile + wrp * ROT_P + lane;
     const bool second = lane + 32 < ROT_B;
 #pragma unroll
     for (int it = 0; it < (ROT_B + 7) / 8; ++it) {
       if (it * 8 + wrp < ROT_B) {                      // warp-uniform
-        const int rowoff = gy * N;
-        tile[ti] = __ldg(src + rowoff + gx0);
-        if (second) tile[ti + 32] = __ldg(src + rowoff + gx1);
+        tp[it * 8 * ROT_P] = __ldg(p0);
+        if (second) tp[it * 8 * ROT_P + 32] = __ldg(p1);
       }
-      gy += step;
-      if (gy >= N) gy -= N;
-      ti += 8 * ROT_P;
+      gy += 8;
+      const bool wrap = gy >= N;
+      gy -= wrap ? N : 0;
+      const int adv = wrap ? back : fwd;
+      p0 += adv;
+      p1 += adv;
     }
   }
   __syncthreads();
   const int c = c0 + lane;
   const double xb0 = a.x * ((r0 + wrp) - ctr) + a.y * (c - ctr) + ctr - (double)o0;   // row coordinate, bbox-relative
   const double xb1 = -a.y * ((r0 + wrp) - ctr) + a.x * (c - ctr) + ctr - (double)o1;  // column coordinate
-  // 32.32 fixed point from here on (coordinates are in [1, 48)): integer part = tap origin, low word = fraction.
-  // The 4 outputs of a thread are 8 rows apart: one 64-bit add per axis instead of fp64 floor/convert chains.
-  long long x0 = __double2ll_rn(xb0 * 4294967296.0), x1 = __double2ll_rn(xb1 * 4294967296.0);
-  const long long DX0 = __double2ll_rn(8.0 * a.x * 4294967296.0), DX1 = __double2ll_rn(-8.0 * a.y * 4294967296.0);
+  // 6.26 unsigned fixed point from here on (coordinates are in [1, 48)): high bits = tap origin, low 26 bits =
+  // fraction (1.5e-8 pixel, below the fp32 weights' resolution).  The 4 outputs of a thread are 8 rows apart: one
+  // 32-bit add per axis (modulo 2^32, so negative steps need no special case) instead of fp64 floor/convert chains.
+  unsigned int x0 = (unsigned int)__double2ll_rn(xb0 * 67108864.0), x1 = (unsigned int)__double2ll_rn(xb1 * 67108864.0);
+  const unsigned int DX0 = (unsigned int)__double2ll_rn(8.0 * a.x * 67108864.0);
+  const unsigned int DX1 = (unsigned int)__double2ll_rn(-8.0 * a.y * 67108864.0);
   const int oidx = (r0 + wrp) * N + c;                  // pixel index inside the image (N*N < 2^31)
   float* dst = out + (size_t)img * N * N + oidx;
   float* dstm = out_masked ? out_masked + (size_t)img * N * N + oidx : nullptr;
@@ -486,9 +498,9 @@ __device__ __forceinline__ void rotate_tile(float* __restrict__ tile, const doub
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     if (FULL || (r0 + wrp + 8 * q < N && c < N)) {
-      const int i0 = (int)(x0 >> 32), j0 = (int)(x1 >> 32);
-      const float t0 = (float)(unsigned int)(x0 & 0xffffffffLL) * 2.3283064365386963e-10f;
-      const float t1 = (float)(unsigned int)(x1 & 0xffffffffLL) * 2.3283064365386963e-10f;
+      const int i0 = (int)(x0 >> 26), j0 = (int)(x1 >> 26);
+      const float t0 = (float)(x0 & 0x3ffffffu) * 1.4901161193847656e-08f;
+      const float t1 = (float)(x1 & 0x3ffffffu) * 1.4901161193847656e-08f;
       float wa[4], wb[4];
       bspline_w(t0, wa);
       bspline_w(t1, wb);
