@@ -321,16 +321,23 @@ __global__ void k_operands_radial(const float2* __restrict__ spec, const float2*
 // entries from shared memory in a fixed order.  The global gather of the kernel above uses a quarter of every
 // 32-byte sector and one CTF lookup per pixel; this one is bound by the spectrum read.
 constexpr int RADIAL_THREADS = 512;
+// The same pass also writes the S3 operands A = C (F - C M) of every pixel it visits (hi/lo split, the job of
+// k_operands_s3 below) and, if FLIP, leaves sign(C) F in place for the C2R of :346-347 — the spectrum is read once
+// for all three operand groups.
+template <bool FLIP>
 __global__ void __launch_bounds__(RADIAL_THREADS, 2)
-k_operands_radial_sm(const float2* __restrict__ spec, const float2* __restrict__ Mspec, const float* __restrict__ cbin,
+k_operands_radial_sm(float2* __restrict__ spec, const float2* __restrict__ Mspec, const float* __restrict__ cbin,
                      const int* __restrict__ fold_bin, const int* __restrict__ fold_start,
                      const int* __restrict__ fold_ent, const int* __restrict__ bin_of_pix,
-                     const int* __restrict__ special_pix, float* __restrict__ zhi, float* __restrict__ zlo, int N,
-                     int Nh, int Na, int Kh, int Kr, int n_special, int n1_blocks, int64_t ldz) {
+                     const int* __restrict__ special_pix, const int* __restrict__ s3_col, float* __restrict__ zhi,
+                     float* __restrict__ zlo, int N, int Nh, int Na, int Kh, int Kr, int n_special, int n1_blocks,
+                     int64_t ldz) {
   extern __shared__ float pw[];
   const int i = blockIdx.x;
   const int w1 = 32 * n1_blocks;
-  const float2* F = spec + (size_t)i * Kh;
+  float2* F = spec + (size_t)i * Kh;
+  float* zh = zhi + (size_t)i * ldz;
+  float* zl = zlo + (size_t)i * ldz;
   const int Kq = Na * Nh;
   float* cb = pw + Kq;                       // this image's CTF row, staged so the per-entry lookups stay on chip
   for (int b = threadIdx.x; b < Kr; b += RADIAL_THREADS) cb[b] = cbin[(size_t)i * Kr + b];
@@ -339,10 +346,10 @@ k_operands_radial_sm(const float2* __restrict__ spec, const float2* __restrict__
   const int step_x = RADIAL_THREADS % Nh, step_a = RADIAL_THREADS / Nh;
   int a = threadIdx.x / Nh, kx = threadIdx.x % Nh;
   // four entries per thread and trip, every load issued before the first use (the kernel is latency-bound otherwise)
-  constexpr int U = 4;
+  constexpr int U = 2;
   for (int e0 = threadIdx.x; e0 < Kq; e0 += U * RADIAL_THREADS) {
     float2 f[U], f2[U], mm[U], m2[U];
-    int bn[U];
+    int bn[U], sc[U], sc2[U], pe2[U];
     float wself[U], wpart[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -355,6 +362,9 @@ k_operands_radial_sm(const float2* __restrict__ spec, const float2* __restrict__
       wself[u] = w;
       wpart[u] = part ? w : 0.0f;
       bn[u] = fold_bin[ec];
+      sc[u] = valid ? s3_col[ec] : -1;
+      sc2[u] = part ? s3_col[e2] : -1;
+      pe2[u] = part ? e2 : -1;
       f[u] = F[ec];
       mm[u] = Mspec[ec];
       f2[u] = F[e2];
@@ -371,6 +381,25 @@ k_operands_radial_sm(const float2* __restrict__ spec, const float2* __restrict__
         const float gx = fmaf(-c, mm[u].x, f[u].x), gy = fmaf(-c, mm[u].y, f[u].y);
         const float hx = fmaf(-c, m2[u].x, f2[u].x), hy = fmaf(-c, m2[u].y, f2[u].y);
         pw[e] = wself[u] * (gx * gx + gy * gy) + wpart[u] * (hx * hx + hy * hy);
+        if (sc[u] >= 0) {
+          float2 h, l;
+          split_tf32(c * gx, h.x, l.x);
+          split_tf32(c * gy, h.y, l.y);
+          *reinterpret_cast<float2*>(zh + sc[u]) = h;
+          *reinterpret_cast<float2*>(zl + sc[u]) = l;
+        }
+        if (sc2[u] >= 0) {
+          float2 h, l;
+          split_tf32(c * hx, h.x, l.x);
+          split_tf32(c * hy, h.y, l.y);
+          *reinterpret_cast<float2*>(zh + sc2[u]) = h;
+          *reinterpret_cast<float2*>(zl + sc2[u]) = l;
+        }
+        if (FLIP) {
+          const float sg = (c > 0.0f) ? 1.0f : ((c < 0.0f) ? -1.0f : 0.0f);
+          F[e] = make_float2(sg * f[u].x, sg * f[u].y);
+          if (pe2[u] >= 0) F[pe2[u]] = make_float2(sg * f2[u].x, sg * f2[u].y);
+        }
       }
     }
   }
@@ -387,17 +416,19 @@ k_operands_radial_sm(const float2* __restrict__ spec, const float2* __restrict__
     } else if (b < Kr + n_special) {
       const int p = special_pix[b - Kr];
       const float cs = cb[bin_of_pix[p]];
-      const float x = cs * fmaf(-cs, Mspec[p].x, F[p].x);
+      float fx = F[p].x;
+      if (FLIP) fx *= (cs > 0.0f) ? 1.0f : ((cs < 0.0f) ? -1.0f : 0.0f);   // pass 1 left sign(C) F here; sign^2 = 1
+      const float x = cs * fmaf(-cs, Mspec[p].x, fx);
       s1 = -0.25f * x;
       s2 = x;
     }
     float h, l;
     split_tf32(s1, h, l);
-    zhi[(size_t)i * ldz + b] = h;
-    zlo[(size_t)i * ldz + b] = l;
+    zh[b] = h;
+    zl[b] = l;
     split_tf32(s2, h, l);
-    zhi[(size_t)i * ldz + w1 + b] = h;
-    zlo[(size_t)i * ldz + w1 + b] = l;
+    zh[w1 + b] = h;
+    zl[w1 + b] = l;
   }
 }
 
@@ -708,13 +739,17 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
              ctx->part_fl.as<double2>(), nS, g.Kh, g.Kr, per_group);
   MEM_LAUNCH(ctx, k_avg_spectra, (g.Kh + 255) / 256, 256, 0, st, ctx->part_cf.as<double2>(), part_cfw,
              ctx->part_c2.as<double>(), ctx->part_fl.as<double2>(), ctx->avgspec.as<float2>(), Mspec, g.Kh, G);
+  bool s3_done = false;      // the shared-memory radial kernel also writes S3 and the flipped spectra
   if (want_D) {
     const size_t pw_bytes = ((size_t)g.Na * g.Nh + g.Kr) * sizeof(float);
     if (pw_bytes <= 200 * 1024) {
-      MEM_CUDA(cudaFuncSetAttribute(k_operands_radial_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pw_bytes));
-      MEM_LAUNCH(ctx, k_operands_radial_sm, nS, RADIAL_THREADS, pw_bytes, st, spec, Mspec, ctx->cbin.as<float>(),
+      auto kern = need_flip ? k_operands_radial_sm<true> : k_operands_radial_sm<false>;
+      MEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pw_bytes));
+      MEM_LAUNCH(ctx, kern, nS, RADIAL_THREADS, pw_bytes, st, spec, Mspec, ctx->cbin.as<float>(),
                  g.fold_bin.as<int>(), g.fold_start.as<int>(), g.fold_ent.as<int>(), g.bin_of_pix.as<int>(),
-                 g.special_pix.as<int>(), zhi, zlo, N, g.Nh, g.Na, g.Kh, g.Kr, g.n_special, g.n1_blocks, g.ldz);
+                 g.special_pix.as<int>(), g.s3_col.as<int>(), zhi, zlo, N, g.Nh, g.Na, g.Kh, g.Kr, g.n_special,
+                 g.n1_blocks, g.ldz);
+      s3_done = true;
     } else {   // boxes above ~ 450 px: the folded power map does not fit shared memory
       MEM_LAUNCH(ctx, k_operands_radial, dim3((32 * g.n1_blocks + 255) / 256, nS), 256, 0, st, spec, Mspec,
                  ctx->cbin.as<float>(), g.bin_start.as<int>(), g.bin_pix.as<int>(), g.bin_of_pix.as<int>(),
@@ -723,7 +758,7 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
     const int from = 64 * g.n1_blocks + 2 * g.K3;
     if (from < g.ldz) MEM_LAUNCH(ctx, k_zero_tail, nS, 64, 0, st, zhi, zlo, nS, g.ldz, from);
   }
-  if (want_D || need_flip)
+  if ((want_D || need_flip) && !s3_done)
     MEM_LAUNCH(ctx, k_operands_s3, dim3((g.Kh + 255) / 256, G), 256, 0, st, spec, Mspec, ctx->cbin.as<float>(),
                g.bin_of_pix.as<int>(), g.s3_col.as<int>(), zhi, zlo, nS, g.Kh, g.Kr, g.ldz, per_group,
                want_D ? 1 : 0, need_flip ? 1 : 0);
