@@ -418,8 +418,8 @@ def run_b200(args):
         # the TF32 dense figure of B200_PROFILING.md's table, 1.1 PFLOP/s; the half-bf16 ratio is reported beside it.
         half_bf16 = 0.5 * float(peaks.get('bf16_tflops', 1590.0))
         peak = 1100.0
-        # dram__bytes_read+write of one launch from the committed ncu capture (profiles/r01_contract_tc2_ncu_full.txt)
-        traffic = 1.4374e9 if (nS, N) == (2000, 256) else None
+        # dram__bytes_read+write of one launch from the committed ncu capture (profiles/r01_top_kernels_ncu_full.txt)
+        traffic = 1.6318e9 if (nS, N) == (2000, 256) else None
         alg = 6.0 * NN * nS * nS                        # 6 N^2 fp32-equivalent flop per ordered pair
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
@@ -436,7 +436,7 @@ def run_b200(args):
                                   # hardware ceiling at the clock sampled during the run: 148 SMs x 2048 TF32 MAC/clk x 2
                                   frac_of_hw_rate_at_sampled_clock=(achieved / (148 * 2048 * 2 * clocks['sm_mhz'] * 1e6 / 1e12))
                                   if (achieved and clocks and clocks.get('sm_mhz')) else None,
-                                  ncu_tensor_pipe_active_pct=87.8 if traffic else None,   # sm__pipe_tensor_cycles_active, % of elapsed, same capture
+                                  ncu_tensor_pipe_active_pct=90.8 if traffic else None,   # sm__pipe_tensor_cycles_active, % of elapsed, same capture
                                   executed_flops_per_launch=flops_launch,
                                   algorithmic_tflops=alg / (k_avg_ms * 1e-3) / 1e12 if k_n else None,
                                   peak_source='TF32 dense 1.1 PFLOP/s (B200_PROFILING.md table); MEASURED_PEAKS.json (%s) has no TF32 '
