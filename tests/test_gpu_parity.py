@@ -78,6 +78,20 @@ def test_golden_volmask(env, golden_dir):
     assert np.array_equal(res['msk2'], g['ref_msk2'])
 
 
+def test_mask_at_bench_box_size(env):
+    """msk2 at N = 256: the fused low-pass column kernel, the second (unmasked) spectrum for the Wiener average and
+    the one-pass operand writer with the in-place phase flip, all fields against the float64 oracle."""
+    _lib, pd_stage, synthetic = env
+    nS, N = 24, 256
+    pd = synthetic.make_pd(nS, N, seed=21, snr=0.5)
+    yy, xx = np.mgrid[:N, :N]
+    msk2 = ((yy - N / 2) ** 2 / (0.42 * N) ** 2 + (xx - N / 2) ** 2 / (0.3 * N) ** 2) < 1
+    res = _gpu(pd_stage, pd, N, msk2=msk2)
+    ref = _oracle(pd, N, rotate_impl='periodic', msk2=msk2)
+    _check_D(res['D'], ref['D'])
+    _check_fields(res, ref)
+
+
 def test_golden_relion(env, golden_dir):
     """RELION branch: cubic 'wrap' shift by (shy-0.5, shx-0.5) on the device vs the reference's ndimage.shift."""
     _lib, pd_stage, _ = env
