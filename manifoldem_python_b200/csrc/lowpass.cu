@@ -84,8 +84,12 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
 // load latency is off the critical path; the 16 filter values of a thread do not depend on the image and are loaded
 // once.
 constexpr int CF_SLABS = 6;
+// stats != NULL: the rows came from k_ingest_rowfft256, i.e. from images that are only shifted by a per-image offset,
+// not yet normalised; (x - mean) / std is linear, so it is applied here: subtract mean * N^2 at (ky, kx) = (0, 0) and
+// scale the filter by 1 / std.
 __global__ void __launch_bounds__(CF_THREADS, 2) k_colfilter256(float2* __restrict__ spec, const float* __restrict__ G,
-                                                             int Nh, int nS, int img_stride) {
+                                                             const float2* __restrict__ stats, int Nh, int nS,
+                                                             int img_stride) {
   extern __shared__ float2 cf_smem[];
   float2* ex = cf_smem;                           // [256][CF_COLS] exchange buffer
   float2* stage = cf_smem + 256 * CF_COLS;        // [256][CF_COLS] next image's slab
@@ -127,10 +131,17 @@ __global__ void __launch_bounds__(CF_THREADS, 2) k_colfilter256(float2* __restri
 #pragma unroll
     for (int n2 = 0; n2 < 16; ++n2) v[n2] = ex[(t * 16 + n2) * CF_COLS + col];
     fft16<-1>(v);                                   // v[k2] = X[t + 16 k2]
+    float scale = 1.0f;
+    if (stats) {
+      const float2 ms = stats[img];                 // (mean - offset, 1 / std): what is left to subtract from the offset image
+      scale = ms.y;
+      if (t == 0 && kx == 0) v[0].x -= ms.x * 65536.0f;
+    }
 #pragma unroll
     for (int k2 = 0; k2 < 16; ++k2) {
-      v[k2].x *= gk[k2];
-      v[k2].y *= gk[k2];
+      const float g = gk[k2] * scale;
+      v[k2].x *= g;
+      v[k2].y *= g;
     }
     fft16<1>(v);                                    // inverse over k2
     __syncthreads();                                // every thread is done reading the forward exchange
@@ -151,13 +162,129 @@ __global__ void __launch_bounds__(CF_THREADS, 2) k_colfilter256(float2* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// a2 + a3 + the row pass of a5 in one kernel (N = 256): read the raw particle once, write the row-transformed half
+// spectrum.  One CTA per image, eight bands of 32 picture rows: the band is staged (transposed for SPIDER stacks,
+// upside down for conjugates) in shared memory, then every 16 threads transform a PAIR of real rows as one complex
+// FFT-256 (z = row1 + i row2) and separate the two half spectra, X1[k] = (Z[k] + conj Z[N-k]) / 2,
+// X2[k] = (Z[k] - conj Z[N-k]) / 2i, with the partner values fetched by warp shuffles.  The moments of a3 are
+// accumulated in the same pass over values shifted by the image's first pixel (keeps the DC term small) and handed
+// to k_colfilter256, which applies the normalisation in Fourier space.
+// ------------------------------------------------------------------------------------------------
+constexpr int IR_BP = 257;      // band pitch (floats): odd, so the transposing stores are conflict-free
+constexpr int IR_EP = 272;      // exchange floats2 per row pair: [16][17]
+__global__ void __launch_bounds__(256, 3) k_ingest_rowfft256(const float* __restrict__ raw, const uint8_t* __restrict__ flip,
+                                                           float2* __restrict__ spec, float2* __restrict__ stats,
+                                                           int transposed) {
+  constexpr int N = 256, Nh = 129;
+  extern __shared__ float2 ir_smem[];
+  float2* ex = ir_smem;                                             // [16 row pairs][16][17]
+  float* band = reinterpret_cast<float*>(ir_smem + 16 * IR_EP);     // [32][IR_BP]
+  __shared__ double red[24];
+  const int i = blockIdx.x;
+  const float* src = raw + (size_t)i * N * N;
+  float2* out = spec + (size_t)i * N * Nh;
+  const bool fl = flip[i] != 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = threadIdx.x >> 4, t = threadIdx.x & 15;
+  const float half = 0.5f * N, r2lim = half * half;
+  const float off = src[0];
+  double s = 0, s2 = 0;
+  int cnt = 0;                                     // pixels outside the disc (the only ones that enter the sums)
+  float2* e = ex + p * IR_EP;
+  const int partner = (lane & 16) + ((16 - t) & 15);
+  for (int b0 = 0; b0 < N; b0 += 32) {
+    float rs = 0.0f, rs2 = 0.0f;
+    if (transposed) {                               // picture[rp][c] = raw[c][rp]; lanes run along rp (contiguous in raw)
+      const int rp = b0 + lane;
+      const int r = fl ? N - 1 - rp : rp;
+      const float x = (float)rp - half + 1.0f, x2 = x * x;     // annularMask.py:24-30, centre (N/2-1, N/2)
+#pragma unroll 8
+      for (int c = warp; c < N; c += 8) {
+        const float v = src[c * N + r] - off;
+        const float y = (float)c - half;
+        const bool in = x2 + y * y < r2lim;
+        const float m = in ? 0.0f : v;
+        cnt += in ? 0 : 1;
+        rs += m;
+        rs2 = fmaf(m, m, rs2);
+        band[lane * IR_BP + c] = v;
+      }
+    } else {
+#pragma unroll
+      for (int k = warp; k < 32; k += 8) {
+        const int rp = b0 + k;
+        const int r = fl ? N - 1 - rp : rp;
+        const float x = (float)rp - half + 1.0f, x2 = x * x;
+#pragma unroll
+        for (int c = lane; c < N; c += 32) {
+          const float v = src[r * N + c] - off;
+          const float y = (float)c - half;
+          const bool in = x2 + y * y < r2lim;
+          const float m = in ? 0.0f : v;
+          cnt += in ? 0 : 1;
+          rs += m;
+          rs2 = fmaf(m, m, rs2);
+          band[k * IR_BP + c] = v;
+        }
+      }
+    }
+    s += (double)rs;
+    s2 += (double)rs2;
+    __syncthreads();
+    float2 v[16];
+    const float* b1 = band + (2 * p) * IR_BP + t;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) v[m] = make_float2(b1[16 * m], b1[IR_BP + 16 * m]);
+    fft16<-1>(v);
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) e[k1 * 17 + t] = cmul(v[k1], c_tw256[(t * k1) & 255]);
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) v[n2] = e[t * 17 + n2];
+    fft16<-1>(v);                                   // v[k2] = Z[t + 16 k2]
+    float2* o1 = out + (b0 + 2 * p) * Nh + t;
+    float2* o2 = o1 + Nh;
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) {                // k = t + 16 k2 <= 127; partner N - k lives in thread 16 - t, slot 15 - k2
+      float2 zn;
+      zn.x = __shfl_sync(0xffffffffu, v[15 - k2].x, partner);
+      zn.y = __shfl_sync(0xffffffffu, v[15 - k2].y, partner);
+      if (t == 0) zn = v[(16 - k2) & 15];           // k = 16 k2: the partner 16 (16 - k2) is the thread's own
+      const float2 zk = v[k2];
+      o1[16 * k2] = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+      o2[16 * k2] = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
+    }
+    if (t == 0) {                                   // k = 128 (Nyquist): real for both rows
+      o1[128] = make_float2(v[8].x, 0.0f);
+      o2[128] = make_float2(v[8].y, 0.0f);
+    }
+    __syncthreads();                                // the band and the exchange rows are rewritten by the next band
+  }
+  double dc = (double)cnt;
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    dc += __shfl_xor_sync(0xffffffffu, dc, o);
+  }
+  if (lane == 0) { red[warp] = s; red[8 + warp] = s2; red[16 + warp] = dc; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s = 0; s2 = 0; dc = 0;
+    for (int w = 0; w < 8; ++w) { s += red[w]; s2 += red[8 + w]; dc += red[16 + w]; }
+    // the population of a3 is b = x (1 - msk) over ALL N^2 pixels, zeros inside the disc included: undo the offset
+    // in the sums (it was applied to the outside pixels only), then the image itself is (x' + off - mean) / std
+    const double o = (double)off, n = (double)N * N;
+    const double S1 = s + o * dc, S2 = s2 + 2.0 * o * s + o * o * dc;
+    const double mean = S1 / n;
+    const double var = S2 / n - mean * mean;
+    stats[i] = make_float2((float)(mean - o), (float)(1.0 / sqrt(var)));
+  }
+}
+
 bool colfilter_supported(int N) { return N == 256; }
 
-int colfilter_run(mem_ctx* ctx, float2* spec, const float* G, int nS, int N, cudaStream_t st) {
-  if (N != 256) {
-    set_error("colfilter: no kernel for N = %d", N);
-    return 1;
-  }
+static int ensure_twiddles(mem_ctx* ctx, cudaStream_t st) {
   static thread_local int tw_device = -1;
   if (tw_device != ctx->device) {     // constant memory is per device; every host thread checks its own context
     float2 tw[256];
@@ -169,12 +296,34 @@ int colfilter_run(mem_ctx* ctx, float2* spec, const float* G, int nS, int N, cud
     MEM_CUDA(cudaStreamSynchronize(st));
     tw_device = ctx->device;
   }
+  return 0;
+}
+
+int ingest_rowfft_run(mem_ctx* ctx, const float* raw, const uint8_t* flip, float2* spec, float2* stats, int nS, int N,
+                      int transposed, cudaStream_t st) {
+  if (N != 256) {
+    set_error("ingest_rowfft: no kernel for N = %d", N);
+    return 1;
+  }
+  MEM_CHECK(ensure_twiddles(ctx, st));
+  const size_t smem = 16 * IR_EP * sizeof(float2) + 32 * IR_BP * sizeof(float);
+  MEM_CUDA(cudaFuncSetAttribute(k_ingest_rowfft256, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MEM_LAUNCH(ctx, k_ingest_rowfft256, nS, 256, smem, st, raw, flip, spec, stats, transposed);
+  return 0;
+}
+
+int colfilter_run(mem_ctx* ctx, float2* spec, const float* G, const float2* stats, int nS, int N, cudaStream_t st) {
+  if (N != 256) {
+    set_error("colfilter: no kernel for N = %d", N);
+    return 1;
+  }
+  MEM_CHECK(ensure_twiddles(ctx, st));
   const int Nh = N / 2 + 1;
   static_assert(CF_SLABS * CF_COLS >= 129, "slabs must cover the half spectrum");
   const int per_slab = std::max(1, std::min(nS, (2 * ctx->sm_count) / CF_SLABS));   // CTAs per slab, two CTAs per SM
   const size_t smem = 2 * 256 * CF_COLS * sizeof(float2);
   MEM_CUDA(cudaFuncSetAttribute(k_colfilter256, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  MEM_LAUNCH(ctx, k_colfilter256, per_slab * CF_SLABS, CF_THREADS, smem, st, spec, G, Nh, nS, per_slab);
+  MEM_LAUNCH(ctx, k_colfilter256, per_slab * CF_SLABS, CF_THREADS, smem, st, spec, G, stats, Nh, nS, per_slab);
   return 0;
 }
 

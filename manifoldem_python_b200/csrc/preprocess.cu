@@ -692,21 +692,25 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
   double2* cs = ctx->rot_cs.as<double2>();
 
   MEM_CUDA(cudaEventRecord(ctx->ev[0], st));
-  // ---- a2/a3 ingest + normalise -> A
+  // ---- a2/a3 ingest + normalise, a5 low-pass -> B
+  const float* picture = io->raw;                 // what the ingest reads: the raw stack, or its RELION-shifted copy
+  int transposed = prm->transposed;
   if (prm->relion_shift) {   // :263-264 shift(order=3, mode='wrap') before the flip / normalisation
     MEM_CHECK(shift_run(ctx, io->raw, io->shift, A, B, nS, N, st));
-    MEM_CHECK(ingest_run(ctx, B, io->flip, A, nS, N, 0, st));
-  } else {
-    MEM_CHECK(ingest_run(ctx, io->raw, io->flip, A, nS, N, prm->transposed, st));
+    picture = B;
+    transposed = 0;
   }
-  // ---- a5 low-pass: A -> spec -> *G -> B
   if (colfilter_supported(N)) {
-    // rows by cuFFT (1-D R2C / C2R), the whole column pass — FFT, * G, inverse FFT — in one kernel of ours: the
-    // spectrum makes one round trip through HBM between the row passes instead of three
-    MEM_CHECK(run_fft(ctx, N, nS, true, A, spec, st, true));
-    MEM_CHECK(colfilter_run(ctx, spec, g.Gtab.as<float>(), nS, N, st));
+    // One pass of ours turns the raw particles into row-transformed half spectra (ingest, moments and the R2C row pass
+    // fused), one more does the whole column pass — FFT, normalisation, * G, inverse FFT — and cuFFT's 1-D C2R
+    // brings the rows back: the data crosses HBM three times instead of seven.
+    MEM_CHECK(ctx->stats.ensure((size_t)nS * sizeof(float2)));
+    float2* stats = ctx->stats.as<float2>();
+    MEM_CHECK(ingest_rowfft_run(ctx, picture, io->flip, spec, stats, nS, N, transposed, st));
+    MEM_CHECK(colfilter_run(ctx, spec, g.Gtab.as<float>(), stats, nS, N, st));
     MEM_CHECK(run_fft(ctx, N, nS, false, B, spec, st, true));
   } else {
+    MEM_CHECK(ingest_run(ctx, picture, io->flip, A, nS, N, transposed, st));
     MEM_CHECK(run_fft(ctx, N, nS, true, A, spec, st));
     const size_t total = (size_t)nS * Kh;
     const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 16);

@@ -92,6 +92,19 @@ def test_mask_at_bench_box_size(env):
     _check_fields(res, ref)
 
 
+def test_unnormalised_stack_at_bench_box_size(env):
+    """Raw particles with a large offset and scale (1000 +- 10) through the fused ingest: the moments are taken on
+    offset-shifted values and the normalisation is applied in Fourier space; same bar as everywhere else."""
+    _lib, pd_stage, synthetic = env
+    nS, N = 16, 256
+    pd = synthetic.make_pd(nS, N, seed=22, snr=0.5)
+    pd = dict(pd, stack=(pd['stack'] * 10.0 + 1000.0).astype(np.float32))
+    res = _gpu(pd_stage, pd, N)
+    ref = _oracle(pd, N, rotate_impl='periodic')
+    _check_D(res['D'], ref['D'])
+    _check_fields(res, ref)
+
+
 def test_golden_relion(env, golden_dir):
     """RELION branch: cubic 'wrap' shift by (shy-0.5, shx-0.5) on the device vs the reference's ndimage.shift."""
     _lib, pd_stage, _ = env
@@ -106,7 +119,7 @@ def test_golden_relion(env, golden_dir):
     _check_fields(res, ref)
 
 
-@pytest.mark.parametrize('N', [100, 300])
+@pytest.mark.parametrize('N', [100, 256, 300])
 def test_relion_shift_large_boxes(env, N):
     """RELION branch at box sizes whose mirror extension (2N-2) takes the long-line prefilter kernels."""
     _lib, pd_stage, synthetic = env
