@@ -558,8 +558,9 @@ static SegGeom make_geom(int L, int E) {
 
 // mirror == 0: periodic boundary (rotatefill); mirror == 1: whole-sample mirror boundary, realised as the
 // periodic filter on the (2N-2)-long mirror extension of every line (ndimage.shift's spline_filter).
+// rows_done != 0: `out` already holds the row-filtered lines (fused upstream, lowpass.cu); only the column pass runs.
 static int prefilter_run(mem_ctx* ctx, const float* in, float* out, int nS, int N, int apply_mask, int mirror,
-                         cudaStream_t st) {
+                         cudaStream_t st, int rows_done = 0) {
   const int L = mirror ? 2 * N - 2 : N;
   if (L > 1024 || N > 512 || N < 16) {
     set_error("box size %d is not supported by the spline prefilter (16 <= N <= 512)", N);
@@ -569,7 +570,9 @@ static int prefilter_run(mem_ctx* ctx, const float* in, float* out, int nS, int 
   const SegGeom gr = make_geom(L, E);
   const dim3 grid((N + 7) / 8, nS);
   const bool rows_exact = !mirror && (N == 64 || N == 128 || N == 256);
-  if (rows_exact) {
+  if (rows_done) {
+    // nothing to do for the rows
+  } else if (rows_exact) {
     if (N == 64) {
       if (apply_mask) MEM_LAUNCH(ctx, (k_prefilter_rows_x<2, true>), grid, 256, 0, st, in, out, gr.zE);
       else MEM_LAUNCH(ctx, (k_prefilter_rows_x<2, false>), grid, 256, 0, st, in, out, gr.zE);
@@ -613,12 +616,13 @@ int shift_run(mem_ctx* ctx, const float* raw, const double* shift, float* tmp, f
 }
 
 // B (low-passed images) -> imgAll (aligned), optional masked copy into B.  A, B: [nS][N][N] scratch.
+// rows_done != 0: A already holds (img * msk) after the row pass of the first prefilter.
 int align_run(mem_ctx* ctx, float* A, float* B, float* imgAll, const double* psi_deg, double psi_p_deg, double2* cs,
-              const uint8_t* msk2, int nS, int N, cudaStream_t st) {
+              const uint8_t* msk2, int nS, int N, cudaStream_t st, int rows_done) {
   MEM_LAUNCH(ctx, k_angles, (nS + 1 + 127) / 128, 128, 0, st, psi_deg, psi_p_deg, cs, nS);
   const dim3 grot((N + ROT_T - 1) / ROT_T, (N + ROT_T - 1) / ROT_T, nS);
   const bool full = (N % ROT_T) == 0;
-  MEM_CHECK(prefilter_run(ctx, B, A, nS, N, 1, 0, st));                    // (img * msk) -> coefficients
+  MEM_CHECK(prefilter_run(ctx, B, A, nS, N, 1, 0, st, rows_done));         // (img * msk) -> coefficients
   if (full) MEM_LAUNCH(ctx, k_rotate<true>, grot, 256, 0, st, A, B, cs, 1, N, (const uint8_t*)nullptr, (float*)nullptr);
   else MEM_LAUNCH(ctx, k_rotate<false>, grot, 256, 0, st, A, B, cs, 1, N, (const uint8_t*)nullptr, (float*)nullptr);
   MEM_CHECK(prefilter_run(ctx, B, A, nS, N, 0, 0, st));

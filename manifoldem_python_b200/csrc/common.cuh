@@ -125,6 +125,8 @@ int colfilter_run(mem_ctx* ctx, float2* spec, const float* G, const float2* stat
 // a2 + a3 + row R2C in one pass for the same box sizes: raw particles -> row-transformed half spectra + (mean, 1/std)
 int ingest_rowfft_run(mem_ctx* ctx, const float* raw, const uint8_t* flip, float2* spec, float2* stats, int nS, int N,
                       int transposed, cudaStream_t st);
+// inverse row pass (C2R) + annular mask + row pass of the periodic spline prefilter: half spectra -> out [nS][N][N]
+int rowifft_prefilter_run(mem_ctx* ctx, const float2* spec, float* out, int nS, int N, cudaStream_t st);
 int contract_run(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, const float* Zlo, float* D,
                  int contraction, int k_chunk_blocks, int split_k, cudaStream_t st);
 int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, const float* Zlo, float* D,

@@ -199,8 +199,8 @@ __global__ void __launch_bounds__(256, 3) k_ingest_rowfft256(const float* __rest
       const int rp = b0 + lane;
       const int r = fl ? N - 1 - rp : rp;
       const float x = (float)rp - half + 1.0f, x2 = x * x;     // annularMask.py:24-30, centre (N/2-1, N/2)
-#pragma unroll 8
-      for (int c = warp; c < N; c += 8) {
+#pragma unroll
+      for (int c = warp; c < N; c += 8) {             // 32 independent loads in flight per thread
         const float v = src[c * N + r] - off;
         const float y = (float)c - half;
         const bool in = x2 + y * y < r2lim;
@@ -282,6 +282,111 @@ __global__ void __launch_bounds__(256, 3) k_ingest_rowfft256(const float* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The way back (N = 256): inverse row transform of the filtered half spectra fused with what follows it in the
+// pipeline, the annular mask (:325) and the row pass of the first periodic spline prefilter (rotatefill.py:24,
+// same recursion as k_prefilter_rows_x<8, true> in align.cu).  One CTA per image, bands of 32 rows: 16 threads build
+// z = X1 + i X2 from the half spectra of a row pair (Z[k] = X1[k] + i X2[k], Z[N-k] = conj X1[k] + i conj X2[k]),
+// run the inverse FFT-256 and leave the two real rows in shared memory; then every warp filters four rows, lane l
+// owning samples [8 l, 8 l + 8), and stores them row-coalesced.  The low-passed image itself never reaches HBM.
+// ------------------------------------------------------------------------------------------------
+#define LP_SPL_Z (-0.26794919243112270647f)
+constexpr int RP_BP = 264;      // band pitch: 256 samples + one pad float per 32 (conflict-free for both access patterns)
+__global__ void __launch_bounds__(256, 3) k_rowifft_prefilter256(const float2* __restrict__ spec, float* __restrict__ outimg) {
+  constexpr int N = 256, Nh = 129, E = 8, H = 20 / E + 2;
+  extern __shared__ float2 ir_smem[];
+  float2* ex = ir_smem;
+  float* band = reinterpret_cast<float*>(ir_smem + 16 * IR_EP);     // [32][RP_BP]
+  const int i = blockIdx.x;
+  const float2* in = spec + (size_t)i * N * Nh;
+  float* dst = outimg + (size_t)i * N * N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = threadIdx.x >> 4, t = threadIdx.x & 15;
+  float2* e = ex + p * IR_EP;
+  constexpr float half = 0.5f * N, r2lim = half * half;
+  const float zE = 2.6571717e-05f;                  // z^8, z = sqrt(3) - 2
+  for (int b0 = 0; b0 < N; b0 += 32) {
+    const float2* x1 = in + (b0 + 2 * p) * Nh;
+    const float2* x2 = x1 + Nh;
+    float2 v[16];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {                   // k = t + 16 m <= 127
+      float2 a = x1[t + 16 * m], b = x2[t + 16 * m];
+      if (m == 0 && t == 0) { a.y = 0.0f; b.y = 0.0f; }            // a C2R ignores the imaginary part of the DC term
+      v[m] = make_float2(a.x - b.y, a.y + b.x);
+    }
+#pragma unroll
+    for (int m = 8; m < 16; ++m) {                  // k = t + 16 m >= 128: conjugate of entry N - k
+      const int kk = N - t - 16 * m;
+      float2 a = x1[kk], b = x2[kk];
+      if (m == 8 && t == 0) { a.y = 0.0f; b.y = 0.0f; }            // ... and of the Nyquist term
+      v[m] = make_float2(a.x + b.y, b.x - a.y);
+    }
+    fft16<1>(v);
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) {
+      const float2 w = c_tw256[(t * n1) & 255];
+      e[n1 * 17 + t] = cmul(v[n1], make_float2(w.x, -w.y));
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) v[k1] = e[t * 17 + k1];
+    fft16<1>(v);                                    // v[m] = z[t + 16 m]: row 2p in .x, row 2p + 1 in .y
+    float* r1 = band + (2 * p) * RP_BP;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const int c = t + 16 * m;
+      r1[c + (c >> 5)] = v[m].x;
+      r1[RP_BP + c + (c >> 5)] = v[m].y;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                   // warp-private rows from here on; unrolled: four independent recursions in flight
+      const int row = warp + 8 * q;
+      float* ln = band + row * RP_BP;
+      const float xm = (float)(b0 + row) - half + 1.0f;
+      const float lim = r2lim - xm * xm;            // keep the pixel iff y * y < lim
+      const int c0 = lane * E;
+      float s[E];
+#pragma unroll
+      for (int j = 0; j < E; ++j) {
+        const float y = (float)(c0 + j) - half;
+        const float val = ln[c0 + j + ((c0 + j) >> 5)];
+        s[j] = (y * y < lim) ? 6.0f * val : 0.0f;
+      }
+      float run = 0.0f;
+#pragma unroll
+      for (int j = 0; j < E; ++j) { run = fmaf(LP_SPL_Z, run, s[j]); s[j] = run; }
+      float carry = 0.0f, f = 1.0f;
+#pragma unroll
+      for (int h = 1; h <= H; ++h) {
+        carry = fmaf(f, __shfl_sync(0xffffffffu, run, (lane - h) & 31), carry);
+        f *= zE;
+      }
+      float zp = LP_SPL_Z * carry;
+#pragma unroll
+      for (int j = 0; j < E; ++j) { s[j] += zp; zp *= LP_SPL_Z; }
+      run = 0.0f;
+#pragma unroll
+      for (int j = E - 1; j >= 0; --j) { run = LP_SPL_Z * (run - s[j]); s[j] = run; }
+      carry = 0.0f; f = 1.0f;
+#pragma unroll
+      for (int h = 1; h <= H; ++h) {
+        carry = fmaf(f, __shfl_sync(0xffffffffu, run, (lane + h) & 31), carry);
+        f *= zE;
+      }
+      zp = LP_SPL_Z * carry;
+#pragma unroll
+      for (int j = E - 1; j >= 0; --j) { s[j] += zp; zp *= LP_SPL_Z; }
+      // lane l holds samples [8 l, 8 l + 8): two 16-byte stores per lane, the warp writes its 1 KB row contiguously
+      float4* orow = reinterpret_cast<float4*>(dst + (b0 + row) * N + c0);
+      orow[0] = make_float4(s[0], s[1], s[2], s[3]);
+      orow[1] = make_float4(s[4], s[5], s[6], s[7]);
+    }
+    __syncthreads();                                // the band is rewritten by the next row pairs
+  }
+}
+
 bool colfilter_supported(int N) { return N == 256; }
 
 static int ensure_twiddles(mem_ctx* ctx, cudaStream_t st) {
@@ -309,6 +414,18 @@ int ingest_rowfft_run(mem_ctx* ctx, const float* raw, const uint8_t* flip, float
   const size_t smem = 16 * IR_EP * sizeof(float2) + 32 * IR_BP * sizeof(float);
   MEM_CUDA(cudaFuncSetAttribute(k_ingest_rowfft256, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   MEM_LAUNCH(ctx, k_ingest_rowfft256, nS, 256, smem, st, raw, flip, spec, stats, transposed);
+  return 0;
+}
+
+int rowifft_prefilter_run(mem_ctx* ctx, const float2* spec, float* out, int nS, int N, cudaStream_t st) {
+  if (N != 256) {
+    set_error("rowifft_prefilter: no kernel for N = %d", N);
+    return 1;
+  }
+  MEM_CHECK(ensure_twiddles(ctx, st));
+  const size_t smem = 16 * IR_EP * sizeof(float2) + 32 * RP_BP * sizeof(float);
+  MEM_CUDA(cudaFuncSetAttribute(k_rowifft_prefilter256, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MEM_LAUNCH(ctx, k_rowifft_prefilter256, nS, 256, smem, st, spec, out);
   return 0;
 }
 

@@ -15,7 +15,7 @@ int ingest_run(mem_ctx* ctx, const float* raw, const uint8_t* flip, float* out, 
 int shift_run(mem_ctx* ctx, const float* raw, const double* shift, float* tmp, float* out, int nS, int N,
               cudaStream_t st);
 int align_run(mem_ctx* ctx, float* A, float* B, float* imgAll, const double* psi_deg, double psi_p_deg, double2* cs,
-              const uint8_t* msk2, int nS, int N, cudaStream_t st);
+              const uint8_t* msk2, int nS, int N, cudaStream_t st, int rows_done);
 
 // ------------------------------------------------------------------------------------------------
 // error string + arena
@@ -693,6 +693,7 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
 
   MEM_CUDA(cudaEventRecord(ctx->ev[0], st));
   // ---- a2/a3 ingest + normalise, a5 low-pass -> B
+  int rows_done = 0;
   const float* picture = io->raw;                 // what the ingest reads: the raw stack, or its RELION-shifted copy
   int transposed = prm->transposed;
   if (prm->relion_shift) {   // :263-264 shift(order=3, mode='wrap') before the flip / normalisation
@@ -708,7 +709,9 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
     float2* stats = ctx->stats.as<float2>();
     MEM_CHECK(ingest_rowfft_run(ctx, picture, io->flip, spec, stats, nS, N, transposed, st));
     MEM_CHECK(colfilter_run(ctx, spec, g.Gtab.as<float>(), stats, nS, N, st));
-    MEM_CHECK(run_fft(ctx, N, nS, false, B, spec, st, true));
+    // inverse row transform fused with the annular mask and the row pass of the first spline prefilter -> A
+    MEM_CHECK(rowifft_prefilter_run(ctx, spec, A, nS, N, st));
+    rows_done = 1;
   } else {
     MEM_CHECK(ingest_run(ctx, picture, io->flip, A, nS, N, transposed, st));
     MEM_CHECK(run_fft(ctx, N, nS, true, A, spec, st));
@@ -719,7 +722,7 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
   }
   MEM_CUDA(cudaEventRecord(ctx->ev[1], st));
   // ---- a7 alignment: two periodic cubic-spline rotations
-  MEM_CHECK(align_run(ctx, A, B, imgAll, io->psi_deg, prm->psi_p_deg, cs, io->msk2, nS, N, st));
+  MEM_CHECK(align_run(ctx, A, B, imgAll, io->psi_deg, prm->psi_p_deg, cs, io->msk2, nS, N, st, rows_done));
   MEM_CUDA(cudaEventRecord(ctx->ev[2], st));
   // ---- a10 FFT of img*msk2 (and of img for the Wiener average when they differ)
   float2* specw = nullptr;
