@@ -101,6 +101,9 @@ __global__ void __launch_bounds__(CF_THREADS, 2) k_colfilter256(float2* __restri
   float gk[16];
 #pragma unroll
   for (int k2 = 0; k2 < 16; ++k2) gk[k2] = live ? G[(t + 16 * k2) * Nh + kxc] : 0.0f;
+  __shared__ float2 tws[256];                     // tws[k1][t] = W256^(t k1)
+  if (threadIdx.x < 256) tws[threadIdx.x] = c_tw256[((threadIdx.x >> 4) * (threadIdx.x & 15)) & 255];
+  __syncthreads();
   int img = blockIdx.x / CF_SLABS;
   if (img < nS) {
     const float2* src = spec + (size_t)img * 256 * Nh + kxc;
@@ -124,8 +127,7 @@ __global__ void __launch_bounds__(CF_THREADS, 2) k_colfilter256(float2* __restri
     fft16<-1>(v);
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) {
-      const float2 w = c_tw256[(t * k1) & 255];
-      ex[(k1 * 16 + t) * CF_COLS + col] = cmul(v[k1], w);
+      ex[(k1 * 16 + t) * CF_COLS + col] = cmul(v[k1], tws[k1 * 16 + t]);
     }
     __syncthreads();
 #pragma unroll
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(CF_THREADS, 2) k_colfilter256(float2* __restri
     __syncthreads();                                // every thread is done reading the forward exchange
 #pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) {
-      const float2 w = c_tw256[(t * n1) & 255];
+      const float2 w = tws[n1 * 16 + t];
       ex[(n1 * 16 + t) * CF_COLS + col] = cmul(v[n1], make_float2(w.x, -w.y));
     }
     __syncthreads();
@@ -181,6 +183,8 @@ __global__ void __launch_bounds__(256, 3) k_ingest_rowfft256(const float* __rest
   float2* ex = ir_smem;                                             // [16 row pairs][16][17]
   float* band = reinterpret_cast<float*>(ir_smem + 16 * IR_EP);     // [32][IR_BP]
   __shared__ double red[24];
+  __shared__ float2 tws[256];                     // tws[k1][t] = W256^(t k1): the constant bank would serialise the 16
+  tws[threadIdx.x] = c_tw256[((threadIdx.x >> 4) * (threadIdx.x & 15)) & 255];   // distinct t of a warp on every lookup
   const int i = blockIdx.x;
   const float* src = raw + (size_t)i * N * N;
   float2* out = spec + (size_t)i * N * Nh;
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(256, 3) k_ingest_rowfft256(const float* __rest
     for (int m = 0; m < 16; ++m) v[m] = make_float2(b1[16 * m], b1[IR_BP + 16 * m]);
     fft16<-1>(v);
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) e[k1 * 17 + t] = cmul(v[k1], c_tw256[(t * k1) & 255]);
+    for (int k1 = 0; k1 < 16; ++k1) e[k1 * 17 + t] = cmul(v[k1], tws[k1 * 16 + t]);
     __syncwarp();
 #pragma unroll
     for (int n2 = 0; n2 < 16; ++n2) v[n2] = e[t * 17 + n2];
@@ -305,6 +309,12 @@ __global__ void __launch_bounds__(256, 3) k_rowifft_prefilter256(const float2* _
   float2* e = ex + p * IR_EP;
   constexpr float half = 0.5f * N, r2lim = half * half;
   const float zE = 2.6571717e-05f;                  // z^8, z = sqrt(3) - 2
+  __shared__ float2 tws[256];                       // tws[n1][t] = conj W256^(t n1), see k_ingest_rowfft256
+  {
+    const float2 w = c_tw256[((threadIdx.x >> 4) * (threadIdx.x & 15)) & 255];
+    tws[threadIdx.x] = make_float2(w.x, -w.y);
+  }
+  __syncthreads();
   for (int b0 = 0; b0 < N; b0 += 32) {
     const float2* x1 = in + (b0 + 2 * p) * Nh;
     const float2* x2 = x1 + Nh;
@@ -324,10 +334,7 @@ __global__ void __launch_bounds__(256, 3) k_rowifft_prefilter256(const float2* _
     }
     fft16<1>(v);
 #pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) {
-      const float2 w = c_tw256[(t * n1) & 255];
-      e[n1 * 17 + t] = cmul(v[n1], make_float2(w.x, -w.y));
-    }
+    for (int n1 = 0; n1 < 16; ++n1) e[n1 * 17 + t] = cmul(v[n1], tws[n1 * 16 + t]);
     __syncwarp();
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) v[k1] = e[t * 17 + k1];

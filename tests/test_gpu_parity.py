@@ -266,6 +266,18 @@ def test_tiny_pds(env, nS):
     _check_fields(res, ref)
 
 
+@pytest.mark.parametrize('nS', [1, 3])
+def test_tiny_pds_at_bench_box_size(env, nS):
+    """The persistent column kernel and the block-per-image row kernels with fewer images than CTAs."""
+    _lib, pd_stage, synthetic = env
+    pd = synthetic.make_pd(nS, 256, seed=60 + nS, snr=1.0)
+    res = _gpu(pd_stage, pd, 256)
+    ref = _oracle(pd, 256, rotate_impl='periodic')
+    if nS > 1:
+        _check_D(res['D'], ref['D'])
+    _check_fields(res, ref)
+
+
 def test_bad_inputs_fail_loudly(env):
     """No silent fallback: unsupported shapes and parameters surface as errors."""
     _lib, pd_stage, synthetic = env
