@@ -390,6 +390,33 @@ def run_b200(args):
         full_ms = ctx.timer_stop() / n_full
         for o in outs:
             o.free()
+    # ---- BASELINE config 2 (one synthetic PD of 1,000 particles at 128^2, full D), device-resident, for reference
+    c2 = None
+    if rank == 0 and not args.no_e2e and (nS, N) == (NS, NPIX):
+        n2, N2 = 1000, 128
+        pds2, rng2 = make_inputs(n2, N2, 2, seed=77)
+        raws2 = [_lib.DeviceArray(ctx, (n2, N2 * N2), np.float32, rng2.standard_normal((n2, N2 * N2), dtype=np.float32))
+                 for _ in pds2]
+        aux2 = [(_lib.DeviceArray(ctx, (n2,), np.uint8, pd['flip']), _lib.DeviceArray(ctx, (n2,), np.float64, pd['psi_deg']),
+                 _lib.DeviceArray(ctx, (n2,), np.float64, pd['df'])) for pd in pds2]
+        D2 = _lib.DeviceArray(ctx, (n2, n2), np.float32)
+        io2, prm2 = [], []
+        for j, pd in enumerate(pds2):
+            io = _lib.PdIO()
+            io.raw, io.flip, io.psi_deg, io.df, io.D = raws2[j].ptr, aux2[j][0].ptr, aux2[j][1].ptr, aux2[j][2].ptr, D2.ptr
+            io2.append(io)
+            prm2.append(pd_params(_lib, n2, N2, pd['psi_p']))
+        reps2 = 40
+        for k in range(4 + reps2):
+            if k == 4:
+                ctx.sync()
+                ctx.timer_start()
+            _lib.check(lib.mem_pd_distance_device(ctx.handle, C.byref(prm2[k % 2]), C.byref(io2[k % 2]), None))
+        ms2 = ctx.timer_stop() / reps2
+        c2 = dict(workload='BASELINE config 2: one PD of 1,000 particles x 128^2, full D', per_pd_ms=ms2,
+                  gpairs_s=n2 * n2 / (ms2 * 1e-3) / 1e9)
+        for a in raws2 + [x for t3 in aux2 for x in t3] + [D2]:
+            a.free()
     if world > 1:
         dist.barrier()
 
@@ -453,7 +480,7 @@ def run_b200(args):
                                          '(1000 PDs at 8 GPUs)' % (nS, N, P), pds_per_gpu=P, nS=nS, N=N,
                                 l2='inputs larger than L2: %d distinct 524 MB stacks cycled' % POOL,
                                 per_pd_ms=ms / args.steps / P, stage_ms_last_pd=stage,
-                                all_record_fields_per_pd_ms=full_ms),
+                                all_record_fields_per_pd_ms=full_ms, single_pd_config_2=c2),
                     clocks=clocks, gpu_launches=launches, e2e=e2e,
                     roofline=dict(bound='tensor', kernel='k_contract_tc2 (tcgen05 cta_group::2 kind::tf32, 3 passes)',
                                   achieved=achieved, peak=peak, unit='TFLOP/s', frac=(achieved / peak) if achieved else None,
