@@ -521,7 +521,7 @@ int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, c
   // default promotion period: 1 k-block for single-CTA tiles; 2 for CTA pairs, whose accumulator hand-over crosses
   // the cluster twice per chunk (commit multicast + remote arrive ~ 650 clk) and needs the longer chunk to hide it
   // The S3 columns (mixed-sign products, 78 % of K) tolerate 4 blocks per promotion at the same measured accuracy
-  // (scripts/gpu_debug.py chunk3): code = period(S1,S2) | period(S3) << 8.
+  // (tests/tools/gpu_debug.py chunk3): code = period(S1,S2) | period(S3) << 8.
   const int chunk = k_chunk_blocks > 0 ? k_chunk_blocks : (two_cta ? (2 | 4 << 8) : 1);
   // tiles of the upper triangle (any element with col >= row)
   std::vector<std::pair<int, int>> tiles;

@@ -1,6 +1,6 @@
 """GPU bring-up report: per-field errors of the CUDA path against the oracle, SIMT vs tcgen05
 contraction, chunk sweeps, quick timings.  Run on the GPU box:
-    python scripts/gpu_debug.py [acc] [time]
+    python tests/tools/gpu_debug.py [acc] [time]
 """
 import ctypes as C
 import os
@@ -9,7 +9,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 from manifoldem_python_b200 import _lib, synthetic, pd_stage   # noqa: E402
