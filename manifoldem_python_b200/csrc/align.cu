@@ -569,7 +569,7 @@ static int prefilter_run(mem_ctx* ctx, const float* in, float* out, int nS, int 
   const int E = (L + 31) / 32;
   const SegGeom gr = make_geom(L, E);
   const dim3 grid((N + 7) / 8, nS);
-  const bool rows_exact = !mirror && (N == 64 || N == 128 || N == 256);
+  const bool rows_exact = !mirror && (N == 64 || N == 128 || N == 256 || N == 320);
   if (rows_done) {
     // nothing to do for the rows
   } else if (rows_exact) {
@@ -579,9 +579,12 @@ static int prefilter_run(mem_ctx* ctx, const float* in, float* out, int nS, int 
     } else if (N == 128) {
       if (apply_mask) MEM_LAUNCH(ctx, (k_prefilter_rows_x<4, true>), grid, 256, 0, st, in, out, gr.zE);
       else MEM_LAUNCH(ctx, (k_prefilter_rows_x<4, false>), grid, 256, 0, st, in, out, gr.zE);
-    } else {
+    } else if (N == 256) {
       if (apply_mask) MEM_LAUNCH(ctx, (k_prefilter_rows_x<8, true>), grid, 256, 0, st, in, out, gr.zE);
       else MEM_LAUNCH(ctx, (k_prefilter_rows_x<8, false>), grid, 256, 0, st, in, out, gr.zE);
+    } else {                                         // 320 = 32 x 10: BASELINE config 5
+      if (apply_mask) MEM_LAUNCH(ctx, (k_prefilter_rows_x<10, true>), grid, 256, 0, st, in, out, gr.zE);
+      else MEM_LAUNCH(ctx, (k_prefilter_rows_x<10, false>), grid, 256, 0, st, in, out, gr.zE);
     }
   } else if (E <= 4) MEM_LAUNCH(ctx, k_prefilter_rows<4>, grid, 256, 0, st, in, out, N, L, gr, apply_mask);
   else if (E <= 8) MEM_LAUNCH(ctx, k_prefilter_rows<8>, grid, 256, 0, st, in, out, N, L, gr, apply_mask);
@@ -593,9 +596,10 @@ static int prefilter_run(mem_ctx* ctx, const float* in, float* out, int nS, int 
   const int Ec = (L + S - 1) / S;
   const SegGeom gc = make_geom(L, Ec);
   const dim3 gcols((N + 31) / 32, nS);
-  if (!mirror && (N == 128 || N == 256)) {
+  if (!mirror && (N == 128 || N == 256 || N == 320)) {
     if (N == 128) MEM_LAUNCH(ctx, k_prefilter_cols_x<8>, gcols, 256, 0, st, out, gc.zE);
-    else MEM_LAUNCH(ctx, k_prefilter_cols_x<16>, gcols, 512, 0, st, out, gc.zE);
+    else if (N == 256) MEM_LAUNCH(ctx, k_prefilter_cols_x<16>, gcols, 512, 0, st, out, gc.zE);
+    else MEM_LAUNCH(ctx, k_prefilter_cols_x<20>, gcols, 640, 0, st, out, gc.zE);
     return 0;
   }
   auto kc_small = k_prefilter_cols<512, 2, 16>;
