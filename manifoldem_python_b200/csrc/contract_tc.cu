@@ -258,6 +258,7 @@ k_contract_tc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
 // tcgen05.ld round trips, so the accumulator turns around well inside one chunk of MMAs.
 // ------------------------------------------------------------------------------------------------
 constexpr int STAGES2 = 3;
+constexpr int PACE_M = 32, PACE_W = 2;                  // milestone spacing (k-blocks) and allowed lead (milestones)
 constexpr int STAGE2_BYTES = 4 * BOX_BYTES;             // 64 KB per CTA
 constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
 constexpr int EPI_WARPS2 = 16;
@@ -302,7 +303,8 @@ __device__ __forceinline__ uint32_t make_idesc2(bool negate_a) {
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 k_contract_tc2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
-               const WorkItem* __restrict__ items, float* __restrict__ ws, int nS, int ldw, int n1, int chunk) {
+               const WorkItem* __restrict__ items, float* __restrict__ ws, int nS, int ldw, int n1, int chunk,
+               int* __restrict__ prog, int n_mil) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -346,7 +348,27 @@ k_contract_tc2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       const int arow = it.row0 + (int)rank * BOX_ROWS, brow = it.col0 + (int)rank * BOX_ROWS;
+      // Pacing (multi-wave launches only): the tiles of a super-block share operand panels through the L2 only while
+      // they read the same k-blocks at about the same time.  Every PACE_M k-blocks the leader's producer counts
+      // itself in at a milestone and does not run more than PACE_W milestones ahead of the slowest tile of its
+      // group (bounded wait: a group that is not fully resident falls back to free running).
+      bool pace = prog != nullptr && rank == 0 && it.pad1 > 1;
+      int* gp = prog ? prog + (size_t)it.pad0 * n_mil : nullptr;
       for (int kb = it.kb0; kb < it.kb1; ++kb) {
+        if (pace) {
+          const int rel = kb - it.kb0;
+          if (rel > 0 && (rel & (PACE_M - 1)) == 0) {
+            const int m = rel / PACE_M;
+            atomicAdd(gp + m, 1);
+            if (m > PACE_W) {                           // milestone 0 is the start and is never counted
+              const volatile int* w = gp + (m - PACE_W);
+              const long long t0 = clock64();
+              while (*w < it.pad1) {
+                if (clock64() - t0 > 1000000LL) { pace = false; break; }
+              }
+            }
+          }
+        }
         int ca, cb;
         if (kb < n1) { ca = kb; cb = kb + n1; }
         else if (kb < 2 * n1) { ca = kb; cb = kb - n1; }
@@ -525,6 +547,7 @@ int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, c
   const int chunk = k_chunk_blocks > 0 ? k_chunk_blocks : (two_cta ? (2 | 4 << 8) : 1);
   // tiles of the upper triangle (any element with col >= row)
   std::vector<std::pair<int, int>> tiles;
+  std::vector<int> tile_sb, sb_count;                    // super-block of every tile, tiles per super-block
   const int TM = two_cta ? 2 * BM : BM;                  // tile rows: a CTA pair covers 256
   const int units = two_cta ? ctx->sm_count / 2 : ctx->sm_count;
   const int tm = (nS + TM - 1) / TM, tn = (nS + BN - 1) / BN;
@@ -534,10 +557,17 @@ int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, c
   // column-by-column order needs ~4.9 TB/s of HBM and the contraction turns memory-bound.
   const int sbi = std::max(1, (int)floor(sqrt((double)units))), sbj = std::max(1, units / sbi);
   for (int sj = 0; sj < tn; sj += sbj)
-    for (int si = 0; si < tm; si += sbi)
+    for (int si = 0; si < tm; si += sbi) {
+      int cnt = 0;
       for (int bj = sj; bj < std::min(tn, sj + sbj); ++bj)
         for (int bi = si; bi < std::min(tm, si + sbi); ++bi)
-          if (bj * BN + BN - 1 >= bi * TM) tiles.push_back({bi, bj});
+          if (bj * BN + BN - 1 >= bi * TM) {
+            tiles.push_back({bi, bj});
+            tile_sb.push_back((int)sb_count.size());
+            ++cnt;
+          }
+      if (cnt) sb_count.push_back(cnt);
+    }
   const int T = (int)tiles.size();
   int split = split_k;
   if (split <= 0) {
@@ -557,7 +587,24 @@ int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, c
   std::vector<WorkItem> items;
   for (int s = 0; s < split; ++s) {
     const int kb0 = (int)((long long)nkb * s / split), kb1 = (int)((long long)nkb * (s + 1) / split);
-    for (auto& t : tiles) items.push_back({t.first * TM, t.second * BN, kb0, kb1, s, 0, 0, 0});
+    for (size_t ti = 0; ti < tiles.size(); ++ti)
+      items.push_back({tiles[ti].first * TM, tiles[ti].second * BN, kb0, kb1, s, 0, 0, 0});
+  }
+  // pacing groups = waves: `units` consecutive work items are resident together (all items have the same length)
+  const int n_groups = ((int)items.size() + units - 1) / units;
+  for (size_t k = 0; k < items.size(); ++k) {
+    const int g = (int)k / units;
+    items[k].pad0 = g;
+    items[k].pad1 = std::min(units, (int)items.size() - g * units);
+  }
+  // pacing counters: only when the launch takes more than one wave of CTA pairs (C3 / C5-sized PDs)
+  int* prog = nullptr;
+  const int n_mil = (nkb + split - 1) / split / PACE_M + 2;
+  if (two_cta && (int)items.size() > units) {
+    const size_t bytes = (size_t)n_groups * n_mil * sizeof(int);
+    MEM_CHECK(ctx->scratch.ensure(bytes));
+    prog = ctx->scratch.as<int>();
+    MEM_CUDA(cudaMemsetAsync(prog, 0, bytes, st));
   }
   MEM_CHECK(ctx->contract_ws.ensure((size_t)split * ldw * ldw * sizeof(float)));
   float* ws = ctx->contract_ws.as<float>();
@@ -584,7 +631,8 @@ int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, c
   }
   MEM_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used], st));
   if (two_cta)
-    MEM_LAUNCH(ctx, k_contract_tc2, 2 * (int)items.size(), NUM_THREADS2, SMEM2_BYTES, st, map_hi, map_lo, d_items, ws, nS, ldw, n1, chunk);
+    MEM_LAUNCH(ctx, k_contract_tc2, 2 * (int)items.size(), NUM_THREADS2, SMEM2_BYTES, st, map_hi, map_lo, d_items, ws, nS, ldw, n1, chunk,
+               prog, n_mil);
   else
     MEM_LAUNCH(ctx, k_contract_tc, (int)items.size(), NUM_THREADS, SMEM_BYTES, st, map_hi, map_lo, d_items, ws, nS, ldw, n1, chunk);
   MEM_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used + 1], st));
