@@ -235,3 +235,55 @@ def test_dropin_shims_resolve():
             sys.modules.pop(name, None)
     finally:
         sys.path.remove(d)
+
+
+def test_fused_lowpass_algebra_model():
+    """NumPy model of what lowpass.cu does at N = 256: (1) two real rows as one complex FFT and the separation of their
+    half spectra, (2) moments taken on offset-shifted pixels outside the disc and the normalisation applied in
+    Fourier space (scale + DC term), (3) the rebuilt full spectrum of a row pair for the inverse transform.
+    The result must equal the straightforward (x - mean(b)) / std(b) -> fft2 * G -> ifft2 of the reference (:276-293)."""
+    rng = np.random.default_rng(3)
+    N = 32
+    x = (1000.0 + 10.0 * rng.standard_normal((N, N)))            # un-normalised particle with a large offset
+    yy, xx = np.mgrid[:N, :N]
+    msk = ((yy - N / 2 + 1) ** 2 + (xx - N / 2) ** 2) < (N / 2) ** 2    # annularMask.py:24-30
+    G = rng.random((N, N // 2 + 1))                               # any real filter table in half-spectrum layout
+    G[0, 0] = 1.0 / (N * N)
+    # reference order of operations
+    b = x * (1 - msk)
+    xn = (x - b.mean()) / b.std()
+    ref = np.fft.irfft2(np.fft.rfft2(xn) * G, s=(N, N)) * (N * N)   # cuFFT-style unnormalised inverse
+    # (1) row pairs
+    off = x[0, 0]
+    xs = x - off
+    spec = np.empty((N, N // 2 + 1), complex)
+    for r in range(0, N, 2):
+        Z = np.fft.fft(xs[r] + 1j * xs[r + 1])
+        Zn = np.conj(Z[(-np.arange(N // 2 + 1)) % N])
+        spec[r] = 0.5 * (Z[:N // 2 + 1] + Zn)
+        spec[r + 1] = -0.5j * (Z[:N // 2 + 1] - Zn)
+    assert np.allclose(spec, np.fft.rfft(xs, axis=1), atol=1e-9)
+    # (2) moments on shifted values, outside pixels only; undo the offset in the sums
+    out = ~msk
+    s1, s2, cnt = xs[out].sum(), (xs[out] ** 2).sum(), out.sum()
+    S1, S2 = s1 + off * cnt, s2 + 2 * off * s1 + off * off * cnt
+    mean = S1 / (N * N)
+    inv = 1.0 / np.sqrt(S2 / (N * N) - mean * mean)
+    assert np.isclose(mean, b.mean()) and np.isclose(inv, 1.0 / b.std())
+    F = np.fft.fft(spec, axis=0)                                   # column pass
+    F[0, 0] -= (mean - off) * N * N                                # what is left of the mean after the offset
+    F *= G * inv
+    colback = np.fft.ifft(F, axis=0) * N                           # unnormalised inverse column pass
+    # (3) rebuild z of a row pair and invert
+    got = np.empty((N, N))
+    k = np.arange(N // 2 + 1)
+    for r in range(0, N, 2):
+        X1, X2 = colback[r].copy(), colback[r + 1].copy()
+        X1[[0, N // 2]] = X1[[0, N // 2]].real                     # a C2R ignores these imaginary parts
+        X2[[0, N // 2]] = X2[[0, N // 2]].real
+        Z = np.empty(N, complex)
+        Z[k] = X1 + 1j * X2
+        Z[(N - k[1:-1])] = np.conj(X1[1:-1]) + 1j * np.conj(X2[1:-1])
+        z = np.fft.ifft(Z) * N
+        got[r], got[r + 1] = z.real, z.imag
+    assert np.abs(got - ref).max() < 1e-9 * np.abs(ref).max()
