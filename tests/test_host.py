@@ -287,3 +287,62 @@ def test_fused_lowpass_algebra_model():
         z = np.fft.ifft(Z) * N
         got[r], got[r + 1] = z.real, z.imag
     assert np.abs(got - ref).max() < 1e-9 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize('N', [16, 15])
+def test_contraction_operand_algebra_model(N):
+    """NumPy model of the operand layout of DESIGN.md §3 against the reference formula (:391-397)
+    D = |C|^2 (|F|^2)^T + transpose - 2 Re(A A^H), A = conj(C) F over the full N x N spectrum:
+    radial binning of the first term, Hermitian half spectrum with weight 2 for the second, the self-conjugate
+    pixels carried in the swap segments, and the common component F - C M removed from every image."""
+    rng = np.random.default_rng(N)
+    nS = 7
+    imgs = rng.standard_normal((nS, N, N))
+    F = np.fft.fft2(imgs)
+    f = np.fft.fftfreq(N, 1.0 / N).round().astype(int)
+    r2 = f[:, None] ** 2 + f[None, :] ** 2
+    df = rng.uniform(1.0, 3.0, nS)
+    C = np.sin(0.05 * r2[None] * df[:, None, None]) - 0.1 * np.cos(0.05 * r2[None] * df[:, None, None])   # even, radial
+    Cf, Ff = C.reshape(nS, -1), F.reshape(nS, -1)
+    A = np.conj(Cf) * Ff
+    T1 = (np.abs(Cf) ** 2) @ (np.abs(Ff) ** 2).T
+    D_ref = T1 + T1.T - 2 * np.real(A @ np.conj(A).T)
+    # half spectrum, common component
+    Nh = N // 2 + 1
+    Fh, Ch, r2h = F[:, :, :Nh], C[:, :, :Nh], r2[:, :Nh]
+    M = (Ch * Fh).sum(0) / (Ch ** 2).sum(0)
+    Gh = Fh - Ch * M
+    even = N % 2 == 0
+    selfcol = np.zeros(Nh, bool)
+    selfcol[0] = True
+    if even:
+        selfcol[N // 2] = True
+    w = np.where(selfcol, 1.0, 2.0)[None, :] * np.ones((N, 1))
+    bins, inv = np.unique(r2h.ravel(), return_inverse=True)
+    Cb = np.stack([np.sin(0.05 * bins * d) - 0.1 * np.cos(0.05 * bins * d) for d in df])
+    P = np.zeros((nS, len(bins)))
+    for i in range(nS):
+        np.add.at(P[i], inv, (w * np.abs(Gh[i]) ** 2).ravel())
+    S1, S2 = Cb ** 2 / 4, P
+    # S3: one representative per conjugate pair (weight 2), (Re, Im) of A; self-conjugate pixels ride in S1/S2 as -x/4, x
+    rep = np.zeros((N, Nh), bool)
+    special = []
+    for ky in range(N):
+        for kx in range(Nh):
+            if not selfcol[kx]:
+                rep[ky, kx] = True
+            else:
+                selfrow = ky == 0 or (even and ky == N // 2)
+                if selfrow:
+                    special.append((ky, kx))
+                elif ky < (N + 1) // 2:
+                    rep[ky, kx] = True
+    Ah = Ch * Gh
+    S3 = np.concatenate([Ah[:, rep].real, Ah[:, rep].imag], axis=1)
+    xs = np.stack([(Ch[:, ky, kx] * Gh[:, ky, kx]).real for ky, kx in special], axis=1)
+    S1 = np.concatenate([S1, -xs / 4], axis=1)
+    S2 = np.concatenate([S2, xs], axis=1)
+    D = 4 * (S1 @ S2.T + S2 @ S1.T - S3 @ S3.T)
+    off = ~np.eye(nS, dtype=bool)
+    assert np.abs(D - D_ref)[off].max() < 1e-9 * D_ref[off].max()
+    assert np.abs(np.diag(D)).max() < 1e-9 * D_ref[off].max()
