@@ -29,13 +29,33 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
 
+// complex add / subtract as ONE packed instruction (FADD2 on sm_100: both halves of a 64-bit register pair)
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+  unsigned long long ua, ub, ud;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(ud) : "l"(ua), "l"(ub));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(ud));
+  return d;
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+  unsigned long long ua, ub, ud;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(ud) : "l"(ua), "l"(ub));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(ud));
+  return d;
+}
+
 // 4-point DFT, exponent sign S: (a, b, c, d) <- (X0, X1, X2, X3)
 template <int S>
 __device__ __forceinline__ void fft4(float2& a, float2& b, float2& c, float2& d) {
-  const float2 s0 = make_float2(a.x + c.x, a.y + c.y), s1 = make_float2(a.x - c.x, a.y - c.y);
-  const float2 s2 = make_float2(b.x + d.x, b.y + d.y), s3 = make_float2(b.x - d.x, b.y - d.y);
-  a = make_float2(s0.x + s2.x, s0.y + s2.y);
-  c = make_float2(s0.x - s2.x, s0.y - s2.y);
+  const float2 s0 = cadd(a, c), s1 = csub(a, c);
+  const float2 s2 = cadd(b, d), s3 = csub(b, d);
+  a = cadd(s0, s2);
+  c = csub(s0, s2);
   if (S < 0) {   // X1 = s1 - i s3, X3 = s1 + i s3
     b = make_float2(s1.x + s3.y, s1.y - s3.x);
     d = make_float2(s1.x - s3.y, s1.y + s3.x);
