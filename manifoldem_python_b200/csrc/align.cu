@@ -2,6 +2,7 @@
 // resamplings per particle, each = separable recursive prefilter (rows, columns) + 4x4-tap gather.
 // All HBM-bound streaming kernels: every pass reads and writes each image exactly once.
 #include "common.cuh"
+#include "spline.cuh"
 
 namespace mem {
 
@@ -92,8 +93,6 @@ __global__ void __launch_bounds__(256) k_ingest(const float* __restrict__ raw, c
 // recursion from a zero carry, and the true carry is  sum_h z^(samples between) * (local end of the
 // h-th previous segment) — z^20 < 4e-12, so a few hops suffice, wrapping around for periodicity.
 // ------------------------------------------------------------------------------------------------
-#define SPL_Z (-0.26794919243112270647f)
-#define SPL_REACH 20   // samples after which z^n is dropped
 
 __device__ __forceinline__ float zpow(int n) {
   float r = 1.0f, b = SPL_Z;
@@ -273,7 +272,6 @@ __global__ void __launch_bounds__(MAXT, MINB) k_prefilter_cols(float* __restrict
 template <int E, bool MASK>
 __global__ void __launch_bounds__(256) k_prefilter_rows_x(const float* __restrict__ in, float* __restrict__ out, float zE) {
   constexpr int N = 32 * E;
-  constexpr int H = SPL_REACH / E + 2;
   __shared__ float line[8][N + E];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp;
@@ -299,30 +297,7 @@ __global__ void __launch_bounds__(256) k_prefilter_rows_x(const float* __restric
   float v[E];
 #pragma unroll
   for (int j = 0; j < E; ++j) v[j] = ln[c0 + j + ((c0 + j) >> 5)];
-  float run = 0.0f;
-#pragma unroll
-  for (int j = 0; j < E; ++j) { run = fmaf(SPL_Z, run, v[j]); v[j] = run; }
-  float carry = 0.0f, f = 1.0f;
-#pragma unroll
-  for (int h = 1; h <= H; ++h) {
-    carry = fmaf(f, __shfl_sync(0xffffffffu, run, (lane - h) & 31), carry);
-    f *= zE;
-  }
-  float zp = SPL_Z * carry;
-#pragma unroll
-  for (int j = 0; j < E; ++j) { v[j] += zp; zp *= SPL_Z; }
-  run = 0.0f;
-#pragma unroll
-  for (int j = E - 1; j >= 0; --j) { run = SPL_Z * (run - v[j]); v[j] = run; }
-  carry = 0.0f; f = 1.0f;
-#pragma unroll
-  for (int h = 1; h <= H; ++h) {
-    carry = fmaf(f, __shfl_sync(0xffffffffu, run, (lane + h) & 31), carry);
-    f *= zE;
-  }
-  zp = SPL_Z * carry;
-#pragma unroll
-  for (int j = E - 1; j >= 0; --j) { v[j] += zp; zp *= SPL_Z; }
+  spline_line_warp<E>(v, zE, lane);
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < E; ++j) ln[c0 + j + ((c0 + j) >> 5)] = v[j];

@@ -14,6 +14,7 @@
 //             inverse FFT-16 over k2, conjugate twiddle, exchange, inverse FFT-16, store rows t + 16 m.
 // Shared memory is touched only by the two exchanges; all its accesses are unit-stride across lanes.
 #include "common.cuh"
+#include "spline.cuh"
 
 #include <math.h>
 #include <algorithm>
@@ -314,10 +315,9 @@ __global__ void __launch_bounds__(256, 3) k_ingest_rowfft256(const float* __rest
 // run the inverse FFT-256 and leave the two real rows in shared memory; then every warp filters four rows, lane l
 // owning samples [8 l, 8 l + 8), and stores them row-coalesced.  The low-passed image itself never reaches HBM.
 // ------------------------------------------------------------------------------------------------
-#define LP_SPL_Z (-0.26794919243112270647f)
 constexpr int RP_BP = 264;      // band pitch: 256 samples + one pad float per 32 (conflict-free for both access patterns)
 __global__ void __launch_bounds__(256, 3) k_rowifft_prefilter256(const float2* __restrict__ spec, float* __restrict__ outimg) {
-  constexpr int N = 256, Nh = 129, E = 8, H = 20 / E + 2;
+  constexpr int N = 256, Nh = 129, E = 8;
   extern __shared__ float2 ir_smem[];
   float2* ex = ir_smem;
   float* band = reinterpret_cast<float*>(ir_smem + 16 * IR_EP);     // [32][RP_BP]
@@ -381,30 +381,7 @@ __global__ void __launch_bounds__(256, 3) k_rowifft_prefilter256(const float2* _
         const float val = ln[c0 + j + ((c0 + j) >> 5)];
         s[j] = (y * y < lim) ? 6.0f * val : 0.0f;
       }
-      float run = 0.0f;
-#pragma unroll
-      for (int j = 0; j < E; ++j) { run = fmaf(LP_SPL_Z, run, s[j]); s[j] = run; }
-      float carry = 0.0f, f = 1.0f;
-#pragma unroll
-      for (int h = 1; h <= H; ++h) {
-        carry = fmaf(f, __shfl_sync(0xffffffffu, run, (lane - h) & 31), carry);
-        f *= zE;
-      }
-      float zp = LP_SPL_Z * carry;
-#pragma unroll
-      for (int j = 0; j < E; ++j) { s[j] += zp; zp *= LP_SPL_Z; }
-      run = 0.0f;
-#pragma unroll
-      for (int j = E - 1; j >= 0; --j) { run = LP_SPL_Z * (run - s[j]); s[j] = run; }
-      carry = 0.0f; f = 1.0f;
-#pragma unroll
-      for (int h = 1; h <= H; ++h) {
-        carry = fmaf(f, __shfl_sync(0xffffffffu, run, (lane + h) & 31), carry);
-        f *= zE;
-      }
-      zp = LP_SPL_Z * carry;
-#pragma unroll
-      for (int j = E - 1; j >= 0; --j) { s[j] += zp; zp *= LP_SPL_Z; }
+      spline_line_warp<E>(s, zE, lane);
       // lane l holds samples [8 l, 8 l + 8): two 16-byte stores per lane, the warp writes its 1 KB row contiguously
       float4* orow = reinterpret_cast<float4*>(dst + (b0 + row) * N + c0);
       orow[0] = make_float4(s[0], s[1], s[2], s[3]);
