@@ -275,7 +275,7 @@ def run_reference(args):
               'faster of the serial mode (all BLAS threads) and the Pool / MPI-schedule emulation (one PD per worker)'
               % (detail['images'], nS, cores, detail['gemm_rows'], detail['gemm_rows']))
     line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=float(np.mean([b for _, b in vals])) * 1e3 * args.pds, higher_is_better=True,
+                ms_per_step=float(np.mean([b for _, b in vals])) * 1e3 * args.pds * max(1, args.gpus), higher_is_better=True,
                 scaling='weak', vs_baseline=None, dtype='f64', data='synthetic', impl='reference',
                 config=dict(workload='BASELINE config 4 shape: PDs of %d particles x %d^2' % (nS, N), pds_per_gpu=args.pds),
                 cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind='port', sample=sample, detail=detail),
