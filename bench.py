@@ -277,7 +277,8 @@ def run_reference(args):
     line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=float(np.mean([b for _, b in vals])) * 1e3 * args.pds * max(1, args.gpus), higher_is_better=True,
                 scaling='weak', vs_baseline=None, dtype='f64', data='synthetic', impl='reference',
-                config=dict(workload='BASELINE config 4 shape: PDs of %d particles x %d^2' % (nS, N), pds_per_gpu=args.pds),
+                config=dict(workload='BASELINE config 4 shape: PDs of %d particles x %d^2, %d PDs per GPU per step '
+                                     '(1000 PDs at 8 GPUs)' % (nS, N, args.pds), pds_per_gpu=args.pds, nS=nS, N=N),
                 cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind='port', sample=sample, detail=detail),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
