@@ -74,6 +74,10 @@ typedef struct {
                             low byte = period inside the S1/S2 columns, bits 8.. = period inside S3 (0 = same);
                             0 = default (CTA pairs: 2 | 4 << 8, single CTA: 1) */
   int32_t split_k;       /* tcgen05: K slices per tile; 0 = auto (fill 148 SMs)                  */
+  int32_t knn_k;         /* > 0 with io.knn_idx / io.knn_val: the k nearest neighbours of every particle
+                            (DMembeddingII.initialize, modules/DMembeddingII.py:43-57) straight behind the
+                            contraction; with io.D == NULL the nS x nS matrix is never assembled */
+  int32_t reserved0;
 } mem_pd_params;
 
 typedef struct {
@@ -92,6 +96,8 @@ typedef struct {
   float*  imgAvg;            /* [N][N] Wiener-filtered average                       (:353-366) */
   float*  imgAvgFlip;        /* [N][N] average of phase-flipped images               (:367) */
   float*  imgAllIntensity;   /* [N][N] mean(imgAllFlip^2)                            (:400) */
+  int32_t* knn_idx;          /* [nS][knn_k] neighbour indices, self first   (DMembeddingII.py:43-57) */
+  double*  knn_val;          /* [nS][knn_k] squared distances, [i][0] = 0                            */
 } mem_pd_io;
 
 /* all pointers in io are DEVICE pointers; work is enqueued on `stream` (a cudaStream_t, NULL = the
@@ -115,6 +121,10 @@ typedef struct {
 } mem_contract_shape;
 int mem_contract_device(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, const float* Zlo,
                         float* D, int32_t contraction, int32_t k_chunk_blocks, int32_t split_k, void* stream);
+/* the same with the kNN lists (a15) taken from the split-K partial tiles; D may be NULL (never assembled) */
+int mem_contract_knn_device(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, const float* Zlo,
+                            float* D, int32_t k, int32_t* knn_idx, double* knn_val, int32_t contraction,
+                            int32_t k_chunk_blocks, int32_t split_k, void* stream);
 /* operand layout for a box size (columns of Z): fills n1_blocks, n3_blocks, ldz */
 int mem_operand_shape(mem_ctx* ctx, int32_t N, mem_contract_shape* out);
 
@@ -125,6 +135,10 @@ int mem_operand_shape(mem_ctx* ctx, int32_t N, mem_contract_shape* out);
 int mem_knn_device(mem_ctx* ctx, const double* D, int32_t nS, int32_t k, int32_t* idx, double* val, void* stream);
 /* a15 on the float32 D that mem_pd_distance_device leaves on the device (D never visits the host) */
 int mem_knn_device_f32(mem_ctx* ctx, const float* D, int32_t nS, int32_t k, int32_t* idx, double* val, void* stream);
+/* which kNN kernel the three kNN paths use (process-wide): 0 = automatic (radix selection of the k winners when
+ * 4 k <= nS and the row fits shared memory, else a full bitonic sort of the row), 1 = always sort, 2 = selection
+ * whenever it fits.  Both kernels return identical lists (ties by index); the switch exists for tests and timing. */
+int mem_knn_mode(int32_t mode);
 /* a16 OR-symmetrised kNN graph (DMembeddingII.op :113-140) in dense form: M [nS][nS] float64 device,
  * M[i][j] = d^2 of the union graph, 0 for the 'zero' (self) entries, -1 where there is no edge. */
 int mem_graph_dense_device(mem_ctx* ctx, const int32_t* idx, const double* val, int32_t nS, int32_t k, double* M,

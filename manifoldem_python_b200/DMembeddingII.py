@@ -40,24 +40,31 @@ def _fit(logEps, logSumWij, a0):
     return popt, resnorm, R_squared
 
 
-def graph_and_sweep(D, k, ctx=None, nS=None):
+def graph_and_sweep(D, k, ctx=None, nS=None, knn=None):
     """Device part up to the Ferguson curve.  `D`: host (nS,nS) array, or a `_lib.DeviceArray` holding the
-    float32 D that the distance stage left on the device (then D never visits the host).
+    float32 D that the distance stage left on the device (then D never visits the host), or None with
+    `knn` = (idx, val) device arrays that the distance stage selected itself (pd_stage.run_pd_resident(knn_k=k,
+    keep_D=False): D was never assembled; the lists are consumed and freed here).
     Returns (M_dev DeviceArray (nS,nS) float64 graph, logEps, logSumWij, idx (nS,k) int32, val (nS,k) float64)."""
     lib = _lib.load()
     ctx = ctx or _ctx()
-    resident = isinstance(D, _lib.DeviceArray)
-    nS = D.shape[0]
-    idx_d = _lib.DeviceArray(ctx, (nS, k), np.int32)
-    val_d = _lib.DeviceArray(ctx, (nS, k), np.float64)
-    if resident:
-        if D.dtype != np.float32:
-            raise TypeError('resident D must be float32')
-        _lib.check(lib.mem_knn_device_f32(ctx.handle, D.ptr, nS, k, idx_d.ptr, val_d.ptr, None))
-        Dd = None
+    Dd = None
+    if knn is not None:
+        idx_d, val_d = knn
+        nS = idx_d.shape[0]
+        if idx_d.shape != (nS, k) or val_d.shape != (nS, k) or idx_d.dtype != np.int32 or val_d.dtype != np.float64:
+            raise TypeError('knn lists must be (nS,k) int32 / float64 device arrays')
     else:
-        Dd = _lib.DeviceArray(ctx, (nS, nS), np.float64, np.ascontiguousarray(D, dtype=np.float64))
-        _lib.check(lib.mem_knn_device(ctx.handle, Dd.ptr, nS, k, idx_d.ptr, val_d.ptr, None))
+        nS = D.shape[0]
+        idx_d = _lib.DeviceArray(ctx, (nS, k), np.int32)
+        val_d = _lib.DeviceArray(ctx, (nS, k), np.float64)
+        if isinstance(D, _lib.DeviceArray):
+            if D.dtype != np.float32:
+                raise TypeError('resident D must be float32')
+            _lib.check(lib.mem_knn_device_f32(ctx.handle, D.ptr, nS, k, idx_d.ptr, val_d.ptr, None))
+        else:
+            Dd = _lib.DeviceArray(ctx, (nS, nS), np.float64, np.ascontiguousarray(D, dtype=np.float64))
+            _lib.check(lib.mem_knn_device(ctx.handle, Dd.ptr, nS, k, idx_d.ptr, val_d.ptr, None))
     M = _lib.DeviceArray(ctx, (nS, nS), np.float64)
     _lib.check(lib.mem_graph_dense_device(ctx.handle, idx_d.ptr, val_d.ptr, nS, k, M.ptr, None))
     # k < nS: sweep over the edges only (row-major compaction), not over the nS^2 slots of the dense graph

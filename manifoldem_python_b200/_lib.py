@@ -15,6 +15,7 @@ SYMBOLS = [
     'mem_version', 'mem_last_error', 'mem_ctx_create', 'mem_ctx_destroy', 'mem_ctx_sync', 'mem_ctx_launch_count',
     'mem_ctx_timer_start', 'mem_ctx_timer_stop', 'mem_ctx_kernel_time', 'mem_host_alloc', 'mem_host_free', 'mem_dev_alloc', 'mem_dev_free', 'mem_copy_h2d', 'mem_copy_d2h',
     'mem_pd_distance_device', 'mem_pd_distance_host', 'mem_pd_last_timings', 'mem_contract_device',
+    'mem_contract_knn_device', 'mem_knn_mode',
     'mem_operand_shape', 'mem_knn_device', 'mem_knn_device_f32', 'mem_graph_dense_device', 'mem_graph_compact_device', 'mem_ferguson_device',
     'mem_laplacian_dense_device', 'mem_symv_host',
 ]
@@ -25,14 +26,15 @@ class PdParams(C.Structure):
                 ('filter_type', C.c_int32), ('filter_order', C.c_int32), ('filter_Qc', C.c_double),
                 ('pix_size', C.c_double), ('Cs', C.c_double), ('EkV', C.c_double), ('gaussEnv', C.c_double),
                 ('AmpContrast', C.c_double), ('psi_p_deg', C.c_double), ('avg_only', C.c_int32),
-                ('contraction', C.c_int32), ('k_chunk_blocks', C.c_int32), ('split_k', C.c_int32)]
+                ('contraction', C.c_int32), ('k_chunk_blocks', C.c_int32), ('split_k', C.c_int32),
+                ('knn_k', C.c_int32), ('reserved0', C.c_int32)]
 
 
 class PdIO(C.Structure):
     _fields_ = [('raw', C.c_void_p), ('flip', C.c_void_p), ('shift', C.c_void_p), ('psi_deg', C.c_void_p),
                 ('df', C.c_void_p), ('msk2', C.c_void_p), ('D', C.c_void_p), ('imgAll', C.c_void_p),
                 ('imgAllFlip', C.c_void_p), ('CTF', C.c_void_p), ('imgAvg', C.c_void_p), ('imgAvgFlip', C.c_void_p),
-                ('imgAllIntensity', C.c_void_p)]
+                ('imgAllIntensity', C.c_void_p), ('knn_idx', C.c_void_p), ('knn_val', C.c_void_p)]
 
 
 class ContractShape(C.Structure):
@@ -77,6 +79,10 @@ def load():
         lib.mem_pd_last_timings.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
         lib.mem_contract_device.argtypes = [C.c_void_p, C.POINTER(ContractShape), C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        lib.mem_contract_knn_device.argtypes = [C.c_void_p, C.POINTER(ContractShape), C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                                C.c_void_p]
+        lib.mem_knn_mode.argtypes = [C.c_int32]
         lib.mem_operand_shape.argtypes = [C.c_void_p, C.c_int32, C.POINTER(ContractShape)]
         lib.mem_knn_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.mem_knn_device_f32.argtypes = lib.mem_knn_device.argtypes

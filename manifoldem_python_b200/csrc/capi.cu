@@ -9,7 +9,6 @@ namespace mem {
 const char* last_error();
 int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* io, cudaStream_t st);
 int knn_device(mem_ctx* ctx, const double* D, int nS, int k, int* idx, double* val, cudaStream_t st);
-int knn_device_f32(mem_ctx* ctx, const float* D, int nS, int k, int* idx, double* val, cudaStream_t st);
 int graph_compact_device(mem_ctx* ctx, const double* M, int nS, double* out, long long* count);
 int graph_dense_device(mem_ctx* ctx, const int* idx, const double* val, int nS, int k, double* M, cudaStream_t st);
 int ferguson_device(mem_ctx* ctx, const double* d2, int64_t n, const double* logEps, int nEps, double thr, double* out);
@@ -58,7 +57,7 @@ int mem_ctx_destroy(mem_ctx* ctx) {
                          &ctx->stats, &ctx->D, &ctx->ctf64, &ctx->small_out, &ctx->contract_ws, &ctx->contract_items, &ctx->scratch,
                          &ctx->geom.Gtab, &ctx->geom.bin_of_pix, &ctx->geom.r2_of_bin, &ctx->geom.bin_start,
                          &ctx->geom.bin_pix, &ctx->geom.s3_col, &ctx->geom.special_pix, &ctx->geom.fold_bin,
-                         &ctx->geom.fold_start, &ctx->geom.fold_ent, &ctx->knn_ws};
+                         &ctx->geom.fold_start, &ctx->geom.fold_ent, &ctx->knn_ws, &ctx->knn_out};
   for (auto* b : bufs) b->release();
   for (auto& e : ctx->ev) cudaEventDestroy(e);
   for (auto& e : ctx->timer) cudaEventDestroy(e);
@@ -187,6 +186,12 @@ int mem_pd_distance_host(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io
     MEM_CHECK(ctx->ctf64.ensure(nS * NN * sizeof(double)));
     d.CTF = ctx->ctf64.as<double>();
   }
+  const bool want_knn = prm->knn_k > 0 && h->knn_idx && h->knn_val && !prm->avg_only;
+  if (want_knn) {   // lists: int32 indices behind the float64 values in one buffer
+    MEM_CHECK(ctx->knn_out.ensure(nS * (size_t)prm->knn_k * (sizeof(double) + sizeof(int32_t))));
+    d.knn_val = ctx->knn_out.as<double>();
+    d.knn_idx = reinterpret_cast<int32_t*>(d.knn_val + nS * (size_t)prm->knn_k);
+  }
   MEM_CHECK(ctx->stats.ensure(3 * NN * sizeof(float)));
   float* small = ctx->stats.as<float>();
   if (h->imgAvg) d.imgAvg = small;
@@ -195,6 +200,10 @@ int mem_pd_distance_host(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io
   MEM_CHECK(pd_distance_device(ctx, prm, &d, st));
   MEM_CUDA(cudaEventRecord(ctx->ev[8], st));
   if (d.D) MEM_CUDA(cudaMemcpyAsync(h->D, d.D, nS * nS * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (want_knn) {
+    MEM_CUDA(cudaMemcpyAsync(h->knn_idx, d.knn_idx, nS * (size_t)prm->knn_k * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MEM_CUDA(cudaMemcpyAsync(h->knn_val, d.knn_val, nS * (size_t)prm->knn_k * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
   if (d.imgAll) MEM_CUDA(cudaMemcpyAsync(h->imgAll, d.imgAll, nS * NN * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (d.imgAllFlip) MEM_CUDA(cudaMemcpyAsync(h->imgAllFlip, d.imgAllFlip, nS * NN * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (d.CTF) MEM_CUDA(cudaMemcpyAsync(h->CTF, d.CTF, nS * NN * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -223,6 +232,28 @@ int mem_contract_device(mem_ctx* ctx, const mem_contract_shape* shp, const float
                         int32_t contraction, int32_t k_chunk_blocks, int32_t split_k, void* stream) {
   MEM_CUDA(cudaSetDevice(ctx->device));
   return contract_run(ctx, shp, Zhi, Zlo, D, contraction, k_chunk_blocks, split_k, pick(ctx, stream));
+}
+
+int mem_contract_knn_device(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, const float* Zlo, float* D,
+                            int32_t k, int32_t* knn_idx, double* knn_val, int32_t contraction, int32_t k_chunk_blocks,
+                            int32_t split_k, void* stream) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  KnnOut knn;
+  knn.k = k; knn.idx = knn_idx; knn.val = knn_val;
+  if (k <= 0 || !knn_idx || !knn_val) {
+    set_error("mem_contract_knn_device: k > 0 and both list pointers are required");
+    return 1;
+  }
+  return contract_run(ctx, shp, Zhi, Zlo, D, contraction, k_chunk_blocks, split_k, pick(ctx, stream), &knn);
+}
+
+int mem_knn_mode(int32_t mode) {
+  if (mode < 0 || mode > 2) {
+    set_error("mem_knn_mode: 0 (auto), 1 (sort) or 2 (selection)");
+    return 1;
+  }
+  knn_set_mode(mode);
+  return 0;
 }
 
 int mem_operand_shape(mem_ctx* ctx, int32_t N, mem_contract_shape* out) {

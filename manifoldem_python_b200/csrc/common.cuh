@@ -106,6 +106,7 @@ struct mem_ctx {
   long long items_key[4] = {-1, -1, -1, -1};   // nS, nkb, split, count
   mem::DevBuf scratch;       // misc (ferguson partials, knn)
   mem::DevBuf knn_ws;        // (key, index) rows of the chunked sort, only for nS > 16,384
+  mem::DevBuf knn_out;       // kNN lists of the host-buffer entry point
   cudaEvent_t ev[10] = {};
   cudaEvent_t timer[2] = {};
   std::vector<cudaEvent_t> kev;   // event pairs around every contraction launch since the last reset
@@ -127,8 +128,15 @@ int ingest_rowfft_run(mem_ctx* ctx, const float* raw, const uint8_t* flip, float
                       int transposed, cudaStream_t st);
 // inverse row pass (C2R) + annular mask + row pass of the periodic spline prefilter: half spectra -> out [nS][N][N]
 int rowifft_prefilter_run(mem_ctx* ctx, const float2* spec, float* out, int nS, int N, cudaStream_t st);
+// kNN lists wanted from the contraction (a15 fused behind a12): idx [nS][k] int32, val [nS][k] float64, device.
+// With D == nullptr the nS x nS matrix is never assembled: the lists are selected from the split-K partial tiles.
+struct KnnOut { int k = 0; int* idx = nullptr; double* val = nullptr; };
 int contract_run(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, const float* Zlo, float* D,
-                 int contraction, int k_chunk_blocks, int split_k, cudaStream_t st);
+                 int contraction, int k_chunk_blocks, int split_k, cudaStream_t st, const KnnOut* knn = nullptr);
 int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, const float* Zlo, float* D,
-                int k_chunk_blocks, int split_k, cudaStream_t st, int two_cta);
+                int k_chunk_blocks, int split_k, cudaStream_t st, int two_cta, const KnnOut* knn = nullptr);
+int knn_device_f32(mem_ctx* ctx, const float* D, int nS, int k, int* idx, double* val, cudaStream_t st);
+int knn_from_workspace(mem_ctx* ctx, const float* ws, int ldw, int nslices, int nS, int k, int* idx, double* val,
+                       cudaStream_t st);
+void knn_set_mode(int mode);
 }  // namespace mem

@@ -49,14 +49,24 @@ __global__ void __launch_bounds__(256) k_contract_simt(const float* __restrict__
 }
 
 int contract_run(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, const float* Zlo, float* D,
-                 int contraction, int k_chunk_blocks, int split_k, cudaStream_t st) {
+                 int contraction, int k_chunk_blocks, int split_k, cudaStream_t st, const KnnOut* knn) {
+  const bool want_knn = knn && knn->k > 0 && knn->idx && knn->val;
+  if (!D && !want_knn) {
+    set_error("contraction: neither D nor kNN lists requested");
+    return 1;
+  }
   if (shp->nS <= 0 || shp->ldz < 32LL * (2 * shp->n1_blocks + shp->n3_blocks) || (shp->ldz & 3)) {
     set_error("bad contraction shape");
     return 1;
   }
   if (contraction == 1) {
+    if (!D) {                                         // the checker always assembles D
+      MEM_CHECK(ctx->D.ensure((size_t)shp->nS * shp->nS * sizeof(float)));
+      D = ctx->D.as<float>();
+    }
     dim3 grid((shp->nS + 15) / 16, (shp->nS + 15) / 16);
     MEM_LAUNCH(ctx, k_contract_simt, grid, 256, 0, st, Zhi, Zlo, D, shp->nS, shp->n1_blocks, shp->n3_blocks, shp->ldz);
+    if (want_knn) MEM_CHECK(knn_device_f32(ctx, D, shp->nS, knn->k, knn->idx, knn->val, st));
     return 0;
   }
   if (contraction != 0 && contraction != 2) {
@@ -64,7 +74,8 @@ int contract_run(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, 
     return 1;
   }
   // 0: product path, CTA-pair tiles (cta_group::2);  2: single-CTA tiles (kept for comparison and tests)
-  return contract_tc(ctx, shp, Zhi, Zlo, D, k_chunk_blocks, split_k, st, contraction == 0 ? 1 : 0);
+  return contract_tc(ctx, shp, Zhi, Zlo, D, k_chunk_blocks, split_k, st, contraction == 0 ? 1 : 0,
+                     want_knn ? knn : nullptr);
 }
 
 }  // namespace mem

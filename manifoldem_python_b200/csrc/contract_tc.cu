@@ -527,7 +527,7 @@ static int make_map(mem_ctx* ctx, CUtensorMap* map, const float* Z, int nS, int6
 }
 
 int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, const float* Zlo, float* D,
-                int k_chunk_blocks, int split_k, cudaStream_t st, int two_cta) {
+                int k_chunk_blocks, int split_k, cudaStream_t st, int two_cta, const KnnOut* knn) {
   const int nS = shp->nS, n1 = shp->n1_blocks, n3 = shp->n3_blocks;
   const int nkb = 2 * n1 + n3;
   if (((uintptr_t)Zhi & 15) || ((uintptr_t)Zlo & 15)) {
@@ -639,8 +639,23 @@ int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, c
   ctx->kev_used += 2;
   ctx->last_tc_items = (two_cta ? 2 : 1) * (int)items.size();   // CTAs, each computing a 128 x 256 tile of its slice
   ctx->last_tc_nkb = (nkb + split - 1) / split;                   // K blocks per CTA
-  dim3 fgrid((nS + 31) / 32, (nS + 31) / 32);
-  MEM_LAUNCH(ctx, k_contract_finalize, fgrid, 256, 0, st, ws, D, nS, ldw, split);
+  // a15 behind a12: the neighbour lists are selected straight from the partial tiles; D is assembled only when
+  // the caller asked for it, or when the list is too long a part of the row for the selection kernel
+  bool knn_done = false;
+  if (knn) {
+    const int rc = knn_from_workspace(ctx, ws, ldw, split, nS, knn->k, knn->idx, knn->val, st);
+    if (rc == 1) return 1;
+    knn_done = (rc == 0);
+    if (!knn_done && !D) {
+      MEM_CHECK(ctx->D.ensure((size_t)nS * nS * sizeof(float)));
+      D = ctx->D.as<float>();
+    }
+  }
+  if (D) {
+    dim3 fgrid((nS + 31) / 32, (nS + 31) / 32);
+    MEM_LAUNCH(ctx, k_contract_finalize, fgrid, 256, 0, st, ws, D, nS, ldw, split);
+  }
+  if (knn && !knn_done) MEM_CHECK(knn_device_f32(ctx, D, nS, knn->k, knn->idx, knn->val, st));
   return 0;
 }
 

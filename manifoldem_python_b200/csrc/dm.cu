@@ -149,12 +149,209 @@ static int knn_chunked(mem_ctx* ctx, const T* D, int nS, int P, int k, int* idx,
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// a15 for k << nS: selection instead of a full sort.  One CTA per point; the row becomes order-preserving unsigned
+// keys in shared memory, an 8-bit-digit radix select (most significant digit first, 256-bin shared-memory
+// histograms) finds the k-th smallest key, the k winners are gathered — exact ties at the threshold in index
+// order — and only those are sorted, by (value, index) like k_knn_sort, so both kernels return identical lists.
+// WS: the row is assembled on the fly from the split-K partial tiles of the contraction
+//     D[i][j] = 4 * sum_s ws[s][min(i,j)][max(i,j)]   (same operation order as k_contract_finalize: bit-identical),
+// so the nS x nS matrix is never written (BASELINE config 3: "kNN epilogue only").
+// ---------------------------------------------------------------------------------------------
+constexpr int KSEL_T = 256;
+constexpr int KSEL_MAXK = 2048;
+
+__device__ __forceinline__ uint32_t ord_key(float f) {
+  if (f == 0.0f) f = 0.0f;                               // -0 and +0 compare equal in the sort: one key
+  const uint32_t u = __float_as_uint(f);
+  return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ uint64_t ord_key(double f) {
+  if (f == 0.0) f = 0.0;
+  const uint64_t u = (uint64_t)__double_as_longlong(f);
+  return u ^ ((u >> 63) ? 0xffffffffffffffffull : 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ord_val(uint32_t u) {
+  u ^= (u >> 31) ? 0x80000000u : 0xffffffffu;
+  return (double)__uint_as_float(u);
+}
+__device__ __forceinline__ double ord_val(uint64_t u) {
+  u ^= (u >> 63) ? 0x8000000000000000ull : 0xffffffffffffffffull;
+  return __longlong_as_double((long long)u);
+}
+template <class T> struct OrdOf { typedef uint32_t U; };
+template <> struct OrdOf<double> { typedef uint64_t U; };
+
+template <class T, bool WS>
+__global__ void __launch_bounds__(KSEL_T) k_knn_select(const T* __restrict__ D, const float* __restrict__ ws, int ldw,
+                                                       int nslices, int nS, int nS_pad, int k, int P2,
+                                                       int* __restrict__ idx, double* __restrict__ val) {
+  typedef typename OrdOf<T>::U U;
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  U* ukey = reinterpret_cast<U*>(sm_raw);               // [nS_pad] the whole row
+  U* selk = ukey + nS_pad;                              // [P2] winners
+  int* seli = reinterpret_cast<int*>(selk + P2);        // [P2]
+  __shared__ int hist[256];
+  __shared__ int wtot[KSEL_T / 32];
+  __shared__ int s_bin, s_rem, s_cnt;
+  const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  // ---- the row as ordered keys; D[i][i] = -inf (DMembeddingII.py:48)
+  for (int j = tid; j < nS; j += KSEL_T) {
+    T v;
+    if (WS) {
+      const size_t a = (size_t)min(i, j), b = (size_t)max(i, j);
+      float acc = 0.0f;
+      for (int s = 0; s < nslices; ++s) acc += ws[((size_t)s * ldw + a) * ldw + b];
+      v = (T)(4.0f * acc);
+    } else {
+      v = D[(size_t)i * nS + j];
+    }
+    ukey[j] = ord_key(j == i ? (T)(-INFINITY) : v);
+  }
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  // ---- radix select: after the last digit `prefix` is the k-th smallest key and `rem` how many of the
+  // entries equal to it belong to the list
+  U prefix = 0, mask = 0;
+  int rem = k;
+  for (int shift = 8 * (int)sizeof(U) - 8; shift >= 0; shift -= 8) {
+    hist[tid] = 0;
+    __syncthreads();
+    for (int j = tid; j < nS; j += KSEL_T) {
+      const U u = ukey[j];
+      if ((u & mask) == prefix) atomicAdd(&hist[(int)((u >> shift) & 0xff)], 1);
+    }
+    __syncthreads();
+    const int h = hist[tid];
+    int inc = h;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wtot[wrp] = inc;
+    __syncthreads();
+    for (int w = 0; w < wrp; ++w) inc += wtot[w];
+    const int exc = inc - h;
+    if (h > 0 && exc < rem && rem <= inc) {              // exactly one digit holds the k-th smallest
+      s_bin = tid;
+      s_rem = rem - exc;
+    }
+    __syncthreads();
+    prefix |= (U)s_bin << shift;
+    mask |= (U)0xff << shift;
+    rem = s_rem;
+  }
+  const U thr = prefix;
+  const int n_less = k - rem;
+  // ---- winners below the threshold (any order: they are sorted afterwards)
+  for (int j = tid; j < nS; j += KSEL_T) {
+    const U u = ukey[j];
+    if (u < thr) {
+      const int slot = atomicAdd(&s_cnt, 1);
+      selk[slot] = u;
+      seli[slot] = j;
+    }
+  }
+  // ---- entries equal to the threshold: the `rem` smallest indices (ordered compaction, chunk by chunk)
+  int running = 0;
+  for (int c0 = 0; c0 < nS && running < rem; c0 += KSEL_T) {
+    const int j = c0 + tid;
+    const bool f = j < nS && ukey[j] == thr;
+    const unsigned b = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) wtot[wrp] = __popc(b);
+    __syncthreads();
+    int off = running, tot = 0;
+#pragma unroll
+    for (int w = 0; w < KSEL_T / 32; ++w) {
+      const int c = wtot[w];
+      if (w < wrp) off += c;
+      tot += c;
+    }
+    if (f) {
+      const int r = off + __popc(b & ((1u << lane) - 1u));
+      if (r < rem) {
+        selk[n_less + r] = thr;
+        seli[n_less + r] = j;
+      }
+    }
+    running += tot;
+    __syncthreads();
+  }
+  for (int a = k + tid; a < P2; a += KSEL_T) {          // padding sorts last
+    selk[a] = ~(U)0;
+    seli[a] = 0x7fffffff;
+  }
+  __syncthreads();
+  // ---- sort the winners by (value, index)
+  for (int size = 2; size <= P2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (P2 >> 1); t += KSEL_T) {
+        const int lo = 2 * t - (t & (stride - 1));
+        knn_cmpx(selk, seli, lo, lo + stride, ((lo & size) == 0));
+      }
+      __syncthreads();
+    }
+  }
+  for (int a = tid; a < k; a += KSEL_T) {
+    idx[(size_t)i * k + a] = seli[a];
+    val[(size_t)i * k + a] = (a == 0) ? 0.0 : ord_val(selk[a]);   // yVal1[0,iS] = 0, :54
+  }
+}
+
+static int g_knn_mode = 0;   // 0 = auto, 1 = always the full sort, 2 = selection whenever it fits
+void knn_set_mode(int mode) { g_knn_mode = mode; }
+
+// shared memory of a selection launch, 0 when the row / list does not fit (the caller sorts instead)
+template <class T>
+static size_t knn_select_smem(int nS, int k, int* nS_pad, int* P2) {
+  typedef typename OrdOf<T>::U U;
+  if (k > KSEL_MAXK) return 0;
+  int p = 32;
+  while (p < k) p <<= 1;
+  *P2 = p;
+  *nS_pad = (nS + 3) & ~3;
+  const size_t bytes = (size_t)*nS_pad * sizeof(U) + (size_t)p * (sizeof(U) + sizeof(int));
+  return bytes <= 200 * 1024 ? bytes : 0;
+}
+template <class T>
+static bool knn_use_select(int nS, int k) {
+  int a, b;
+  if (g_knn_mode == 1 || knn_select_smem<T>(nS, k, &a, &b) == 0) return false;
+  return g_knn_mode == 2 || 4 * k <= nS;               // a list that is most of the row: sort the row
+}
+template <class T, bool WS>
+static int knn_select_launch(mem_ctx* ctx, const T* D, const float* ws, int ldw, int nslices, int nS, int k, int* idx,
+                             double* val, cudaStream_t st) {
+  int nS_pad = 0, P2 = 0;
+  const size_t smem = knn_select_smem<T>(nS, k, &nS_pad, &P2);
+  if (!smem || k < 1 || k > nS) {
+    set_error("knn selection: unsupported shape (k=%d nS=%d)", k, nS);
+    return 1;
+  }
+  MEM_CUDA(cudaFuncSetAttribute((k_knn_select<T, WS>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MEM_LAUNCH(ctx, (k_knn_select<T, WS>), nS, KSEL_T, smem, st, D, ws, ldw, nslices, nS, nS_pad, k, P2, idx, val);
+  return 0;
+}
+// kNN lists straight from the split-K workspace of the contraction; returns 2 when the shape needs the assembled D
+int knn_from_workspace(mem_ctx* ctx, const float* ws, int ldw, int nslices, int nS, int k, int* idx, double* val,
+                       cudaStream_t st) {
+  if (k < 1 || k > nS) {
+    set_error("knn: need 1 <= k <= nS (k=%d nS=%d)", k, nS);
+    return 1;
+  }
+  if (!knn_use_select<float>(nS, k)) return 2;
+  return knn_select_launch<float, true>(ctx, (const float*)nullptr, ws, ldw, nslices, nS, k, idx, val, st);
+}
+
 template <class T>
 static int knn_device_t(mem_ctx* ctx, const T* D, int nS, int k, int* idx, double* val, cudaStream_t st) {
   if (k < 1 || k > nS) {
     set_error("knn: need 1 <= k <= nS (k=%d nS=%d)", k, nS);
     return 1;
   }
+  if (knn_use_select<T>(nS, k))
+    return knn_select_launch<T, false>(ctx, D, (const float*)nullptr, 0, 0, nS, k, idx, val, st);
   int P = 1;
   while (P < nS) P <<= 1;
   if (P > KNN_CH) return knn_chunked<T>(ctx, D, nS, P, k, idx, val, st);

@@ -668,7 +668,12 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
     MEM_CHECK(ctx->imgFlip.ensure(img_bytes));
     imgFlip = ctx->imgFlip.as<float>();
   }
-  const bool want_D = (io->D != nullptr) && !prm->avg_only;
+  const bool want_knn = prm->knn_k > 0 && io->knn_idx && io->knn_val && !prm->avg_only;
+  if (prm->knn_k > 0 && !prm->avg_only && (!io->knn_idx || !io->knn_val)) {
+    set_error("knn_k = %d but io.knn_idx / io.knn_val are not set", prm->knn_k);
+    return 1;
+  }
+  const bool want_D = (io->D != nullptr || want_knn) && !prm->avg_only;
   if (want_D) {
     MEM_CHECK(ctx->zhi.ensure((size_t)nS * g.ldz * sizeof(float)));
     MEM_CHECK(ctx->zlo.ensure((size_t)nS * g.ldz * sizeof(float)));
@@ -789,7 +794,10 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
   if (want_D) {
     mem_contract_shape shp;
     shp.nS = nS; shp.n1_blocks = g.n1_blocks; shp.n3_blocks = g.n3_blocks; shp.ldz = g.ldz;
-    MEM_CHECK(contract_run(ctx, &shp, zhi, zlo, io->D, prm->contraction, prm->k_chunk_blocks, prm->split_k, st));
+    KnnOut knn;
+    knn.k = prm->knn_k; knn.idx = io->knn_idx; knn.val = io->knn_val;
+    MEM_CHECK(contract_run(ctx, &shp, zhi, zlo, io->D, prm->contraction, prm->k_chunk_blocks, prm->split_k, st,
+                           want_knn ? &knn : nullptr));
   }
   MEM_CUDA(cudaEventRecord(ctx->ev[5], st));
   return 0;

@@ -77,9 +77,11 @@ def open_stack(imgFileName, N, relion):
 # ----------------------------------------------------------------------------- the C-ABI call
 def run_pd(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast, gaussEnv=np.inf, filterPar=None,
            msk2=None, relion=False, sh=None, avg_only=False, ctx=None, fields=('D', 'imgAll', 'imgAllFlip', 'CTF'),
-           contraction=0, k_chunk_blocks=0, split_k=0, float64=True, angles=None):
+           contraction=0, k_chunk_blocks=0, split_k=0, float64=True, angles=None, knn_k=0):
     """Returns the dict the reference pickles (same keys / shapes; float64 unless float64=False).
-    `fields` selects which of the heavy per-image outputs are materialised."""
+    `fields` selects which of the heavy per-image outputs are materialised.  knn_k > 0 adds `knn_idx` (nS,k) int32
+    and `knn_val` (nS,k) float64 — the lists DMembeddingII.initialize (:43-57) would take from D — selected on the
+    device straight behind the contraction; without 'D' in `fields` the nS x nS matrix is then never assembled."""
     lib = _lib.load()
     ctx = ctx or _lib.default_context()
     if filterPar is None:
@@ -103,7 +105,7 @@ def run_pd(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast, gaussEnv
                         filter_Qc=float(filterPar['Qc']), pix_size=float(pix_size), Cs=float(Cs), EkV=float(EkV),
                         gaussEnv=float(gaussEnv), AmpContrast=float(AmpContrast), psi_p_deg=float(psi_p),
                         avg_only=1 if avg_only else 0, contraction=int(contraction),
-                        k_chunk_blocks=int(k_chunk_blocks), split_k=int(split_k))
+                        k_chunk_blocks=int(k_chunk_blocks), split_k=int(split_k), knn_k=int(knn_k))
     outs = {}
 
     def want(name, shape, dtype):
@@ -121,6 +123,9 @@ def run_pd(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast, gaussEnv
         io.msk2 = m2.ctypes.data
     if 'D' in fields and not avg_only:
         io.D = want('D', (nS, nS), np.float32)
+    if knn_k and not avg_only:
+        io.knn_idx = want('knn_idx', (nS, int(knn_k)), np.int32)
+        io.knn_val = want('knn_val', (nS, int(knn_k)), np.float64)
     if 'imgAll' in fields:
         io.imgAll = want('imgAll', (nS, N, N), np.float32)
     if 'imgAllFlip' in fields:
@@ -143,14 +148,18 @@ def run_pd(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast, gaussEnv
                imgAllIntensity=cast(outs['imgAllIntensity']) if 'imgAllIntensity' in outs else None,
                version=VERSION)
     res['_psi_p'] = psi_p
+    if 'knn_idx' in outs:
+        res['knn_idx'], res['knn_val'] = outs['knn_idx'], outs['knn_val']
     return res
 
 
 def run_pd_resident(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast, gaussEnv=np.inf, filterPar=None,
-                    ctx=None, angles=None):
+                    ctx=None, angles=None, knn_k=0, keep_D=True):
     """Distance stage with the result kept ON THE DEVICE: returns a `_lib.DeviceArray` (nS,nS) float32 holding D,
     for consumers that run there too (DMembeddingII.graph_and_sweep accepts it) — the N x N matrix never
-    round-trips through the host (BASELINE config 3: kNN / kernel construction only)."""
+    round-trips through the host (BASELINE config 3: kNN / kernel construction only).
+    knn_k > 0: also (or, with keep_D=False, only) the kNN lists as device arrays — returns (D | None, idx, val);
+    with keep_D=False the lists come from the contraction's partial tiles and D is never assembled."""
     lib = _lib.load()
     ctx = ctx or _lib.default_context()
     if filterPar is None:
@@ -163,15 +172,22 @@ def run_pd_resident(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast,
     bufs = [_lib.DeviceArray(ctx, raw.shape, np.float32, raw), _lib.DeviceArray(ctx, (nS,), np.uint8, flip),
             _lib.DeviceArray(ctx, (nS,), np.float64, -(180 / math.pi) * Psi),
             _lib.DeviceArray(ctx, (nS,), np.float64, np.ascontiguousarray(df, dtype=np.float64))]
-    D = _lib.DeviceArray(ctx, (nS, nS), np.float32)
+    D = _lib.DeviceArray(ctx, (nS, nS), np.float32) if (keep_D or not knn_k) else None
     prm = _lib.PdParams(nS=nS, N=N, transposed=1, relion_shift=0, filter_type=FILTERS[filterPar['type']],
                         filter_order=int(filterPar['N']), filter_Qc=float(filterPar['Qc']), pix_size=float(pix_size),
                         Cs=float(Cs), EkV=float(EkV), gaussEnv=float(gaussEnv), AmpContrast=float(AmpContrast),
-                        psi_p_deg=float(psi_p))
+                        psi_p_deg=float(psi_p), knn_k=int(knn_k))
     io = _lib.PdIO()
-    io.raw, io.flip, io.psi_deg, io.df, io.D = bufs[0].ptr, bufs[1].ptr, bufs[2].ptr, bufs[3].ptr, D.ptr
+    io.raw, io.flip, io.psi_deg, io.df = bufs[0].ptr, bufs[1].ptr, bufs[2].ptr, bufs[3].ptr
+    if D is not None:
+        io.D = D.ptr
+    idx = val = None
+    if knn_k:
+        idx = _lib.DeviceArray(ctx, (nS, int(knn_k)), np.int32)
+        val = _lib.DeviceArray(ctx, (nS, int(knn_k)), np.float64)
+        io.knn_idx, io.knn_val = idx.ptr, val.ptr
     _lib.check(lib.mem_pd_distance_device(ctx.handle, C.byref(prm), C.byref(io), None))
     ctx.sync()
     for b in bufs:
         b.free()
-    return D
+    return (D, idx, val) if knn_k else D

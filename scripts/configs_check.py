@@ -71,6 +71,43 @@ if 'c3' in sys.argv:
         d = D[i].copy()
         d[i] = -np.inf
         assert set(np.argsort(d, kind='stable')[:k]) == set(idx[i])
+    # a15 alone, CUDA events: full sort of every row vs selection on the resident D vs lists taken from the
+    # contraction's partial tiles (D never assembled)
+    Dd, _ = run_shape(nS, 256, reps=1, keepD=True)
+    idx_d = _lib.DeviceArray(ctx, (nS, k), np.int32)
+    val_d = _lib.DeviceArray(ctx, (nS, k), np.float64)
+    t_knn = {}
+    for name, mode in (('sort', 1), ('selection', 2)):
+        _lib.check(lib.mem_knn_mode(mode))
+        for r in range(3):
+            ctx.timer_start()
+            _lib.check(lib.mem_knn_device_f32(ctx.handle, Dd.ptr, nS, k, idx_d.ptr, val_d.ptr, None))
+            t_knn[name] = ctx.timer_stop()
+        if mode == 1:
+            idx_sort, val_sort = idx_d.download(), val_d.download()
+    _lib.check(lib.mem_knn_mode(0))
+    assert np.array_equal(idx_sort, idx_d.download()) and np.array_equal(val_sort, val_d.download())
+    Dd.free()
+    pds, rng = bench.make_inputs(nS, 256, 1, seed=nS + 256)
+    pd = pds[0]
+    raw = _lib.DeviceArray(ctx, (nS, 256 * 256), np.float32, rng.standard_normal((nS, 256 * 256), dtype=np.float32))
+    small = [_lib.DeviceArray(ctx, (nS,), np.uint8, pd['flip']), _lib.DeviceArray(ctx, (nS,), np.float64, pd['psi_deg']),
+             _lib.DeviceArray(ctx, (nS,), np.float64, pd['df'])]
+    prm = bench.pd_params(_lib, nS, 256, pd['psi_p'])
+    prm.knn_k = k
+    io = _lib.PdIO()
+    io.raw, io.flip, io.psi_deg, io.df = raw.ptr, small[0].ptr, small[1].ptr, small[2].ptr
+    io.knn_idx, io.knn_val = idx_d.ptr, val_d.ptr
+    for r in range(3):
+        ctx.timer_start()
+        _lib.check(lib.mem_pd_distance_device(ctx.handle, C.byref(prm), C.byref(io), None))
+        t_fused = ctx.timer_stop()
+    assert np.array_equal(idx_sort, idx_d.download()) and np.array_equal(val_sort, val_d.download())
+    print('C3 a15 (k=%d) on the resident D: bitonic sort %.2f ms, radix selection %.2f ms; whole PD with the lists '
+          'selected from the partial tiles, no D: %.2f ms (PD with D: %.2f ms); lists identical' %
+          (k, t_knn['sort'], t_knn['selection'], t_fused, ms))
+    for a in [raw, idx_d, val_d] + small:
+        a.free()
     L = DMembeddingII.laplacian(M, nS, 3.0 * np.sqrt(np.median(val[:, 1:])))
     t2 = time.time()
     M.free()

@@ -97,10 +97,14 @@ def test_knn_rows_longer_than_one_smem_sort(nS, dtype):
     idx_d = _lib.DeviceArray(ctx, (nS, k), np.int32)
     val_d = _lib.DeviceArray(ctx, (nS, k), np.float64)
     fn = lib.mem_knn_device_f32 if dtype == np.float32 else lib.mem_knn_device
-    _lib.check(fn(ctx.handle, Dd.ptr, nS, k, idx_d.ptr, val_d.ptr, None))
-    idx, val = idx_d.download(), val_d.download()
-    for a in (Dd, idx_d, val_d):
-        a.free()
+    _lib.check(lib.mem_knn_mode(1))                                          # the sort (automatic choice here: selection)
+    try:
+        _lib.check(fn(ctx.handle, Dd.ptr, nS, k, idx_d.ptr, val_d.ptr, None))
+        idx, val = idx_d.download(), val_d.download()
+    finally:
+        _lib.check(lib.mem_knn_mode(0))
+        for a in (Dd, idx_d, val_d):
+            a.free()
     for i in list(range(0, nS, 1237)) + [nS - 1]:
         row = D[i].astype(np.float64)
         row[i] = -np.inf

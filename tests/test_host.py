@@ -346,3 +346,31 @@ def test_contraction_operand_algebra_model(N):
     off = ~np.eye(nS, dtype=bool)
     assert np.abs(D - D_ref)[off].max() < 1e-9 * D_ref[off].max()
     assert np.abs(np.diag(D)).max() < 1e-9 * D_ref[off].max()
+
+
+def test_knn_selection_model_matches_a_full_sort():
+    """The radix selection of k_knn_select (csrc/dm.cu), restated thread for thread on the CPU
+    (tests/tools/knn_select_model.py): same lists as sorting the whole row by (value, index) — threshold ties,
+    signed zeros, negative values, k = 1 and k = nS included, float32 and float64 keys."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'tests', 'tools'))
+    import knn_select_model as m
+    rng = np.random.default_rng(1)
+    for dt in (np.float32, np.float64):
+        for nS, k, kind in [(40, 7, 'ties'), (300, 40, 'rand'), (600, 100, 'int'), (777, 1, 'rand'), (513, 128, 'neg'),
+                            (64, 16, 'zeros'), (33, 33, 'int')]:
+            if kind == 'ties':
+                D = np.full((nS, nS), 5.0)
+            elif kind == 'rand':
+                D = rng.random((nS, nS)) * 1e3
+            elif kind == 'int':
+                D = rng.integers(0, 20, (nS, nS)).astype(float)
+            elif kind == 'neg':
+                D = rng.standard_normal((nS, nS))
+            else:
+                D = np.where(rng.random((nS, nS)) < 0.5, 0.0, -0.0)
+            D = D.astype(dt)
+            for i in (0, nS // 2, nS - 1):
+                idx, val = m.select_row(D[i], i, k)
+                idx_r, val_r = m.reference_row(D[i], i, k)
+                assert np.array_equal(idx, idx_r) and np.array_equal(val, val_r), (dt, nS, k, kind, i)
