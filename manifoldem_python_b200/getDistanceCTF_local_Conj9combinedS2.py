@@ -67,13 +67,17 @@ def op(input_data, filterPar, imgFileName, sh, nStot, options, fields=None):
     if getattr(p, 'mask_vol_file', ''):                                   # :303-310
         from . import projectMask
         msk2 = projectMask.op(_read_mrc_volume(p.mask_vol_file), angles[1])
+    # 'sidecar' records (myio.py) keep the float32 the GPU produced and promote on read; 'pickle' records hold the
+    # reference's float64 arrays
+    layout = myio.default_layout()
     res = pd_stage.run_pd(ind, q, df, stack, nStot, N, p.pix_size, p.Cs, p.EkV, p.AmpContrast,
                           gaussEnv=getattr(p, 'gaussEnv', np.inf), filterPar=filterPar, msk2=msk2, relion=relion,
                           sh=sh, avg_only=bool(options.get('avgOnly', False)), ctx=_ctx(), angles=angles,
-                          fields=fields or ('D', 'imgAll', 'imgAllFlip', 'CTF'))
+                          fields=fields or ('D', 'imgAll', 'imgAllFlip', 'CTF'), float64=(layout != 'sidecar'))
     if options.get('parallel') and res['CTF'] is not None:
         res['CTF'] = res['CTF'].reshape(-1, N, N)                         # that branch leaves CTF un-flattened (:378-389)
     res['options'] = options
-    myio.fout1(outFile, _KEYS, [res[k] for k in _KEYS])
+    promote = {k: np.float64 for k in _KEYS if isinstance(res[k], np.ndarray) and res[k].dtype == np.float32}
+    myio.fout1(outFile, _KEYS, [res[k] for k in _KEYS], layout=layout, promote=promote)
     # marker AFTER the dump: signifies a non-corrupted pickle (:415-419)
     open(os.path.join(p.dist_prog, '%s' % (prD)), 'a').close()

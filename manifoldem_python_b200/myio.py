@@ -1,20 +1,150 @@
-"""Pickle in/out with the reference's semantics (modules/myio.py:21-59): fin1 returns the dict or
-None on ANY failure; fout1 writes {key: value} with pickle.HIGHEST_PROTOCOL."""
+"""Record in/out with the reference's semantics (modules/myio.py:21-59) and, on request, a lighter on-disk layout.
+
+fin1(filename) -> dict or None on ANY failure; fout1(filename, keys, values); fout2(filename, dict) — the three
+functions all 57 call sites of the reference use.
+
+Two layouts, chosen per write (argument `layout`, else `p.record_layout`, else $MANIFOLDEM_B200_RECORD, else
+'pickle'):
+
+'pickle'   one pickle.HIGHEST_PROTOCOL file of {key: value}: byte-compatible with the reference's own myio, so
+           un-replaced reference modules keep reading it.  A C4-sized PD record is 3.2 GB of float64 that every
+           consumer unpickles whole, although manifoldTrimmingAuto reads only D and ind.
+
+'sidecar'  SURVEY.md §8f rank 3.  `filename` stays a small pickle (scalars, small arrays and a manifest); every
+           array of >= SIDECAR_MIN_BYTES goes to `filename.<key>.npy` in the dtype it was computed in (float32
+           from the GPU: half the bytes, no host-side float64 copy before the dump).  fin1 returns a `Record`
+           (a dict) that opens a sidecar only when its key is read and promotes it to the dtype the reference
+           stores (float64) at that moment — the values are identical to the 'pickle' layout (float32 -> float64
+           is exact), the consumer of D no longer pays for imgAll / imgAllFlip / CTF.  Needs this module in place
+           of the reference's (manifoldem_python_b200/dropin/myio.py); the reference's own fin1 would return the
+           manifest dict and fail loudly on data['D'].
+
+Write order keeps the resume protocol (getDistanceCTF...py:415-419): sidecars, then the manifest through a
+temporary file + rename, and only then does the caller touch its marker.
+"""
+import os
 import pickle
+
+import numpy as np
+
+MAGIC = '__manifoldem_b200_record__'
+SIDECAR_MIN_BYTES = 1 << 16
+_LAYOUTS = ('pickle', 'sidecar')
+
+
+def default_layout():
+    cfgs = []
+    try:
+        import p                                   # the reference's config module when running inside ManifoldEM
+        if hasattr(p, 'nPix'):
+            cfgs.append(p)
+    except ImportError:
+        pass
+    from . import p as own
+    cfgs.append(own)
+    for cfg in cfgs:
+        lay = getattr(cfg, 'record_layout', None)
+        if lay:
+            return lay
+    return os.environ.get('MANIFOLDEM_B200_RECORD', 'pickle')
+
+
+class Record(dict):
+    """dict of a 'sidecar' record: heavy arrays are read (np.load, memory-mapped) and promoted on first access."""
+
+    def __init__(self, small, arrays, base, keys=None):
+        super().__init__()
+        self._lazy = dict(arrays)
+        self._base = base
+        for k in (keys or list(small) + list(arrays)):   # the writer's key order; keys(), len(), `in` as a plain dict
+            super().__setitem__(k, small[k] if k in small else None)
+
+    def _load(self, k):
+        spec = self._lazy.pop(k)
+        a = np.load(os.path.join(os.path.dirname(self._base), spec['file']), mmap_mode='r')
+        if tuple(a.shape) != tuple(spec['shape']):
+            raise IOError('sidecar %s has shape %s, manifest says %s' % (spec['file'], a.shape, spec['shape']))
+        a = np.array(a, dtype=spec.get('promote') or a.dtype)     # private, writeable (consumers mutate D in place)
+        super().__setitem__(k, a)
+        return a
+
+    def __getitem__(self, k):
+        if k in self._lazy:
+            return self._load(k)
+        return super().__getitem__(k)
+
+    def get(self, k, default=None):
+        return self[k] if k in self else default
+
+    def raw(self, k):
+        """The array as stored (no promotion, read-only memory map) — for consumers that keep float32."""
+        if k in self._lazy:
+            spec = self._lazy[k]
+            return np.load(os.path.join(os.path.dirname(self._base), spec['file']), mmap_mode='r')
+        return super().__getitem__(k)
+
+    def materialise(self):
+        for k in list(self._lazy):
+            self._load(k)
+        return self
+
+    def items(self):
+        self.materialise()
+        return super().items()
+
+    def values(self):
+        self.materialise()
+        return super().values()
+
+    def __reduce__(self):                          # pickling a Record stores the plain dict
+        return (dict, (dict(self.materialise()),))
 
 
 def fin1(filename):
     try:
         with open(filename, 'rb') as f:
-            return pickle.load(f)
+            data = pickle.load(f)
+        if isinstance(data, dict) and data.get(MAGIC) == 2:
+            return Record(data['small'], data['arrays'], filename, data.get('keys'))
+        return data
     except Exception:
         return None
 
 
-def fout1(filename, key_list, v_list):
-    with open(filename, 'wb') as f:
-        pickle.dump(dict(zip(key_list, v_list)), f, protocol=pickle.HIGHEST_PROTOCOL)
+def _write_npy(path, a):
+    a = np.ascontiguousarray(a)
+    with open(path, 'wb') as f:
+        np.lib.format.write_array_header_1_0(f, np.lib.format.header_data_from_array_1_0(a))
+        f.write(memoryview(a).cast('B'))
 
 
-def fout2(filename, d):
-    fout1(filename, list(d.keys()), list(d.values()))
+def fout1(filename, key_list, v_list, layout=None, promote=None):
+    """`promote`: {key: dtype} the reader restores for that key (e.g. float32 on disk -> float64 like the reference)."""
+    layout = layout or default_layout()
+    if layout not in _LAYOUTS:
+        raise ValueError('record layout %r (known: %s)' % (layout, ', '.join(_LAYOUTS)))
+    if layout == 'pickle':
+        with open(filename, 'wb') as f:
+            pickle.dump(dict(zip(key_list, v_list)), f, protocol=pickle.HIGHEST_PROTOCOL)
+        return
+    promote = promote or {}
+    small, arrays = {}, {}
+    base = os.path.basename(filename)
+    for k, v in zip(key_list, v_list):
+        if isinstance(v, np.ndarray) and v.dtype != object and v.nbytes >= SIDECAR_MIN_BYTES:
+            name = '%s.%s.npy' % (base, k)
+            _write_npy(os.path.join(os.path.dirname(filename), name), v)
+            arrays[k] = dict(file=name, shape=tuple(v.shape), dtype=str(v.dtype),
+                             promote=str(np.dtype(promote[k])) if k in promote else None)
+        elif isinstance(v, np.ndarray) and k in promote:
+            small[k] = v.astype(promote[k])
+        else:
+            small[k] = v
+    tmp = filename + '.tmp'
+    with open(tmp, 'wb') as f:
+        pickle.dump({MAGIC: 2, 'keys': list(key_list), 'small': small, 'arrays': arrays}, f, protocol=pickle.HIGHEST_PROTOCOL)
+    os.replace(tmp, filename)
+
+
+def fout2(filename, d, layout=None):
+    fout1(filename, list(d.keys()), list(d.values()), layout=layout)

@@ -374,3 +374,110 @@ def test_knn_selection_model_matches_a_full_sort():
                 idx, val = m.select_row(D[i], i, k)
                 idx_r, val_r = m.reference_row(D[i], i, k)
                 assert np.array_equal(idx, idx_r) and np.array_equal(val, val_r), (dt, nS, k, kind, i)
+
+
+def test_sidecar_record_layout(tmp_path):
+    """heavy arrays in float32 .npy sidecars, promoted to the reference's float64 when (and only
+    when) a consumer reads the key; values identical to the 'pickle' layout; manifest written last, atomically."""
+    from manifoldem_python_b200 import myio
+    rng = np.random.default_rng(0)
+    nS, N = 40, 32
+    rec = dict(D=rng.random((nS, nS)).astype(np.float32), ind=np.arange(nS), imgAll=rng.random((nS, N, N)).astype(np.float32),
+               CTF=rng.random((nS, N * N)), msk2=1, PD=rng.random(3), imgAvg=rng.random((4, 4)).astype(np.float32),
+               version='v', options=dict(a=1), imgAllFlip=None)
+    promote = {k: np.float64 for k, v in rec.items() if isinstance(v, np.ndarray) and v.dtype == np.float32}
+    f_side, f_pick = str(tmp_path / 'side_prD_0'), str(tmp_path / 'pick_prD_0')
+    myio.fout1(f_side, list(rec), list(rec.values()), layout='sidecar', promote=promote)
+    myio.fout1(f_pick, list(rec), [v.astype(np.float64) if k in promote else v for k, v in rec.items()], layout='pickle')
+    files = sorted(os.listdir(tmp_path))
+    assert 'side_prD_0.imgAll.npy' in files and 'side_prD_0.CTF.npy' in files and 'side_prD_0.tmp' not in files
+    assert 'side_prD_0.D.npy' not in files                    # 6.4 KB: below the sidecar threshold, stays inside
+    assert os.path.getsize(f_side) < 40000
+    a, b = myio.fin1(f_side), myio.fin1(f_pick)
+    assert isinstance(a, myio.Record) and type(b) is dict
+    assert list(a.keys()) != [] and set(a.keys()) == set(b.keys()) and len(a) == len(b) and 'imgAll' in a
+    assert a._lazy.keys() == {'imgAll', 'CTF'}                # nothing heavy read yet
+    assert a['D'].dtype == np.float64 and np.array_equal(a['D'], b['D'])
+    assert a._lazy.keys() == {'imgAll', 'CTF'}
+    raw = a.raw('imgAll')
+    assert raw.dtype == np.float32 and not raw.flags.writeable
+    img = a['imgAll']
+    assert img.dtype == np.float64 and img.flags.writeable and np.array_equal(img, b['imgAll'])
+    assert a['imgAll'] is img and a._lazy.keys() == {'CTF'}
+    assert a.get('CTF').dtype == np.float64 and np.array_equal(a['CTF'], b['CTF'])
+    assert a.get('nope', 5) == 5 and a['imgAllFlip'] is None and a['msk2'] == 1 and a['options'] == dict(a=1)
+    assert a['imgAvg'].dtype == np.float64 and np.array_equal(a['imgAvg'], b['imgAvg'])
+    c = myio.fin1(f_side)
+    for (k, v), (k2, v2) in zip(sorted(c.items(), key=lambda t: t[0]), sorted(b.items(), key=lambda t: t[0])):
+        assert k == k2 and (np.array_equal(v, v2) if isinstance(v2, np.ndarray) else v == v2), k
+    assert pickle.loads(pickle.dumps(myio.fin1(f_side))).keys() == b.keys()
+    # a missing / truncated sidecar fails loudly on access, an unreadable manifest gives None like the reference
+    os.remove(str(tmp_path / 'side_prD_0.CTF.npy'))
+    d = myio.fin1(f_side)
+    assert np.array_equal(d['D'], b['D'])
+    with pytest.raises(Exception):
+        d['CTF']
+    with pytest.raises(ValueError):
+        myio.fout1(f_side, ['a'], [1], layout='hdf5')
+    # layout selection: argument > p.record_layout > environment > 'pickle'
+    from manifoldem_python_b200 import p
+    assert myio.default_layout() == 'pickle'
+    os.environ['MANIFOLDEM_B200_RECORD'] = 'sidecar'
+    try:
+        assert myio.default_layout() == 'sidecar'
+        p.record_layout = 'pickle'
+        assert myio.default_layout() == 'pickle'
+    finally:
+        del os.environ['MANIFOLDEM_B200_RECORD']
+        del p.record_layout
+
+
+def test_worker_writes_both_layouts_without_touching_the_gpu(tmp_path, monkeypatch):
+    """The per-PD worker's record logic (keys, dtypes, marker after the dump) with the device call replaced by a
+    stub: the 'sidecar' record read back through myio equals the 'pickle' record of the same results."""
+    from manifoldem_python_b200 import getDistanceCTF_local_Conj9combinedS2 as worker
+    from manifoldem_python_b200 import myio, p, pd_stage
+    p.init()
+    nS, N = 12, 64
+    p.nPix, p.pix_size, p.Cs, p.EkV, p.AmpContrast, p.mask_vol_file = N, 1.0, 2.0, 300.0, 0.1, ''
+    p.dist_prog = str(tmp_path / 'prog') + os.sep
+    os.makedirs(p.dist_prog)
+    stackf = tmp_path / 'stack.dat'
+    np.zeros((nS, N, N), np.float32).tofile(stackf)
+    rng = np.random.default_rng(3)
+    f32 = dict(D=rng.random((nS, nS)), imgAll=rng.random((nS, N, N)), imgAllFlip=rng.random((nS, N, N)),
+               imgAvg=rng.random((N, N)), imgAvgFlip=rng.random((N, N)), imgAllIntensity=rng.random((N, N)))
+    f32 = {k: v.astype(np.float32) for k, v in f32.items()}
+    ctf = rng.random((nS, N * N))
+    seen = {}
+
+    def fake_run_pd(ind, q, df, stack, nStot, Nn, *a, float64=True, **kw):
+        seen['float64'] = float64
+        cast = (lambda x: x.astype(np.float64)) if float64 else (lambda x: x)
+        res = {k: cast(v) for k, v in f32.items()}
+        res.update(ind=ind, q=q, df=df, CTF=ctf, msk2=1, PD=np.ones(3), PDs=np.ones((3, nS)), Psis=np.zeros((nS, 1)),
+                   imgLabels=np.ones(nS, int), Dnom=np.ones((nS, 1)), Nom=np.ones((nS, 1)), version=pd_stage.VERSION)
+        return res
+    monkeypatch.setattr(pd_stage, 'run_pd', fake_run_pd)
+    monkeypatch.setattr(worker, '_ctx', lambda: None)
+    q = np.tile(np.array([[1.0], [0.0], [0.0], [0.0]]), (1, nS))
+    opts = dict(verbose=False, avgOnly=False, visual=False, parallel=False, relion_data=False, thres=2000)
+    recs = {}
+    for prD, layout in enumerate(('pickle', 'sidecar')):
+        p.record_layout = layout
+        out = str(tmp_path / ('IMGs_prD_%d' % prD))
+        worker.op([np.arange(nS), q, np.full(nS, 1e4), out, prD], dict(type='Butter', Qc=0.5, N=8), str(stackf),
+                  (np.zeros(nS), np.zeros(nS)), 2 * nS, opts)
+        assert seen['float64'] == (layout == 'pickle')
+        assert os.path.exists(os.path.join(p.dist_prog, str(prD)))
+        recs[layout] = myio.fin1(out)
+    del p.record_layout
+    a, b = recs['sidecar'], recs['pickle']
+    assert isinstance(a, myio.Record) and type(b) is dict and list(a.keys()) == list(b.keys()) == worker._KEYS
+    assert os.path.getsize(str(tmp_path / 'IMGs_prD_1.imgAll.npy')) < 0.51 * nS * N * N * 8 + 200
+    for k in worker._KEYS:
+        va, vb = a[k], b[k]
+        if isinstance(vb, np.ndarray):
+            assert va.dtype == vb.dtype and np.array_equal(va, vb), k
+        else:
+            assert va == vb, k
