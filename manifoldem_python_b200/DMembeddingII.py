@@ -40,12 +40,13 @@ def _fit(logEps, logSumWij, a0):
     return popt, resnorm, R_squared
 
 
-def graph_and_sweep(D, k, ctx=None, nS=None, knn=None):
+def graph_and_sweep(D, k, ctx=None, nS=None, knn=None, want_lists=True):
     """Device part up to the Ferguson curve.  `D`: host (nS,nS) array, or a `_lib.DeviceArray` holding the
     float32 D that the distance stage left on the device (then D never visits the host), or None with
     `knn` = (idx, val) device arrays that the distance stage selected itself (pd_stage.run_pd_resident(knn_k=k,
     keep_D=False): D was never assembled; the lists are consumed and freed here).
-    Returns (M_dev DeviceArray (nS,nS) float64 graph, logEps, logSumWij, idx (nS,k) int32, val (nS,k) float64)."""
+    Returns (M_dev DeviceArray (nS,nS) float64 graph, logEps, logSumWij, idx (nS,k) int32, val (nS,k) float64);
+    idx, val are None with want_lists=False (op() does not need them: at k = nS = 2,000 their download is 48 MB)."""
     lib = _lib.load()
     ctx = ctx or _ctx()
     Dd = None
@@ -90,7 +91,7 @@ def graph_and_sweep(D, k, ctx=None, nS=None, knn=None):
     logSumWij = np.zeros(len(logEps))
     _lib.check(lib.mem_ferguson_device(ctx.handle, vals.ptr, n_vals, logEps.ctypes.data, len(logEps), float(thr),
                                        logSumWij.ctypes.data))
-    idx, val = idx_d.download(), val_d.download()
+    idx, val = (idx_d.download(), val_d.download()) if want_lists else (None, None)
     for a in (Dd, idx_d, val_d, compact):
         if a is not None:
             a.free()
@@ -130,7 +131,7 @@ def op(D, k, tune, prefsigma):
     p = _cfg()
     nS = D.shape[0]
     k = int(k)
-    M, logEps, logSumWij, _, _ = graph_and_sweep(D, k)
+    M, logEps, logSumWij, _, _ = graph_and_sweep(D, k, want_lists=False)
     D[np.arange(nS), np.arange(nS)] = -np.inf                                    # :48, in place like the reference
     a0 = (np.random.rand(4, 1) - .5)                                             # :142 (unseeded in the reference)
     popt, resnorm, R_squared = _fit(logEps, logSumWij, a0)

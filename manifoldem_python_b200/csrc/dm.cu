@@ -469,10 +469,38 @@ int graph_compact_device(mem_ctx* ctx, const double* M, int nS, double* out, lon
   return 0;
 }
 
+// column sums: CTA = 32 columns x 32 row lanes; lane r adds rows r, r+32, ... in four independent chains, then the
+// 32 partial sums of a column are added in a fixed order (deterministic; coalesced 256-byte row segments)
+__global__ void __launch_bounds__(1024) k_colsum(const double* __restrict__ W, int rows, int cols,
+                                                 double* __restrict__ d, int take_sqrt) {
+  __shared__ double part[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  if (j < cols) {
+    int i = ty;
+    for (; i + 96 < rows; i += 128) {
+      a0 += W[(size_t)i * cols + j];
+      a1 += W[(size_t)(i + 32) * cols + j];
+      a2 += W[(size_t)(i + 64) * cols + j];
+      a3 += W[(size_t)(i + 96) * cols + j];
+    }
+    for (; i < rows; i += 32) a0 += W[(size_t)i * cols + j];
+  }
+  part[ty][tx] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (ty == 0 && j < cols) {
+    double t = 0;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) t += part[r][tx];
+    d[j] = take_sqrt ? sqrt(t) : t;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // a17  fergusonE.op :36-43 — for every eps: sum over present entries with d2/(2 eps) < thr of
 // exp(-d2/(2 eps)).  Each thread keeps 8 distances in registers and sweeps all eps; per-eps block
-// sums go to partial[block][eps], reduced in a fixed order by k_ferguson_reduce (deterministic).
+// sums go to partial[block][eps], reduced over the blocks in a fixed order by k_colsum (deterministic).
 // ---------------------------------------------------------------------------------------------
 constexpr int FG_V = 8, FG_THREADS = 256, FG_ET = 32;
 __global__ void __launch_bounds__(FG_THREADS) k_ferguson(const double* __restrict__ d2, size_t n,
@@ -508,12 +536,63 @@ __global__ void __launch_bounds__(FG_THREADS) k_ferguson(const double* __restric
     __syncthreads();
   }
 }
-__global__ void k_ferguson_reduce(const double* __restrict__ partial, int nBlocks, int nEps, double* __restrict__ out) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= nEps) return;
-  double t = 0;
-  for (int b = 0; b < nBlocks; ++b) t += partial[(size_t)b * nEps + e];
-  out[e] = t;
+
+// The sweep proper (nEps = 1,501): lanes own eps values, the distances of the CTA's chunk are broadcast from shared
+// memory, so there is no cross-lane reduction at all.  For one distance only ~207 of the 1,501 eps give anything but
+// exactly 0 (past the cut d2/(2 eps) >= thr) or exactly 1 (d2/(2 eps) < 2^-54): a warp works through tiles of 64
+// consecutive eps and decides per distance, from the tile's largest and smallest 1/(2 eps), whether the whole tile is
+// cut (skip), saturated (count) or needs the exponentials — a warp-uniform branch, since all lanes hold the same
+// distance.  Tiles that lie entirely below d2/(2 eps) = 1e-3 take a degree-4 Taylor polynomial (error < 1e-17), so a
+// distance costs about 110 exponentials + 150 polynomials instead of 1,501 exponentials.  Same partial[block][eps]
+// layout as k_ferguson; both are reduced over the blocks in a fixed order by k_colsum.
+constexpr int FT_V = 2048, FT_THREADS = 256;
+// exp(-x) for 0 <= x < 1e-3
+__device__ __forceinline__ double exp_small(double x) {
+  return fma(x, fma(x, fma(x, fma(x, 1.0 / 24.0, -1.0 / 6.0), 0.5), -1.0), 1.0);
+}
+__global__ void __launch_bounds__(FT_THREADS) k_ferguson_tiles(const double* __restrict__ d2, size_t n,
+                                                               const double* __restrict__ inv2eps, int nEps, double thr,
+                                                               double* __restrict__ partial) {
+  __shared__ double sv[FT_V];
+  const size_t base = (size_t)blockIdx.x * FT_V;
+  for (int t = threadIdx.x; t < FT_V; t += FT_THREADS) {
+    const size_t j = base + t;
+    sv[t] = (j < n) ? d2[j] : -1.0;   // negative = absent
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nTiles = (nEps + 63) / 64;
+  const double tiny = 5.5511151231257827e-17;   // 2^-54: exp(-x) rounds to 1
+  const bool shortcuts = thr >= 1e-3;           // both shortcuts assume the term is on the near side of the cut
+  for (int tile = warp; tile < nTiles; tile += FT_THREADS / 32) {
+    const int e0 = tile * 64 + lane, e1 = e0 + 32;
+    const double s0 = inv2eps[min(e0, nEps - 1)], s1 = inv2eps[min(e1, nEps - 1)];
+    double smax = fmax(s0, s1), smin = fmin(s0, s1);
+    for (int o = 16; o > 0; o >>= 1) {
+      smax = fmax(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+      smin = fmin(smin, __shfl_xor_sync(0xffffffffu, smin, o));
+    }
+    double acc0 = 0, acc1 = 0;
+    int nsat = 0;
+    for (int v = 0; v < FT_V; ++v) {
+      const double d = sv[v];
+      if (d < 0.0 || d * smin >= thr) continue;       // absent, or every eps of the tile is past the cut
+      if (shortcuts && d * smax < tiny) {             // every term of the tile is exactly 1
+        ++nsat;
+        continue;
+      }
+      const double x0 = d * s0, x1 = d * s1;
+      if (shortcuts && d * smax < 1e-3) {             // whole tile below 1e-3: degree-4 Taylor, error < x^5/120 < 1e-17
+        acc0 += exp_small(x0);
+        acc1 += exp_small(x1);
+        continue;
+      }
+      if (x0 < thr) acc0 += exp(-x0);
+      if (x1 < thr) acc1 += exp(-x1);
+    }
+    if (e0 < nEps) partial[(size_t)blockIdx.x * nEps + e0] = acc0 + (double)nsat;
+    if (e1 < nEps) partial[(size_t)blockIdx.x * nEps + e1] = acc1 + (double)nsat;
+  }
 }
 
 int ferguson_device(mem_ctx* ctx, const double* d2, int64_t n, const double* logEps, int nEps, double thr,
@@ -527,8 +606,10 @@ int ferguson_device(mem_ctx* ctx, const double* d2, int64_t n, const double* log
   double* d_out = d_inv + nEps;
   double* d_part = d_out + nEps;
   MEM_CUDA(cudaMemcpyAsync(d_inv, inv.data(), nEps * sizeof(double), cudaMemcpyHostToDevice, st));
-  MEM_LAUNCH(ctx, k_ferguson, nBlocks, FG_THREADS, 0, st, d2, (size_t)n, d_inv, nEps, thr, d_part);
-  MEM_LAUNCH(ctx, k_ferguson_reduce, (nEps + 127) / 128, 128, 0, st, d_part, nBlocks, nEps, d_out);
+  static_assert(FT_V == FG_THREADS * FG_V, "both sweep kernels cut the distances into the same chunks");
+  if (nEps >= 64) MEM_LAUNCH(ctx, k_ferguson_tiles, nBlocks, FT_THREADS, 0, st, d2, (size_t)n, d_inv, nEps, thr, d_part);
+  else MEM_LAUNCH(ctx, k_ferguson, nBlocks, FG_THREADS, 0, st, d2, (size_t)n, d_inv, nEps, thr, d_part);
+  MEM_LAUNCH(ctx, k_colsum, (nEps + 31) / 32, 1024, 0, st, d_part, nBlocks, nEps, d_out, 0);   // fixed order
   std::vector<double> sums(nEps);
   MEM_CUDA(cudaMemcpyAsync(sums.data(), d_out, nEps * sizeof(double), cudaMemcpyDeviceToHost, st));
   MEM_CUDA(cudaStreamSynchronize(st));
@@ -545,14 +626,6 @@ __global__ void k_lap_weights(const double* __restrict__ M, double* __restrict__
     const double m = M[e];
     W[e] = (m >= 0.0) ? exp(-m * inv_s2) : 0.0;
   }
-}
-// column sums: thread per column, fixed row order
-__global__ void k_colsum(const double* __restrict__ W, int nS, double* __restrict__ d, int take_sqrt) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nS) return;
-  double t = 0;
-  for (int i = 0; i < nS; ++i) t += W[(size_t)i * nS + j];
-  d[j] = take_sqrt ? sqrt(t) : t;
 }
 __global__ void k_lap_scale(double* __restrict__ W, int nS, const double* __restrict__ d) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
@@ -581,9 +654,9 @@ int laplacian_dense_device(mem_ctx* ctx, const double* M, int nS, double sigma, 
   double* d = W + nn;
   const int g1 = (int)std::min<size_t>((nn + 255) / 256, (size_t)ctx->sm_count * 32);
   MEM_LAUNCH(ctx, k_lap_weights, g1, 256, 0, st, M, W, nn, 1.0 / (sigma * sigma));
-  MEM_LAUNCH(ctx, k_colsum, (nS + 127) / 128, 128, 0, st, W, nS, d, 0);
+  MEM_LAUNCH(ctx, k_colsum, (nS + 31) / 32, 1024, 0, st, W, nS, nS, d, 0);
   MEM_LAUNCH(ctx, k_lap_scale, dim3((nS + 255) / 256, nS), 256, 0, st, W, nS, d);
-  MEM_LAUNCH(ctx, k_colsum, (nS + 127) / 128, 128, 0, st, W, nS, d, 1);
+  MEM_LAUNCH(ctx, k_colsum, (nS + 31) / 32, 1024, 0, st, W, nS, nS, d, 1);
   MEM_LAUNCH(ctx, k_lap_scale, dim3((nS + 255) / 256, nS), 256, 0, st, W, nS, d);
   MEM_LAUNCH(ctx, k_lap_sym, dim3((nS + 31) / 32, (nS + 31) / 32), 256, 0, st, W, L, nS);
   return 0;

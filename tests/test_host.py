@@ -481,3 +481,38 @@ def test_worker_writes_both_layouts_without_touching_the_gpu(tmp_path, monkeypat
             assert va.dtype == vb.dtype and np.array_equal(va, vb), k
         else:
             assert va == vb, k
+
+
+def test_ferguson_tile_skipping_model():
+    """k_ferguson_tiles (csrc/dm.cu) skips a 64-eps tile for a distance when its smallest 1/(2 eps) already puts the
+    distance past the cut, and counts the distance as 1 for the whole tile when its largest 1/(2 eps) gives
+    d2/(2 eps) < 2^-54.  NumPy restatement of exactly that rule against the plain definition (fergusonE.py:36-43)."""
+    rng = np.random.default_rng(4)
+    d2 = np.concatenate([10.0 ** rng.uniform(-3, 9, 500), [0.0, 0.0, 1e-30, 1e300], -np.ones(7)])   # -1 = absent
+    logEps = np.arange(-150, 150.2, 0.2)
+    s = 1.0 / (2.0 * np.exp(logEps))
+    for thr in (10.0, 37.5, np.inf):
+        present = d2[d2 >= 0]
+        x = present[:, None] * s[None, :]
+        with np.errstate(over='ignore'):
+            direct = np.where(x < thr, np.exp(-x), 0.0).sum(0)
+        tiled = np.zeros_like(direct)
+        tiny = 2.0 ** -54
+        n_exp = 0
+        for t0 in range(0, len(s), 64):
+            st = s[t0:t0 + 64]
+            smax, smin = st.max(), st.min()
+            acc, nsat = np.zeros(len(st)), 0
+            for d in d2:
+                if d < 0 or d * smin >= thr:
+                    continue
+                if d * smax < tiny:
+                    nsat += 1
+                    continue
+                xt = d * st
+                acc += np.where(xt < thr, np.exp(-xt), 0.0)
+                n_exp += len(st)
+            tiled[t0:t0 + 64] = acc + nsat
+        assert np.allclose(tiled, direct, rtol=1e-13, atol=0), thr
+        if thr == 10.0:
+            assert n_exp < 0.25 * present.size * len(s)              # the point of the exercise
