@@ -418,6 +418,35 @@ def run_b200(args):
                   gpairs_s=n2 * n2 / (ms2 * 1e-3) / 1e9)
         for a in raws2 + [x for t3 in aux2 for x in t3] + [D2]:
             a.free()
+    # ---- BASELINE config 3 (one PD of 5,000 particles at 256^2, k = 100 neighbour lists only): the lists are selected
+    # from the contraction's partial tiles, D is never assembled.  Particles: rows of three of the pool stacks.
+    c3 = None
+    if rank == 0 and not args.no_e2e and (nS, N) == (NS, NPIX) and POOL * nS >= 5000:
+        n3, k3 = 5000, 100
+        pds3, _ = make_inputs(n3, N, 1, seed=78)
+        raw3 = _lib.DeviceArray(ctx, (n3, NN), np.float32, np.concatenate([h.array for h in h_raw])[:n3])
+        aux3 = [_lib.DeviceArray(ctx, (n3,), np.uint8, pds3[0]['flip']), _lib.DeviceArray(ctx, (n3,), np.float64, pds3[0]['psi_deg']),
+                _lib.DeviceArray(ctx, (n3,), np.float64, pds3[0]['df'])]
+        idx3, val3 = _lib.DeviceArray(ctx, (n3, k3), np.int32), _lib.DeviceArray(ctx, (n3, k3), np.float64)
+        prm3 = pd_params(_lib, n3, N, pds3[0]['psi_p'])
+        prm3.knn_k = k3
+        io3 = _lib.PdIO()
+        io3.raw, io3.flip, io3.psi_deg, io3.df = raw3.ptr, aux3[0].ptr, aux3[1].ptr, aux3[2].ptr
+        io3.knn_idx, io3.knn_val = idx3.ptr, val3.ptr
+        reps3 = 5
+        for k in range(2 + reps3):
+            if k == 2:
+                ctx.sync()
+                ctx.timer_start()
+            _lib.check(lib.mem_pd_distance_device(ctx.handle, C.byref(prm3), C.byref(io3), None))
+        ms3 = ctx.timer_stop() / reps3
+        nb = idx3.download()
+        assert np.array_equal(nb[:, 0], np.arange(n3)) and nb.min() >= 0 and nb.max() < n3
+        c3 = dict(workload='BASELINE config 3: one PD of 5,000 particles x 256^2, k = 100 neighbour lists only (no D)',
+                  per_pd_ms=ms3, gpairs_s=n3 * n3 / (ms3 * 1e-3) / 1e9, knn_k=k3, stage_ms=ctx.timings())
+        for a in [raw3, idx3, val3] + aux3:
+            a.free()
+        ctx.kernel_time(reset=True)
     if world > 1:
         dist.barrier()
 
@@ -481,7 +510,7 @@ def run_b200(args):
                                          '(1000 PDs at 8 GPUs)' % (nS, N, P), pds_per_gpu=P, nS=nS, N=N,
                                 l2='inputs larger than L2: %d distinct 524 MB stacks cycled' % POOL,
                                 per_pd_ms=ms / args.steps / P, stage_ms_last_pd=stage,
-                                all_record_fields_per_pd_ms=full_ms, single_pd_config_2=c2),
+                                all_record_fields_per_pd_ms=full_ms, single_pd_config_2=c2, single_pd_config_3=c3),
                     clocks=clocks, gpu_launches=launches, e2e=e2e,
                     roofline=dict(bound='tensor', kernel='k_contract_tc2 (tcgen05 cta_group::2 kind::tf32, 3 passes)',
                                   achieved=achieved, peak=peak, unit='TFLOP/s', frac=(achieved / peak) if achieved else None,

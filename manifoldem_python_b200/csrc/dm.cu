@@ -537,61 +537,92 @@ __global__ void __launch_bounds__(FG_THREADS) k_ferguson(const double* __restric
   }
 }
 
-// The sweep proper (nEps = 1,501): lanes own eps values, the distances of the CTA's chunk are broadcast from shared
-// memory, so there is no cross-lane reduction at all.  For one distance only ~207 of the 1,501 eps give anything but
-// exactly 0 (past the cut d2/(2 eps) >= thr) or exactly 1 (d2/(2 eps) < 2^-54): a warp works through tiles of 64
-// consecutive eps and decides per distance, from the tile's largest and smallest 1/(2 eps), whether the whole tile is
-// cut (skip), saturated (count) or needs the exponentials — a warp-uniform branch, since all lanes hold the same
-// distance.  Tiles that lie entirely below d2/(2 eps) = 1e-3 take a degree-4 Taylor polynomial (error < 1e-17), so a
-// distance costs about 110 exponentials + 150 polynomials instead of 1,501 exponentials.  Same partial[block][eps]
-// layout as k_ferguson; both are reduced over the blocks in a fixed order by k_colsum.
-constexpr int FT_V = 2048, FT_THREADS = 256;
+// The sweep proper (nEps = 1,501).  For one graph entry only ~207 of the 1,501 eps give anything but exactly 0
+// (past the cut d2/(2 eps) >= thr) or exactly 1 (d2/(2 eps) < 2^-54), and only ~46 of those need a real
+// exponential: below d2/(2 eps) = 1e-3 a degree-4 Taylor polynomial is exact to 1e-17.  Which of the four classes an
+// (entry, eps) pair falls in is monotone in d2, so the CTA first sorts its 2,048 entries in shared memory; for a tile
+// of 32 consecutive eps (one per lane) three binary searches with the tile's largest / smallest 1/(2 eps) then cut the
+// sorted chunk into [saturated | polynomial | exponential | cut].  The saturated entries are a count, the cut ones are
+// skipped, the 8 warps share the two middle ranges (entries broadcast from shared memory, no cross-lane reduction, no
+// per-entry tests) and their sums are added in a fixed order.  ~77 exp + ~184 polynomials per entry instead of 1,501
+// exp.  Same partial[block][eps] layout as k_ferguson; both are reduced over the blocks in a fixed order by k_colsum.
+constexpr int FT_V = 2048, FT_THREADS = 256, FT_WARPS = FT_THREADS / 32;
 // exp(-x) for 0 <= x < 1e-3
 __device__ __forceinline__ double exp_small(double x) {
   return fma(x, fma(x, fma(x, fma(x, 1.0 / 24.0, -1.0 / 6.0), 0.5), -1.0), 1.0);
 }
-__global__ void __launch_bounds__(FT_THREADS) k_ferguson_tiles(const double* __restrict__ d2, size_t n,
-                                                               const double* __restrict__ inv2eps, int nEps, double thr,
-                                                               double* __restrict__ partial) {
+// entries of the sorted chunk for which d * s < bound (monotone in d >= 0)
+__device__ __forceinline__ int count_below(const double* sv, double s, double bound) {
+  int lo = 0, hi = FT_V;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (sv[mid] * s < bound) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+__global__ void __launch_bounds__(FT_THREADS) k_ferguson_sorted(const double* __restrict__ d2, size_t n,
+                                                                const double* __restrict__ inv2eps, int nEps, double thr,
+                                                                double* __restrict__ partial) {
   __shared__ double sv[FT_V];
+  __shared__ double red[FT_WARPS][32];
+  __shared__ int bounds[64][3];                     // per tile: end of saturated, of polynomial, of exponential range
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t base = (size_t)blockIdx.x * FT_V;
-  for (int t = threadIdx.x; t < FT_V; t += FT_THREADS) {
+  for (int t = tid; t < FT_V; t += FT_THREADS) {
     const size_t j = base + t;
-    sv[t] = (j < n) ? d2[j] : -1.0;   // negative = absent
+    const double v = (j < n) ? d2[j] : -1.0;
+    sv[t] = v >= 0.0 ? v : INFINITY;                // absent (negative) entries sort to the end: always cut
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nTiles = (nEps + 63) / 64;
-  const double tiny = 5.5511151231257827e-17;   // 2^-54: exp(-x) rounds to 1
-  const bool shortcuts = thr >= 1e-3;           // both shortcuts assume the term is on the near side of the cut
-  for (int tile = warp; tile < nTiles; tile += FT_THREADS / 32) {
-    const int e0 = tile * 64 + lane, e1 = e0 + 32;
-    const double s0 = inv2eps[min(e0, nEps - 1)], s1 = inv2eps[min(e1, nEps - 1)];
-    double smax = fmax(s0, s1), smin = fmin(s0, s1);
-    for (int o = 16; o > 0; o >>= 1) {
-      smax = fmax(smax, __shfl_xor_sync(0xffffffffu, smax, o));
-      smin = fmin(smin, __shfl_xor_sync(0xffffffffu, smin, o));
-    }
-    double acc0 = 0, acc1 = 0;
-    int nsat = 0;
-    for (int v = 0; v < FT_V; ++v) {
-      const double d = sv[v];
-      if (d < 0.0 || d * smin >= thr) continue;       // absent, or every eps of the tile is past the cut
-      if (shortcuts && d * smax < tiny) {             // every term of the tile is exactly 1
-        ++nsat;
-        continue;
+  for (int size = 2; size <= FT_V; size <<= 1)      // bitonic sort, ascending
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < FT_V / 2; t += FT_THREADS) {
+        const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+        const double a = sv[lo], b = sv[hi];
+        if ((a > b) == ((lo & size) == 0)) { sv[lo] = b; sv[hi] = a; }
       }
-      const double x0 = d * s0, x1 = d * s1;
-      if (shortcuts && d * smax < 1e-3) {             // whole tile below 1e-3: degree-4 Taylor, error < x^5/120 < 1e-17
-        acc0 += exp_small(x0);
-        acc1 += exp_small(x1);
-        continue;
-      }
-      if (x0 < thr) acc0 += exp(-x0);
-      if (x1 < thr) acc1 += exp(-x1);
+      __syncthreads();
     }
-    if (e0 < nEps) partial[(size_t)blockIdx.x * nEps + e0] = acc0 + (double)nsat;
-    if (e1 < nEps) partial[(size_t)blockIdx.x * nEps + e1] = acc1 + (double)nsat;
+  const double tiny = 5.5511151231257827e-17;       // 2^-54: exp(-x) rounds to 1
+  const bool shortcuts = thr >= 1e-3;               // both shortcuts assume the term is on the near side of the cut
+  const int nTiles = (nEps + 31) / 32;
+  for (int t0 = 0; t0 < nTiles; t0 += 64) {         // 64 tiles (2,048 eps) per round: one round for the 1,501-point grid
+    const int tiles = min(64, nTiles - t0);
+    if (tid < 3 * tiles) {
+      const int tile = t0 + tid / 3, what = tid % 3;
+      double smax = 0.0, smin = INFINITY;
+      for (int e = tile * 32; e < min(nEps, tile * 32 + 32); ++e) {
+        smax = fmax(smax, inv2eps[e]);
+        smin = fmin(smin, inv2eps[e]);
+      }
+      int c;
+      if (what == 0) c = shortcuts ? count_below(sv, smax, tiny) : 0;
+      else if (what == 1) c = shortcuts ? count_below(sv, smax, 1e-3) : 0;
+      else c = count_below(sv, smin, thr);
+      bounds[tid / 3][what] = c;
+    }
+    __syncthreads();
+    for (int tt = 0; tt < tiles; ++tt) {
+      const int e = (t0 + tt) * 32 + lane;
+      const double s = inv2eps[min(e, nEps - 1)];
+      const int n_sat = bounds[tt][0], n_poly = max(bounds[tt][1], n_sat), n_exp = max(bounds[tt][2], n_poly);
+      double acc = 0.0;
+      for (int v = n_sat + warp; v < n_poly; v += FT_WARPS) acc += exp_small(sv[v] * s);
+      for (int v = n_poly + warp; v < n_exp; v += FT_WARPS) {
+        const double x = sv[v] * s;
+        if (x < thr) acc += exp(-x);
+      }
+      red[warp][lane] = acc;
+      __syncthreads();
+      if (warp == 0 && e < nEps) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < FT_WARPS; ++w) t += red[w][lane];
+        partial[(size_t)blockIdx.x * nEps + e] = t + (double)n_sat;
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -607,7 +638,7 @@ int ferguson_device(mem_ctx* ctx, const double* d2, int64_t n, const double* log
   double* d_part = d_out + nEps;
   MEM_CUDA(cudaMemcpyAsync(d_inv, inv.data(), nEps * sizeof(double), cudaMemcpyHostToDevice, st));
   static_assert(FT_V == FG_THREADS * FG_V, "both sweep kernels cut the distances into the same chunks");
-  if (nEps >= 64) MEM_LAUNCH(ctx, k_ferguson_tiles, nBlocks, FT_THREADS, 0, st, d2, (size_t)n, d_inv, nEps, thr, d_part);
+  if (nEps >= 64) MEM_LAUNCH(ctx, k_ferguson_sorted, nBlocks, FT_THREADS, 0, st, d2, (size_t)n, d_inv, nEps, thr, d_part);
   else MEM_LAUNCH(ctx, k_ferguson, nBlocks, FG_THREADS, 0, st, d2, (size_t)n, d_inv, nEps, thr, d_part);
   MEM_LAUNCH(ctx, k_colsum, (nEps + 31) / 32, 1024, 0, st, d_part, nBlocks, nEps, d_out, 0);   // fixed order
   std::vector<double> sums(nEps);

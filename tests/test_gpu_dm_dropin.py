@@ -284,3 +284,47 @@ def test_manifold_trimming_dropin(tmp_path):
     assert np.array_equal(rec['posPath'], pos[pos1])
     for j in range(3):
         assert abs(np.corrcoef(rec['psi'][:, j], out[1][:, j])[0, 1]) >= 0.9999
+
+
+def test_sidecar_records_through_the_worker(tmp_path):
+    """The per-PD worker with p.record_layout = 'sidecar': every key read back through myio equals the default
+    pickle record of the same PD bit for bit (float32 on disk, promoted to the reference's float64 on access), the
+    heavy arrays sit in .npy files beside a small manifest, and manifoldTrimmingAuto.op consumes the record."""
+    from manifoldem_python_b200 import manifoldTrimmingAuto as mta, getDistanceCTF_local_Conj9combinedS2 as worker
+    from manifoldem_python_b200 import myio, p, synthetic
+    N, nS = 64, 60
+    pd = synthetic.make_pd(nS, N, seed=62, snr=2.0)
+    p.init()
+    p.user_dir, p.proj_name = str(tmp_path), 'rec'
+    p.create_dir()
+    em = pd['em']
+    p.nPix, p.pix_size, p.Cs, p.EkV, p.AmpContrast = N, em['pix_size'], em['Cs'], em['EkV'], em['AmpContrast']
+    stack_file = str(tmp_path / 'stack.dat')
+    pd['stack'].tofile(stack_file)
+    opts = dict(verbose=False, avgOnly=False, visual=False, parallel=False, relion_data=False, thres=2000)
+    recs = {}
+    try:
+        for prD, layout in enumerate(('pickle', 'sidecar')):
+            p.record_layout = layout
+            f = '{}prD_{}'.format(p.dist_file, prD)
+            worker.op([pd['ind'], pd['q'], pd['df'], f, prD], dict(type='Butter', Qc=0.5, N=8), stack_file, pd['sh'],
+                      pd['nStot'], opts)
+            assert os.path.exists(os.path.join(p.dist_prog, str(prD)))
+            recs[layout] = myio.fin1(f)
+    finally:
+        del p.record_layout
+    a, b = recs['sidecar'], recs['pickle']
+    assert isinstance(a, myio.Record) and list(a.keys()) == list(b.keys())
+    assert os.path.getsize('{}prD_1'.format(p.dist_file)) < 0.05 * os.path.getsize('{}prD_0'.format(p.dist_file))
+    assert os.path.exists('{}prD_1.imgAll.npy'.format(p.dist_file))
+    assert a.raw('imgAll').dtype == np.float32 and a.raw('CTF').dtype == np.float64
+    for k in b:
+        if isinstance(b[k], np.ndarray):
+            assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), k
+        else:
+            assert a[k] == b[k], k
+    np.random.seed(5)
+    mta.op(['{}prD_1'.format(p.dist_file), '{}prD_1'.format(p.psi_file), str(tmp_path / 'eig.txt'), 1], 0, 3.0, 5.0,
+           False, dict(outputFile='', Is=True))
+    rec = myio.fin1('{}prD_1'.format(p.psi_file))
+    assert rec['psi'].shape[0] == len(rec['posPath']) and os.path.exists(os.path.join(p.psi_prog, '1'))

@@ -483,36 +483,42 @@ def test_worker_writes_both_layouts_without_touching_the_gpu(tmp_path, monkeypat
             assert va == vb, k
 
 
-def test_ferguson_tile_skipping_model():
-    """k_ferguson_tiles (csrc/dm.cu) skips a 64-eps tile for a distance when its smallest 1/(2 eps) already puts the
-    distance past the cut, and counts the distance as 1 for the whole tile when its largest 1/(2 eps) gives
-    d2/(2 eps) < 2^-54.  NumPy restatement of exactly that rule against the plain definition (fergusonE.py:36-43)."""
+def test_ferguson_sorted_chunk_model():
+    """k_ferguson_sorted (csrc/dm.cu) sorts the CTA's entries and cuts the sorted chunk, per tile of 32 eps, into
+    [saturated: d2/(2 eps) < 2^-54 for the tile's largest 1/(2 eps) -> counted as 1 | degree-4 Taylor: < 1e-3 |
+    exp | past the cut for the tile's smallest 1/(2 eps) -> skipped] with three binary searches.  NumPy restatement
+    of exactly that rule against the plain definition (fergusonE.py:36-43)."""
     rng = np.random.default_rng(4)
     d2 = np.concatenate([10.0 ** rng.uniform(-3, 9, 500), [0.0, 0.0, 1e-30, 1e300], -np.ones(7)])   # -1 = absent
     logEps = np.arange(-150, 150.2, 0.2)
     s = 1.0 / (2.0 * np.exp(logEps))
-    for thr in (10.0, 37.5, np.inf):
+    sv = np.sort(np.where(d2 >= 0, d2, np.inf))
+    tiny = 2.0 ** -54
+    for thr in (10.0, 37.5, np.inf, 1e-6):
         present = d2[d2 >= 0]
         x = present[:, None] * s[None, :]
         with np.errstate(over='ignore'):
             direct = np.where(x < thr, np.exp(-x), 0.0).sum(0)
         tiled = np.zeros_like(direct)
-        tiny = 2.0 ** -54
-        n_exp = 0
-        for t0 in range(0, len(s), 64):
-            st = s[t0:t0 + 64]
+        shortcuts = thr >= 1e-3
+        n_exp_calls = 0
+        for t0 in range(0, len(s), 32):
+            st = s[t0:t0 + 32]
             smax, smin = st.max(), st.min()
-            acc, nsat = np.zeros(len(st)), 0
-            for d in d2:
-                if d < 0 or d * smin >= thr:
-                    continue
-                if d * smax < tiny:
-                    nsat += 1
-                    continue
+            with np.errstate(invalid='ignore', over='ignore'):
+                n_sat = int((sv * smax < tiny).sum()) if shortcuts else 0      # monotone in d: a prefix of the chunk
+                n_poly = max(int((sv * smax < 1e-3).sum()) if shortcuts else 0, n_sat)
+                n_exp = max(int((sv * smin < thr).sum()), n_poly)
+                assert (np.diff((sv * smin < thr).astype(int)) <= 0).all()
+            acc = np.zeros(len(st))
+            for d in sv[n_sat:n_poly]:
+                xt = d * st
+                acc += 1 + xt * (-1 + xt * (0.5 + xt * (-1 / 6 + xt / 24)))
+            for d in sv[n_poly:n_exp]:
                 xt = d * st
                 acc += np.where(xt < thr, np.exp(-xt), 0.0)
-                n_exp += len(st)
-            tiled[t0:t0 + 64] = acc + nsat
+                n_exp_calls += len(st)
+            tiled[t0:t0 + 32] = acc + n_sat
         assert np.allclose(tiled, direct, rtol=1e-13, atol=0), thr
         if thr == 10.0:
-            assert n_exp < 0.25 * present.size * len(s)              # the point of the exercise
+            assert n_exp_calls < 0.08 * present.size * len(s)          # the point of the exercise
