@@ -170,3 +170,29 @@ def test_contract_knn_entry_point_and_bad_requests():
         _lib.check(lib.mem_contract_device(ctx.handle, C.byref(shp), zhi.ptr, zlo.ptr, None, 0, 0, 0, None))
     for a in (zhi, zlo, Dd, idx_d, val_d):
         a.free()
+
+
+def test_full_size_config4_pd_lists_and_properties():
+    """BASELINE config 4 PD at full size (2,000 particles x 256^2), no oracle: D is symmetric with a ~zero diagonal,
+    a duplicated particle is at distance ~0 from its twin, and the k = 100 neighbour lists selected from the partial
+    tiles (D not requested) are exactly the lexsort of the D the other call returns; each twin is the other's nearest
+    neighbour."""
+    from manifoldem_python_b200 import pd_stage, synthetic
+    nS, N, k = 2000, 256, 100
+    rng = np.random.default_rng(11)
+    stack = rng.standard_normal((nS, N * N), dtype=np.float32)
+    stack[1] = stack[0]
+    em = synthetic.make_pd(4, 16, seed=0)['em']
+    q = synthetic.euler_to_quat(0.7 + 0.03 * rng.standard_normal(nS), 1.1 + 0.03 * rng.standard_normal(nS),
+                                rng.uniform(0, 2 * np.pi, nS))
+    df = rng.uniform(10000, 30000, nS)
+    q[:, 1], df[1] = q[:, 0], df[0]
+    run = lambda fields, kk: pd_stage.run_pd(np.arange(nS), q, df, stack.reshape(-1), 2 * nS, N, em['pix_size'], em['Cs'],
+                                             em['EkV'], em['AmpContrast'], fields=fields, knn_k=kk, float64=False)
+    D = run(('D',), 0)['D']
+    assert np.array_equal(D, D.T) and np.abs(np.diag(D)).max() <= 1e-5 * D.max() and abs(D[0, 1]) <= 1e-5 * D.max()
+    only = run((), k)
+    ref = _lexsort_lists(D, k, range(0, nS, 7))
+    for i, (o, v) in ref.items():
+        assert np.array_equal(only['knn_idx'][i], o) and np.array_equal(only['knn_val'][i], v), i
+    assert only['knn_idx'][0, 1] == 1 and only['knn_idx'][1, 1] == 0
