@@ -159,6 +159,12 @@ int mem_laplacian_dense_device(mem_ctx* ctx, const double* M, int32_t nS, double
  * L [nS][nS] float64 on the device, x and y [nS] float64 on the HOST.  Synchronises. */
 int mem_symv_host(mem_ctx* ctx, const double* L, int32_t nS, const double* x, double* y);
 
+/* ---- upstream of the distance stage: S2 tessellation (modules/S2tessellation.py) ---------- */
+/* classS2 (:59-63): for every particle direction pts[i] (unit 3-vectors, [n][3] float64) the index of the nearest
+ * bin centre (centres [nG][3] float64, Euclidean distance in float64, smallest index on a tie) -> idx [n] int32.
+ * HOST pointers; synchronises. */
+int mem_s2_assign_host(mem_ctx* ctx, const double* centres, int32_t nG, const double* pts, int64_t n, int32_t* idx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@ int graph_dense_device(mem_ctx* ctx, const int* idx, const double* val, int nS, 
 int ferguson_device(mem_ctx* ctx, const double* d2, int64_t n, const double* logEps, int nEps, double thr, double* out);
 int laplacian_dense_device(mem_ctx* ctx, const double* M, int nS, double sigma, double* L, cudaStream_t st);
 int symv_host(mem_ctx* ctx, const double* L, int nS, const double* x_host, double* y_host);
+int s2_assign_host(mem_ctx* ctx, const double* centres, int nG, const double* pts, long long n, int* idx);
 }  // namespace mem
 
 using namespace mem;
@@ -310,6 +311,10 @@ int mem_laplacian_dense_device(mem_ctx* ctx, const double* M, int32_t nS, double
 int mem_symv_host(mem_ctx* ctx, const double* L, int32_t nS, const double* x, double* y) {
   MEM_CUDA(cudaSetDevice(ctx->device));
   return symv_host(ctx, L, nS, x, y);
+}
+int mem_s2_assign_host(mem_ctx* ctx, const double* centres, int32_t nG, const double* pts, int64_t n, int32_t* idx) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  return s2_assign_host(ctx, centres, nG, pts, (long long)n, idx);
 }
 
 }  // extern "C"

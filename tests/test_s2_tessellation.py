@@ -1,0 +1,97 @@
+"""S2 tessellation drop-in against vectors produced by the unmodified reference
+(tests/golden/make_golden_s2.py -> tests/golden/s2_tessellation.npz).
+
+CPU: the oracle's nearest-bin assignment and the drop-in's host logic (bin centres, thresholds, grouping; the device
+call replaced by the oracle inside the test only).  GPU: the CUDA assignment through the C ABI — integer work, exact."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'tests', 'tools'))
+from s2_inputs import CASES, quats                      # noqa: E402
+
+
+@pytest.fixture(scope='module')
+def golden(golden_dir):
+    return np.load(os.path.join(golden_dir, 's2_tessellation.npz'), allow_pickle=False)
+
+
+def _check_case(S2t, g, tag, n, width, lo, hi, seed):
+    q = quats(n, seed)
+    assert np.array_equal(q[:, :32], g[tag + '_q_head']) and np.allclose(q.sum(1), g[tag + '_q_sum'], rtol=0, atol=1e-9)
+    CG1, CG, nG, S2, S20_th, S20, NC = S2t.op(q, width, lo, False, hi)
+    assert int(nG) == int(g[tag + '_nG']) and np.array_equal(S20, g[tag + '_S20'])
+    assert np.array_equal(S2[:, :64], g[tag + '_S2_head']) and S2.shape == (3, n)
+    IND = np.full(n, -1, dtype=np.int64)
+    for i, a in enumerate(CG1):
+        assert (np.diff(a) > 0).all()
+        IND[a] = i
+    assert np.array_equal(IND, g[tag + '_IND'].astype(np.int64))
+    assert np.array_equal(NC, g[tag + '_NC']) and np.array_equal(S20_th, g[tag + '_S20_th'])
+    assert np.array_equal([len(a) for a in CG], g[tag + '_CG_len'])
+    assert np.array_equal([a[0] for a in CG], g[tag + '_CG_first'])
+    assert np.array_equal([a[-1] for a in CG], g[tag + '_CG_last'])
+    assert np.array_equal([int(np.sum(a)) for a in CG], g[tag + '_CG_sum'])
+
+
+def test_bin_centres_match_the_reference(golden):
+    from manifoldem_python_b200 import S2tessellation as S2t
+    for K in (7, 100, 1000):
+        pts, passes = S2t.sphere_points(K)
+        assert np.array_equal(pts, golden['sphere_%d' % K]) and passes == int(golden['sphere_%d_iter' % K])
+
+
+def test_oracle_assignment_matches_the_reference(golden):
+    from oracle import s2_tessellation as os2
+    from manifoldem_python_b200 import S2tessellation as S2t
+    for tag, n, width, lo, hi, seed in CASES:
+        S2 = S2t.get_S2(quats(n, seed))
+        ind = os2.nearest_bin(golden[tag + '_S20'].T, S2.T)
+        assert np.array_equal(ind, golden[tag + '_IND'].astype(np.int64)), tag
+
+
+@pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
+def test_host_logic_with_the_oracle_assignment(golden, case, monkeypatch):
+    from oracle import s2_tessellation as os2
+    from manifoldem_python_b200 import S2tessellation as S2t
+
+    def cpu_class(X, Q, ctx=None):
+        ind = os2.nearest_bin(X, Q).reshape(-1, 1)
+        return ind, np.bincount(ind[:, 0])
+    monkeypatch.setattr(S2t, 'classS2', cpu_class)
+    _check_case(S2t, golden, *case)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
+def test_gpu_tessellation_matches_the_reference(golden, case):
+    from manifoldem_python_b200 import S2tessellation as S2t
+    _check_case(S2t, golden, *case)
+
+
+@pytest.mark.gpu
+def test_gpu_assignment_large_and_edge_cases():
+    """10^6 directions against 4,071 centres equal the oracle's argmin; ties go to the smallest index; one centre,
+    zero directions and bad shapes behave."""
+    from oracle import s2_tessellation as os2
+    from manifoldem_python_b200 import S2tessellation as S2t
+    rng = np.random.default_rng(9)
+    X, _ = S2t.sphere_points(4071)
+    Q = rng.standard_normal((1000000, 3))
+    Q /= np.linalg.norm(Q, axis=1, keepdims=True)
+    IND, NC = S2t.classS2(X, Q)
+    assert IND.shape == (1000000, 1) and NC.sum() == 1000000
+    sel = rng.integers(0, 1000000, 20000)
+    assert np.array_equal(IND[sel, 0], os2.nearest_bin(X, Q[sel]))
+    Xt = np.array([[1.0, 0, 0], [0, 1.0, 0], [1.0, 0, 0], [0, 0, 1.0]])
+    IND, NC = S2t.classS2(Xt, np.array([[1.0, 0, 0], [0.6, 0.6, 0.0], [0, 0, -1.0]]))
+    assert list(IND[:, 0]) == [0, 0, 0] and list(NC) == [3]
+    IND, _ = S2t.classS2(Xt[:1], Q[:5])
+    assert list(IND[:, 0]) == [0] * 5
+    IND, NC = S2t.classS2(Xt, np.zeros((0, 3)))
+    assert IND.shape == (0, 1) and len(NC) == 0
+    with pytest.raises(ValueError):
+        S2t.classS2(Xt[:, :2], Q[:5])
