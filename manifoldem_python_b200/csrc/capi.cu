@@ -40,6 +40,7 @@ int mem_ctx_create(int device, mem_ctx** out) {
   MEM_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
   for (auto& e : ctx->ev) MEM_CUDA(cudaEventCreate(&e));
   for (auto& e : ctx->timer) MEM_CUDA(cudaEventCreate(&e));
+  MEM_CUDA(cudaEventCreateWithFlags(&ctx->done, cudaEventBlockingSync | cudaEventDisableTiming));
   *out = ctx;
   return 0;
 }
@@ -62,6 +63,7 @@ int mem_ctx_destroy(mem_ctx* ctx) {
   for (auto* b : bufs) b->release();
   for (auto& e : ctx->ev) cudaEventDestroy(e);
   for (auto& e : ctx->timer) cudaEventDestroy(e);
+  if (ctx->done) cudaEventDestroy(ctx->done);
   for (auto& e : ctx->kev) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -212,7 +214,9 @@ int mem_pd_distance_host(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io
   if (d.imgAvgFlip) MEM_CUDA(cudaMemcpyAsync(h->imgAvgFlip, d.imgAvgFlip, NN * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (d.imgAllIntensity) MEM_CUDA(cudaMemcpyAsync(h->imgAllIntensity, d.imgAllIntensity, NN * sizeof(float), cudaMemcpyDeviceToHost, st));
   MEM_CUDA(cudaEventRecord(ctx->ev[9], st));
-  MEM_CUDA(cudaStreamSynchronize(st));
+  // several PDs are in flight per GPU, one host thread each (and one process per GPU): wait without spinning
+  MEM_CUDA(cudaEventRecord(ctx->done, st));
+  MEM_CUDA(cudaEventSynchronize(ctx->done));
   return 0;
 }
 

@@ -109,6 +109,7 @@ struct mem_ctx {
   mem::DevBuf knn_out;       // kNN lists of the host-buffer entry point
   cudaEvent_t ev[10] = {};
   cudaEvent_t timer[2] = {};
+  cudaEvent_t done = nullptr;     // blocking-sync event: host-buffer calls sleep instead of spinning while the GPU works
   std::vector<cudaEvent_t> kev;   // event pairs around every contraction launch since the last reset
   size_t kev_used = 0;
   int last_tc_items = 0, last_tc_nkb = 0;   // geometry of the last tcgen05 launch (executed-flop accounting)
