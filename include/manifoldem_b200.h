@@ -105,6 +105,10 @@ typedef struct {
 int mem_pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* io, void* stream);
 /* all pointers in io are HOST pointers; stages H2D, runs, copies results back, synchronises. */
 int mem_pd_distance_host(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* io);
+/* the CTF field alone (ctemh_cryoFrank.op, modules/ctemh_cryoFrank.py:24-44, as :339 / :393 store it): uses nS, N,
+ * pix_size, Cs, EkV, gaussEnv, AmpContrast of prm; df [nS] and CTF [nS][N*N] float64 are HOST pointers.  Same kernel as
+ * inside mem_pd_distance_*, so a record that keeps df instead of the field reads back bit-identical values. */
+int mem_ctf_host(mem_ctx* ctx, const mem_pd_params* prm, const double* df, double* CTF);
 /* CUDA-event timings (ms) of the last mem_pd_distance_* call on ctx:
  * [0] ingest+lowpass  [1] align (2x prefilter+rotate)  [2] FFT+CTF+operands  [3] flip/averages
  * [4] contraction     [5] total device                 [6] h2d   [7] d2h            */

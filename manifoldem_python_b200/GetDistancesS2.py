@@ -89,7 +89,7 @@ def _run_jobs(jobs, filterPar, imgFileName, sh, size, options, nPix, on_done):
 
 
 _CFG_KEYS = ('nPix', 'pix_size', 'Cs', 'EkV', 'AmpContrast', 'gaussEnv', 'mask_vol_file', 'dist_prog', 'dist_file',
-             'relion_data', 'ncpu', 'record_layout')
+             'relion_data', 'ncpu', 'record_layout', 'record_virtual_ctf', 'record_skip')
 
 
 def op(*argv):

@@ -15,6 +15,7 @@ int ferguson_device(mem_ctx* ctx, const double* d2, int64_t n, const double* log
 int laplacian_dense_device(mem_ctx* ctx, const double* M, int nS, double sigma, double* L, cudaStream_t st);
 int symv_host(mem_ctx* ctx, const double* L, int nS, const double* x_host, double* y_host);
 int s2_assign_host(mem_ctx* ctx, const double* centres, int nG, const double* pts, long long n, int* idx);
+int ctf_host(mem_ctx* ctx, const mem_pd_params* prm, const double* df, double* out);
 }  // namespace mem
 
 using namespace mem;
@@ -218,6 +219,11 @@ int mem_pd_distance_host(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io
   MEM_CUDA(cudaEventRecord(ctx->done, st));
   MEM_CUDA(cudaEventSynchronize(ctx->done));
   return 0;
+}
+
+int mem_ctf_host(mem_ctx* ctx, const mem_pd_params* prm, const double* df, double* CTF) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  return ctf_host(ctx, prm, df, CTF);
 }
 
 int mem_pd_last_timings(mem_ctx* ctx, float* ms, int n) {

@@ -803,4 +803,25 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
   return 0;
 }
 
+// a8 alone (ctemh_cryoFrank.op, ctemh_cryoFrank.py:24-44, as stored in the record: ifftshift-ed, float64, flattened):
+// df [nS] and out [nS][N*N] are HOST pointers; the same kernel as inside the PD pipeline, so a record that stores df
+// instead of the 8 N^2 bytes per particle of the CTF field gets bit-identical values back.  Synchronises.
+int ctf_host(mem_ctx* ctx, const mem_pd_params* prm, const double* df, double* out) {
+  const int nS = prm->nS, N = prm->N;
+  if (nS < 1 || N < 2) {
+    set_error("ctf: bad shape (nS=%d N=%d)", nS, N);
+    return 1;
+  }
+  cudaStream_t st = ctx->stream;
+  const size_t NN = (size_t)N * N;
+  MEM_CHECK(ctx->df.ensure((size_t)nS * sizeof(double)));
+  MEM_CHECK(ctx->ctf64.ensure((size_t)nS * NN * sizeof(double)));
+  MEM_CUDA(cudaMemcpyAsync(ctx->df.p, df, (size_t)nS * sizeof(double), cudaMemcpyHostToDevice, st));
+  MEM_LAUNCH(ctx, k_ctf_full, dim3(((int)NN + 255) / 256, nS), 256, 0, st, ctx->df.as<double>(), ctx->ctf64.as<double>(), N,
+             make_ctf_const(prm));
+  MEM_CUDA(cudaMemcpyAsync(out, ctx->ctf64.p, (size_t)nS * NN * sizeof(double), cudaMemcpyDeviceToHost, st));
+  MEM_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 }  // namespace mem

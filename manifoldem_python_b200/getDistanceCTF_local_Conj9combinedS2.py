@@ -70,14 +70,27 @@ def op(input_data, filterPar, imgFileName, sh, nStot, options, fields=None):
     # 'sidecar' records (myio.py) keep the float32 the GPU produced and promote on read; 'pickle' records hold the
     # reference's float64 arrays
     layout = myio.default_layout()
+    want = tuple(fields or ('D', 'imgAll', 'imgAllFlip', 'CTF'))
+    virtual = {}
+    if layout == 'sidecar':
+        # p.record_skip: heavy arrays not to store at all (e.g. ('imgAllFlip',): no consumer reads it);
+        # p.record_virtual_ctf (default on): keep df and the microscope constants, rebuild the CTF field when it is read
+        want = tuple(f for f in want if f not in tuple(getattr(p, 'record_skip', ())))
+        if 'CTF' in want and getattr(p, 'record_virtual_ctf', True) and not options.get('avgOnly', False):
+            nS_ = len(np.asarray(ind))
+            virtual['CTF'] = dict(virtual='ctf', df_key='df', N=N, pix_size=float(p.pix_size), Cs=float(p.Cs),
+                                  EkV=float(p.EkV), gaussEnv=float(getattr(p, 'gaussEnv', np.inf)),
+                                  AmpContrast=float(p.AmpContrast),
+                                  shape=(nS_, N, N) if options.get('parallel') else (nS_, N * N))
+            want = tuple(f for f in want if f != 'CTF')
     res = pd_stage.run_pd(ind, q, df, stack, nStot, N, p.pix_size, p.Cs, p.EkV, p.AmpContrast,
                           gaussEnv=getattr(p, 'gaussEnv', np.inf), filterPar=filterPar, msk2=msk2, relion=relion,
                           sh=sh, avg_only=bool(options.get('avgOnly', False)), ctx=_ctx(), angles=angles,
-                          fields=fields or ('D', 'imgAll', 'imgAllFlip', 'CTF'), float64=(layout != 'sidecar'))
+                          fields=want, float64=(layout != 'sidecar'))
     if options.get('parallel') and res['CTF'] is not None:
         res['CTF'] = res['CTF'].reshape(-1, N, N)                         # that branch leaves CTF un-flattened (:378-389)
     res['options'] = options
     promote = {k: np.float64 for k in _KEYS if isinstance(res[k], np.ndarray) and res[k].dtype == np.float32}
-    myio.fout1(outFile, _KEYS, [res[k] for k in _KEYS], layout=layout, promote=promote)
+    myio.fout1(outFile, _KEYS, [res[k] for k in _KEYS], layout=layout, promote=promote, virtual=virtual)
     # marker AFTER the dump: signifies a non-corrupted pickle (:415-419)
     open(os.path.join(p.dist_prog, '%s' % (prD)), 'a').close()

@@ -61,6 +61,10 @@ class Record(dict):
 
     def _load(self, k):
         spec = self._lazy.pop(k)
+        if spec.get('virtual') == 'ctf':
+            a = _ctf_field(self[spec['df_key']], spec)
+            super().__setitem__(k, a)
+            return a
         a = np.load(os.path.join(os.path.dirname(self._base), spec['file']), mmap_mode='r')
         if tuple(a.shape) != tuple(spec['shape']):
             raise IOError('sidecar %s has shape %s, manifest says %s' % (spec['file'], a.shape, spec['shape']))
@@ -78,7 +82,7 @@ class Record(dict):
 
     def raw(self, k):
         """The array as stored (no promotion, read-only memory map) — for consumers that keep float32."""
-        if k in self._lazy:
+        if k in self._lazy and not self._lazy[k].get('virtual'):
             spec = self._lazy[k]
             return np.load(os.path.join(os.path.dirname(self._base), spec['file']), mmap_mode='r')
         return super().__getitem__(k)
@@ -100,6 +104,23 @@ class Record(dict):
         return (dict, (dict(self.materialise()),))
 
 
+def _ctf_field(df, spec):
+    """A record written with virtual={'CTF': ...} keeps df and the microscope constants instead of the 8 N^2 bytes per
+    particle of the CTF field (ctemh_cryoFrank.op; 1 GB of a C4-sized record): the field is produced when the key is
+    read, by the kernel that produced it inside the distance stage (C ABI mem_ctf_host) — bit-identical values."""
+    import ctypes as C
+    from . import _lib
+    from .getDistanceCTF_local_Conj9combinedS2 import _ctx
+    lib = _lib.load()
+    df = np.ascontiguousarray(df, dtype=np.float64)
+    nS, N = df.shape[0], int(spec['N'])
+    prm = _lib.PdParams(nS=nS, N=N, pix_size=float(spec['pix_size']), Cs=float(spec['Cs']), EkV=float(spec['EkV']),
+                        gaussEnv=float(spec['gaussEnv']), AmpContrast=float(spec['AmpContrast']))
+    out = np.empty((nS, N * N), dtype=np.float64)
+    _lib.check(lib.mem_ctf_host(_ctx().handle, C.byref(prm), df.ctypes.data, out.ctypes.data))
+    return out.reshape(spec['shape'])
+
+
 def fin1(filename):
     try:
         with open(filename, 'rb') as f:
@@ -118,8 +139,10 @@ def _write_npy(path, a):
         f.write(memoryview(a).cast('B'))
 
 
-def fout1(filename, key_list, v_list, layout=None, promote=None):
-    """`promote`: {key: dtype} the reader restores for that key (e.g. float32 on disk -> float64 like the reference)."""
+def fout1(filename, key_list, v_list, layout=None, promote=None, virtual=None):
+    """`promote`: {key: dtype} the reader restores for that key (e.g. float32 on disk -> float64 like the reference).
+    `virtual` ('sidecar' only): {key: spec} for fields that are not stored but produced when read; known spec:
+    dict(virtual='ctf', df_key, N, pix_size, Cs, EkV, gaussEnv, AmpContrast, shape)."""
     layout = layout or default_layout()
     if layout not in _LAYOUTS:
         raise ValueError('record layout %r (known: %s)' % (layout, ', '.join(_LAYOUTS)))
@@ -128,10 +151,13 @@ def fout1(filename, key_list, v_list, layout=None, promote=None):
             pickle.dump(dict(zip(key_list, v_list)), f, protocol=pickle.HIGHEST_PROTOCOL)
         return
     promote = promote or {}
+    virtual = virtual or {}
     small, arrays = {}, {}
     base = os.path.basename(filename)
     for k, v in zip(key_list, v_list):
-        if isinstance(v, np.ndarray) and v.dtype != object and v.nbytes >= SIDECAR_MIN_BYTES:
+        if k in virtual:
+            arrays[k] = dict(virtual[k])
+        elif isinstance(v, np.ndarray) and v.dtype != object and v.nbytes >= SIDECAR_MIN_BYTES:
             name = '%s.%s.npy' % (base, k)
             _write_npy(os.path.join(os.path.dirname(filename), name), v)
             arrays[k] = dict(file=name, shape=tuple(v.shape), dtype=str(v.dtype),

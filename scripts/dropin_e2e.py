@@ -1,6 +1,6 @@
 """The stage as a user of the reference runs it — GetDistancesS2.op (drop-in) from a SPIDER stack on disk to the per-PD
-records on disk, then manifoldTrimmingAuto.op on every record — with the reference's record layout and with the
-'sidecar' layout.  Wall clock per PD; white-noise particles (timing only).
+records on disk, then manifoldTrimmingAuto.op on every record — with the reference's record layout, with the
+'sidecar' layout holding every array and with its default (CTF field virtual, imgAllFlip skipped).  Wall clock per PD; white-noise particles (timing only).
     python scripts/dropin_e2e.py [n_pd] [nS] [N] [dir]           default 4 PDs x 2000 x 256^2
 """
 import os
@@ -35,14 +35,16 @@ q[:, n_half:] = q[:, :n_half]
 df = np.tile(rng.uniform(10000.0, 30000.0, n_half), 2)
 CG = [np.arange(i * nS, (i + 1) * nS) for i in range(n_pd)]
 
-for layout in ('pickle', 'sidecar'):
+for layout in ('pickle', 'sidecar-full', 'sidecar'):
     p.init()
     p.user_dir, p.proj_name = work, 'run_' + layout
     p.create_dir()
     p.pix_size, p.Cs, p.EkV, p.AmpContrast = 1.255, 2.26, 300.0, 0.1
     p.relion_data, p.ncpu, p.num_part, p.numberofJobs = False, 1, n_half, n_pd
     p.img_stack_file = stack_file
-    p.record_layout = layout
+    p.record_layout = layout.split('-')[0]
+    p.record_virtual_ctf = (layout == 'sidecar')           # 'sidecar-full': every array of the reference's record stored
+    p.record_skip = ('imgAllFlip',) if layout == 'sidecar' else ()
     myio.fout1(p.tess_file, ['CG', 'df', 'q', 'sh'], [CG, df, q, (np.zeros(n_half), np.zeros(n_half))], layout='pickle')
     GetDistancesS2.op()                                  # warm-up pass over every PD (plans, workspaces, page cache)
     for f in os.listdir(p.dist_prog):
@@ -58,7 +60,12 @@ for layout in ('pickle', 'sidecar'):
         D, ind = data['D'], data['ind']
         assert D.shape == (nS, nS) and D.dtype == np.float64
     t_read = (time.time() - t0) / n_pd
-    msg = '%-8s distance stage %.3f s / PD (record %.2f GB), consumer reads D + ind in %.3f s / PD' % (layout, t_dist, size / 1e9, t_read)
+    t0 = time.time()
+    ctf = myio.fin1('{}prD_{}'.format(p.dist_file, 0))['CTF']      # what psiAnalysisParS2.py:61-65 reads besides imgAll
+    assert ctf.shape == (nS, N * N) and ctf.dtype == np.float64
+    t_ctf = time.time() - t0
+    del ctf
+    msg = '%-12s distance stage %.3f s / PD (record %.2f GB), consumer reads D + ind in %.3f s / PD, the CTF field in %.3f s' % (layout, t_dist, size / 1e9, t_read, t_ctf)
     if trim:
         t0 = time.time()
         for prD in range(n_pd):

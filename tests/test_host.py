@@ -457,12 +457,16 @@ def test_worker_writes_both_layouts_without_touching_the_gpu(tmp_path, monkeypat
         res = {k: cast(v) for k, v in f32.items()}
         res.update(ind=ind, q=q, df=df, CTF=ctf, msk2=1, PD=np.ones(3), PDs=np.ones((3, nS)), Psis=np.zeros((nS, 1)),
                    imgLabels=np.ones(nS, int), Dnom=np.ones((nS, 1)), Nom=np.ones((nS, 1)), version=pd_stage.VERSION)
+        for k in ('imgAll', 'imgAllFlip', 'CTF'):              # like run_pd: heavy arrays not asked for are None
+            if k not in kw['fields']:
+                res[k] = None
         return res
     monkeypatch.setattr(pd_stage, 'run_pd', fake_run_pd)
     monkeypatch.setattr(worker, '_ctx', lambda: None)
     q = np.tile(np.array([[1.0], [0.0], [0.0], [0.0]]), (1, nS))
     opts = dict(verbose=False, avgOnly=False, visual=False, parallel=False, relion_data=False, thres=2000)
     recs = {}
+    p.record_virtual_ctf = False                             # the CTF field stored like the other arrays
     for prD, layout in enumerate(('pickle', 'sidecar')):
         p.record_layout = layout
         out = str(tmp_path / ('IMGs_prD_%d' % prD))
@@ -471,7 +475,20 @@ def test_worker_writes_both_layouts_without_touching_the_gpu(tmp_path, monkeypat
         assert seen['float64'] == (layout == 'pickle')
         assert os.path.exists(os.path.join(p.dist_prog, str(prD)))
         recs[layout] = myio.fin1(out)
-    del p.record_layout
+    # default sidecar record: the CTF field is virtual (df + microscope constants in the manifest, no file), and
+    # p.record_skip drops arrays no consumer reads
+    del p.record_virtual_ctf
+    p.record_skip = ('imgAllFlip',)
+    out = str(tmp_path / 'IMGs_prD_2')
+    worker.op([np.arange(nS), q, np.full(nS, 1e4), out, 2], dict(type='Butter', Qc=0.5, N=8), str(stackf),
+              (np.zeros(nS), np.zeros(nS)), 2 * nS, opts)
+    del p.record_skip, p.record_layout
+    c = myio.fin1(out)
+    assert list(c.keys()) == worker._KEYS and c['imgAllFlip'] is None
+    assert c._lazy['CTF'] == dict(virtual='ctf', df_key='df', N=N, pix_size=1.0, Cs=2.0, EkV=300.0, gaussEnv=np.inf,
+                                  AmpContrast=0.1, shape=(nS, N * N))
+    assert not os.path.exists(out + '.CTF.npy') and not os.path.exists(out + '.imgAllFlip.npy')
+    assert os.path.exists(out + '.imgAll.npy') and np.array_equal(c['df'], np.full(nS, 1e4))
     a, b = recs['sidecar'], recs['pickle']
     assert isinstance(a, myio.Record) and type(b) is dict and list(a.keys()) == list(b.keys()) == worker._KEYS
     assert os.path.getsize(str(tmp_path / 'IMGs_prD_1.imgAll.npy')) < 0.51 * nS * N * N * 8 + 200
