@@ -139,6 +139,11 @@ int mem_operand_shape(mem_ctx* ctx, int32_t N, mem_contract_shape* out);
 int mem_knn_device(mem_ctx* ctx, const double* D, int32_t nS, int32_t k, int32_t* idx, double* val, void* stream);
 /* a15 on the float32 D that mem_pd_distance_device leaves on the device (D never visits the host) */
 int mem_knn_device_f32(mem_ctx* ctx, const float* D, int32_t nS, int32_t k, int32_t* idx, double* val, void* stream);
+/* D[posPath][:, posPath] of the trimming loop (modules/manifoldTrimmingAuto.py:50,63) on a D that stays on the device:
+ * out[a][b] = D[sel[a]][sel[b]]; D [nS][nS] and out [m][m] are device arrays of 4-byte (float32) or 8-byte (float64)
+ * elements, sel [m] int32 is a HOST array (copied before the call returns). */
+int mem_gather_square_device(mem_ctx* ctx, const void* D, int32_t elem_bytes, int32_t nS, const int32_t* sel, int32_t m,
+                             void* out, void* stream);
 /* which kNN kernel the three kNN paths use (process-wide): 0 = automatic (radix selection of the k winners when
  * 4 k <= nS and the row fits shared memory, else a full bitonic sort of the row), 1 = always sort, 2 = selection
  * whenever it fits.  Both kernels return identical lists (ties by index); the switch exists for tests and timing. */

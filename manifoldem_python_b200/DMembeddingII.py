@@ -60,9 +60,10 @@ def graph_and_sweep(D, k, ctx=None, nS=None, knn=None, want_lists=True):
         idx_d = _lib.DeviceArray(ctx, (nS, k), np.int32)
         val_d = _lib.DeviceArray(ctx, (nS, k), np.float64)
         if isinstance(D, _lib.DeviceArray):
-            if D.dtype != np.float32:
-                raise TypeError('resident D must be float32')
-            _lib.check(lib.mem_knn_device_f32(ctx.handle, D.ptr, nS, k, idx_d.ptr, val_d.ptr, None))
+            if D.dtype not in (np.float32, np.float64) or D.shape != (nS, nS):
+                raise TypeError('resident D must be a square float32 or float64 device array')
+            knn = lib.mem_knn_device_f32 if D.dtype == np.float32 else lib.mem_knn_device
+            _lib.check(knn(ctx.handle, D.ptr, nS, k, idx_d.ptr, val_d.ptr, None))
         else:
             Dd = _lib.DeviceArray(ctx, (nS, nS), np.float64, np.ascontiguousarray(D, dtype=np.float64))
             _lib.check(lib.mem_knn_device(ctx.handle, Dd.ptr, nS, k, idx_d.ptr, val_d.ptr, None))
@@ -127,12 +128,39 @@ def device_operator(L_dev, nS, ctx=None):
     return LinearOperator((nS, nS), matvec=matvec, dtype=np.float64)
 
 
+def upload(D, ctx=None):
+    """D on the device for embed() / take(): float32 stays float32 (the dtype the distance stage computed it in and the
+    sidecar record stores — half the bytes, identical lists), anything else goes up as float64."""
+    D = np.asarray(D)
+    dt = np.float32 if D.dtype == np.float32 else np.float64
+    return _lib.DeviceArray(ctx or _ctx(), D.shape, dt, np.ascontiguousarray(D, dtype=dt))
+
+
+def take(D_dev, sel, ctx=None):
+    """D[sel][:, sel] on the device (manifoldTrimmingAuto.py:50,63): a new (m,m) device array of the same dtype."""
+    lib = _lib.load()
+    ctx = ctx or _ctx()
+    sel = np.ascontiguousarray(sel, dtype=np.int32)
+    m = sel.shape[0]
+    out = _lib.DeviceArray(ctx, (m, m), D_dev.dtype)
+    _lib.check(lib.mem_gather_square_device(ctx.handle, D_dev.ptr, D_dev.dtype.itemsize, D_dev.shape[0], sel.ctypes.data, m,
+                                            out.ptr, None))
+    return out
+
+
 def op(D, k, tune, prefsigma):
+    out = embed(D, int(k), tune)
+    nS = D.shape[0]
+    D[np.arange(nS), np.arange(nS)] = -np.inf                                    # :48, in place like the reference
+    return out
+
+
+def embed(D, k, tune):
+    """op() without the side effect on the caller's matrix; D may also be a device array from upload() / take() or
+    pd_stage.run_pd_resident — the trimming loop re-embeds subsets of one resident D."""
     p = _cfg()
     nS = D.shape[0]
-    k = int(k)
     M, logEps, logSumWij, _, _ = graph_and_sweep(D, k, want_lists=False)
-    D[np.arange(nS), np.arange(nS)] = -np.inf                                    # :48, in place like the reference
     a0 = (np.random.rand(4, 1) - .5)                                             # :142 (unseeded in the reference)
     popt, resnorm, R_squared = _fit(logEps, logSumWij, a0)
     nEigs = min(getattr(p, 'num_eigs', 15), nS - 3)                              # :149

@@ -18,6 +18,7 @@ SYMBOLS = [
     'mem_contract_knn_device', 'mem_knn_mode',
     'mem_operand_shape', 'mem_knn_device', 'mem_knn_device_f32', 'mem_graph_dense_device', 'mem_graph_compact_device', 'mem_ferguson_device',
     'mem_laplacian_dense_device', 'mem_symv_host', 'mem_s2_assign_host', 'mem_ctf_host',
+    'mem_gather_square_device',
 ]
 
 
@@ -93,6 +94,8 @@ def load():
                                             C.c_void_p]
         lib.mem_laplacian_dense_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]
         lib.mem_symv_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        lib.mem_gather_square_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                                 C.c_void_p, C.c_void_p]
         lib.mem_ctf_host.argtypes = [C.c_void_p, C.POINTER(PdParams), C.c_void_p, C.c_void_p]
         lib.mem_s2_assign_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
         _lib = lib

@@ -16,6 +16,8 @@ int laplacian_dense_device(mem_ctx* ctx, const double* M, int nS, double sigma, 
 int symv_host(mem_ctx* ctx, const double* L, int nS, const double* x_host, double* y_host);
 int s2_assign_host(mem_ctx* ctx, const double* centres, int nG, const double* pts, long long n, int* idx);
 int ctf_host(mem_ctx* ctx, const mem_pd_params* prm, const double* df, double* out);
+int gather_square_device(mem_ctx* ctx, const void* D, int elem_bytes, int nS, const int* sel_host, int m, void* out,
+                         cudaStream_t st);
 }  // namespace mem
 
 using namespace mem;
@@ -256,6 +258,12 @@ int mem_contract_knn_device(mem_ctx* ctx, const mem_contract_shape* shp, const f
     return 1;
   }
   return contract_run(ctx, shp, Zhi, Zlo, D, contraction, k_chunk_blocks, split_k, pick(ctx, stream), &knn);
+}
+
+int mem_gather_square_device(mem_ctx* ctx, const void* D, int32_t elem_bytes, int32_t nS, const int32_t* sel, int32_t m,
+                             void* out, void* stream) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  return gather_square_device(ctx, D, elem_bytes, nS, sel, m, out, pick(ctx, stream));
 }
 
 int mem_knn_mode(int32_t mode) {

@@ -721,4 +721,37 @@ int symv_host(mem_ctx* ctx, const double* L, int nS, const double* x_host, doubl
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// manifoldTrimmingAuto.py:50,63 — D[posPath][:, posPath] on a D that stays on the device: out[a][b] = D[sel[a]][sel[b]].
+// The trimming loop re-embeds ever smaller subsets of one PD; only the index list travels, not the matrix.
+// ---------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256) k_gather_square(const T* __restrict__ D, int nS, const int* __restrict__ sel, int m,
+                                                       T* __restrict__ out) {
+  const int a = blockIdx.y;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= m) return;
+  out[(size_t)a * m + b] = D[(size_t)sel[a] * nS + sel[b]];
+}
+int gather_square_device(mem_ctx* ctx, const void* D, int elem_bytes, int nS, const int* sel_host, int m, void* out,
+                         cudaStream_t st) {
+  if (m < 1 || nS < 1 || (elem_bytes != 4 && elem_bytes != 8)) {
+    set_error("gather: need m >= 1, nS >= 1 and 4- or 8-byte elements (m=%d nS=%d bytes=%d)", m, nS, elem_bytes);
+    return 1;
+  }
+  for (int a = 0; a < m; ++a)
+    if (sel_host[a] < 0 || sel_host[a] >= nS) {
+      set_error("gather: index %d out of range at position %d (nS=%d)", sel_host[a], a, nS);
+      return 1;
+    }
+  MEM_CHECK(ctx->small_out.ensure((size_t)m * sizeof(int)));
+  int* d_sel = ctx->small_out.as<int>();
+  MEM_CUDA(cudaMemcpyAsync(d_sel, sel_host, (size_t)m * sizeof(int), cudaMemcpyHostToDevice, st));
+  MEM_CUDA(cudaStreamSynchronize(st));                       // sel_host may be a temporary of the caller
+  const dim3 grid((m + 255) / 256, m);
+  if (elem_bytes == 4) MEM_LAUNCH(ctx, k_gather_square<float>, grid, 256, 0, st, (const float*)D, nS, d_sel, m, (float*)out);
+  else MEM_LAUNCH(ctx, k_gather_square<double>, grid, 256, 0, st, (const double*)D, nS, d_sel, m, (double*)out);
+  return 0;
+}
+
 }  // namespace mem

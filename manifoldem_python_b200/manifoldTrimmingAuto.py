@@ -3,8 +3,9 @@
 the points whose leading three diffusion coordinates lie outside radius `rad` and re-embed, then write the
 psi pickle, the resume marker (after the dump) and the eigenvalue spectrum text file.
 
-Same signature and outputs as the reference; the heavy part of every DMembeddingII.op call (kNN, graph,
-Ferguson sweep, Gaussian-kernel Laplacian) runs on the GPU.
+Same signature and outputs as the reference; the heavy part of every embedding (kNN, graph, Ferguson sweep,
+Gaussian-kernel Laplacian) runs on the GPU, and so does the sub-matrix selection of the trimming loop: D is uploaded
+once per PD and stays on the device.
 """
 import os
 
@@ -24,30 +25,41 @@ def op(input_data, posPath, tune, rad, visual, doSave):
     p = _cfg()
     dist_file, psi_file, eig_file, prD = input_data[0], input_data[1], input_data[2], input_data[3]
     data = myio.fin1(dist_file)
-    D = data['D']
     ind = data['ind']
-    nS = D.shape[1]
-    if isinstance(posPath, int) and posPath == 0:                 # :48-49
-        posPath = np.arange(nS)
-    D = D[posPath][:, posPath]
-    nS = D.shape[1]
-    k = nS
-    lamb, psi, sigma, mu, logEps, logSumWij, popt, R_squared = DMembeddingII.op(D, k, tune, 60000)   # :54
-    posPath1 = get_psiPath(psi, rad, 0)
-    while len(posPath1) < nS:                                      # :61-70
-        nS = len(posPath1)
-        D1 = D[posPath1][:, posPath1]
-        k = D1.shape[0]
-        lamb, psi, sigma, mu, logEps, logSumWij, popt, R_squared = DMembeddingII.op(D1, k, tune, 600000)
-        lamb = lamb[lamb > 0]
-        posPathInt = get_psiPath(psi, rad, 0)
-        posPath1 = posPath1[posPathInt]
-    posPath = posPath[posPath1]
-    if doSave['Is']:                                               # :79-87
+    # D goes to the device once, in the dtype it is stored in (a sidecar record holds the float32 the distance stage
+    # computed: half the upload, same neighbour lists); every D[posPath][:, posPath] of the loop (:50, :63) is a device
+    # gather, so per pass only an index list goes up and the embedding comes back
+    stored = data.raw('D') if isinstance(data, myio.Record) else data['D']
+    nS = stored.shape[1]
+    resident = [DMembeddingII.upload(stored)]
+    try:
+        if isinstance(posPath, int) and posPath == 0:             # :48-49
+            posPath = np.arange(nS)
+        else:
+            posPath = np.asarray(posPath)
+            resident.append(DMembeddingII.take(resident[-1], posPath))
+            nS = len(posPath)
+        D = resident[-1]                                          # D[posPath][:, posPath]
+        lamb, psi, sigma, mu, logEps, logSumWij, popt, R_squared = DMembeddingII.embed(D, nS, tune)     # :54, k = nS
+        keep = get_psiPath(psi, rad, 0)                           # indices into D
+        while len(keep) < nS:                                     # :61-70 drop the outliers, embed what is left
+            nS = len(keep)
+            sub = DMembeddingII.take(D, keep)
+            try:
+                lamb, psi, sigma, mu, logEps, logSumWij, popt, R_squared = DMembeddingII.embed(sub, nS, tune)
+            finally:
+                sub.free()
+            lamb = lamb[lamb > 0]
+            keep = keep[get_psiPath(psi, rad, 0)]
+    finally:
+        for a in resident:
+            a.free()
+    posPath = posPath[keep]
+    if doSave['Is']:                                              # :79-87
         myio.fout1(psi_file, ['lamb', 'psi', 'sigma', 'mu', 'posPath', 'ind', 'logEps', 'logSumWij', 'popt', 'R_squared'],
-                   [lamb, psi, sigma, mu, posPath, ind, logEps, logSumWij, popt, R_squared])
+                   [lamb, psi, sigma, mu, posPath, ind, logEps, logSumWij, popt, R_squared], layout='pickle')
         open(os.path.join(p.psi_prog, '%s' % (prD)), 'a').close()  # marker after the dump
-    if os.path.exists(eig_file):                                   # :89-92
+    if os.path.exists(eig_file):                                  # :89-92
         os.remove(eig_file)
     with open(eig_file, 'a') as f:
         for i in range(len(lamb) - 1):

@@ -329,3 +329,33 @@ def test_sidecar_records_through_the_worker(tmp_path):
            False, dict(outputFile='', Is=True))
     rec = myio.fin1('{}prD_1'.format(p.psi_file))
     assert rec['psi'].shape[0] == len(rec['posPath']) and os.path.exists(os.path.join(p.psi_prog, '1'))
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_device_submatrix_and_resident_embedding(dtype):
+    """DMembeddingII.take == D[sel][:, sel] (manifoldTrimmingAuto.py:50,63) on the device, and embedding a resident
+    matrix gives what op() gives for the same host matrix (float32 storage included: identical neighbour lists)."""
+    from manifoldem_python_b200 import DMembeddingII, _lib, p
+    p.init()
+    rng = np.random.default_rng(8)
+    nS = 300
+    tau = rng.random(nS)
+    X = np.stack([np.cos(3 * tau), np.sin(3 * tau), 0.2 * rng.standard_normal(nS)], 1)
+    D = (((X[:, None, :] - X[None, :, :]) ** 2).sum(-1) * 1e4).astype(np.float32).astype(dtype)
+    D = np.maximum(D, D.T)
+    Dd = DMembeddingII.upload(D)
+    assert Dd.dtype == dtype
+    sel = np.sort(rng.choice(nS, 123, replace=False))
+    sub = DMembeddingII.take(Dd, sel)
+    assert sub.shape == (123, 123) and np.array_equal(sub.download(), D[sel][:, sel])
+    np.random.seed(3)
+    a = DMembeddingII.embed(sub, 123, 3.0)
+    np.random.seed(3)
+    b = DMembeddingII.op(D[sel][:, sel].astype(np.float64), 123, 3.0, 0)
+    assert np.array_equal(a[5], b[5]) and a[2] == b[2]                        # logSumWij, sigma
+    for j in range(3):
+        assert abs(np.corrcoef(a[1][:, j], b[1][:, j])[0, 1]) >= 0.9999
+    with pytest.raises(RuntimeError):
+        DMembeddingII.take(Dd, np.array([0, nS]))
+    for x in (Dd, sub):
+        x.free()
