@@ -43,6 +43,15 @@ def _ctx():
     return ctx
 
 
+def _arena():
+    """Reused pinned host buffers of this worker thread (pd_stage.HostArena)."""
+    arena = getattr(_tls, 'arena', None)
+    if arena is None:
+        arena = pd_stage.HostArena()
+        _tls.arena = arena
+    return arena
+
+
 def _read_mrc_volume(path):
     """3-D mask volume (:305-306): MRC2014, modes 0/1/2/6, as mrcfile's .data (z,y,x)."""
     hdr = np.fromfile(path, dtype='<i4', count=256)
@@ -86,7 +95,7 @@ def op(input_data, filterPar, imgFileName, sh, nStot, options, fields=None):
     res = pd_stage.run_pd(ind, q, df, stack, nStot, N, p.pix_size, p.Cs, p.EkV, p.AmpContrast,
                           gaussEnv=getattr(p, 'gaussEnv', np.inf), filterPar=filterPar, msk2=msk2, relion=relion,
                           sh=sh, avg_only=bool(options.get('avgOnly', False)), ctx=_ctx(), angles=angles,
-                          fields=want, float64=(layout != 'sidecar'))
+                          fields=want, float64=(layout != 'sidecar'), arena=_arena())
     if options.get('parallel') and res['CTF'] is not None:
         res['CTF'] = res['CTF'].reshape(-1, N, N)                         # that branch leaves CTF un-flattened (:378-389)
     res['options'] = options

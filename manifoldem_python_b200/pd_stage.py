@@ -74,14 +74,46 @@ def open_stack(imgFileName, N, relion):
     return np.memmap(imgFileName, dtype='<f4', mode='r', offset=1024 + nsymbt, shape=(nz, ny, nx))
 
 
+class HostArena:
+    """Pinned host buffers reused from one PD to the next by the thread that owns them: a fresh 0.5 GB NumPy array per
+    PD costs more in page faults than the copy it receives, and pinned memory lets the H2D / D2H copies of the
+    host-buffer entry point run at PCIe speed.  Arrays handed out stay valid until the same name is asked for again."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, name, shape, dtype):
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape))
+        buf = self._bufs.get(name)
+        if buf is None or buf.nbytes < n * dtype.itemsize:
+            if buf is not None and hasattr(buf, 'free'):
+                buf.free()
+            try:
+                buf = _lib.PinnedArray((max(n * dtype.itemsize, 1),), np.uint8)
+            except RuntimeError:                       # no pinned memory left: pageable, still reused
+                buf = np.empty(max(n * dtype.itemsize, 1), dtype=np.uint8)
+            self._bufs[name] = buf
+        flat = buf.array if hasattr(buf, 'array') else buf
+        return flat[:n * dtype.itemsize].view(dtype).reshape(shape)
+
+    def close(self):
+        for b in self._bufs.values():
+            if hasattr(b, 'free'):
+                b.free()
+        self._bufs = {}
+
+
 # ----------------------------------------------------------------------------- the C-ABI call
 def run_pd(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast, gaussEnv=np.inf, filterPar=None,
            msk2=None, relion=False, sh=None, avg_only=False, ctx=None, fields=('D', 'imgAll', 'imgAllFlip', 'CTF'),
-           contraction=0, k_chunk_blocks=0, split_k=0, float64=True, angles=None, knn_k=0):
+           contraction=0, k_chunk_blocks=0, split_k=0, float64=True, angles=None, knn_k=0, arena=None):
     """Returns the dict the reference pickles (same keys / shapes; float64 unless float64=False).
     `fields` selects which of the heavy per-image outputs are materialised.  knn_k > 0 adds `knn_idx` (nS,k) int32
     and `knn_val` (nS,k) float64 — the lists DMembeddingII.initialize (:43-57) would take from D — selected on the
-    device straight behind the contraction; without 'D' in `fields` the nS x nS matrix is then never assembled."""
+    device straight behind the contraction; without 'D' in `fields` the nS x nS matrix is then never assembled.
+    `arena` (a HostArena owned by the calling thread): the gathered stack and the outputs live in its reused pinned
+    buffers — the arrays of the result are then only valid until the next call with the same arena."""
     lib = _lib.load()
     ctx = ctx or _lib.default_context()
     if filterPar is None:
@@ -93,7 +125,7 @@ def run_pd(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast, gaussEnv
     df = np.ascontiguousarray(df, dtype=np.float64)
     nS = ind.shape[0]
     PDs, PD, psi_p, Psi, s, c = angles if angles is not None else host_angles(q)
-    raw, flip, base = gather(stack, ind, nStot, N)
+    raw, flip, base = gather(stack, ind, nStot, N, out=arena.get('raw', (nS, N * N), np.float32) if arena else None)
     shift = None
     if relion:                                         # (:263) shi = (sh[1][idx] - 0.5, sh[0][idx] - 0.5)
         shift = np.ascontiguousarray(np.stack((np.asarray(sh[1])[base] - 0.5, np.asarray(sh[0])[base] - 0.5), axis=1),
@@ -109,7 +141,7 @@ def run_pd(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast, gaussEnv
     outs = {}
 
     def want(name, shape, dtype):
-        a = np.empty(shape, dtype=dtype)
+        a = arena.get(name, shape, dtype) if arena else np.empty(shape, dtype=dtype)
         outs[name] = a
         return a.ctypes.data
 

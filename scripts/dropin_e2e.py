@@ -35,7 +35,8 @@ q[:, n_half:] = q[:, :n_half]
 df = np.tile(rng.uniform(10000.0, 30000.0, n_half), 2)
 CG = [np.arange(i * nS, (i + 1) * nS) for i in range(n_pd)]
 
-for layout in ('pickle', 'sidecar-full', 'sidecar'):
+layouts = [a.split('=')[1].split(',') for a in sys.argv if a.startswith('--layouts=')]
+for layout in (layouts[0] if layouts else ('pickle', 'sidecar-full', 'sidecar')):
     p.init()
     p.user_dir, p.proj_name = work, 'run_' + layout
     p.create_dir()

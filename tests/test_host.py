@@ -539,3 +539,22 @@ def test_ferguson_sorted_chunk_model():
         assert np.allclose(tiled, direct, rtol=1e-13, atol=0), thr
         if thr == 10.0:
             assert n_exp_calls < 0.08 * present.size * len(s)          # the point of the exercise
+
+
+def test_host_arena_reuses_buffers(monkeypatch):
+    """pd_stage.HostArena: one buffer per name, reused while it is big enough, regrown otherwise; falls back to
+    pageable memory when pinned memory cannot be had (here: no GPU, cudaMallocHost fails)."""
+    from manifoldem_python_b200 import pd_stage
+    arena = pd_stage.HostArena()
+    a = arena.get('raw', (10, 16), np.float32)
+    a[...] = 3.0
+    b = arena.get('raw', (5, 16), np.float32)
+    assert b.shape == (5, 16) and b.dtype == np.float32 and np.shares_memory(a, b) and (b == 3.0).all()
+    c = arena.get('raw', (40, 16), np.float64)
+    assert c.shape == (40, 16) and c.dtype == np.float64 and not np.shares_memory(a, c)
+    d = arena.get('D', (4, 4), np.float32)
+    assert not np.shares_memory(c, d)
+    c[...] = 1.0
+    d[...] = 2.0
+    assert (c == 1.0).all() and (d == 2.0).all()
+    arena.close()
