@@ -44,7 +44,12 @@ def _ctx():
 
 
 def _arena():
-    """Reused pinned host buffers of this worker thread (pd_stage.HostArena)."""
+    """Reused pinned host buffers of this worker thread (pd_stage.HostArena) — opt-in, MANIFOLDEM_B200_PINNED_ARENA=1.
+    Measured on the B200 box with 3 PDs of 2,000 x 256^2 per GetDistancesS2.op call (scripts/dropin_e2e.py): pinning
+    1-2.6 GB per worker thread costs more than the page faults and pageable copies it removes (0.65 against 0.43 s per
+    PD), so it only pays on runs with many PDs per worker thread; off by default."""
+    if os.environ.get('MANIFOLDEM_B200_PINNED_ARENA', '0') != '1':
+        return None
     arena = getattr(_tls, 'arena', None)
     if arena is None:
         arena = pd_stage.HostArena()
