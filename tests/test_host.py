@@ -558,3 +558,16 @@ def test_host_arena_reuses_buffers(monkeypatch):
     d[...] = 2.0
     assert (c == 1.0).all() and (d == 2.0).all()
     arena.close()
+
+
+def test_header_is_plain_c():
+    """include/manifoldem_b200.h is the C ABI a maintainer binds: it must compile as C99 on its own."""
+    import shutil
+    import subprocess
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('no gcc')
+    hdr = os.path.join(ROOT, 'include', 'manifoldem_b200.h')
+    r = subprocess.run([gcc, '-std=c99', '-Wall', '-Wextra', '-pedantic', '-fsyntax-only', '-x', 'c', hdr],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and not r.stderr.strip(), r.stderr
