@@ -95,3 +95,44 @@ def test_gpu_assignment_large_and_edge_cases():
     assert IND.shape == (0, 1) and len(NC) == 0
     with pytest.raises(ValueError):
         S2t.classS2(Xt[:, :2], Q[:5])
+
+
+REF_STAR = '/root/reference/demo/RyR1GCs_clustRem.star'
+
+
+@pytest.mark.skipif(not os.path.exists(REF_STAR), reason='reference demo star only exists in the build container')
+def test_demo_star_gives_the_53_projection_directions(monkeypatch):
+    """BASELINE config 1 bookkeeping: the orientations of the repo demo (read with the reference's own
+    star reader), augmented and tessellated with the manual's settings — aperture index 4 at 5 A / 360 A => width
+    4*5/360, thresholds 100 / 2000 — give 53 projection directions with 117..450 particles, sum nS^2 = 3,130,240.
+    Host logic of the drop-in with the oracle's nearest-bin assignment; build container only."""
+    import builtins
+    import types
+    for name in ('matplotlib', 'matplotlib.pyplot', 'mrcfile', 'mpl_toolkits', 'mpl_toolkits.mplot3d', 'mpi4py'):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules['mpl_toolkits.mplot3d'].Axes3D = object
+    ref_mod = '/root/reference/modules'
+    monkeypatch.syspath_prepend(ref_mod)
+    _open = builtins.open
+    monkeypatch.setattr(builtins, 'open', lambda f, mode='r', *a, **k: _open(f, mode.replace('U', ''), *a, **k))
+    before = set(sys.modules)
+    try:
+        import read_alignfile
+        import util
+        sh, q, U, V = read_alignfile.get_from_relion(REF_STAR, flip=True)
+        q = util.augment(q)
+    finally:                                                # leave no reference module behind for other tests
+        for name in set(sys.modules) - before:
+            if getattr(sys.modules[name], '__file__', None) and str(sys.modules[name].__file__).startswith('/root/reference'):
+                del sys.modules[name]
+    from oracle import s2_tessellation as os2
+    from manifoldem_python_b200 import S2tessellation as S2t
+
+    def cpu_class(X, Q, ctx=None):
+        ind = os2.nearest_bin(X, Q).reshape(-1, 1)
+        return ind, np.bincount(ind[:, 0])
+    monkeypatch.setattr(S2t, 'classS2', cpu_class)
+    CG1, CG, nG, S2, S20_th, S20, NC = S2t.op(q, 4 * 5.0 / 360, 100, False, 2000)
+    occ = np.array([len(a) for a in CG])
+    assert int(nG) == 4071 and len(CG) == 53
+    assert occ.min() == 117 and occ.max() == 450 and int(np.median(occ)) == 206 and int((occ ** 2).sum()) == 3130240
