@@ -100,6 +100,12 @@ class Record(dict):
         self.materialise()
         return super().values()
 
+    def __iter__(self):                            # defined so that dict(record) / {**record} go through __getitem__
+        return super().__iter__()                  # (CPython copies a dict subclass's raw slots unless __iter__ is overridden)
+
+    def copy(self):
+        return dict(self.materialise())
+
     def __reduce__(self):                          # pickling a Record stores the plain dict
         return (dict, (dict(self.materialise()),))
 

@@ -411,6 +411,8 @@ def test_sidecar_record_layout(tmp_path):
     for (k, v), (k2, v2) in zip(sorted(c.items(), key=lambda t: t[0]), sorted(b.items(), key=lambda t: t[0])):
         assert k == k2 and (np.array_equal(v, v2) if isinstance(v2, np.ndarray) else v == v2), k
     assert pickle.loads(pickle.dumps(myio.fin1(f_side))).keys() == b.keys()
+    for plain in (dict(myio.fin1(f_side)), {**myio.fin1(f_side)}, myio.fin1(f_side).copy()):   # copies see the arrays too
+        assert type(plain) is dict and np.array_equal(plain['imgAll'], b['imgAll']) and np.array_equal(plain['CTF'], b['CTF'])
     # a missing / truncated sidecar fails loudly on access, an unreadable manifest gives None like the reference
     os.remove(str(tmp_path / 'side_prD_0.CTF.npy'))
     d = myio.fin1(f_side)
