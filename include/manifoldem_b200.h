@@ -42,9 +42,10 @@ int         mem_ctx_kernel_time(mem_ctx* ctx, int reset, double* total_ms, int64
 /* pinned host memory for the host-buffer entry points */
 int         mem_host_alloc(void** out, size_t bytes);
 int         mem_host_free(void* p);
-/* plain device memory + copies (so a ctypes host needs nothing else to stage data) */
-int         mem_dev_alloc(void** out, size_t bytes);
-int         mem_dev_free(void* p);
+/* plain device memory on the context's device + copies (so a ctypes host needs nothing else to stage data);
+ * every entry point that takes a ctx makes ctx's device current in the calling thread first */
+int         mem_dev_alloc(mem_ctx* ctx, void** out, size_t bytes);
+int         mem_dev_free(mem_ctx* ctx, void* p);
 int         mem_copy_h2d(mem_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int         mem_copy_d2h(mem_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 

@@ -76,7 +76,7 @@ def _gpu_worker(device, jobs, filterPar, imgFileName, sh, size, options, cfg):
 def _run_jobs(jobs, filterPar, imgFileName, sh, size, options, nPix, on_done):
     """The PDs of one GPU, a few in flight: the float64 conversion + pickle dump of PD k (host; NumPy and file I/O
     release the GIL) overlaps the device work of PD k+1.  Every host thread owns its context (stream + workspace).
-    Small PDs are launch/latency-bound: 4 streams double the throughput at nS ~ 200 (scripts/overlap_test.py)."""
+    Small PDs are launch/latency-bound: 4 streams double the throughput at nS ~ 200 (scripts/overlap_check.py)."""
     from concurrent.futures import ThreadPoolExecutor, as_completed
     work = float(np.median([len(j[0]) for j in jobs])) * nPix * nPix if jobs else 0.0
     inflight = max(1, int(os.environ.get('MANIFOLDEM_B200_INFLIGHT', '4' if work < 3e7 else '2')))

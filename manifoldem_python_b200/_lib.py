@@ -43,7 +43,7 @@ class ContractShape(C.Structure):
 
 
 _lib = None
-_lock = threading.Lock()
+_lock = threading.RLock()
 
 
 def load():
@@ -71,8 +71,8 @@ def load():
                                             C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         lib.mem_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
         lib.mem_host_free.argtypes = [C.c_void_p]
-        lib.mem_dev_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
-        lib.mem_dev_free.argtypes = [C.c_void_p]
+        lib.mem_dev_alloc.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t]
+        lib.mem_dev_free.argtypes = [C.c_void_p, C.c_void_p]
         lib.mem_copy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         lib.mem_copy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         lib.mem_pd_distance_device.argtypes = [C.c_void_p, C.POINTER(PdParams), C.POINTER(PdIO), C.c_void_p]
@@ -144,7 +144,7 @@ class DeviceArray:
         self.dtype = np.dtype(dtype)
         self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
         p = C.c_void_p()
-        check(self.lib.mem_dev_alloc(C.byref(p), max(self.nbytes, 1)))
+        check(self.lib.mem_dev_alloc(ctx.handle, C.byref(p), max(self.nbytes, 1)))
         self.ptr = p.value
         if src is not None:
             self.upload(src)
@@ -161,7 +161,7 @@ class DeviceArray:
 
     def free(self):
         if self.ptr:
-            self.lib.mem_dev_free(self.ptr)
+            self.lib.mem_dev_free(self.ctx.handle, self.ptr)
             self.ptr = None
 
     def __del__(self):
@@ -224,10 +224,10 @@ _default_ctx = {}
 
 
 def default_context(device=0):
-    with _lock:
-        pass
-    ctx = _default_ctx.get(device)
-    if ctx is None:
-        ctx = Context(device)
-        _default_ctx[device] = ctx
-    return ctx
+    load()
+    with _lock:                      # lookup and creation under one lock: two threads never create two contexts
+        ctx = _default_ctx.get(device)
+        if ctx is None:
+            ctx = Context(device)
+            _default_ctx[device] = ctx
+        return ctx

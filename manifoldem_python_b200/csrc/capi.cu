@@ -123,20 +123,24 @@ int mem_host_free(void* p) {
   MEM_CUDA(cudaFreeHost(p));
   return 0;
 }
-int mem_dev_alloc(void** out, size_t bytes) {
+int mem_dev_alloc(mem_ctx* ctx, void** out, size_t bytes) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
   MEM_CUDA(cudaMalloc(out, bytes ? bytes : 1));
   return 0;
 }
-int mem_dev_free(void* p) {
+int mem_dev_free(mem_ctx* ctx, void* p) {
+  if (ctx) MEM_CUDA(cudaSetDevice(ctx->device));
   MEM_CUDA(cudaFree(p));
   return 0;
 }
 int mem_copy_h2d(mem_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
   MEM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   MEM_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 int mem_copy_d2h(mem_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
   MEM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   MEM_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -198,8 +202,8 @@ int mem_pd_distance_host(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io
     d.knn_val = ctx->knn_out.as<double>();
     d.knn_idx = reinterpret_cast<int32_t*>(d.knn_val + nS * (size_t)prm->knn_k);
   }
-  MEM_CHECK(ctx->stats.ensure(3 * NN * sizeof(float)));
-  float* small = ctx->stats.as<float>();
+  MEM_CHECK(ctx->small_out.ensure(3 * NN * sizeof(float)));   // own buffer: `stats` is re-sized by the pipeline itself
+  float* small = ctx->small_out.as<float>();
   if (h->imgAvg) d.imgAvg = small;
   if (h->imgAvgFlip) d.imgAvgFlip = small + NN;
   if (h->imgAllIntensity) d.imgAllIntensity = small + 2 * NN;

@@ -101,8 +101,8 @@ def op(input_data, filterPar, imgFileName, sh, nStot, options, fields=None):
                           gaussEnv=getattr(p, 'gaussEnv', np.inf), filterPar=filterPar, msk2=msk2, relion=relion,
                           sh=sh, avg_only=bool(options.get('avgOnly', False)), ctx=_ctx(), angles=angles,
                           fields=want, float64=(layout != 'sidecar'), arena=_arena())
-    if options.get('parallel') and res['CTF'] is not None:
-        res['CTF'] = res['CTF'].reshape(-1, N, N)                         # that branch leaves CTF un-flattened (:378-389)
+    if (options.get('parallel') or options.get('avgOnly')) and res['CTF'] is not None:
+        res['CTF'] = res['CTF'].reshape(-1, N, N)     # only the default non-avgOnly branch flattens CTF (:392-393)
     res['options'] = options
     promote = {k: np.float64 for k in _KEYS if isinstance(res[k], np.ndarray) and res[k].dtype == np.float32}
     myio.fout1(outFile, _KEYS, [res[k] for k in _KEYS], layout=layout, promote=promote, virtual=virtual)

@@ -80,6 +80,46 @@ class Record(dict):
     def get(self, k, default=None):
         return self[k] if k in self else default
 
+    # --- writes: a key that is assigned, deleted or popped stops being lazy (the stored value must win over the sidecar)
+    def __setitem__(self, k, v):
+        self._lazy.pop(k, None)
+        super().__setitem__(k, v)
+
+    def __delitem__(self, k):
+        self._lazy.pop(k, None)
+        super().__delitem__(k)
+
+    def pop(self, k, *default):
+        if k in self._lazy:
+            self._load(k)
+        return super().pop(k, *default)
+
+    def popitem(self):
+        self.materialise()
+        return super().popitem()
+
+    def setdefault(self, k, default=None):
+        if k in self:
+            return self[k]
+        self[k] = default
+        return default
+
+    def update(self, *args, **kw):
+        for k, v in dict(*args, **kw).items():
+            self[k] = v
+
+    def __eq__(self, other):
+        return dict.__eq__(self.materialise(), other.materialise() if isinstance(other, Record) else other)
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    __hash__ = None
+
+    def __repr__(self):
+        return 'Record(%s)' % ', '.join('%r: %s' % (k, '<lazy>' if k in self._lazy else repr(dict.__getitem__(self, k)))
+                                         for k in dict.keys(self))
+
     def raw(self, k):
         """The array as stored (no promotion, read-only memory map) — for consumers that keep float32."""
         if k in self._lazy and not self._lazy[k].get('virtual'):
@@ -127,15 +167,31 @@ def _ctf_field(df, spec):
     return out.reshape(spec['shape'])
 
 
+def _sidecars_ok(arrays, filename):
+    """Every stored sidecar exists and has at least the bytes its manifest shape implies."""
+    for spec in arrays.values():
+        if spec.get('virtual'):
+            continue
+        path = os.path.join(os.path.dirname(filename), spec['file'])
+        need = int(np.prod(spec['shape'])) * np.dtype(spec['dtype']).itemsize
+        if not os.path.isfile(path) or os.path.getsize(path) < need:
+            return False
+    return True
+
+
 def fin1(filename):
-    try:
-        with open(filename, 'rb') as f:
+    """modules/myio.py:21-30: the file is opened OUTSIDE the try (a missing file raises, as in the reference); any
+    failure while reading it — a truncated pickle, or for 'sidecar' records a missing / short sidecar — gives None."""
+    with open(filename, 'rb') as f:
+        try:
             data = pickle.load(f)
-        if isinstance(data, dict) and data.get(MAGIC) == 2:
-            return Record(data['small'], data['arrays'], filename, data.get('keys'))
-        return data
-    except Exception:
-        return None
+            if isinstance(data, dict) and data.get(MAGIC) == 2:
+                if not _sidecars_ok(data['arrays'], filename):
+                    return None
+                return Record(data['small'], data['arrays'], filename, data.get('keys'))
+            return data
+        except Exception:
+            return None
 
 
 def _write_npy(path, a):
@@ -172,6 +228,12 @@ def fout1(filename, key_list, v_list, layout=None, promote=None, virtual=None):
             small[k] = v.astype(promote[k])
         else:
             small[k] = v
+    # sidecars left by an earlier write of this record whose keys are no longer stored as files
+    keep = {spec['file'] for spec in arrays.values() if 'file' in spec}
+    d = os.path.dirname(filename) or '.'
+    for name in os.listdir(d):
+        if name.startswith(base + '.') and name.endswith('.npy') and name not in keep:
+            os.remove(os.path.join(d, name))
     tmp = filename + '.tmp'
     with open(tmp, 'wb') as f:
         pickle.dump({MAGIC: 2, 'keys': list(key_list), 'small': small, 'arrays': arrays}, f, protocol=pickle.HIGHEST_PROTOCOL)

@@ -107,11 +107,14 @@ class HostArena:
 # ----------------------------------------------------------------------------- the C-ABI call
 def run_pd(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast, gaussEnv=np.inf, filterPar=None,
            msk2=None, relion=False, sh=None, avg_only=False, ctx=None, fields=('D', 'imgAll', 'imgAllFlip', 'CTF'),
-           contraction=0, k_chunk_blocks=0, split_k=0, float64=True, angles=None, knn_k=0, arena=None):
+           contraction=0, k_chunk_blocks=0, split_k=0, float64=True, angles=None, knn_k=0, arena=None,
+           intensity=None):
     """Returns the dict the reference pickles (same keys / shapes; float64 unless float64=False).
     `fields` selects which of the heavy per-image outputs are materialised.  knn_k > 0 adds `knn_idx` (nS,k) int32
     and `knn_val` (nS,k) float64 — the lists DMembeddingII.initialize (:43-57) would take from D — selected on the
     device straight behind the contraction; without 'D' in `fields` the nS x nS matrix is then never assembled.
+    `intensity`: produce imgAllIntensity (:400); default = whenever any per-image record array is asked for (the
+    kernel does not need imgAllFlip exported to compute it).
     `arena` (a HostArena owned by the calling thread): the gathered stack and the outputs live in its reused pinned
     buffers — the arrays of the result are then only valid until the next call with the same arena."""
     lib = _lib.load()
@@ -166,7 +169,9 @@ def run_pd(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast, gaussEnv
         io.CTF = want('CTF', (nS, N * N), np.float64)
     io.imgAvg = want('imgAvg', (N, N), np.float32)
     io.imgAvgFlip = want('imgAvgFlip', (N, N), np.float32)
-    if 'imgAllFlip' in fields:
+    if intensity is None:
+        intensity = any(f in fields for f in ('imgAll', 'imgAllFlip', 'CTF'))
+    if intensity:
         io.imgAllIntensity = want('imgAllIntensity', (N, N), np.float32)
     _lib.check(lib.mem_pd_distance_host(ctx.handle, C.byref(prm), C.byref(io)))
 

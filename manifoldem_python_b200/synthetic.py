@@ -108,3 +108,58 @@ def make_pd(nS, N, seed=0, snr=0.1, conj_frac=1.0 / 3, n_blobs=20, tilt_sigma=0.
     shy = np.zeros(n_half)
     return dict(stack=stack.reshape(-1), ind=ind, q=q, df=df, sh=(shx, shy), nStot=nStot, tau=tau,
                 em=dict(nPix=N, pix_size=_PIX, Cs=_CS, EkV=_EKV, AmpContrast=_AMPC))
+
+
+def make_pd_fast(nS, N, seed=0, snr=0.1, conj_frac=1.0 / 3, n_blobs=20, tilt_sigma=0.03, pd_phi=0.7, pd_theta=1.1,
+                 chunk=256, out=None, with_ctf=True):
+    """Same model as make_pd, vectorised over chunks of particles (BLAS for the blobs, batched multi-threaded FFT
+    for the CTF modulation, float32 noise) so that PDs of BASELINE config sizes (2,000 - 20,000 particles at
+    256^2 / 320^2) are generated in seconds.  Different random stream from make_pd; same dict.
+    `out`: optional preallocated (nS, N*N) float32 array (e.g. pinned memory) that receives the stack."""
+    from scipy import fft as sfft
+    rng = np.random.default_rng(seed)
+    nStot = 2 * nS
+    conj = rng.random(nS) < conj_frac
+    ind = np.arange(nS, dtype=np.int64) + np.where(conj, nS, 0)
+    tau = rng.random(nS)
+    psi = rng.uniform(0, 2 * np.pi, nS)
+    q = euler_to_quat(pd_phi + tilt_sigma * rng.standard_normal(nS), pd_theta + tilt_sigma * rng.standard_normal(nS), psi)
+    df = rng.uniform(10000.0, 30000.0, nS)
+    PDs = 2 * np.vstack((q[1] * q[3] - q[0] * q[2], q[0] * q[1] + q[2] * q[3], q[0] ** 2 + q[3] ** 2 - 0.5))
+    PD = PDs.sum(1) / np.linalg.norm(PDs.sum(1))
+    sn = -(1 + PD[2]) * q[3] - PD[0] * q[1] - PD[1] * q[2]
+    cn = (1 + PD[2]) * q[0] + PD[1] * q[1] - PD[0] * q[2]
+    Psi = 2 * np.arctan(sn / cn)
+    r = 0.35 * N * np.sqrt(rng.random(n_blobs))
+    a = rng.uniform(0, 2 * np.pi, n_blobs)
+    bx, by = r * np.cos(a), r * np.sin(a)
+    bs = rng.uniform(0.02, 0.06, n_blobs) * N
+    amp = rng.uniform(0.5, 1.5, n_blobs).astype(np.float32)
+    grid = (np.arange(N) - (N - 1) / 2.0).astype(np.float32)
+    f = np.fft.fftfreq(N, d=1.0 / N)
+    k2 = ((f[:, None] ** 2 + f[None, :N // 2 + 1] ** 2) / (N / 2.0) ** 2 / (2 * _PIX) ** 2)
+    wav = 12.3986 / np.sqrt((1022.0 + _EKV) * _EKV)
+    stack = out if out is not None else np.empty((nS, N * N), dtype=np.float32)
+    for i0 in range(0, nS, chunk):
+        sl = slice(i0, min(nS, i0 + chunk))
+        m = sl.stop - sl.start
+        cx = np.tile(bx, (m, 1)); cy = np.tile(by, (m, 1)); s = np.tile(bs, (m, 1))
+        cx[:, 0] += 0.25 * N * (tau[sl] - 0.5)
+        s[:, 0] *= 1.0 + 0.5 * tau[sl]
+        ca, sa = np.cos(Psi[sl])[:, None], np.sin(Psi[sl])[:, None]
+        ry, rx = (ca * cy - sa * cx).astype(np.float32), (sa * cy + ca * cx).astype(np.float32)
+        s32 = s.astype(np.float32)
+        U = np.exp(-(grid[None, :, None] - ry[:, None, :]) ** 2 / (2 * s32[:, None, :] ** 2)) * amp     # (m, N, blobs)
+        V = np.exp(-(grid[None, :, None] - rx[:, None, :]) ** 2 / (2 * s32[:, None, :] ** 2))
+        img = np.matmul(U, V.transpose(0, 2, 1))                                                      # (m, N, N)
+        if with_ctf:
+            g = (0.5 * np.pi * _CS * 1e7 * wav ** 3 * k2[None] - np.pi * wav * df[sl, None, None]) * k2[None]
+            ctf = (np.sin(g) - _AMPC * np.cos(g)).astype(np.float32)
+        if with_ctf:
+            img = sfft.irfft2(sfft.rfft2(img, workers=-1) * ctf, s=(N, N), workers=-1).astype(np.float32)
+        sig = img.reshape(m, -1).std(axis=1)
+        img += rng.standard_normal((m, N, N), dtype=np.float32) * (sig / np.sqrt(snr)).astype(np.float32)[:, None, None]
+        img[conj[sl]] = img[conj[sl], ::-1, :]
+        stack[sl] = img.transpose(0, 2, 1).reshape(m, N * N)
+    return dict(stack=stack.reshape(-1), ind=ind, q=q, df=df, sh=(np.zeros(nS), np.zeros(nS)), nStot=nStot, tau=tau,
+                PD=PD, em=dict(nPix=N, pix_size=_PIX, Cs=_CS, EkV=_EKV, AmpContrast=_AMPC))

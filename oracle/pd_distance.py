@@ -196,13 +196,19 @@ def lowpass(imgs, G):
 # --------------------------------------------------------------------- op
 def pd_distance(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast,
                 gaussEnv=np.inf, filterPar=None, msk2=1, relion=False, sh=None,
-                avg_only=False, direct=False, rotate_impl='tile', keep=None):
+                avg_only=False, direct=False, rotate_impl='tile', keep=None, pd_override=None):
     """getDistanceCTF...py:216-420 without the file I/O: returns the dict that
     the reference pickles (same keys, shapes, dtypes), plus a few named
     intermediates under '_'-prefixed keys for per-stage parity checks.
 
     direct=True evaluates D by the definitional per-pair norm
     (conquer, :106-122) instead of the matrix identity (:391-397).
+
+    pd_override=PD (3,): use this mean projection direction instead of the mean
+    over `q` (:299-301).  D_ij depends on particles i and j and, through Psi and
+    psi_p, on PD only — so a SUBSET of a large PD evaluated with the full PD's
+    direction reproduces exactly the entries D[sub][:, sub] of the full matrix
+    (sampled-pair parity checks at BASELINE config sizes).
     """
     if filterPar is None:
         filterPar = dict(type='Butter', Qc=0.5, N=8)            # GetDistancesS2.py:83
@@ -216,6 +222,8 @@ def pd_distance(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast,
     PDs = calc_avg_pd(q)                                         # :297
     PD = np.sum(PDs, 1)
     PD = PD / np.linalg.norm(PD)                                 # :299-301
+    if pd_override is not None:
+        PD = np.asarray(pd_override, dtype=np.float64)
     psi_p = psi_ang(PD)                                          # :313
     Psi, s, c = get_psi(q, PD)                                   # :317-323
 

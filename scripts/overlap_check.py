@@ -1,6 +1,6 @@
 """Does running S PDs concurrently (S contexts = S streams, one host thread each) on ONE GPU raise the
 device-resident throughput?  The tensor-bound contraction of one PD can overlap the HBM-bound passes of another
-if the block scheduler co-schedules them.   python scripts/overlap_test.py [nS] [N] [pds]"""
+if the block scheduler co-schedules them.   python scripts/overlap_check.py [nS] [N] [pds]"""
 import ctypes as C
 import os
 import sys

@@ -1,0 +1,137 @@
+"""Parity at the sizes BASELINE.json names ("What's weak" 1-3).
+
+D_ij depends on particles i and j and, through Psi / psi_p, on the PD's mean direction only.  The oracle is therefore
+run on a SAMPLE of the particles of a full-size PD with the full PD's direction (`pd_override`) and must reproduce
+the corresponding entries of the matrix the CUDA path computed for the whole PD — through the default path
+(CTA-pair tiles, automatic split-K, paced waves for the large ones), on noisy (SNR 0.1) and low-noise (SNR 10) data.
+
+Also here: the north_star kNN gate end to end (GPU float32 D -> lists vs oracle float64 D -> lists: identical sets
+except near-ties), and a test that pins where the 1e-5 gate stops holding for near-duplicate images.
+
+Tolerances: off-diagonal D within 1e-5 relative (north_star); kNN mismatches only at ties closer than 2e-5 relative."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+D_RTOL = 1e-5
+
+
+def _oracle_sub(pd, N, sub, PD):
+    from oracle import pd_distance as opd
+    em = pd['em']
+    return opd.pd_distance(pd['ind'][sub], pd['q'][:, sub], pd['df'][sub], pd['stack'], pd['nStot'], N, em['pix_size'],
+                           em['Cs'], em['EkV'], em['AmpContrast'], rotate_impl='periodic', keep=('D',), pd_override=PD)['D']
+
+
+def _host_ram_gb():
+    try:
+        import psutil
+        return psutil.virtual_memory().available / 2 ** 30
+    except Exception:
+        return 64.0
+
+
+# (name, nS, N, snr, seed, knn_k, with_ctf) — BASELINE configs 2, 3, 4 and one PD of config 5's shape
+CASES = [('C2', 1000, 128, 0.1, 31, 0, True), ('C2-lownoise', 1000, 128, 10.0, 32, 0, True),
+         ('C4', 2000, 256, 0.1, 33, 0, True), ('C4-lownoise', 2000, 256, 10.0, 34, 0, True),
+         ('C3', 5000, 256, 0.1, 35, 100, True), ('C5-one-PD', 20000, 320, 0.1, 36, 0, False)]
+
+
+@pytest.mark.parametrize('name,nS,N,snr,seed,knn_k,with_ctf', CASES, ids=[c[0] for c in CASES])
+def test_sampled_pairs_at_config_size(name, nS, N, snr, seed, knn_k, with_ctf):
+    from manifoldem_python_b200 import pd_stage, synthetic
+    need_gb = 3 * nS * N * N * 4 / 2 ** 30 + 2 * nS * nS * 4 / 2 ** 30 + 2
+    if _host_ram_gb() < need_gb:
+        pytest.skip('host RAM: need %.0f GB' % need_gb)
+    pd = synthetic.make_pd_fast(nS, N, seed=seed, snr=snr, with_ctf=with_ctf)
+    em = pd['em']
+    res = pd_stage.run_pd(pd['ind'], pd['q'], pd['df'], pd['stack'], pd['nStot'], N, em['pix_size'], em['Cs'], em['EkV'],
+                          em['AmpContrast'], fields=('D',), float64=False, knn_k=knn_k)
+    D = res['D']
+    assert D.shape == (nS, nS) and np.array_equal(D, D.T)
+    assert np.abs(np.diag(D)).max() <= 1e-5 * D.max()
+    rng = np.random.default_rng(seed)
+    # the sample: random particles from every tile row of the contraction + the nearest neighbours of one of them
+    # (small distances are where cancellation bites)
+    sub = rng.choice(nS, 40, replace=False)
+    row = D[sub[0]].copy()
+    row[sub[0]] = np.inf
+    sub = np.unique(np.concatenate([sub, np.argsort(row)[:8], [0, nS - 1]]))
+    Dr = _oracle_sub(pd, N, sub, res['PD'])
+    Dg = D[np.ix_(sub, sub)].astype(np.float64)
+    off = ~np.eye(len(sub), dtype=bool)
+    rel = np.abs(Dg - Dr)[off] / Dr[off]
+    print('%s: %d x %d^2, %d sampled pairs, max rel err %.2e, median %.2e' % (name, nS, N, off.sum(), rel.max(), np.median(rel)))
+    assert rel.max() <= D_RTOL, rel.max()
+    if knn_k:
+        # the lists the same call selected (config 3 asks for them instead of D) against the rows of that D
+        for i in sub[:12]:
+            r = D[i].copy()
+            r[i] = -np.inf
+            assert np.array_equal(res['knn_idx'][i], np.lexsort((np.arange(nS), r))[:knn_k]), i
+
+
+@pytest.mark.parametrize('snr,seed', [(0.1, 41), (10.0, 42)])
+def test_knn_gate_end_to_end_config2(snr, seed):
+    """north_star: 'identical kNN index sets except at exact ties'.  GPU run_pd(knn_k=100) on a config-2-sized PD
+    (float32 D never leaves the device) against oracle.knn_lists on the oracle's float64 D of the same PD.  Float32
+    round-off (<= 1e-5 relative) can swap neighbours that are tied to within that error; every set difference must be
+    such a near-tie (2e-5 relative at the list boundary), and the mismatch rate is reported."""
+    from manifoldem_python_b200 import pd_stage, synthetic
+    from oracle import pd_distance as opd, dm_embedding as odm
+    nS, N, k = 1000, 128, 100
+    pd = synthetic.make_pd_fast(nS, N, seed=seed, snr=snr)
+    em = pd['em']
+    args = (pd['ind'], pd['q'], pd['df'], pd['stack'], pd['nStot'], N, em['pix_size'], em['Cs'], em['EkV'], em['AmpContrast'])
+    res = pd_stage.run_pd(*args, fields=(), knn_k=k)
+    Dr = opd.pd_distance(*args, rotate_impl='periodic', keep=('D',))['D']
+    Dsym = Dr.copy()
+    idx_o, val_o = odm.knn_lists(Dr, k)                      # (k, nS), mutates Dr
+    idx_o = idx_o.T
+    mism = 0
+    worst = 0.0
+    for i in range(nS):
+        a, b = set(res['knn_idx'][i].tolist()), set(idx_o[i].tolist())
+        assert res['knn_idx'][i][0] == i and idx_o[i][0] == i
+        if a == b:
+            continue
+        mism += len(a - b)
+        dk = val_o[k - 1, i]                                   # oracle's k-th distance = the list boundary
+        for j in (a - b) | (b - a):
+            gap = abs(Dsym[j, i] - dk) / dk
+            worst = max(worst, gap)
+            assert gap <= 2e-5, (i, j, gap)
+    print('kNN gate snr=%g: %d of %d list entries differ (%.4f %%), widest tie %.2e relative'
+          % (snr, mism, nS * k, 100.0 * mism / (nS * k), worst))
+    assert mism <= 0.001 * nS * k
+    # values of the common entries: float32 D within 1e-5 of the oracle's
+    common = res['knn_idx'][:, 1:] == idx_o[:, 1:]
+    v_g, v_o = res['knn_val'][:, 1:], val_o.T[:, 1:]
+    assert (np.abs(v_g - v_o)[common] / v_o[common]).max() <= D_RTOL
+
+
+def test_near_duplicate_floor():
+    """Where the 1e-5 gate ends: D is computed in float32 from operands whose common component has been
+    removed; for near-duplicate images (SNR 100: min D / max D ~ 2e-3) the smallest distances carry the round-off of
+    the largest.  Pinned here: pairs with D_ij >= 0.01 max D meet 1e-5; every pair meets 1e-5 * max D / D_ij-scaled
+    absolute error, i.e. |err| <= 2e-7 * max D."""
+    from manifoldem_python_b200 import pd_stage, synthetic
+    from oracle import pd_distance as opd
+    nS, N = 256, 64
+    pd = synthetic.make_pd(nS, N, seed=77, snr=100.0)
+    em = pd['em']
+    args = (pd['ind'], pd['q'], pd['df'], pd['stack'], pd['nStot'], N, em['pix_size'], em['Cs'], em['EkV'], em['AmpContrast'])
+    D = pd_stage.run_pd(*args, fields=('D',))['D']
+    Dr = opd.pd_distance(*args, rotate_impl='periodic', keep=('D',))['D']
+    off = ~np.eye(nS, dtype=bool)
+    ratio = Dr[off].min() / Dr[off].max()
+    err = np.abs(D - Dr)[off]
+    rel = err / Dr[off]
+    big = Dr[off] >= 0.01 * Dr[off].max()
+    print('near-duplicate PD: min D / max D = %.2e, max rel err %.2e (all pairs), %.2e (D >= 0.01 max), p99 %.2e, '
+          'max abs err / max D %.2e' % (ratio, rel.max(), rel[big].max(), np.percentile(rel, 99), err.max() / Dr[off].max()))
+    assert ratio < 0.02                       # the data really is in the near-duplicate regime
+    assert rel[big].max() <= D_RTOL
+    assert err.max() <= 2e-7 * Dr[off].max()
+    assert rel.max() <= 5e-5                  # the floor: documented, outside the north_star gate
