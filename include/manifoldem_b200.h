@@ -29,6 +29,10 @@ const char* mem_last_error(void);
 int         mem_ctx_create(int device, mem_ctx** out);
 int         mem_ctx_destroy(mem_ctx* ctx);
 int         mem_ctx_sync(mem_ctx* ctx);
+/* tuning / test switches of a context, by name; unknown names are an error.
+ *   "legacy_rotate"  1 = the generic rotation kernel for every box size (default 0: boxes that are a multiple of 32
+ *                    take the float4-staged / four-images-per-tap kernels of rotate.cu; results are bit-identical) */
+int         mem_ctx_set_option(mem_ctx* ctx, const char* name, int32_t value);
 /* kernels launched by this library on ctx since the last reset (bench.py gpu_launches) */
 int64_t     mem_ctx_launch_count(mem_ctx* ctx, int reset);
 /* CUDA-event stopwatch on the context's stream (bench.py times its steps on the launching stream) */

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libmanifoldem_b200.so')
 
 SYMBOLS = [
-    'mem_version', 'mem_last_error', 'mem_ctx_create', 'mem_ctx_destroy', 'mem_ctx_sync', 'mem_ctx_launch_count',
+    'mem_version', 'mem_last_error', 'mem_ctx_create', 'mem_ctx_destroy', 'mem_ctx_sync', 'mem_ctx_set_option', 'mem_ctx_launch_count',
     'mem_ctx_timer_start', 'mem_ctx_timer_stop', 'mem_ctx_kernel_time', 'mem_host_alloc', 'mem_host_free', 'mem_dev_alloc', 'mem_dev_free', 'mem_copy_h2d', 'mem_copy_d2h',
     'mem_pd_distance_device', 'mem_pd_distance_host', 'mem_pd_last_timings', 'mem_contract_device',
     'mem_contract_knn_device', 'mem_knn_mode',
@@ -65,6 +65,7 @@ def load():
         lib.mem_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         lib.mem_ctx_destroy.argtypes = [C.c_void_p]
         lib.mem_ctx_sync.argtypes = [C.c_void_p]
+        lib.mem_ctx_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int32]
         lib.mem_ctx_timer_start.argtypes = [C.c_void_p]
         lib.mem_ctx_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         lib.mem_ctx_kernel_time.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64),
@@ -183,6 +184,9 @@ class Context:
 
     def sync(self):
         check(self.lib.mem_ctx_sync(self.handle))
+
+    def set_option(self, name, value):
+        check(self.lib.mem_ctx_set_option(self.handle, name.encode(), int(value)))
 
     def launches(self, reset=False):
         return int(self.lib.mem_ctx_launch_count(self.handle, 1 if reset else 0))

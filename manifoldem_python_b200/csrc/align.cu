@@ -598,6 +598,16 @@ int shift_run(mem_ctx* ctx, const float* raw, const double* shift, float* tmp, f
 // rows_done != 0: A already holds (img * msk) after the row pass of the first prefilter.
 int align_run(mem_ctx* ctx, float* A, float* B, float* imgAll, const double* psi_deg, double psi_p_deg, double2* cs,
               const uint8_t* msk2, int nS, int N, cudaStream_t st, int rows_done) {
+  if (rotate_fast_supported(N) && !ctx->legacy_rotate) {
+    MEM_CHECK(ctx->rot_pid.ensure((size_t)nS));
+    uint8_t* pid = ctx->rot_pid.as<uint8_t>();
+    MEM_CHECK(rotate_angles_run(ctx, psi_deg, psi_p_deg, cs, pid, nS, st));
+    MEM_CHECK(prefilter_run(ctx, B, A, nS, N, 1, 0, st, rows_done));         // (img * msk) -> coefficients
+    MEM_CHECK(rotate_img_run(ctx, A, B, cs, pid, nS, N, st));
+    MEM_CHECK(prefilter_run(ctx, B, A, nS, N, 0, 0, st));
+    MEM_CHECK(rotate_common_run(ctx, A, imgAll, cs + nS, -psi_p_deg, nS, N, msk2, msk2 ? B : (float*)nullptr, st));
+    return 0;
+  }
   MEM_LAUNCH(ctx, k_angles, (nS + 1 + 127) / 128, 128, 0, st, psi_deg, psi_p_deg, cs, nS);
   const dim3 grot((N + ROT_T - 1) / ROT_T, (N + ROT_T - 1) / ROT_T, nS);
   const bool full = (N % ROT_T) == 0;

@@ -56,7 +56,7 @@ int mem_ctx_destroy(mem_ctx* ctx) {
     cufftDestroy(kv.second.r2c);
     cufftDestroy(kv.second.c2r);
   }
-  mem::DevBuf* bufs[] = {&ctx->fft_work, &ctx->raw, &ctx->flip, &ctx->shift, &ctx->psi, &ctx->df, &ctx->msk2, &ctx->rot_cs,
+  mem::DevBuf* bufs[] = {&ctx->fft_work, &ctx->raw, &ctx->flip, &ctx->shift, &ctx->psi, &ctx->df, &ctx->msk2, &ctx->rot_cs, &ctx->rot_pid, &ctx->rot_pitch_tab,
                          &ctx->imgA, &ctx->imgB, &ctx->imgAll, &ctx->imgFlip, &ctx->spec, &ctx->spec2, &ctx->cbin, &ctx->zhi,
                          &ctx->zlo, &ctx->part_cf, &ctx->part_cfw, &ctx->part_c2, &ctx->part_fl, &ctx->part_int, &ctx->avgspec, &ctx->avgimg,
                          &ctx->stats, &ctx->D, &ctx->ctf64, &ctx->small_out, &ctx->contract_ws, &ctx->contract_items, &ctx->scratch,
@@ -77,6 +77,19 @@ int mem_ctx_sync(mem_ctx* ctx) {
   MEM_CUDA(cudaSetDevice(ctx->device));
   MEM_CUDA(cudaStreamSynchronize(ctx->stream));
   MEM_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+
+int mem_ctx_set_option(mem_ctx* ctx, const char* name, int32_t value) {
+  if (!ctx || !name) {
+    set_error("mem_ctx_set_option: null argument");
+    return 1;
+  }
+  if (!strcmp(name, "legacy_rotate")) ctx->legacy_rotate = value;
+  else {
+    set_error("mem_ctx_set_option: unknown option '%s'", name);
+    return 1;
+  }
   return 0;
 }
 

@@ -97,7 +97,7 @@ struct mem_ctx {
   std::map<long long, mem::FftPlan> plans;   // key = N * 2^20 + batch
   mem::DevBuf fft_work;
   // workspace for one PD
-  mem::DevBuf raw, flip, shift, psi, df, msk2, rot_cs;
+  mem::DevBuf raw, flip, shift, psi, df, msk2, rot_cs, rot_pid, rot_pitch_tab;
   mem::DevBuf imgA, imgB, imgAll, imgFlip, spec, spec2, cbin, zhi, zlo;
   mem::DevBuf part_cf, part_cfw, part_c2, part_fl, part_int, avgspec, avgimg, stats;
   mem::DevBuf D, ctf64, small_out;
@@ -115,6 +115,7 @@ struct mem_ctx {
   int last_tc_items = 0, last_tc_nkb = 0;   // geometry of the last tcgen05 launch (executed-flop accounting)
   float timings[8] = {};
   void* tmap_encode = nullptr;   // cuTensorMapEncodeTiled entry point
+  int legacy_rotate = 0;         // tests: 1 = the generic k_rotate for every box (mem_ctx_set_option)
 };
 
 namespace mem {
@@ -140,4 +141,12 @@ int knn_device_f32(mem_ctx* ctx, const float* D, int nS, int k, int* idx, double
 int knn_from_workspace(mem_ctx* ctx, const float* ws, int ldw, int nslices, int nS, int k, int* idx, double* val,
                        cudaStream_t st);
 void knn_set_mode(int mode);
+// rotate.cu: the two rotations of a7 for boxes that are a multiple of 32 (other boxes: k_rotate in align.cu)
+bool rotate_fast_supported(int N);
+int rotate_angles_run(mem_ctx* ctx, const double* psi_deg, double psi_p_deg, double2* cs, uint8_t* pid, int nS,
+                      cudaStream_t st);
+int rotate_img_run(mem_ctx* ctx, const float* coef, float* out, const double2* cs, const uint8_t* pid, int nS, int N,
+                   cudaStream_t st);
+int rotate_common_run(mem_ctx* ctx, const float* coef, float* out, const double2* cs_common, double angle_deg, int nS,
+                      int N, const uint8_t* msk2, float* out_masked, cudaStream_t st);
 }  // namespace mem
