@@ -1,16 +1,21 @@
 #!/usr/bin/env python
 """bench.py — CTF pairwise distances/s of the per-PD distance stage on B200 (BASELINE.json metric).
 
-  python bench.py [--gpus N --steps K --warmup W]                 one process per GPU (torchrun for N>1)
+  python bench.py [--gpus N --steps K --warmup W]                    one process per GPU (torchrun for N>1)
   python bench.py --impl reference [--gpus N --steps K --warmup W]   the reference's CPU algorithm (oracle port)
 
-Workload (weak scaling): every rank processes PDS_PER_GPU synthetic projection directions of
-BASELINE config 4's shape (2,000 particles x 256^2) per step; at 8 GPUs one step is the whole
-1,000-PD S2 run.  A "pair" is one entry of the nS x nS matrix D the reference materialises.
-`value`  : whole-job G pairs/s with the raw particle stacks already resident in HBM.
-`e2e`    : the same through the host-buffer C-ABI call (pinned host stacks -> D on the host),
-           H2D and D2H inside the timed region, three PDs in flight per GPU.
-`roofline`: executed TF32 tensor flops of the tcgen05 contraction per launch / its CUDA-event time.
+Workload (weak scaling): every rank processes PDS_PER_GPU synthetic projection directions of BASELINE config 4's
+shape (2,000 particles x 256^2) per step; at 8 GPUs one step is the whole 1,000-PD S2 run.  A "pair" is one entry of
+the nS x nS matrix D the reference materialises.
+
+`value`      whole-job G pairs/s with the raw particle stacks already resident in HBM (CUDA events, max over ranks).
+`e2e`        the same through the host-buffer C-ABI call (pinned host stacks -> D on the host), H2D and D2H inside
+             the timed region, three PDs in flight per GPU; `h2d_ceiling` = the box's concurrent pinned H2D rate
+             measured by a bare copy loop on every rank at the same moment (the end-to-end roofline).
+`roofline`   dominant kernel (tcgen05 contraction): executed TF32 flops per launch / its CUDA-event time, against half
+             the measured bf16 rate of MEASURED_PEAKS.json; the SM clock inside the kernel from a clock64 probe.
+`hbm_roofline`  the HBM-bound pre-processing stages: algorithmic bytes (20 N^2 per image) / stage time.
+`details`    other BASELINE configs (1: the demo's 53 PDs, 2, 3, 5: one PD) and the record-producing variants.
 """
 import argparse
 import ctypes as C
@@ -32,6 +37,8 @@ POOL = 4                          # distinct raw stacks cycled through (each 524
 EM = dict(pix_size=1.255, Cs=2.26, EkV=300.0, AmpContrast=0.1)
 METRIC = 'CTF pairwise distances/sec'
 UNIT = 'Gpairs/s'
+REF_VS_PORT = os.path.join(ROOT, 'profiles', 'r02_reference_vs_port_cpu.txt')
+CONTRACT_NCU = os.path.join(ROOT, 'profiles', 'r02_contract_tc2_ncu.json')
 
 
 def parse():
@@ -45,16 +52,38 @@ def parse():
     ap.add_argument('--N', type=int, default=NPIX)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-details', action='store_true', help='skip the other BASELINE configs / record variants')
     return ap.parse_args()
+
+
+def workload_config(nS, N, P):
+    """The `config` object — identical in the B200 arm and the reference arm."""
+    return dict(workload='BASELINE config 4 shape: PDs of %d particles x %d^2, %d PDs per GPU per step '
+                         '(1000 PDs at 8 GPUs)' % (nS, N, P), pds_per_gpu=P, nS=nS, N=N,
+                l2='inputs larger than L2: %d distinct %d MB stacks cycled' % (POOL, nS * N * N * 4 // 1000000))
 
 
 # ----------------------------------------------------------------------------------------- helpers
 def load_peaks():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
-            return json.load(f), 'measured'
+            return json.load(f), 'MEASURED_PEAKS.json'
     except Exception:
-        return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0), 'fallback'
+        return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0), 'fallback of B200_PROFILING.md'
+
+
+def reference_vs_port():
+    """Ratio (unmodified reference op() time / oracle port time) measured in the build container, where
+    /root/reference exists (scripts/ref_vs_port_cpu.py -> profiles/r02_reference_vs_port_cpu.txt)."""
+    try:
+        vals = []
+        for ln in open(REF_VS_PORT):
+            if 'reference / port =' in ln:
+                vals.append(float(ln.split('reference / port =')[1].split(';')[0]))
+        return dict(ratio_mean=float(np.mean(vals)), ratios=vals, file=os.path.relpath(REF_VS_PORT, ROOT),
+                    where='build container (the reference does not travel to the GPU box)') if vals else None
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -100,8 +129,7 @@ class ClockSampler:
 
 
 def measure_cublas_tf32(index):
-    """cuBLAS TF32 GEMM (8192^3, best of 5 after warm-up) measured in this run, next to the roofline's official
-    denominator (MEASURED_PEAKS.json has no TF32 entry): context for the reader, not the `peak` field."""
+    """cuBLAS TF32 GEMM (8192^3, best of 5 after warm-up) measured in this run: context for the reader."""
     try:
         import torch
         dev = torch.device('cuda', index)
@@ -128,8 +156,7 @@ def measure_cublas_tf32(index):
 
 
 def bind_to_gpu_numa_node(index):
-    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU, so that the pinned host
-    stacks of the e2e leg live on that socket (8 ranks otherwise share one socket's memory controllers)."""
+    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -170,7 +197,8 @@ def pd_params(_lib, nS, N, psi_p):
 
 # ----------------------------------------------------------------------------------------- reference arm
 def _ref_images_worker(args):
-    """Per-image part of the reference algorithm (ingest .. FFT) for a slice of particles."""
+    """Per-image part of the reference algorithm (ingest .. FFT) for a slice of particles; returns
+    (wall seconds, per-stage seconds)."""
     nS_s, N, seed = args
     os.environ.setdefault('OMP_NUM_THREADS', '1')
     from manifoldem_python_b200 import synthetic
@@ -180,9 +208,22 @@ def _ref_images_worker(args):
     q = synthetic.euler_to_quat(0.7 + 0.03 * rng.standard_normal(nS_s), 1.1 + 0.03 * rng.standard_normal(nS_s),
                                 rng.uniform(0, 2 * np.pi, nS_s))
     df = rng.uniform(10000.0, 30000.0, nS_s)
+    tm = {}
     t0 = time.perf_counter()
     opd.pd_distance(np.arange(nS_s), q, df, stack, 2 * nS_s, N, EM['pix_size'], EM['Cs'], EM['EkV'], EM['AmpContrast'],
-                    avg_only=True, rotate_impl='tile', keep=('imgAvg',))
+                    avg_only=True, rotate_impl='tile', keep=('imgAvg',), timings=tm)
+    return time.perf_counter() - t0, tm
+
+
+def _gemm_block(rows, N, seed):
+    rng = np.random.default_rng(seed)
+    K = N * N
+    CTF = rng.standard_normal((rows, K))
+    fy = rng.standard_normal((rows, K)) + 1j * rng.standard_normal((rows, K))
+    t0 = time.perf_counter()
+    CTFfy = CTF.conj() * fy
+    D = np.dot(np.abs(CTF) ** 2, (np.abs(fy) ** 2).T)
+    D = D + D.T - 2 * np.real(np.dot(CTFfy, CTFfy.conj().T))
     return time.perf_counter() - t0
 
 
@@ -194,66 +235,88 @@ def _ref_gemm_worker(args):
         threadpool_limits(limits=1)
     except Exception:
         pass
-    rng = np.random.default_rng(seed)
-    K = N * N
-    CTF = rng.standard_normal((rows, K))
-    fy = rng.standard_normal((rows, K)) + 1j * rng.standard_normal((rows, K))
-    t0 = time.perf_counter()
-    CTFfy = CTF.conj() * fy
-    D = np.dot(np.abs(CTF) ** 2, (np.abs(fy) ** 2).T)
-    D = D + D.T - 2 * np.real(np.dot(CTFfy, CTFfy.conj().T))
-    return time.perf_counter() - t0
+    return _gemm_block(rows, N, seed)
+
+
+def _pickle_seconds(nS_s, N):
+    """myio.fout1 (:409-412) of the per-image float64 record arrays of nS_s particles (3 x nS_s x N^2 x 8 bytes)."""
+    import pickle
+    import tempfile
+    a = np.zeros((3, nS_s, N * N))
+    with tempfile.NamedTemporaryFile(dir='/dev/shm' if os.path.isdir('/dev/shm') else None) as f:
+        t0 = time.perf_counter()
+        pickle.dump(dict(a=a), f, protocol=pickle.HIGHEST_PROTOCOL)
+        f.flush()
+        return time.perf_counter() - t0
 
 
 def cpu_reference_sample(nS, N, n_img, cores, contraction_rows):
     """Bounded sample of the reference's CPU algorithm on one PD of shape (nS, N):
     (1) the per-image stages (ingest, low-pass, 2x rotatefill on the 3x3 tile, CTF, 3 FFTs) on n_img particles,
         spread over `cores` worker processes — these stages are linear in nS;
-    (2) the two GEMMs of :391-397 (float64 / complex128, all BLAS threads) on `contraction_rows` x nS pairs.
-    Per-PD time = nS/n_img * t_images + nS/contraction_rows * t_gemm: the reference's serial mode (p.ncpu = 1) with
-    the per-image loop ideally parallel.  Also timed: the Pool mode (GetDistancesS2.py:110-113) and its MPI twin's
-    static round-robin (GetDistancesS2_mpi.py:14-15) — one whole PD per worker process, one BLAS thread each, `cores`
-    PDs at once; for equal PDs the two schedules coincide.  Returns (pairs/s of the faster mode, detail dict)."""
+    (2) the two GEMMs of :391-397 (float64 / complex128, all BLAS threads) on `contraction_rows`^2 pairs;
+    (3) the pickle dump of the per-image record arrays of n_img particles (linear in nS).
+    Per-PD time = nS/n_img * t_images + (nS/contraction_rows)^2 * t_gemm + nS/n_img * t_pickle: the reference's
+    serial mode (p.ncpu = 1) with the per-image loop ideally parallel.  Also timed: the Pool mode
+    (GetDistancesS2.py:110-113) and its MPI twin's static round-robin (GetDistancesS2_mpi.py:14-15) — one whole PD per
+    worker process, one BLAS thread each, `cores` PDs at once; for equal PDs the two schedules coincide.
+    Returns (pairs/s of the faster mode, detail dict with the per-stage split)."""
     import multiprocessing as mp
     per = max(1, n_img // cores)
     jobs = [(per, N, 100 + i) for i in range(max(1, n_img // per))]
     rows1 = min(contraction_rows, 200)
     with mp.get_context('spawn').Pool(min(cores, len(jobs))) as pool:
-        t_img = max(pool.map(_ref_images_worker, jobs))     # slowest worker's compute time (spawn/import excluded)
+        res = pool.map(_ref_images_worker, jobs)
+        t_img = max(r[0] for r in res)                      # slowest worker's compute time (spawn/import excluded)
         t_gemm1 = max(pool.map(_ref_gemm_worker, [(rows1, N, 7 + i) for i in range(min(cores, len(jobs)))]))
+    stages = {}
+    for _, tm in res:
+        for k, v in tm.items():
+            stages[k] = max(stages.get(k, 0.0), v)
     n_done = per * len(jobs)
-    rng = np.random.default_rng(0)
     rows = contraction_rows
-    K = N * N
-    CTF = rng.standard_normal((rows, K))
-    fy = rng.standard_normal((rows, K)) + 1j * rng.standard_normal((rows, K))
     try:                                  # torchrun exports OMP_NUM_THREADS=1: give the GEMMs every core back
         from threadpoolctl import threadpool_limits
         limiter = threadpool_limits(limits=cores)
     except Exception:
         limiter = None
-    t0 = time.perf_counter()
-    CTFfy = CTF.conj() * fy
-    D = np.dot(np.abs(CTF) ** 2, (np.abs(fy) ** 2).T)
-    D = D + D.T - 2 * np.real(np.dot(CTFfy, CTFfy.conj().T))
-    t_gemm = time.perf_counter() - t0
+    t_gemm = _gemm_block(rows, N, 0)
     if limiter is not None:
         limiter.restore_original_limits()
+    t_pick = _pickle_seconds(min(per, 32), N) * per / min(per, 32)
     # rows x rows block measured; the full matrix has (nS/rows)^2 such blocks
-    t_pd = (nS / n_done) * t_img + (nS / rows) ** 2 * t_gemm
+    s_img, s_gemm, s_pick = (nS / n_done) * t_img, (nS / rows) ** 2 * t_gemm, (nS / per) * t_pick
+    t_pd = s_img + s_gemm + s_pick
     # Pool / MPI-schedule emulation: a worker runs its PD alone (per images in t_img, one BLAS thread), `workers` at once
     workers = min(cores, len(jobs))
-    t_pd_worker = (nS / per) * t_img + (nS / rows1) ** 2 * t_gemm1
+    t_pd_worker = (nS / per) * t_img + (nS / rows1) ** 2 * t_gemm1 + (nS / per) * t_pick
     v_serial, v_pool = nS * nS / t_pd / 1e9, workers * nS * nS / t_pd_worker / 1e9
+    scale = (nS / per)
     detail = dict(images=n_done, t_images_s=round(t_img, 3), gemm_rows=rows, t_gemm_s=round(t_gemm, 3),
                   per_pd_s=round(t_pd, 2),
-                  stage_split_per_pd_s=dict(per_image_stages=round((nS / n_done) * t_img, 2),
-                                            gemm=round((nS / rows) ** 2 * t_gemm, 2)),
+                  stage_split_per_pd_s=dict(per_image_stages=round(s_img, 2), gemm=round(s_gemm, 2), pickle=round(s_pick, 2)),
+                  per_image_stage_split_one_worker_per_pd_s={k: round(v * scale, 2) for k, v in stages.items()},
                   serial_mode_gpairs_s=v_serial,
                   pool_and_mpi_schedule_emulation=dict(gpairs_s=v_pool, workers=workers, blas_threads_per_worker=1,
                                                        per_pd_per_worker_s=round(t_pd_worker, 1), gemm_rows=rows1,
                                                        t_gemm_s=round(t_gemm1, 3)))
-    return max(v_serial, v_pool), detail
+    return max(v_serial, v_pool), detail, t_pd
+
+
+def cpu_split_other_configs(cores):
+    """serial / Pool(MPI-schedule) split of the reference algorithm for config 2 (1,000 x 128^2) and for a
+    median demo PD of config 1 (206 x 256^2), on bounded samples (2 images per core)."""
+    out = {}
+    for name, nS, N in (('config_2', 1000, 128), ('config_1_median_pd', 206, 256)):
+        try:
+            v, d, _ = cpu_reference_sample(nS, N, 2 * cores, cores, contraction_rows=min(nS, 400))
+            out[name] = dict(nS=nS, N=N, gpairs_s=v, per_pd_s=d['per_pd_s'], stage_split_per_pd_s=d['stage_split_per_pd_s'],
+                             per_image_stage_split_one_worker_per_pd_s=d['per_image_stage_split_one_worker_per_pd_s'],
+                             serial_mode_gpairs_s=d['serial_mode_gpairs_s'],
+                             pool_and_mpi_schedule_gpairs_s=d['pool_and_mpi_schedule_emulation']['gpairs_s'])
+        except Exception as e:
+            out[name] = dict(error=repr(e))
+    return out
 
 
 def run_reference(args):
@@ -262,26 +325,148 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     nS, N = args.nS, args.N
-    vals = []
+    vals, walls = [], []
     detail = None
     n_img = 4 * cores
     for i in range(args.warmup + args.steps):
-        v, detail = cpu_reference_sample(nS, N, n_img, cores, contraction_rows=min(nS, 500))
+        t0 = time.perf_counter()
+        v, detail, t_pd = cpu_reference_sample(nS, N, n_img, cores, contraction_rows=min(nS, 500))
         if i >= args.warmup:
             vals.append((v, nS * nS / (v * 1e9)))     # seconds per PD at the reported rate
+            walls.append(time.perf_counter() - t0)
     v = float(np.mean([a for a, _ in vals]))
     sample = ('%d of %d particles through the per-image stages on %d processes + a %dx%d block of the fp64 '
-              'dgemm/zgemm; per-PD time extrapolated linearly in images and quadratically in the block; value = the '
-              'faster of the serial mode (all BLAS threads) and the Pool / MPI-schedule emulation (one PD per worker)'
+              'dgemm/zgemm + the pickle of those particles; per-PD time extrapolated linearly in images and quadratically '
+              'in the block; value = the faster of the serial mode (all BLAS threads) and the Pool / MPI-schedule emulation '
+              '(one PD per worker); ms_per_step = wall time of one such sample'
               % (detail['images'], nS, cores, detail['gemm_rows'], detail['gemm_rows']))
     line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=float(np.mean([b for _, b in vals])) * 1e3 * args.pds * max(1, args.gpus), higher_is_better=True,
+                ms_per_step=float(np.mean(walls)) * 1e3, higher_is_better=True,
                 scaling='weak', vs_baseline=None, dtype='f64', data='synthetic', impl='reference',
-                config=dict(workload='BASELINE config 4 shape: PDs of %d particles x %d^2, %d PDs per GPU per step '
-                                     '(1000 PDs at 8 GPUs)' % (nS, N, args.pds), pds_per_gpu=args.pds, nS=nS, N=N),
-                cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind='port', sample=sample, detail=detail),
+                config=workload_config(nS, N, args.pds),
+                cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind='port', sample=sample, detail=detail,
+                                  extrapolated_step_ms=float(np.mean([b for _, b in vals])) * 1e3 * args.pds * max(1, args.gpus),
+                                  unmodified_reference_vs_port=reference_vs_port()),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------- B200 arm: side workloads
+def _timed_pds(ctx, lib, _lib, prms, ios, warm, reps):
+    for k in range(warm + reps):
+        if k == warm:
+            ctx.sync()
+            ctx.timer_start()
+        _lib.check(lib.mem_pd_distance_device(ctx.handle, C.byref(prms[k % len(prms)]), C.byref(ios[k % len(ios)]), None))
+    return ctx.timer_stop() / reps
+
+
+def config1_block(ctx, lib, _lib, local, N):
+    """BASELINE config 1: the demo's 53 projection directions (117..450 particles; bookkeeping from the star through the
+    reference's reader and tessellation, tests/golden/demo_config1.npz) with synthetic images at box N, inputs
+    resident; one stream, and 2 PDs in flight on 2 streams."""
+    from manifoldem_python_b200 import workloads
+    pds, em = workloads.demo_config1()
+    rng = np.random.default_rng(3)
+    dev = []
+    for pd in pds:
+        n = len(pd['ind'])
+        prm = pd_params(_lib, n, N, pd['psi_p'])
+        prm.pix_size, prm.Cs, prm.EkV, prm.AmpContrast = em['pix_size'], em['Cs'], em['EkV'], em['AmpContrast']
+        d = dict(raw=_lib.DeviceArray(ctx, (n, N * N), np.float32, rng.standard_normal((n, N * N), dtype=np.float32)),
+                 flip=_lib.DeviceArray(ctx, (n,), np.uint8, pd['flip']), psi=_lib.DeviceArray(ctx, (n,), np.float64, pd['psi_deg']),
+                 df=_lib.DeviceArray(ctx, (n,), np.float64, pd['df']), D=_lib.DeviceArray(ctx, (n, n), np.float32), prm=prm)
+        io = _lib.PdIO()
+        io.raw, io.flip, io.psi_deg, io.df, io.D = d['raw'].ptr, d['flip'].ptr, d['psi'].ptr, d['df'].ptr, d['D'].ptr
+        d['io'] = io
+        dev.append(d)
+    pairs = float(sum(len(pd['ind']) ** 2 for pd in pds))
+    images = sum(len(pd['ind']) for pd in pds)
+    order = sorted(range(len(pds)), key=lambda i: -len(pds[i]['ind']))
+    out = dict(workload='BASELINE config 1: the demo star\'s 53 PDs (117..450 particles, %d in all, %d pairs), synthetic '
+                        'images at %d^2, inputs resident' % (images, int(pairs), N), N=N, pds=len(pds))
+    for S in (1, 2):
+        ctxs = [ctx] + [_lib.Context(local) for _ in range(S - 1)]
+        best = 1e9
+        for rep in range(4):
+            for c in ctxs:
+                c.sync()
+            t0 = time.perf_counter()
+            for k, i in enumerate(order):
+                _lib.check(lib.mem_pd_distance_device(ctxs[k % S].handle, C.byref(dev[i]['prm']), C.byref(dev[i]['io']), None))
+            for c in ctxs:
+                c.sync()
+            if rep:
+                best = min(best, time.perf_counter() - t0)
+        out['streams_%d' % S] = dict(ms=best * 1e3, gpairs_s=pairs / best / 1e9, images_per_s=images / best)
+        for c in ctxs[1:]:
+            c.close()
+    # what bounds it: the per-image pre-processing (20 N^2 algorithmic bytes per image), not the pairs
+    best = min(out['streams_1']['ms'], out['streams_2']['ms']) * 1e-3
+    out['gpairs_s'] = pairs / best / 1e9
+    out['hbm_alg_gbs'] = 20.0 * N * N * images / best / 1e9
+    for d in dev:
+        for k in ('raw', 'flip', 'psi', 'df', 'D'):
+            d[k].free()
+    return out
+
+
+def config5_block(ctx, lib, _lib, local):
+    """BASELINE config 5, one PD: 20,000 particles at 320^2 (73 GB of workspace on one B200), D requested."""
+    import torch
+    n5, N5 = 20000, 320
+    free_b, _tot = torch.cuda.mem_get_info(local)
+    if free_b < 110e9:
+        return dict(skipped='needs ~85 GB of free HBM, %.0f GB free' % (free_b / 1e9))
+    raw = torch.randn(n5, N5 * N5, device='cuda:%d' % local, dtype=torch.float32)
+    pds5, _ = make_inputs(n5, N5, 1, seed=79)
+    aux = [_lib.DeviceArray(ctx, (n5,), np.uint8, pds5[0]['flip']), _lib.DeviceArray(ctx, (n5,), np.float64, pds5[0]['psi_deg']),
+           _lib.DeviceArray(ctx, (n5,), np.float64, pds5[0]['df'])]
+    D5 = _lib.DeviceArray(ctx, (n5, n5), np.float32)
+    prm = pd_params(_lib, n5, N5, pds5[0]['psi_p'])
+    io = _lib.PdIO()
+    io.raw, io.flip, io.psi_deg, io.df, io.D = raw.data_ptr(), aux[0].ptr, aux[1].ptr, aux[2].ptr, D5.ptr
+    torch.cuda.synchronize()
+    ms = _timed_pds(ctx, lib, _lib, [prm], [io], 1, 2)
+    st = ctx.timings()
+    out = dict(workload='BASELINE config 5, one PD: 20,000 particles x 320^2, full D', per_pd_ms=ms,
+               gpairs_s=n5 * n5 / (ms * 1e-3) / 1e9, stage_ms=st, pds_in_config=200,
+               whole_config_estimate_s=200 * ms * 1e-3)
+    for a in aux + [D5]:
+        a.free()
+    del raw
+    torch.cuda.empty_cache()
+    return out
+
+
+def h2d_ceiling(ctx, _lib, lib, local, barrier):
+    """Concurrent pinned-host -> device copy rate of this rank while every other rank does the same (the roofline of the
+    e2e leg: 524 MB of raw particles per PD).  8 copies of 512 MB from one pinned buffer."""
+    n = 512 << 20
+    h = _lib.PinnedArray((n,), np.uint8)
+    h.array[::4096] = 1
+    d = _lib.DeviceArray(ctx, (n,), np.uint8)
+    _lib.check(lib.mem_copy_h2d(ctx.handle, d.ptr, h.ptr, n))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(8):
+        _lib.check(lib.mem_copy_h2d(ctx.handle, d.ptr, h.ptr, n))
+    dt = time.perf_counter() - t0
+    barrier()
+    d.free()
+    h.free()
+    return 8 * n / dt / 1e9
+
+
+def contraction_ncu():
+    """dram bytes / tensor-pipe figures of the contraction from the committed ncu capture of this round."""
+    try:
+        with open(CONTRACT_NCU) as f:
+            d = json.load(f)
+        d['file'] = os.path.relpath(CONTRACT_NCU, ROOT)
+        return d
+    except Exception:
+        return None
 
 
 # ----------------------------------------------------------------------------------------- B200 arm
@@ -358,6 +543,7 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launches(reset=True)
     k_ms, k_n, k_items, k_kb = ctx.kernel_time(reset=True)
+    k_mhz, k_probe_ms = ctx.kernel_clock()
     stage = ctx.timings()
     t = torch.tensor([ms, float(launches)], dtype=torch.float64, device='cuda:%d' % local)
     if world > 1:
@@ -369,10 +555,11 @@ def run_b200(args):
     pairs_step = float(nS) * nS * P * world
     value = pairs_step * args.steps / (ms * 1e-3) / 1e9
 
+    details = {}
+    side = rank == 0 and not args.no_e2e and not args.no_details
     # ---- the same PDs with every array of the reference's per-PD record produced on the device as well (imgAll,
     # imgAllFlip, float64 CTF, Wiener / flip averages, intensity): reported beside the headline, which asks for D only
-    full_ms = None
-    if rank == 0 and not args.no_e2e:
+    if side:
         outs = [_lib.DeviceArray(ctx, (nS, NN), np.float32), _lib.DeviceArray(ctx, (nS, NN), np.float32),
                 _lib.DeviceArray(ctx, (nS, NN), np.float64), _lib.DeviceArray(ctx, (NN,), np.float32),
                 _lib.DeviceArray(ctx, (NN,), np.float32), _lib.DeviceArray(ctx, (NN,), np.float32)]
@@ -382,18 +569,11 @@ def run_b200(args):
             io.raw, io.flip, io.psi_deg, io.df, io.D = d_raw[j].ptr, d_flip[j].ptr, d_psi[j].ptr, d_df[j].ptr, d_D.ptr
             (io.imgAll, io.imgAllFlip, io.CTF, io.imgAvg, io.imgAvgFlip, io.imgAllIntensity) = [o.ptr for o in outs]
             fio.append(io)
-        n_full = 8
-        for k in range(2 + n_full):
-            if k == 2:
-                ctx.sync()
-                ctx.timer_start()
-            _lib.check(lib.mem_pd_distance_device(ctx.handle, C.byref(prms[k % POOL]), C.byref(fio[k % POOL]), None))
-        full_ms = ctx.timer_stop() / n_full
+        details['all_record_fields_per_pd_ms'] = _timed_pds(ctx, lib, _lib, prms, fio, 2, 8)
         for o in outs:
             o.free()
-    # ---- BASELINE config 2 (one synthetic PD of 1,000 particles at 128^2, full D), device-resident, for reference
-    c2 = None
-    if rank == 0 and not args.no_e2e and (nS, N) == (NS, NPIX):
+    # ---- BASELINE config 2 (one synthetic PD of 1,000 particles at 128^2, full D), device-resident
+    if side and (nS, N) == (NS, NPIX):
         n2, N2 = 1000, 128
         pds2, rng2 = make_inputs(n2, N2, 2, seed=77)
         raws2 = [_lib.DeviceArray(ctx, (n2, N2 * N2), np.float32, rng2.standard_normal((n2, N2 * N2), dtype=np.float32))
@@ -407,21 +587,14 @@ def run_b200(args):
             io.raw, io.flip, io.psi_deg, io.df, io.D = raws2[j].ptr, aux2[j][0].ptr, aux2[j][1].ptr, aux2[j][2].ptr, D2.ptr
             io2.append(io)
             prm2.append(pd_params(_lib, n2, N2, pd['psi_p']))
-        reps2 = 40
-        for k in range(4 + reps2):
-            if k == 4:
-                ctx.sync()
-                ctx.timer_start()
-            _lib.check(lib.mem_pd_distance_device(ctx.handle, C.byref(prm2[k % 2]), C.byref(io2[k % 2]), None))
-        ms2 = ctx.timer_stop() / reps2
-        c2 = dict(workload='BASELINE config 2: one PD of 1,000 particles x 128^2, full D', per_pd_ms=ms2,
-                  gpairs_s=n2 * n2 / (ms2 * 1e-3) / 1e9)
+        ms2 = _timed_pds(ctx, lib, _lib, prm2, io2, 4, 40)
+        details['config_2'] = dict(workload='BASELINE config 2: one PD of 1,000 particles x 128^2, full D', per_pd_ms=ms2,
+                                   gpairs_s=n2 * n2 / (ms2 * 1e-3) / 1e9, stage_ms=ctx.timings())
         for a in raws2 + [x for t3 in aux2 for x in t3] + [D2]:
             a.free()
     # ---- BASELINE config 3 (one PD of 5,000 particles at 256^2, k = 100 neighbour lists only): the lists are selected
     # from the contraction's partial tiles, D is never assembled.  Particles: rows of three of the pool stacks.
-    c3 = None
-    if rank == 0 and not args.no_e2e and (nS, N) == (NS, NPIX) and POOL * nS >= 5000:
+    if side and (nS, N) == (NS, NPIX) and POOL * nS >= 5000:
         n3, k3 = 5000, 100
         pds3, _ = make_inputs(n3, N, 1, seed=78)
         raw3 = _lib.DeviceArray(ctx, (n3, NN), np.float32, np.concatenate([h.array for h in h_raw])[:n3])
@@ -433,26 +606,25 @@ def run_b200(args):
         io3 = _lib.PdIO()
         io3.raw, io3.flip, io3.psi_deg, io3.df = raw3.ptr, aux3[0].ptr, aux3[1].ptr, aux3[2].ptr
         io3.knn_idx, io3.knn_val = idx3.ptr, val3.ptr
-        reps3 = 5
-        for k in range(2 + reps3):
-            if k == 2:
-                ctx.sync()
-                ctx.timer_start()
-            _lib.check(lib.mem_pd_distance_device(ctx.handle, C.byref(prm3), C.byref(io3), None))
-        ms3 = ctx.timer_stop() / reps3
+        ms3 = _timed_pds(ctx, lib, _lib, [prm3], [io3], 2, 5)
         nb = idx3.download()
         assert np.array_equal(nb[:, 0], np.arange(n3)) and nb.min() >= 0 and nb.max() < n3
-        c3 = dict(workload='BASELINE config 3: one PD of 5,000 particles x 256^2, k = 100 neighbour lists only (no D)',
-                  per_pd_ms=ms3, gpairs_s=n3 * n3 / (ms3 * 1e-3) / 1e9, knn_k=k3, stage_ms=ctx.timings())
+        details['config_3'] = dict(workload='BASELINE config 3: one PD of 5,000 particles x 256^2, k = 100 neighbour lists only (no D)',
+                                   per_pd_ms=ms3, gpairs_s=n3 * n3 / (ms3 * 1e-3) / 1e9, knn_k=k3, stage_ms=ctx.timings())
         for a in [raw3, idx3, val3] + aux3:
             a.free()
-        ctx.kernel_time(reset=True)
+    # ---- BASELINE config 1 (the demo's 53 PDs) at 256^2 and 128^2
+    if side and (nS, N) == (NS, NPIX):
+        try:
+            details['config_1'] = dict(N256=config1_block(ctx, lib, _lib, local, 256), N128=config1_block(ctx, lib, _lib, local, 128))
+        except Exception as e:
+            details['config_1'] = dict(error=repr(e))
     # ---- rows a15-a18 on the D the last PD left on the device (k = nS, the way manifoldTrimmingAuto calls
     # DMembeddingII.op): kNN, graph, Ferguson sweep, Gaussian-kernel Laplacian; wall clock around the device chain
-    dm = None
-    if rank == 0 and not args.no_e2e:
+    if side:
         try:
             from manifoldem_python_b200 import DMembeddingII
+            _lib.check(lib.mem_pd_distance_device(ctx.handle, C.byref(prms[0]), C.byref(ios[0]), None))
             ctx.sync()
             sig = 3.0 * float(np.sqrt(np.median(d_D.download()[0, 1:])))
             for rep in range(2):                     # second pass = warm workspaces
@@ -464,18 +636,21 @@ def run_b200(args):
                 t2 = time.perf_counter()
                 M_dev.free()
                 L_dev.free()
-            dm = dict(workload='kNN (k = nS) + graph + Ferguson sweep on the resident D of one PD, then the Laplacian '
-                               '(host wall clock around the device chain, allocations included)',
-                      nS=nS, k=nS, knn_graph_sweep_ms=(t1 - t0) * 1e3, laplacian_ms=(t2 - t1) * 1e3,
-                      logSumWij_finite=bool(np.isfinite(_ls).all()))
+            details['embedding_front_end'] = dict(
+                workload='kNN (k = nS) + graph + Ferguson sweep on the resident D of one PD, then the Laplacian '
+                         '(host wall clock around the device chain, allocations included)',
+                nS=nS, k=nS, knn_graph_sweep_ms=(t1 - t0) * 1e3, laplacian_ms=(t2 - t1) * 1e3,
+                logSumWij_finite=bool(np.isfinite(_ls).all()))
         except Exception as e:                       # the embedding front end is reported beside the headline, never instead of it
-            dm = dict(error=repr(e))
+            details['embedding_front_end'] = dict(error=repr(e))
+    ctx.kernel_time(reset=True)
     if world > 1:
         dist.barrier()
 
-    # ---- e2e: host buffers through mem_pd_distance_host, 3 PDs in flight
+    # ---- e2e: host buffers through mem_pd_distance_host, 3 PDs in flight; and the bare concurrent H2D ceiling
     e2e = None
     if not args.no_e2e:
+        ceil_gbs = h2d_ceiling(ctx, _lib, lib, local, barrier)
         nthreads = 3
         ctxs = [ctx] + [_lib.Context(local) for _ in range(nthreads - 1)]
         h_D = [_lib.PinnedArray((nS, nS), np.float32) for _ in range(nthreads)]
@@ -502,71 +677,162 @@ def run_b200(args):
         for cx in ctxs:
             cx.sync()
         dt = time.perf_counter() - t0
-        te = torch.tensor([dt], dtype=torch.float64, device='cuda:%d' % local)
+        te = torch.tensor([dt, -ceil_gbs], dtype=torch.float64, device='cuda:%d' % local)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        dt = float(te[0])
-        e2e = dict(value=float(nS) * nS * P_e * world * e_steps / dt / 1e9, unit=UNIT,
-                   h2d_bytes_per_step=int(P_e * (nS * NN * 4 + nS * 17)), d2h_bytes_per_step=int(P_e * nS * nS * 4),
+        dt, ceil_min = float(te[0]), -float(te[1])
+        h2d_b, d2h_b = int(P_e * (nS * NN * 4 + nS * 17)), int(P_e * nS * nS * 4)
+        e2e_val = float(nS) * nS * P_e * world * e_steps / dt / 1e9
+        per_gpu_h2d = h2d_b * e_steps / dt / 1e9
+        e2e = dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=h2d_b, d2h_bytes_per_step=d2h_b,
                    pds_per_step=P_e, steps=e_steps, in_flight=nthreads,
+                   h2d_gbs_per_gpu=per_gpu_h2d,
+                   h2d_ceiling=dict(gbs_per_gpu_slowest_rank=ceil_min, gbs_this_rank=ceil_gbs, ranks_copying_at_once=world,
+                                    how='8 x 512 MB cudaMemcpyAsync from pinned memory, all ranks between the same barriers'),
+                   frac_of_h2d_ceiling=per_gpu_h2d / ceil_min if ceil_min > 0 else None,
                    note='wall clock bracketed by stream syncs + barrier; H2D of each raw stack from pinned memory and D2H of D inside')
+        for cx in ctxs[1:]:
+            cx.close()
+
+    # ---- e2e through the reference's own API: stack on disk -> GetDistancesS2.op -> per-PD records
+    dropin = None
+    if side and (nS, N) == (NS, NPIX):
+        try:
+            dropin = dropin_block(h_raw, pds, nS, N)
+        except Exception as e:
+            dropin = dict(error=repr(e))
+    c5 = None
+    if side and (nS, N) == (NS, NPIX):
+        for a in d_raw + [d_D]:
+            a.free()
+        try:
+            c5 = config5_block(ctx, lib, _lib, local)
+        except Exception as e:
+            c5 = dict(error=repr(e))
+        details['config_5_one_pd'] = c5
 
     if rank == 0:
         peaks, peak_src = load_peaks()
         tf32_cublas = measure_cublas_tf32(local)
-        # executed TF32 tensor flops of one contraction launch: items x (128x256 tile) x K x 2 x 3 passes
-        flops_launch = float(k_items) * 128 * 256 * 2 * 3 * 32.0 * k_kb      # CTAs x tile x K per CTA x 3 passes
+        # executed TF32 tensor flops of one contraction launch: CTAs x (128x256 tile) x K per CTA x 2 x 3 passes
+        flops_launch = float(k_items) * 128 * 256 * 2 * 3 * 32.0 * k_kb
         k_avg_ms = k_ms / max(1, k_n)
         achieved = flops_launch / (k_avg_ms * 1e-3) / 1e12 if k_n else None
-        # MEASURED_PEAKS.json has no TF32 entry.  Half its measured bf16 burst (cuBLAS; TF32 runs at half the bf16 rate)
-        # was the planning value, but this kernel sustains more than that, so it is not a ceiling: the denominator is
-        # the TF32 dense figure of B200_PROFILING.md's table, 1.1 PFLOP/s; the half-bf16 ratio is reported beside it.
-        half_bf16 = 0.5 * float(peaks.get('bf16_tflops', 1590.0))
-        peak = 1100.0
-        # dram__bytes_read+write of one launch from the committed ncu capture (profiles/r01_top_kernels_ncu_full.txt)
-        traffic = 1.6318e9 if (nS, N) == (2000, 256) else None
+        # MEASURED_PEAKS.json has no TF32 entry: TF32 runs at half the bf16 rate, so the denominator is half its measured
+        # bf16 burst (the kernel is timed alone per launch); half the sustained figure is reported beside it
+        peak = 0.5 * float(peaks.get('bf16_tflops', 1590.0))
+        peak_sus = 0.5 * float(peaks.get('bf16_tflops_sustained', 1400.0))
+        ncu = contraction_ncu()
         alg = 6.0 * NN * nS * nS                        # 6 N^2 fp32-equivalent flop per ordered pair
+        hw_at_clock = 148 * 2048 * 2 * k_mhz * 1e6 / 1e12 if k_mhz else None   # 148 SMs x 2048 TF32 MAC/clk x 2
+        hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+        pre_ms = stage['ingest_lowpass'] + stage['align'] + stage['fft_ctf_operands'] + stage['flip_avg']
+        ldz = 32 * (2 * 186 + 2048) if N == 256 else None
+        stage_alg = dict(ingest_lowpass=8.0 * NN * nS, align=8.0 * NN * nS,
+                         fft_ctf_operands=(4.0 * NN + (8.0 * ldz if ldz else 16.0 * NN)) * nS)
+        hbm_roof = dict(bound='hbm', peak=hbm_peak, unit='GB/s', peak_source=peak_src,
+                        whole_preprocessing=dict(algorithmic_bytes=20.0 * NN * nS, ms=pre_ms,
+                                                 achieved=20.0 * NN * nS / (pre_ms * 1e-3) / 1e9,
+                                                 frac=20.0 * NN * nS / (pre_ms * 1e-3) / 1e9 / hbm_peak),
+                        stages={k: dict(algorithmic_bytes=b, ms=stage[k], achieved=b / (stage[k] * 1e-3) / 1e9,
+                                        frac=b / (stage[k] * 1e-3) / 1e9 / hbm_peak) for k, b in stage_alg.items()},
+                        note='stage times = CUDA events of the last timed PD; algorithmic bytes: SURVEY §8d (raw fp32 in, '
+                             'four fp32 operand planes out) split per stage as read-once / write-once of each stage')
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
                     dtype='f32 (3xTF32 tensor-core products, fp32 accumulate)', data='synthetic',
-                    config=dict(workload='BASELINE config 4 shape: PDs of %d particles x %d^2, %d PDs per GPU per step '
-                                         '(1000 PDs at 8 GPUs)' % (nS, N, P), pds_per_gpu=P, nS=nS, N=N,
-                                l2='inputs larger than L2: %d distinct 524 MB stacks cycled' % POOL,
-                                per_pd_ms=ms / args.steps / P, stage_ms_last_pd=stage,
-                                all_record_fields_per_pd_ms=full_ms, single_pd_config_2=c2, single_pd_config_3=c3,
-                                embedding_front_end=dm),
+                    config=workload_config(nS, N, P),
                     clocks=clocks, gpu_launches=launches, e2e=e2e,
                     roofline=dict(bound='tensor', kernel='k_contract_tc2 (tcgen05 cta_group::2 kind::tf32, 3 passes)',
                                   achieved=achieved, peak=peak, unit='TFLOP/s', frac=(achieved / peak) if achieved else None,
-                                  traffic=traffic, avg_launch_ms=k_avg_ms, launches=k_n,
+                                  peak_source='0.5 x bf16_tflops (burst) of %s: TF32 runs at half the bf16 rate' % peak_src,
+                                  half_bf16_sustained=peak_sus, frac_vs_half_bf16_sustained=(achieved / peak_sus) if achieved else None,
+                                  nominal_tf32_dense=1100.0, frac_vs_nominal=(achieved / 1100.0) if achieved else None,
+                                  traffic=(ncu or {}).get('dram_bytes_per_launch'), ncu_capture=ncu,
+                                  avg_launch_ms=k_avg_ms, launches=k_n,
+                                  sm_mhz_in_kernel=k_mhz, sm_mhz_probe='clock64 / globaltimer inside CTA 0 of the last launch',
+                                  tensor_pipe_rate_at_kernel_clock=hw_at_clock,
+                                  frac_of_tensor_pipe_at_kernel_clock=(achieved / hw_at_clock) if (achieved and hw_at_clock) else None,
                                   cublas_tf32_tflops_measured_in_run=tf32_cublas,
-                                  # hardware ceiling at the clock sampled during the run: 148 SMs x 2048 TF32 MAC/clk x 2
-                                  frac_of_hw_rate_at_sampled_clock=(achieved / (148 * 2048 * 2 * clocks['sm_mhz'] * 1e6 / 1e12))
-                                  if (achieved and clocks and clocks.get('sm_mhz')) else None,
-                                  ncu_tensor_pipe_active_pct=90.8 if traffic else None,   # sm__pipe_tensor_cycles_active, % of elapsed, same capture
                                   executed_flops_per_launch=flops_launch,
+                                  algorithmic_flops_per_launch=alg,
                                   algorithmic_tflops=alg / (k_avg_ms * 1e-3) / 1e12 if k_n else None,
-                                  peak_source='TF32 dense 1.1 PFLOP/s (B200_PROFILING.md table); MEASURED_PEAKS.json (%s) has no TF32 '
-                                              'entry and half its bf16 burst is below what this kernel sustains' % peak_src,
-                                  half_measured_bf16_tflops=half_bf16,
-                                  frac_vs_half_measured_bf16=(achieved / half_bf16) if achieved else None,
-                                  share_of_step=k_ms / ms if ms else None))
+                                  share_of_step=k_ms / ms if ms else None),
+                    hbm_roofline=hbm_roof,
+                    details=dict(per_pd_ms=ms / args.steps / P, stage_ms_last_pd=stage, numa_cpus=numa, **details),
+                    e2e_dropin=dropin)
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             try:
                 os.sched_setaffinity(0, range(cores))       # the CPU arm gets every host core back
             except Exception:
                 pass
-            v, detail = cpu_reference_sample(nS, N, 4 * cores, cores, contraction_rows=min(nS, 500))
+            v, detail, _ = cpu_reference_sample(nS, N, 4 * cores, cores, contraction_rows=min(nS, 500))
             line['cpu_baseline'] = dict(value=v, unit=UNIT, cores=cores, kind='port', detail=detail,
+                                        unmodified_reference_vs_port=reference_vs_port(),
+                                        other_configs=None if args.no_details else cpu_split_other_configs(cores),
                                         sample='%d of %d particles through the per-image stages + a %dx%d block of the '
-                                               'fp64 GEMMs, extrapolated to one PD; value = the faster of the serial mode (all BLAS '
-                                               'threads) and the Pool / MPI-schedule emulation (one PD per worker process)'
+                                               'fp64 GEMMs + the pickle of those particles, extrapolated to one PD; value = the '
+                                               'faster of the serial mode (all BLAS threads) and the Pool / MPI-schedule '
+                                               'emulation (one PD per worker process)'
                                                % (detail['images'], nS, detail['gemm_rows'], detail['gemm_rows']))
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def dropin_block(h_raw, pds, nS, N):
+    """Disk -> GetDistancesS2.op (the reference's stage driver signature) -> per-PD records, 8 PDs of the bench shape:
+    a SPIDER stack + tessellation pickle on local disk, the drop-in modules, record layout 'sidecar' (float32 arrays,
+    virtual CTF) and the reference's single float64 pickle."""
+    import shutil
+    import tempfile
+    from manifoldem_python_b200 import GetDistancesS2, myio, p, synthetic
+    n_pd = 8
+    os.environ['MANIFOLDEM_B200_GPUS'] = '1'                  # this block measures ONE GPU (rank 0's)
+    os.environ['MANIFOLDEM_B200_DEVICE'] = os.environ.get('LOCAL_RANK', '0')
+    base = tempfile.mkdtemp(prefix='mem_b200_bench_', dir='/dev/shm' if os.path.isdir('/dev/shm') else None)
+    out = dict(workload='%d PDs of %d x %d^2: stack on disk -> GetDistancesS2.op -> records' % (n_pd, nS, N), where=base)
+    try:
+        stack = os.path.join(base, 'stack.dat')
+        with open(stack, 'wb') as f:
+            for k in range(n_pd):
+                f.write(memoryview(h_raw[k % len(h_raw)].array).cast('B'))
+        n_half = n_pd * nS
+        rng = np.random.default_rng(11)
+        q = np.concatenate([synthetic.euler_to_quat(0.7 + 0.03 * rng.standard_normal(nS), 1.1 + 0.03 * rng.standard_normal(nS),
+                                                    rng.uniform(0, 2 * np.pi, nS)) for _ in range(n_pd)], axis=1)
+        q = np.concatenate([q, q], axis=1)                      # augmented set (conjugates appended); only first halves used
+        df = np.tile(rng.uniform(10000.0, 30000.0, n_half), 2)
+        CG = [np.arange(k * nS, (k + 1) * nS) for k in range(n_pd)]
+        for layout in ('sidecar', 'pickle'):
+            p.init()
+            p.nPix, p.pix_size, p.Cs, p.EkV, p.AmpContrast = N, EM['pix_size'], EM['Cs'], EM['EkV'], EM['AmpContrast']
+            p.mask_vol_file, p.relion_data, p.num_part, p.ncpu = '', False, n_half, 1
+            p.img_stack_file = stack
+            p.dist_dir = os.path.join(base, 'dist_' + layout) + os.sep
+            p.dist_prog = os.path.join(p.dist_dir, 'progress') + os.sep
+            os.makedirs(p.dist_prog)
+            p.dist_file = os.path.join(p.dist_dir, 'IMGs_')
+            p.tess_file = os.path.join(base, 'tess_' + layout)
+            p.numberofJobs = n_pd
+            p.record_layout = layout
+            myio.fout1(p.tess_file, ['CG', 'q', 'df', 'sh'], [CG, q, df, (np.zeros(n_half), np.zeros(n_half))], layout='pickle')
+            t0 = time.perf_counter()
+            GetDistancesS2.op()
+            dt = time.perf_counter() - t0
+            done = len(os.listdir(p.dist_prog))
+            size = sum(os.path.getsize(os.path.join(p.dist_dir, f)) for f in os.listdir(p.dist_dir)
+                       if os.path.isfile(os.path.join(p.dist_dir, f)))
+            out[layout] = dict(s_per_pd=dt / n_pd, pds_done=done, record_gb_per_pd=size / n_pd / 1e9,
+                               gpairs_s=n_pd * float(nS) * nS / dt / 1e9)
+            shutil.rmtree(p.dist_dir, ignore_errors=True)
+            if hasattr(p, 'record_layout'):
+                del p.record_layout
+    finally:
+        shutil.rmtree(base, ignore_errors=True)
+    return out
 
 
 if __name__ == '__main__':

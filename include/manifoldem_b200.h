@@ -43,9 +43,17 @@ int         mem_ctx_timer_stop(mem_ctx* ctx, float* ms);
  * (executed-flop accounting for the roofline) */
 int         mem_ctx_kernel_time(mem_ctx* ctx, int reset, double* total_ms, int64_t* launches, int32_t* items,
                                 int32_t* k_blocks);
+/* SM clock (MHz) the LAST tcgen05 contraction launch on ctx actually ran at, from a clock64 / globaltimer probe inside
+ * the kernel (CTA 0), and the probe's own wall time of that CTA in ms.  Synchronises. */
+int         mem_ctx_kernel_clock(mem_ctx* ctx, double* sm_mhz, double* kernel_ms);
 /* pinned host memory for the host-buffer entry points */
 int         mem_host_alloc(void** out, size_t bytes);
 int         mem_host_free(void* p);
+/* a2 gather (getDistanceCTF_local_Conj9combinedS2.py:246-262 reads the members of a PD one by one from the memory-mapped
+ * stack): dst[k] = src[rows[k]], rows of row_bytes bytes, copied by `threads` host threads (<= 0: 4) — e.g. straight
+ * from the mapped file into pinned memory.  Plain host memory on both sides; no CUDA call. */
+int         mem_gather_rows_host(void* dst, const void* src, const int64_t* rows, int64_t n, size_t row_bytes,
+                                 int32_t threads);
 /* plain device memory on the context's device + copies (so a ctypes host needs nothing else to stage data);
  * every entry point that takes a ctx makes ctx's device current in the calling thread first */
 int         mem_dev_alloc(mem_ctx* ctx, void** out, size_t bytes);

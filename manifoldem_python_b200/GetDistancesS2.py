@@ -114,7 +114,11 @@ def op(*argv):
         progress.emit(int((offset / float(p.numberofJobs)) * 100))
     print('Processing {} projection directions.'.format(len(input_data)))
 
-    n_workers = min(_n_gpus(), max(1, int(getattr(p, 'ncpu', 1))), max(1, len(input_data)))
+    # one worker process per visible B200, whatever p.ncpu says (the GUI's default p.ncpu = 1 would otherwise leave
+    # seven GPUs of a box idle); MANIFOLDEM_B200_GPUS=n restricts it
+    n_workers = min(_n_gpus(), max(1, len(input_data)))
+    if n_workers != max(1, int(getattr(p, 'ncpu', 1))):
+        print('GetDistancesS2: %d GPU worker(s) (p.ncpu = %s is a CPU setting and is not used)' % (n_workers, getattr(p, 'ncpu', 1)))
     if n_workers <= 1:
         state = {'offset': offset}                                                   # :102-108
 

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libmanifoldem_b200.so')
 
 SYMBOLS = [
     'mem_version', 'mem_last_error', 'mem_ctx_create', 'mem_ctx_destroy', 'mem_ctx_sync', 'mem_ctx_set_option', 'mem_ctx_launch_count',
-    'mem_ctx_timer_start', 'mem_ctx_timer_stop', 'mem_ctx_kernel_time', 'mem_host_alloc', 'mem_host_free', 'mem_dev_alloc', 'mem_dev_free', 'mem_copy_h2d', 'mem_copy_d2h',
+    'mem_ctx_timer_start', 'mem_ctx_timer_stop', 'mem_ctx_kernel_time', 'mem_ctx_kernel_clock', 'mem_host_alloc', 'mem_host_free', 'mem_gather_rows_host', 'mem_dev_alloc', 'mem_dev_free', 'mem_copy_h2d', 'mem_copy_d2h',
     'mem_pd_distance_device', 'mem_pd_distance_host', 'mem_pd_last_timings', 'mem_contract_device',
     'mem_contract_knn_device', 'mem_knn_mode',
     'mem_operand_shape', 'mem_knn_device', 'mem_knn_device_f32', 'mem_graph_dense_device', 'mem_graph_compact_device', 'mem_ferguson_device',
@@ -70,8 +70,10 @@ def load():
         lib.mem_ctx_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         lib.mem_ctx_kernel_time.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64),
                                             C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        lib.mem_ctx_kernel_clock.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         lib.mem_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
         lib.mem_host_free.argtypes = [C.c_void_p]
+        lib.mem_gather_rows_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_size_t, C.c_int32]
         lib.mem_dev_alloc.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t]
         lib.mem_dev_free.argtypes = [C.c_void_p, C.c_void_p]
         lib.mem_copy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
@@ -211,6 +213,12 @@ class Context:
         check(self.lib.mem_ctx_kernel_time(self.handle, 1 if reset else 0, C.byref(tot), C.byref(n), C.byref(items),
                                            C.byref(kb)))
         return float(tot.value), int(n.value), int(items.value), int(kb.value)
+
+    def kernel_clock(self):
+        """(SM MHz, CTA-0 wall ms) of the last tcgen05 contraction launch, from the in-kernel clock probe."""
+        mhz, ms = C.c_double(), C.c_double()
+        check(self.lib.mem_ctx_kernel_clock(self.handle, C.byref(mhz), C.byref(ms)))
+        return float(mhz.value), float(ms.value)
 
     def close(self):
         if self.handle:

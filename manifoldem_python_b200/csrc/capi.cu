@@ -4,6 +4,7 @@
 #include <math.h>
 #include <algorithm>
 #include <set>
+#include <thread>
 
 namespace mem {
 const char* last_error();
@@ -59,7 +60,7 @@ int mem_ctx_destroy(mem_ctx* ctx) {
   mem::DevBuf* bufs[] = {&ctx->fft_work, &ctx->raw, &ctx->flip, &ctx->shift, &ctx->psi, &ctx->df, &ctx->msk2, &ctx->rot_cs, &ctx->rot_pid, &ctx->rot_pitch_tab,
                          &ctx->imgA, &ctx->imgB, &ctx->imgAll, &ctx->imgFlip, &ctx->spec, &ctx->spec2, &ctx->cbin, &ctx->zhi,
                          &ctx->zlo, &ctx->part_cf, &ctx->part_cfw, &ctx->part_c2, &ctx->part_fl, &ctx->part_int, &ctx->avgspec, &ctx->avgimg,
-                         &ctx->stats, &ctx->D, &ctx->ctf64, &ctx->small_out, &ctx->contract_ws, &ctx->contract_items, &ctx->scratch,
+                         &ctx->stats, &ctx->D, &ctx->ctf64, &ctx->small_out, &ctx->contract_ws, &ctx->contract_items, &ctx->clk_probe, &ctx->scratch,
                          &ctx->geom.Gtab, &ctx->geom.bin_of_pix, &ctx->geom.r2_of_bin, &ctx->geom.bin_start,
                          &ctx->geom.bin_pix, &ctx->geom.s3_col, &ctx->geom.special_pix, &ctx->geom.fold_bin,
                          &ctx->geom.fold_start, &ctx->geom.fold_ent, &ctx->knn_ws, &ctx->knn_out};
@@ -125,6 +126,42 @@ int mem_ctx_kernel_time(mem_ctx* ctx, int reset, double* total_ms, int64_t* laun
   if (items) *items = ctx->last_tc_items;
   if (k_blocks) *k_blocks = ctx->last_tc_nkb;
   if (reset) ctx->kev_used = 0;
+  return 0;
+}
+
+int mem_ctx_kernel_clock(mem_ctx* ctx, double* sm_mhz, double* kernel_ms) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  MEM_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (!ctx->clk_probe.p) {
+    set_error("mem_ctx_kernel_clock: no tcgen05 contraction has run on this context");
+    return 1;
+  }
+  unsigned long long v[4];
+  MEM_CUDA(cudaMemcpy(v, ctx->clk_probe.p, sizeof(v), cudaMemcpyDeviceToHost));
+  const double ns = (double)(v[3] - v[1]), cyc = (double)(v[2] - v[0]);
+  if (sm_mhz) *sm_mhz = ns > 0 ? cyc / ns * 1e3 : 0.0;
+  if (kernel_ms) *kernel_ms = ns * 1e-6;
+  return 0;
+}
+
+int mem_gather_rows_host(void* dst, const void* src, const int64_t* rows, int64_t n, size_t row_bytes, int32_t threads) {
+  if (!dst || !src || !rows || n < 0) {
+    set_error("mem_gather_rows_host: null argument");
+    return 1;
+  }
+  const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(threads > 0 ? threads : 4, 64), n));
+  auto work = [=](int t) {
+    const int64_t k0 = n * t / T, k1 = n * (t + 1) / T;
+    for (int64_t k = k0; k < k1; ++k)
+      memcpy((char*)dst + (size_t)k * row_bytes, (const char*)src + (size_t)rows[k] * row_bytes, row_bytes);
+  };
+  if (T == 1) {
+    work(0);
+    return 0;
+  }
+  std::vector<std::thread> th;
+  for (int t = 0; t < T; ++t) th.emplace_back(work, t);
+  for (auto& x : th) x.join();
   return 0;
 }
 

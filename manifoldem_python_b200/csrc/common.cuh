@@ -103,6 +103,7 @@ struct mem_ctx {
   mem::DevBuf D, ctf64, small_out;
   mem::DevBuf contract_ws;   // split-K partial tiles
   mem::DevBuf contract_items;   // work-item table of the last contraction shape
+  mem::DevBuf clk_probe;        // {clock64, globaltimer} at the start and end of CTA 0 of the last k_contract_tc2
   long long items_key[4] = {-1, -1, -1, -1};   // nS, nkb, split, count
   mem::DevBuf scratch;       // misc (ferguson partials, knn)
   mem::DevBuf knn_ws;        // (key, index) rows of the chunked sort, only for nS > 16,384

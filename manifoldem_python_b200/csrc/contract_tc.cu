@@ -304,11 +304,19 @@ __device__ __forceinline__ uint32_t make_idesc2(bool negate_a) {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 k_contract_tc2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                const WorkItem* __restrict__ items, float* __restrict__ ws, int nS, int ldw, int n1, int chunk,
-               int* __restrict__ prog, int n_mil) {
+               int* __restrict__ prog, int n_mil, unsigned long long* __restrict__ clk) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bars = base + STAGES2 * STAGE2_BYTES;
+  // clock probe (bench.py roofline): SM cycles and wall nanoseconds over the life of CTA 0 -> the SM clock this launch
+  // actually ran at (the kernel is power-capped well below the clock nvidia-smi samples between launches)
+  if (clk && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    clk[0] = (unsigned long long)clock64();
+    clk[1] = t;
+  }
   // 8-byte slots: full[0..2], empty[3..5], tmem_full[6..7], tmem_empty[8..9]; tmem base at +96
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES2 * STAGE2_BYTES + 96);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -463,6 +471,12 @@ k_contract_tc2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   cluster_sync_all();     // the peer may still be reading its TMEM half / arriving on the leader's barriers
+  if (clk && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    clk[2] = (unsigned long long)clock64();
+    clk[3] = t;
+  }
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
@@ -606,6 +620,7 @@ int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, c
     prog = ctx->scratch.as<int>();
     MEM_CUDA(cudaMemsetAsync(prog, 0, bytes, st));
   }
+  MEM_CHECK(ctx->clk_probe.ensure(4 * sizeof(unsigned long long)));
   MEM_CHECK(ctx->contract_ws.ensure((size_t)split * ldw * ldw * sizeof(float)));
   float* ws = ctx->contract_ws.as<float>();
   const long long key3 = (long long)items.size() * 2 + two_cta;
@@ -632,7 +647,7 @@ int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, c
   MEM_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used], st));
   if (two_cta)
     MEM_LAUNCH(ctx, k_contract_tc2, 2 * (int)items.size(), NUM_THREADS2, SMEM2_BYTES, st, map_hi, map_lo, d_items, ws, nS, ldw, n1, chunk,
-               prog, n_mil);
+               prog, n_mil, ctx->clk_probe.as<unsigned long long>());
   else
     MEM_LAUNCH(ctx, k_contract_tc, (int)items.size(), NUM_THREADS, SMEM_BYTES, st, map_hi, map_lo, d_items, ws, nS, ldw, n1, chunk);
   MEM_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used + 1], st));

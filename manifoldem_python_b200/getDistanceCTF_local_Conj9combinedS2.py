@@ -19,6 +19,8 @@ _KEYS = ['D', 'ind', 'q', 'df', 'CTF', 'imgAll', 'msk2', 'PD', 'PDs', 'Psis', 'i
          'imgAllFlip', 'imgLabels', 'Dnom', 'Nom', 'imgAllIntensity', 'version', 'options']
 
 _tls = threading.local()
+_slots = {}                      # device -> list of idle (Context, HostArena) pairs; they live as long as the process
+_slots_lock = threading.Lock()
 
 
 def _cfg():
@@ -33,28 +35,47 @@ def _cfg():
     return own
 
 
+def _device():
+    return int(os.environ.get('MANIFOLDEM_B200_DEVICE', '0'))
+
+
+class _Slot:
+    """A CUDA context (stream + device workspace + FFT plans) and a pinned host arena, checked out by one host thread
+    for the duration of one op() call and handed back afterwards.  The reference calls op() from short-lived worker
+    threads / processes (GetDistancesS2.py:110-113); keeping the slots at module level is what lets the 5 GB device
+    workspace, the cuFFT plans and the pinned staging buffers of PD k serve PD k + 1 (with
+    thread-local contexts every GetDistancesS2.op call paid for them again)."""
+
+    def __init__(self, dev):
+        self.ctx = _lib.Context(dev)
+        self.arena = pd_stage.HostArena() if os.environ.get('MANIFOLDEM_B200_PINNED_ARENA', '1') != '0' else None
+
+
+class _checkout:
+    def __enter__(self):
+        dev = _device()
+        with _slots_lock:
+            free = _slots.setdefault(dev, [])
+            self.slot = free.pop() if free else None
+        if self.slot is None:
+            self.slot = _Slot(dev)
+        self.dev = dev
+        return self.slot
+
+    def __exit__(self, *exc):
+        with _slots_lock:
+            _slots[self.dev].append(self.slot)
+        return False
+
+
 def _ctx():
-    """One CUDA context object per host thread and device (callable from a non-main thread; the GUI does)."""
-    dev = int(os.environ.get('MANIFOLDEM_B200_DEVICE', '0'))
+    """A context for callers outside op() (myio's virtual CTF field): one per host thread and device."""
+    dev = _device()
     ctx = getattr(_tls, 'ctx', None)
     if ctx is None or ctx.device != dev:
         ctx = _lib.Context(dev)
         _tls.ctx = ctx
     return ctx
-
-
-def _arena():
-    """Reused pinned host buffers of this worker thread (pd_stage.HostArena) — opt-in, MANIFOLDEM_B200_PINNED_ARENA=1.
-    Measured on the B200 box with 3 PDs of 2,000 x 256^2 per GetDistancesS2.op call (scripts/dropin_e2e.py): pinning
-    1-2.6 GB per worker thread costs more than the page faults and pageable copies it removes (0.65 against 0.43 s per
-    PD), so it only pays on runs with many PDs per worker thread; off by default."""
-    if os.environ.get('MANIFOLDEM_B200_PINNED_ARENA', '0') != '1':
-        return None
-    arena = getattr(_tls, 'arena', None)
-    if arena is None:
-        arena = pd_stage.HostArena()
-        _tls.arena = arena
-    return arena
 
 
 def _read_mrc_volume(path):
@@ -97,14 +118,15 @@ def op(input_data, filterPar, imgFileName, sh, nStot, options, fields=None):
                                   AmpContrast=float(p.AmpContrast),
                                   shape=(nS_, N, N) if options.get('parallel') else (nS_, N * N))
             want = tuple(f for f in want if f != 'CTF')
-    res = pd_stage.run_pd(ind, q, df, stack, nStot, N, p.pix_size, p.Cs, p.EkV, p.AmpContrast,
-                          gaussEnv=getattr(p, 'gaussEnv', np.inf), filterPar=filterPar, msk2=msk2, relion=relion,
-                          sh=sh, avg_only=bool(options.get('avgOnly', False)), ctx=_ctx(), angles=angles,
-                          fields=want, float64=(layout != 'sidecar'), arena=_arena())
-    if (options.get('parallel') or options.get('avgOnly')) and res['CTF'] is not None:
-        res['CTF'] = res['CTF'].reshape(-1, N, N)     # only the default non-avgOnly branch flattens CTF (:392-393)
-    res['options'] = options
-    promote = {k: np.float64 for k in _KEYS if isinstance(res[k], np.ndarray) and res[k].dtype == np.float32}
-    myio.fout1(outFile, _KEYS, [res[k] for k in _KEYS], layout=layout, promote=promote, virtual=virtual)
+    with _checkout() as slot:      # the arrays of `res` live in the slot's pinned arena until the record is on disk
+        res = pd_stage.run_pd(ind, q, df, stack, nStot, N, p.pix_size, p.Cs, p.EkV, p.AmpContrast,
+                              gaussEnv=getattr(p, 'gaussEnv', np.inf), filterPar=filterPar, msk2=msk2, relion=relion,
+                              sh=sh, avg_only=bool(options.get('avgOnly', False)), ctx=slot.ctx, angles=angles,
+                              fields=want, float64=(layout != 'sidecar'), arena=slot.arena)
+        if (options.get('parallel') or options.get('avgOnly')) and res['CTF'] is not None:
+            res['CTF'] = res['CTF'].reshape(-1, N, N)     # only the default non-avgOnly branch flattens CTF (:392-393)
+        res['options'] = options
+        promote = {k: np.float64 for k in _KEYS if isinstance(res[k], np.ndarray) and res[k].dtype == np.float32}
+        myio.fout1(outFile, _KEYS, [res[k] for k in _KEYS], layout=layout, promote=promote, virtual=virtual)
     # marker AFTER the dump: signifies a non-corrupted pickle (:415-419)
     open(os.path.join(p.dist_prog, '%s' % (prD)), 'a').close()

@@ -5,6 +5,7 @@ Reference: modules/getDistanceCTF_local_Conj9combinedS2.py:216-420.
 """
 import ctypes as C
 import math
+import os
 
 import numpy as np
 
@@ -57,8 +58,17 @@ def gather(stack, ind, nStot, N, out=None):
     if out is None:
         out = np.empty((nS, N * N), dtype=np.float32)
     flat = stack.reshape(-1, N * N) if stack.ndim != 2 else stack
-    order = np.argsort(base, kind='stable')            # read the file front to back
-    out[order] = flat[base[order]]
+    if flat.dtype == np.float32 and flat.flags.c_contiguous and out.flags.c_contiguous and nS >= 64:
+        # a few host threads memcpy the rows straight from the mapped file into the (pinned) destination; the
+        # reference re-opens the memmap for every particle (:254-256)
+        if base.min() < 0 or base.max() >= flat.shape[0]:
+            raise IndexError('particle index outside the stack')
+        rows = np.ascontiguousarray(base, dtype=np.int64)
+        _lib.check(_lib.load().mem_gather_rows_host(out.ctypes.data, flat.ctypes.data, rows.ctypes.data, nS,
+                                                    N * N * 4, int(os.environ.get('MANIFOLDEM_B200_GATHER_THREADS', '4'))))
+    else:
+        order = np.argsort(base, kind='stable')            # read the file front to back
+        out[order] = flat[base[order]]
     return out, conj.astype(np.uint8), base
 
 

@@ -196,7 +196,8 @@ def lowpass(imgs, G):
 # --------------------------------------------------------------------- op
 def pd_distance(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast,
                 gaussEnv=np.inf, filterPar=None, msk2=1, relion=False, sh=None,
-                avg_only=False, direct=False, rotate_impl='tile', keep=None, pd_override=None):
+                avg_only=False, direct=False, rotate_impl='tile', keep=None, pd_override=None,
+                timings=None):
     """getDistanceCTF...py:216-420 without the file I/O: returns the dict that
     the reference pickles (same keys, shapes, dtypes), plus a few named
     intermediates under '_'-prefixed keys for per-stage parity checks.
@@ -209,16 +210,29 @@ def pd_distance(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast,
     psi_p, on PD only — so a SUBSET of a large PD evaluated with the full PD's
     direction reproduces exactly the entries D[sub][:, sub] of the full matrix
     (sampled-pair parity checks at BASELINE config sizes).
+
+    timings: optional dict that receives the wall seconds of the stages (ingest, lowpass, rotate, ctf, fft, averages,
+    gemm) — the per-stage CPU split bench.py reports for the reference algorithm.
     """
+    import time as _time
+    _t = [_time.perf_counter()]
+
+    def _lap(name):
+        now = _time.perf_counter()
+        if timings is not None:
+            timings[name] = timings.get(name, 0.0) + now - _t[0]
+        _t[0] = now
     if filterPar is None:
         filterPar = dict(type='Butter', Qc=0.5, N=8)            # GetDistancesS2.py:83
     ind = np.asarray(ind)
     nS = ind.shape[0]
     msk = annular_mask(0, N / 2., N, N)                          # :242
     y, imgLabels = ingest(stack, ind, nStot, N, msk, relion, sh)  # :246-283
+    _lap('ingest')
     Q = create_grid(N)                                           # :286
     G = ifftshift(create_filter(filterPar['type'], filterPar['N'], filterPar['Qc'], Q))
     y = lowpass(y, G)                                            # :290-293
+    _lap('lowpass')
     PDs = calc_avg_pd(q)                                         # :297
     PD = np.sum(PDs, 1)
     PD = PD / np.linalg.norm(PD)                                 # :299-301
@@ -235,16 +249,20 @@ def pd_distance(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast,
         img = y[iS] * msk
         img = rotatefill(img, -(180 / math.pi) * Psi[iS], rotate_impl)
         img = rotatefill(img, -psi_p, rotate_impl)
+        _lap('rotate')
         CTF[iS] = ifftshift(ctemh_cryo_frank(Q / (2 * pix_size), Cs, df[iS], EkV, gaussEnv, AmpContrast))
+        _lap('ctf')
         fy[iS] = fft2(img * msk2)
         imgAllFlip[iS] = ifft2(np.sign(CTF[iS]) * fy[iS]).real
         imgAll[iS] = img
+        _lap('fft')
     imgAvgFlip = imgAllFlip.sum(0)
 
     wiener_dom = -(np.sum(CTF ** 2, axis=0) + 1. / 5)            # :354, :422-430 (SNR=5)
     imgAvg = ifft2(fft2(imgAll, axes=(-2, -1)) * (CTF / wiener_dom), axes=(-2, -1)).real.sum(0)
     imgAvg = imgAvg * msk2 / nS                                  # :366-367
     imgAvgFlip = imgAvgFlip * msk2 / nS
+    _lap('averages')
 
     D = np.zeros((nS, nS))
     CTF_out = CTF
@@ -260,6 +278,7 @@ def pd_distance(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast,
             CTFfy = CTF_out.conj() * fyf
             D = np.dot(np.abs(CTF_out) ** 2, (np.abs(fyf) ** 2).T)
             D = D + D.T - 2 * np.real(np.dot(CTFfy, CTFfy.conj().T))
+    _lap('gemm')
     imgAllIntensity = np.mean(imgAllFlip ** 2, axis=0)           # :400
 
     out = dict(D=D, ind=ind, q=q, df=df, CTF=CTF_out, imgAll=imgAll, msk2=msk2, PD=PD, PDs=PDs,

@@ -484,7 +484,8 @@ def test_worker_writes_both_layouts_without_touching_the_gpu(tmp_path, monkeypat
                 res[k] = None
         return res
     monkeypatch.setattr(pd_stage, 'run_pd', fake_run_pd)
-    monkeypatch.setattr(worker, '_ctx', lambda: None)
+    import types
+    monkeypatch.setattr(worker, '_Slot', lambda dev: types.SimpleNamespace(ctx=None, arena=None))
     q = np.tile(np.array([[1.0], [0.0], [0.0], [0.0]]), (1, nS))
     opts = dict(verbose=False, avgOnly=False, visual=False, parallel=False, relion_data=False, thres=2000)
     recs = {}
