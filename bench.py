@@ -18,6 +18,7 @@ the nS x nS matrix D the reference materialises.
 `details`    other BASELINE configs (1: the demo's 53 PDs, 2, 3, 5: one PD) and the record-producing variants.
 """
 import argparse
+import contextlib
 import ctypes as C
 import json
 import os
@@ -820,7 +821,8 @@ def dropin_block(h_raw, pds, nS, N):
             p.record_layout = layout
             myio.fout1(p.tess_file, ['CG', 'q', 'df', 'sh'], [CG, q, df, (np.zeros(n_half), np.zeros(n_half))], layout='pickle')
             t0 = time.perf_counter()
-            GetDistancesS2.op()
+            with contextlib.redirect_stdout(sys.stderr):        # the stage driver prints like the reference's; stdout = ONE JSON line
+                GetDistancesS2.op()
             dt = time.perf_counter() - t0
             done = len(os.listdir(p.dist_prog))
             size = sum(os.path.getsize(os.path.join(p.dist_dir, f)) for f in os.listdir(p.dist_dir)
