@@ -186,6 +186,11 @@ int mem_symv_host(mem_ctx* ctx, const double* L, int32_t nS, const double* x, do
  * bin centre (centres [nG][3] float64, Euclidean distance in float64, smallest index on a tie) -> idx [n] int32.
  * HOST pointers; synchronises. */
 int mem_s2_assign_host(mem_ctx* ctx, const double* centres, int32_t nG, const double* pts, int64_t n, int32_t* idx);
+/* FindCCGraph.CalcPairwiseDistS2 (modules/FindCCGraph.py:227-273): U [nU][3], V [nV][3] float64 = the selected columns
+ * of the 3 x N matrix X, one point per row -> dot [nU][nV] = U V^T and dist [nU][nV] = sqrt(Dsq), Dsq < 1e-6 -> 0, with
+ * Dsq[i][j] = (|u_j|^2 + |v_j|^2) - 2 u_i.v_j exactly as the reference's NumPy broadcast evaluates :267 (nU == nV
+ * required, like the broadcast).  HOST pointers; synchronises. */
+int mem_s2_pairwise_host(mem_ctx* ctx, const double* U, int32_t nU, const double* V, int32_t nV, double* dot, double* dist);
 
 #ifdef __cplusplus
 }

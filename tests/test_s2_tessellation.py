@@ -136,3 +136,38 @@ def test_demo_star_gives_the_53_projection_directions(monkeypatch):
     occ = np.array([len(a) for a in CG])
     assert int(nG) == 4071 and len(CG) == 53
     assert occ.min() == 117 and occ.max() == 450 and int(np.median(occ)) == 206 and int((occ ** 2).sum()) == 3130240
+
+
+# ---- FindCCGraph.CalcPairwiseDistS2 (modules/FindCCGraph.py:227-273) -------------------------------------------------
+@pytest.fixture(scope='module')
+def golden_pw(golden_dir):
+    return np.load(os.path.join(golden_dir, 's2_pairwise.npz'), allow_pickle=False)
+
+
+def _pairwise_cases(golden, golden_pw):
+    yield 'a', golden['a_S20_th'], None, None, golden_pw['a_dot'], golden_pw['a_dist']
+    yield 'b', golden['b_S20_th'], None, None, golden_pw['b_dot'], golden_pw['b_dist']
+    yield 'idx', golden['a_S20_th'], golden_pw['idx_u'], golden_pw['idx_v'], golden_pw['idx_dot'], golden_pw['idx_dist']
+    yield 'nonunit', golden_pw['nonunit_X'], np.arange(0, 30), np.arange(10, 40), golden_pw['nonunit_dot'], golden_pw['nonunit_dist']
+
+
+def test_oracle_pairwise_matches_the_reference(golden, golden_pw):
+    from oracle import s2_tessellation as os2
+    for tag, X, iu, iv, dot, dist in _pairwise_cases(golden, golden_pw):
+        d, e = os2.pairwise_dist_s2(X, iu, iv)
+        # BLAS may fuse the three products differently: 1 ulp on the dot product, sqrt of a difference near the 1e-6 cut
+        assert np.abs(d - dot).max() <= 4e-16 * max(1.0, np.abs(dot).max()), tag
+        assert np.array_equal(e == 0, dist == 0) and np.abs(e - dist).max() <= 1e-12 * max(1.0, dist.max()), tag
+
+
+@pytest.mark.gpu
+def test_pairwise_dist_s2_on_the_device(golden, golden_pw):
+    from manifoldem_python_b200 import FindCCGraph as F
+    for tag, X, iu, iv, dot, dist in _pairwise_cases(golden, golden_pw):
+        d, e = F.CalcPairwiseDistS2(X) if iu is None else F.CalcPairwiseDistS2(X, iu, iv)
+        assert d.shape == dot.shape and np.abs(d - dot).max() <= 4e-16 * max(1.0, np.abs(dot).max()), tag
+        assert np.array_equal(e == 0, dist == 0) and np.abs(e - dist).max() <= 1e-12 * max(1.0, dist.max()), tag
+    with pytest.raises(ValueError):
+        F.CalcPairwiseDistS2(golden['a_S20_th'], np.arange(3), np.arange(5))
+    with pytest.raises(AssertionError):
+        F.CalcPairwiseDistS2(golden['a_S20_th'], np.arange(3))
