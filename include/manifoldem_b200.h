@@ -181,6 +181,17 @@ int mem_laplacian_dense_device(mem_ctx* ctx, const double* M, int32_t nS, double
  * L [nS][nS] float64 on the device, x and y [nS] float64 on the HOST.  Synchronises. */
 int mem_symv_host(mem_ctx* ctx, const double* L, int32_t nS, const double* x, double* y);
 
+/* a19 on the device (replaces sembeddingonFly.py:27 eigsh(l, k = nEigs + 1, maxiter = 300)): Lanczos
+ * with full re-orthogonalisation on the resident Laplacian.  mem_lanczos_steps_device enqueues steps j0 .. j1 - 1
+ * (j0 == 0 also builds the deterministic start vector) without synchronising: V [ld_ab][nS] float64 Krylov basis (row per
+ * vector), ab [2][ld_ab] float64 = alpha_j in row 0, beta_j (= ||w|| after step j - 1) in row 1; j1 < ld_ab.  The host reads
+ * `ab` between blocks of steps (eigen-decomposition of the j x j tridiagonal matrix, residual estimates) and finally asks
+ * for the Ritz vectors X [k][nS] = S^T V of the k <= 32 wanted pairs, S [j][k] float64 on the HOST. */
+int mem_lanczos_steps_device(mem_ctx* ctx, const double* L, int32_t nS, double* V, double* ab, int32_t ld_ab, int32_t j0,
+                             int32_t j1, void* stream);
+int mem_lanczos_ritz_device(mem_ctx* ctx, const double* V, int32_t nS, int32_t j, const double* S_host, int32_t k, double* X,
+                            void* stream);
+
 /* ---- upstream of the distance stage: S2 tessellation (modules/S2tessellation.py) ---------- */
 /* classS2 (:59-63): for every particle direction pts[i] (unit 3-vectors, [n][3] float64) the index of the nearest
  * bin centre (centres [nG][3] float64, Euclidean distance in float64, smallest index on a tie) -> idx [n] int32.

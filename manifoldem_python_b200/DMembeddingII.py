@@ -3,9 +3,10 @@
 op(D, k, tune, prefsigma) -> (lamb, psi, sigma, mu, logEps, logSumWij, popt, R_squared)
 
 On the GPU (C ABI): kNN lists (a15), OR-symmetrised graph (a16), the 1,501-point Ferguson sweep (a17 — 97 %
-of the reference's time), Gaussian kernel + alpha = 1 + symmetric normalisations (a18).  On the host, with the
-same SciPy calls as the reference: the 4-parameter tanh fit (curve_fit, fergusonE.py:45-57) and the ARPACK
-eigen-solve (eigsh, sembeddingonFly.py:27-35), so sigma and the eigenvectors follow the same code path.
+of the reference's time), Gaussian kernel + alpha = 1 + symmetric normalisations (a18), and the eigen-solve (a19,
+sembeddingonFly.py:27-35) as Lanczos with full re-orthogonalisation on the resident Laplacian (eigsh_device; the
+reference's ARPACK call with the operator applied on the device stays selectable, p.eig_solver = 'arpack').  On the
+host, with the same SciPy call as the reference: the 4-parameter tanh fit (curve_fit, fergusonE.py:45-57).
 D is mutated in place (diagonal <- -inf) like the reference (:48).
 """
 import ctypes as C
@@ -128,6 +129,64 @@ def device_operator(L_dev, nS, ctx=None):
     return LinearOperator((nS, nS), matvec=matvec, dtype=np.float64)
 
 
+def lanczos_ritz_selection(alpha, beta, k, nS, tol):
+    """Host part of eigsh_device between two blocks of steps: alpha (j,), beta (j + 1,) with beta[i] = ||w|| after step
+    i - 1 (beta[0] unused).  Returns (theta (k',), S (j_eff, k') Ritz coefficients, j_eff, converged) for the k' <= k
+    Ritz pairs of largest magnitude (ARPACK's which='LM').  A beta that vanishes (invariant subspace, or j = nS) truncates
+    the recurrence there and makes the pairs exact."""
+    from scipy.linalg import eigh_tridiagonal
+    j = alpha.shape[0]
+    scale = max(np.abs(alpha).max(), np.abs(beta[1:j + 1]).max(), np.finfo(float).tiny)
+    small = np.nonzero(beta[1:j + 1] <= 1e-13 * scale)[0]
+    exact = small.size > 0 or j >= nS
+    j_eff = min(j, nS, int(small[0]) + 1 if small.size else j)
+    if j_eff == 1:
+        theta, S = alpha[:1].copy(), np.ones((1, 1))
+    else:
+        theta, S = eigh_tridiagonal(alpha[:j_eff], beta[1:j_eff])
+    order = np.argsort(-np.abs(theta), kind='stable')[:k]
+    theta, S = theta[order], S[:, order]
+    if exact:
+        return theta, S, j_eff, True
+    res = np.abs(beta[j_eff]) * np.abs(S[-1, :])
+    ok = res <= tol * np.maximum(np.finfo(float).eps ** (2.0 / 3.0), np.abs(theta))
+    return theta, S, j_eff, bool(ok.all()) and theta.shape[0] == k
+
+
+def eigsh_device(L_dev, nS, k, tol=1e-12, block=16, m_max=None, ctx=None):
+    """The k eigenpairs of largest magnitude of the symmetric (nS,nS) float64 device matrix L_dev — what
+    sembeddingonFly.py:27 asks ARPACK for — by Lanczos with full re-orthogonalisation on the device (eig.cu): the host
+    enqueues `block` steps at a time and only reads the 2 x j recurrence coefficients in between.
+    Returns (vals (k,), vecs (nS,k), info) in ARPACK's layout (unit-norm columns, no particular order);
+    info = dict(steps, converged).  Convergence: |beta_j s_ji| <= tol * max(eps^(2/3), |theta_i|) for every wanted pair."""
+    lib = _lib.load()
+    ctx = ctx or _ctx()
+    k = int(min(k, nS - 1))
+    m_max = int(min(nS, m_max or max(20 * k, 640)))
+    V = _lib.DeviceArray(ctx, (m_max + 1, nS), np.float64)
+    ab = _lib.DeviceArray(ctx, (2, m_max + 1), np.float64)
+    j = 0
+    try:
+        while True:
+            j1 = min(m_max, max(j + block, 2 * k + 1) if j == 0 else j + block)
+            _lib.check(lib.mem_lanczos_steps_device(ctx.handle, L_dev.ptr, nS, V.ptr, ab.ptr, m_max + 1, j, j1, None))
+            j = j1
+            c = ab.download()
+            theta, S, j_eff, done = lanczos_ritz_selection(c[0, :j], c[1, :j + 1], k, nS, tol)
+            if done or j >= m_max:
+                break
+        kk = theta.shape[0]
+        X = _lib.DeviceArray(ctx, (kk, nS), np.float64)
+        Sc = np.ascontiguousarray(S, dtype=np.float64)
+        _lib.check(lib.mem_lanczos_ritz_device(ctx.handle, V.ptr, nS, j_eff, Sc.ctypes.data, kk, X.ptr, None))
+        vecs = X.download().T.copy()
+        X.free()
+    finally:
+        V.free()
+        ab.free()
+    return theta, vecs, dict(steps=j, converged=done)
+
+
 def upload(D, ctx=None):
     """D on the device for embed() / take(): float32 stays float32 (the dtype the distance stage computed it in and the
     sidecar record stores — half the bytes, identical lists), anything else goes up as float64."""
@@ -168,10 +227,17 @@ def embed(D, k, tune):
     L = laplacian(M, nS, sigma, resident=True)
     M.free()
     try:
-        vals, vecs = eigsh(device_operator(L, nS), k=nEigs + 1, maxiter=300)     # sembeddingonFly.py:27
-    except ArpackNoConvergence as e:
-        vals, vecs = e.eigenvalues, e.eigenvectors
-        print("eigsh not converging in 300 iterations...")
+        if getattr(p, 'eig_solver', 'lanczos') == 'arpack':
+            # the reference's own call (sembeddingonFly.py:27) with the operator applied on the device: kept for cross-checks
+            try:
+                vals, vecs = eigsh(device_operator(L, nS), k=nEigs + 1, maxiter=300)
+            except ArpackNoConvergence as e:
+                vals, vecs = e.eigenvalues, e.eigenvectors
+                print("eigsh not converging in 300 iterations...")
+        else:
+            vals, vecs, info = eigsh_device(L, nS, nEigs + 1)
+            if not info['converged']:
+                print("eigsh not converging in 300 iterations...")
     finally:
         L.free()
     ix = np.argsort(vals)[::-1]

@@ -17,7 +17,7 @@ SYMBOLS = [
     'mem_pd_distance_device', 'mem_pd_distance_host', 'mem_pd_last_timings', 'mem_contract_device',
     'mem_contract_knn_device', 'mem_knn_mode',
     'mem_operand_shape', 'mem_knn_device', 'mem_knn_device_f32', 'mem_graph_dense_device', 'mem_graph_compact_device', 'mem_ferguson_device',
-    'mem_laplacian_dense_device', 'mem_symv_host', 'mem_s2_assign_host', 'mem_s2_pairwise_host', 'mem_ctf_host',
+    'mem_laplacian_dense_device', 'mem_symv_host', 'mem_lanczos_steps_device', 'mem_lanczos_ritz_device', 'mem_s2_assign_host', 'mem_s2_pairwise_host', 'mem_ctf_host',
     'mem_gather_square_device',
 ]
 
@@ -101,6 +101,10 @@ def load():
                                                  C.c_void_p, C.c_void_p]
         lib.mem_ctf_host.argtypes = [C.c_void_p, C.POINTER(PdParams), C.c_void_p, C.c_void_p]
         lib.mem_s2_assign_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+        lib.mem_lanczos_steps_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                                 C.c_int32, C.c_void_p]
+        lib.mem_lanczos_ritz_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                                C.c_void_p]
         lib.mem_s2_pairwise_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         _lib = lib
         return lib

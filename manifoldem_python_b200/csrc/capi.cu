@@ -16,6 +16,10 @@ int ferguson_device(mem_ctx* ctx, const double* d2, int64_t n, const double* log
 int laplacian_dense_device(mem_ctx* ctx, const double* M, int nS, double sigma, double* L, cudaStream_t st);
 int symv_host(mem_ctx* ctx, const double* L, int nS, const double* x_host, double* y_host);
 int s2_assign_host(mem_ctx* ctx, const double* centres, int nG, const double* pts, long long n, int* idx);
+int lanczos_steps_device(mem_ctx* ctx, const double* L, int nS, double* V, double* ab, int ld_ab, int j0, int j1,
+                         cudaStream_t st);
+int lanczos_ritz_device(mem_ctx* ctx, const double* V, int nS, int j, const double* S_host, int k, double* X,
+                        cudaStream_t st);
 int s2_pairwise_host(mem_ctx* ctx, const double* U, int nU, const double* V, int nV, double* dot, double* dist);
 int ctf_host(mem_ctx* ctx, const mem_pd_params* prm, const double* df, double* out);
 int gather_square_device(mem_ctx* ctx, const void* D, int elem_bytes, int nS, const int* sel_host, int m, void* out,
@@ -388,6 +392,18 @@ int mem_symv_host(mem_ctx* ctx, const double* L, int32_t nS, const double* x, do
 int mem_s2_assign_host(mem_ctx* ctx, const double* centres, int32_t nG, const double* pts, int64_t n, int32_t* idx) {
   MEM_CUDA(cudaSetDevice(ctx->device));
   return s2_assign_host(ctx, centres, nG, pts, (long long)n, idx);
+}
+
+int mem_lanczos_steps_device(mem_ctx* ctx, const double* L, int32_t nS, double* V, double* ab, int32_t ld_ab, int32_t j0,
+                             int32_t j1, void* stream) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  return lanczos_steps_device(ctx, L, nS, V, ab, ld_ab, j0, j1, pick(ctx, stream));
+}
+
+int mem_lanczos_ritz_device(mem_ctx* ctx, const double* V, int32_t nS, int32_t j, const double* S_host, int32_t k, double* X,
+                            void* stream) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  return lanczos_ritz_device(ctx, V, nS, j, S_host, k, X, pick(ctx, stream));
 }
 
 int mem_s2_pairwise_host(mem_ctx* ctx, const double* U, int32_t nU, const double* V, int32_t nV, double* dot, double* dist) {

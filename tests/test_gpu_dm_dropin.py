@@ -359,3 +359,57 @@ def test_device_submatrix_and_resident_embedding(dtype):
         DMembeddingII.take(Dd, np.array([0, nS]))
     for x in (Dd, sub):
         x.free()
+
+
+def _diffusion_like_matrix(nS, seed):
+    """Symmetric normalised Gaussian-kernel matrix of points on a noisy curve: top eigenvalue 1, decaying spectrum."""
+    rng = np.random.default_rng(seed)
+    t = np.sort(rng.uniform(0, 1, nS))
+    X = np.stack([np.cos(3 * t), np.sin(3 * t), t], 1) + 0.02 * rng.standard_normal((nS, 3))
+    d2 = ((X[:, None, :] - X[None, :, :]) ** 2).sum(-1)
+    W = np.exp(-d2 / 0.05)
+    d = W.sum(1)
+    W = W / np.outer(d, d)
+    d = np.sqrt(W.sum(1))
+    L = W / np.outer(d, d)
+    return np.abs(L + L.T) / 2
+
+
+@pytest.mark.parametrize('nS,k', [(40, 16), (333, 16), (2000, 16), (2000, 5)])
+def test_device_lanczos_vs_dense_eigh(nS, k):
+    """eigsh_device (sembeddingonFly.py:27 on the device) against numpy's dense eigh of the same matrix: eigenvalues to
+    1e-10, every eigenvector |cos| >= 1 - 1e-8 (the north-star gate is |corr| >= 0.9999)."""
+    from manifoldem_python_b200 import DMembeddingII, _lib
+    from manifoldem_python_b200.getDistanceCTF_local_Conj9combinedS2 import _ctx
+    L = _diffusion_like_matrix(nS, 5 + nS)
+    w, U = np.linalg.eigh(L)
+    order = np.argsort(-np.abs(w))[:k]
+    Ld = _lib.DeviceArray(_ctx(), (nS, nS), np.float64, L)
+    vals, vecs, info = DMembeddingII.eigsh_device(Ld, nS, k)
+    Ld.free()
+    assert info['converged'] and vals.shape == (k,) and vecs.shape == (nS, k)
+    ix = np.argsort(-np.abs(vals))
+    assert np.allclose(vals[ix], w[order], rtol=0, atol=1e-10)
+    assert np.allclose(np.linalg.norm(vecs, axis=0), 1.0, atol=1e-12)
+    for a, b in zip(ix, order):
+        assert abs(vecs[:, a] @ U[:, b]) >= 1 - 1e-8, (a, b)
+    # orthonormal Ritz vectors
+    assert np.abs(vecs.T @ vecs - np.eye(k)).max() < 1e-10
+
+
+def test_both_eigen_solvers_give_the_same_embedding(golden_dir):
+    """embed() through the device Lanczos (default) and through the reference's ARPACK call with the device operator."""
+    from manifoldem_python_b200 import DMembeddingII, p
+    p.init()
+    g = _load_dm(golden_dir)
+    out = {}
+    for solver in ('lanczos', 'arpack'):
+        p.eig_solver = solver
+        np.random.seed(7)
+        out[solver] = DMembeddingII.embed(g['D'].copy(), 72, 3.0)
+    del p.eig_solver
+    a, b = out['lanczos'], out['arpack']
+    assert np.allclose(a[0], b[0], rtol=1e-9, atol=1e-11)                 # lamb
+    assert np.allclose(a[3], b[3], rtol=1e-7, atol=1e-12)                 # mu
+    for j in range(8):
+        assert abs(np.corrcoef(a[1][:, j], b[1][:, j])[0, 1]) > 0.999999, j

@@ -594,3 +594,45 @@ def test_header_is_plain_c():
     r = subprocess.run([gcc, '-std=c99', '-Wall', '-Wextra', '-pedantic', '-fsyntax-only', '-x', 'c', hdr],
                        capture_output=True, text=True)
     assert r.returncode == 0 and not r.stderr.strip(), r.stderr
+
+
+def test_lanczos_host_selection_against_dense_eigh():
+    """Host half of eigsh_device (DMembeddingII.lanczos_ritz_selection): a NumPy Lanczos with full re-orthogonalisation
+    stands in for the device kernels (same recurrence, same coefficient layout); the selection must report convergence
+    only when the residual estimates allow it, pick the largest-magnitude pairs, and treat j = nS / a vanishing beta as exact."""
+    from manifoldem_python_b200.DMembeddingII import lanczos_ritz_selection
+    rng = np.random.default_rng(3)
+    nS, k = 60, 6
+    Q, _ = np.linalg.qr(rng.standard_normal((nS, nS)))
+    lam = np.concatenate([[1.0, -0.9, 0.8, 0.7, 0.65, 0.6], 0.3 * rng.uniform(-1, 1, nS - 6)])
+    L = (Q * lam) @ Q.T
+    L = (L + L.T) / 2
+
+    def lanczos(L, steps, v0):
+        n = L.shape[0]
+        V = np.zeros((steps + 1, n))
+        alpha, beta = np.zeros(steps), np.zeros(steps + 1)
+        V[0] = v0 / np.linalg.norm(v0)
+        for j in range(steps):
+            w = L @ V[j]
+            for _ in range(2):
+                h = V[:j + 1] @ w
+                alpha[j] += h[j]
+                w = w - V[:j + 1].T @ h
+            beta[j + 1] = np.linalg.norm(w)
+            V[j + 1] = w / beta[j + 1] if beta[j + 1] > 0 else 0
+        return V, alpha, beta
+
+    V, alpha, beta = lanczos(L, 12, rng.standard_normal(nS))
+    theta, S, j_eff, done = lanczos_ritz_selection(alpha, beta, k, nS, 1e-12)
+    assert not done and j_eff == 12 and theta.shape == (k,)
+    V, alpha, beta = lanczos(L, nS, rng.standard_normal(nS))
+    theta, S, j_eff, done = lanczos_ritz_selection(alpha, beta, k, nS, 1e-12)
+    assert done and np.allclose(np.sort(theta), np.sort(lam[:6]), atol=1e-10)
+    X = V[:j_eff].T @ S
+    assert np.abs(L @ X - X * theta).max() < 1e-9
+    # invariant subspace: a start vector inside the span of 4 eigenvectors breaks down after 4 steps (exact pairs, k' = 4)
+    v0 = Q[:, :4] @ np.array([1.0, 2.0, -1.0, 0.5])
+    V, alpha, beta = lanczos(L, 8, v0)
+    theta, S, j_eff, done = lanczos_ritz_selection(alpha, beta, k, nS, 1e-12)
+    assert done and j_eff == 4 and np.allclose(np.sort(theta), np.sort(lam[:4]), atol=1e-9)
