@@ -100,3 +100,64 @@ def test_dm_embedding(golden_dir, k):
     for j in range(4):                                            # leading eigenvectors, sign-free
         c = abs(np.corrcoef(psi[:, j], ref_psi[:, j])[0, 1])
         assert c > 1 - 1e-8, (j, c)
+
+
+# ---- NLSA / psi analysis: oracle vs the unmodified reference's outputs -------------------------------
+NLSA_SEED = 4321
+
+
+def _cols_match(a, b, tol):
+    """Columns equal up to a sign each (eigenvectors: ARPACK / LAPACK leave the sign free)."""
+    scale = np.abs(b).max()
+    for j in range(b.shape[1]):
+        d = min(np.abs(a[:, j] - b[:, j]).max(), np.abs(a[:, j] + b[:, j]).max())
+        assert d <= tol * scale, (j, d, scale)
+
+
+def nlsa_outputs_match(out, g, pre, tol_lin, tol_eig):
+    """NLSA.op outputs against the reference's: IMGT and sdiag are sign-free quantities; Topo_mean, psiC1, VX^T and psirec
+    are eigen/singular vectors (sign per column free); tau is defined up to tau <-> 1 - tau (sign of psirec[:, 0])."""
+    IMGT, Topo_mean, psirec, psiC1, sdiag, VX, mu, tau = out
+    assert np.allclose(IMGT, g[pre + 'IMGT'], rtol=0, atol=tol_lin)
+    assert np.allclose(sdiag, g[pre + 'sdiag'], rtol=10 * tol_lin, atol=1e-12)
+    _cols_match(Topo_mean, g[pre + 'Topo_mean'], 10 * tol_lin)
+    _cols_match(psiC1[:, :6], g[pre + 'psiC1'][:, :6], tol_eig)
+    _cols_match(VX.T, g[pre + 'VX'].T, tol_eig)
+    _cols_match(psirec[:, :4], g[pre + 'psirec'][:, :4], 10 * tol_eig)
+    assert np.allclose(mu, g[pre + 'mu'], rtol=10 * tol_eig, atol=1e-12)
+    rt = g[pre + 'tau']
+    assert min(np.abs(tau - rt).max(), np.abs(tau - (1 - rt)).max()) <= 1e-5
+
+
+def _nlsa_case(g, tag, psinum):
+    from oracle import nlsa as onl
+    nS, N = int(g['nS']), int(g['N'])
+    conOrderRange, psiTrunc, tune, ConOrder = g['params']
+    ConOrder, psiTrunc = int(ConOrder), int(psiTrunc)
+    posPath = g['posPath']
+    PosPsi1 = np.argsort(g['psi'][:, psinum])
+    assert np.array_equal(PosPsi1, g['%s_psi%d_PosPsi1' % (tag, psinum)])
+    DD = g['D'][posPath][:, posPath][PosPsi1][:, PosPsi1]
+    par = dict(num=nS, ConOrder=ConOrder, k=nS - ConOrder, tune=float(tune), nS=nS, save=False, psiTrunc=psiTrunc)
+    msk2 = 1 if tag == 'm1' else g['disc']
+    np.random.seed(NLSA_SEED + psinum)
+    return onl.nlsa(par, DD, posPath, PosPsi1, g['imgAll'], msk2, g['CTF']), '%s_psi%d_' % (tag, psinum)
+
+
+@pytest.mark.parametrize('tag,psinum', [('m1', 0), ('m1', 1), ('md', 0), ('md', 1)])
+def test_nlsa_oracle_vs_reference(golden_dir, tag, psinum):
+    g = _load(golden_dir, 'nlsa_nS80_N24.npz')
+    (IMGT, Topo_mean, psirec, psiC1, sdiag, VX, mu, tau), pre = _nlsa_case(g, tag, psinum)
+    nlsa_outputs_match((IMGT, Topo_mean, psirec, psiC1, sdiag, VX, mu, tau), g, pre, 1e-9, 1e-7)
+
+
+def test_psi_analysis_class_representatives_vs_reference(golden_dir):
+    from oracle import nlsa as onl
+    g = _load(golden_dir, 'nlsa_nS80_N24.npz')
+    for psinum in (0, 1):
+        pre = 'm1_psi%d_' % psinum
+        # the psiAnalysisParS2 run drew other random numbers than the direct NLSA.op run (tau may come out as 1 - tau):
+        # feed its own (already rescaled: idempotent) tau and the sign-free IMGT of the direct run
+        IMG1, tau, tauinds = onl.class_representatives(g[pre + 'IMGT'], g['pa_psi%d_tau' % psinum], 50)
+        assert np.array_equal(tauinds, g['pa_psi%d_tauinds' % psinum]) and np.array_equal(tau, g['pa_psi%d_tau' % psinum])
+        assert np.allclose(IMG1, g['pa_psi%d_IMG1' % psinum], rtol=0, atol=1e-9)
