@@ -192,6 +192,32 @@ int mem_lanczos_steps_device(mem_ctx* ctx, const double* L, int32_t nS, double* 
 int mem_lanczos_ritz_device(mem_ctx* ctx, const double* V, int32_t nS, int32_t j, const double* S_host, int32_t k, double* X,
                             void* stream);
 
+/* ---- NLSA / psi analysis (modules/NLSA.py:23-158, get_wiener.py, svdRF.py, L2_distance.py) -------------
+ * All float64, device pointers unless marked HOST.  `sel` [num] int32 (device) = posPath[PosPsi1], the snapshot order of the
+ * psi being analysed; nI = num - ConOrder; Nh = N/2 + 1; E = psiTrunc.  The CTF planes must be even (CTF(-k) = CTF(k), true
+ * of every CTF the distance stage writes): the Wiener-weighted sums are taken on the Hermitian half plane. */
+/* once per PD: H [n][N][Nh] complex128 = rfft2(img[i]) * CTF[i], Ch [n][N][Nh] = CTF half planes (NLSA.py:73-76 hoisted) */
+int mem_nlsa_spectra_device(mem_ctx* ctx, const double* img, const double* ctf, int32_t n, int32_t N, void* H, double* Ch,
+                            void* stream);
+/* NLSA.py:30-33: ConD [nI][nI] = sum_{i < ConOrder} DD[r + i][c + i], DD = D[sel][:, sel]; D [nAll][nAll] float32 or float64 */
+int mem_nlsa_cond_device(mem_ctx* ctx, const void* D, int32_t elem_bytes, int32_t nAll, const int32_t* sel, int32_t num,
+                         int32_t ConOrder, double* ConD, void* stream);
+/* NLSA.py:66-86 + get_wiener.py: A [ConOrder N^2][E] = the Wiener-filtered, masked snapshot stack times mu_psi [nI][E] (HOST),
+ * row ii N^2 + c N + r for picture pixel (r, c); msk2 [N][N] float64 or NULL (= 1).  Synchronises once (mu_psi upload). */
+int mem_nlsa_supervectors_device(mem_ctx* ctx, const void* H, const double* Ch, const int32_t* sel, const double* mu_psi,
+                                 int32_t num, int32_t ConOrder, int32_t E, int32_t N, const double* msk2, double* A,
+                                 void* stream);
+/* svdRF.py:21: AtA [E][E] (HOST) = A^T A.  Synchronises. */
+int mem_nlsa_gram_small_device(mem_ctx* ctx, const double* A, int64_t rows, int32_t E, double* AtA, void* stream);
+/* svdRF.py:25 + NLSA.py:95-103: U [rows][E] = A M with M [E][E] (HOST) = V S^-1; topo_mean [Npix][E] (HOST) = mean over the
+ * ConOrder blocks of U.  Synchronises. */
+int mem_nlsa_project_device(mem_ctx* ctx, const double* A, int64_t rows, int32_t E, const double* M, double* U, int32_t Npix,
+                            int32_t ConOrder, double* topo_mean, void* stream);
+/* NLSA.py:106-144: IMGT [nC][Npix] = frames rebuilt from the first two singular triplets (Q [2][nI] HOST = diag(s) V^T psiC^T),
+ * each normalised to mean 0 / std 1; D2 [nC][nC] = L2_distance(IMGT, IMGT)**2 (NULL: skip). */
+int mem_nlsa_reconstruct_device(mem_ctx* ctx, const double* U, int32_t Npix, int32_t ConOrder, int32_t E, const double* Q,
+                                int32_t nI, int32_t nC, double* IMGT, double* D2, void* stream);
+
 /* ---- upstream of the distance stage: S2 tessellation (modules/S2tessellation.py) ---------- */
 /* classS2 (:59-63): for every particle direction pts[i] (unit 3-vectors, [n][3] float64) the index of the nearest
  * bin centre (centres [nG][3] float64, Euclidean distance in float64, smallest index on a tie) -> idx [n] int32.

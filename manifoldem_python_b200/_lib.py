@@ -17,7 +17,8 @@ SYMBOLS = [
     'mem_pd_distance_device', 'mem_pd_distance_host', 'mem_pd_last_timings', 'mem_contract_device',
     'mem_contract_knn_device', 'mem_knn_mode',
     'mem_operand_shape', 'mem_knn_device', 'mem_knn_device_f32', 'mem_graph_dense_device', 'mem_graph_compact_device', 'mem_ferguson_device',
-    'mem_laplacian_dense_device', 'mem_symv_host', 'mem_lanczos_steps_device', 'mem_lanczos_ritz_device', 'mem_s2_assign_host', 'mem_s2_pairwise_host', 'mem_ctf_host',
+    'mem_laplacian_dense_device', 'mem_symv_host', 'mem_nlsa_spectra_device', 'mem_nlsa_cond_device', 'mem_nlsa_supervectors_device', 'mem_nlsa_gram_small_device',
+    'mem_nlsa_project_device', 'mem_nlsa_reconstruct_device', 'mem_lanczos_steps_device', 'mem_lanczos_ritz_device', 'mem_s2_assign_host', 'mem_s2_pairwise_host', 'mem_ctf_host',
     'mem_gather_square_device',
 ]
 
@@ -105,6 +106,13 @@ def load():
                                                  C.c_int32, C.c_void_p]
         lib.mem_lanczos_ritz_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                                 C.c_void_p]
+        vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+        lib.mem_nlsa_spectra_device.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
+        lib.mem_nlsa_cond_device.argtypes = [vp, vp, i32, i32, vp, i32, i32, vp, vp]
+        lib.mem_nlsa_supervectors_device.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]
+        lib.mem_nlsa_gram_small_device.argtypes = [vp, vp, i64, i32, vp, vp]
+        lib.mem_nlsa_project_device.argtypes = [vp, vp, i64, i32, vp, vp, i32, i32, vp, vp]
+        lib.mem_nlsa_reconstruct_device.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, vp]
         lib.mem_s2_pairwise_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         _lib = lib
         return lib

@@ -20,6 +20,17 @@ int lanczos_steps_device(mem_ctx* ctx, const double* L, int nS, double* V, doubl
                          cudaStream_t st);
 int lanczos_ritz_device(mem_ctx* ctx, const double* V, int nS, int j, const double* S_host, int k, double* X,
                         cudaStream_t st);
+int nlsa_spectra_device(mem_ctx* ctx, const double* img, const double* ctf, int n, int N, double2* H, double* Ch,
+                        cudaStream_t st);
+int nlsa_cond_device(mem_ctx* ctx, const void* D, int elem_bytes, int nAll, const int* sel, int num, int ConOrder,
+                     double* out, cudaStream_t st);
+int nlsa_supervectors_device(mem_ctx* ctx, const double2* H, const double* Ch, const int* sel, const double* mu_psi_host,
+                             int num, int ConOrder, int E, int N, const double* msk2, double* A, cudaStream_t st);
+int nlsa_gram_small_device(mem_ctx* ctx, const double* A, long long rows, int E, double* AtA_host, cudaStream_t st);
+int nlsa_project_device(mem_ctx* ctx, const double* A, long long rows, int E, const double* M_host, double* U, int Npix,
+                        int ConOrder, double* topo_host, cudaStream_t st);
+int nlsa_reconstruct_device(mem_ctx* ctx, const double* U, int Npix, int ConOrder, int E, const double* Q_host, int nI, int nC,
+                            double* IMGT, double* D2, cudaStream_t st);
 int s2_pairwise_host(mem_ctx* ctx, const double* U, int nU, const double* V, int nV, double* dot, double* dist);
 int ctf_host(mem_ctx* ctx, const mem_pd_params* prm, const double* df, double* out);
 int gather_square_device(mem_ctx* ctx, const void* D, int elem_bytes, int nS, const int* sel_host, int m, void* out,
@@ -404,6 +415,38 @@ int mem_lanczos_ritz_device(mem_ctx* ctx, const double* V, int32_t nS, int32_t j
                             void* stream) {
   MEM_CUDA(cudaSetDevice(ctx->device));
   return lanczos_ritz_device(ctx, V, nS, j, S_host, k, X, pick(ctx, stream));
+}
+
+int mem_nlsa_spectra_device(mem_ctx* ctx, const double* img, const double* ctf, int32_t n, int32_t N, void* H, double* Ch,
+                            void* stream) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  return nlsa_spectra_device(ctx, img, ctf, n, N, reinterpret_cast<double2*>(H), Ch, pick(ctx, stream));
+}
+int mem_nlsa_cond_device(mem_ctx* ctx, const void* D, int32_t elem_bytes, int32_t nAll, const int32_t* sel, int32_t num,
+                         int32_t ConOrder, double* ConD, void* stream) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  return nlsa_cond_device(ctx, D, elem_bytes, nAll, sel, num, ConOrder, ConD, pick(ctx, stream));
+}
+int mem_nlsa_supervectors_device(mem_ctx* ctx, const void* H, const double* Ch, const int32_t* sel, const double* mu_psi,
+                                 int32_t num, int32_t ConOrder, int32_t E, int32_t N, const double* msk2, double* A,
+                                 void* stream) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  return nlsa_supervectors_device(ctx, reinterpret_cast<const double2*>(H), Ch, sel, mu_psi, num, ConOrder, E, N, msk2, A,
+                                  pick(ctx, stream));
+}
+int mem_nlsa_gram_small_device(mem_ctx* ctx, const double* A, int64_t rows, int32_t E, double* AtA, void* stream) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  return nlsa_gram_small_device(ctx, A, (long long)rows, E, AtA, pick(ctx, stream));
+}
+int mem_nlsa_project_device(mem_ctx* ctx, const double* A, int64_t rows, int32_t E, const double* M, double* U, int32_t Npix,
+                            int32_t ConOrder, double* topo_mean, void* stream) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  return nlsa_project_device(ctx, A, (long long)rows, E, M, U, Npix, ConOrder, topo_mean, pick(ctx, stream));
+}
+int mem_nlsa_reconstruct_device(mem_ctx* ctx, const double* U, int32_t Npix, int32_t ConOrder, int32_t E, const double* Q,
+                                int32_t nI, int32_t nC, double* IMGT, double* D2, void* stream) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  return nlsa_reconstruct_device(ctx, U, Npix, ConOrder, E, Q, nI, nC, IMGT, D2, pick(ctx, stream));
 }
 
 int mem_s2_pairwise_host(mem_ctx* ctx, const double* U, int32_t nU, const double* V, int32_t nV, double* dot, double* dist) {

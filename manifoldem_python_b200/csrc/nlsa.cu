@@ -1,0 +1,458 @@
+// nlsa.cu — the NLSA / psi-analysis stage (modules/NLSA.py:23-158 with get_wiener.py:10-22,
+// svdRF.py:19-32, L2_distance.py:33-41) on the arrays the distance stage leaves behind (D, imgAll, CTF).  All float64:
+// the reference computes this stage in float64 and its outputs feed an SVD and a second diffusion map.
+//
+// What changes against the reference is the amount of work, not the result:
+//   * NLSA.py:66-86 Wiener-filters ConOrder x (num - ConOrder) images one by one (an fft2 / ifft2 pair each: 78,400 pairs
+//     at num = 2,000, ConOrder = 40) and multiplies the stack by mu_psi.  Everything in that loop is linear, so the
+//     weighted sum over the snapshots is taken in Fourier space,
+//         G[ii][e](k) = sum_i  F[ind3(ii, i)](k) CTF[ind3](k) / wiener_dom[i](k) * mu_psi[i][e],     ind3 = ConOrder - ii + i - 1,
+//     on the Hermitian half plane (images are real, the CTF is even), and only ConOrder x psiTrunc inverse transforms
+//     remain.  One forward transform per particle, shared by every psi of the PD (k_nlsa_weight_spectra).
+//   * the snapshot order of a psi (posPath[PosPsi1]) is an index list `sel` applied inside the kernels; D, the spectra
+//     and the CTF half planes are uploaded / computed once per PD and never permuted in memory.
+//   * IMGT (NLSA.py:113-126) is rank 2 by construction (ConImgT = sum_{r<2} U_r s_r V_r^T):
+//         IMGT[p][c] = sum_{i < ConOrder} sum_{r < 2} U[i Npix + p][r] * Q[r][i + c],   Q = diag(s) V^T psiC^T (2 x nI, host).
+// Layouts: spectra H [n][N][Nh] complex128 (cuFFT D2Z), A / U [ConOrder N^2][E] row-major with the reference's
+// transposed pixel order (row = ii N^2 + c N + r for picture pixel (r, c), NLSA.py:79), IMGT [nC][Npix] (frame-major).
+#include "common.cuh"
+
+namespace mem {
+
+#define NL_CUFFT(x) MEM_CUFFT(x)
+
+// H[img][k] = rfft2(img)[k] * CTF[img][k_full];  Ch[img][k] = CTF half plane
+__global__ void k_nlsa_weight_spectra(double2* __restrict__ H, const double* __restrict__ ctf, double* __restrict__ Ch,
+                                      int N, int Nh, size_t total) {
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t img = e / ((size_t)N * Nh);
+    const int rem = (int)(e - img * (size_t)N * Nh);
+    const int r = rem / Nh, c = rem - r * Nh;
+    const double w = ctf[(img * N + r) * N + c];
+    double2 h = H[e];
+    h.x *= w;
+    h.y *= w;
+    H[e] = h;
+    Ch[e] = w;
+  }
+}
+
+// NLSA.py:30-33: ConD[r][c] = sum_{i < ConOrder} DD[r + i][c + i], DD = D[sel][:, sel]; same summation order
+template <class T>
+__global__ void __launch_bounds__(256) k_nlsa_cond(const T* __restrict__ D, int nAll, const int* __restrict__ sel, int nI,
+                                                   int ConOrder, double* __restrict__ out) {
+  const int c = blockIdx.x * 256 + threadIdx.x, r = blockIdx.y;
+  if (c >= nI) return;
+  double acc = 0.0;
+  for (int i = 0; i < ConOrder; ++i) acc += (double)D[(size_t)sel[r + i] * nAll + sel[c + i]];
+  out[(size_t)r * nI + c] = acc;
+}
+
+// get_wiener.py:16-20: wd[i] = sum_{ii < ConOrder} CTF1[ConOrder - ii + i]^2 + 1/5 (that order); stores 1 / wd
+__global__ void __launch_bounds__(256) k_nlsa_wiener(const double* __restrict__ Ch, const int* __restrict__ sel, int nI,
+                                                     int ConOrder, int Kh, double* __restrict__ iw) {
+  const int k = blockIdx.x * 256 + threadIdx.x, i = blockIdx.y;
+  if (k >= Kh) return;
+  double acc = 0.0;
+  for (int ii = 0; ii < ConOrder; ++ii) {
+    const double c = Ch[(size_t)sel[ConOrder - ii + i] * Kh + k];
+    acc = acc + c * c;
+  }
+  iw[(size_t)i * Kh + k] = 1.0 / (acc + 1.0 / 5);
+}
+
+// G[ii][e][k] = sum_i H[sel[i + ConOrder - ii - 1]][k] * (mu_psi[i][e] * iw[i][k]);  ST shifts x E columns per thread
+constexpr int NL_ST = 4, NL_EMAX = 8;
+__global__ void __launch_bounds__(128) k_nlsa_supervector_spectra(const double2* __restrict__ H, const int* __restrict__ sel,
+                                                                  const double* __restrict__ iw,
+                                                                  const double* __restrict__ mu_psi, int nI, int ConOrder,
+                                                                  int E, int e0, int Kh, double2* __restrict__ G) {
+  extern __shared__ double s_mu[];                       // [chunk][NL_EMAX]
+  const int k = blockIdx.x * 128 + threadIdx.x;
+  const int ii0 = blockIdx.y * NL_ST;
+  const int ne = min(NL_EMAX, E - e0);
+  double2 acc[NL_ST][NL_EMAX];
+#pragma unroll
+  for (int s = 0; s < NL_ST; ++s)
+#pragma unroll
+    for (int e = 0; e < NL_EMAX; ++e) acc[s][e] = make_double2(0.0, 0.0);
+  constexpr int CH = 128;
+  for (int i0 = 0; i0 < nI; i0 += CH) {
+    const int ni = min(CH, nI - i0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < ni * NL_EMAX; t += 128) {
+      const int i = t / NL_EMAX, e = t - i * NL_EMAX;
+      s_mu[t] = e < ne ? mu_psi[(size_t)(i0 + i) * E + e0 + e] : 0.0;
+    }
+    __syncthreads();
+    if (k < Kh) {
+      for (int i = 0; i < ni; ++i) {
+        const double w = iw[(size_t)(i0 + i) * Kh + k];
+        double wm[NL_EMAX];
+#pragma unroll
+        for (int e = 0; e < NL_EMAX; ++e) wm[e] = s_mu[i * NL_EMAX + e] * w;
+#pragma unroll
+        for (int s = 0; s < NL_ST; ++s) {
+          const int ii = ii0 + s;
+          if (ii < ConOrder) {
+            const double2 h = H[(size_t)sel[i0 + i + ConOrder - ii - 1] * Kh + k];
+#pragma unroll
+            for (int e = 0; e < NL_EMAX; ++e) {
+              acc[s][e].x = fma(h.x, wm[e], acc[s][e].x);
+              acc[s][e].y = fma(h.y, wm[e], acc[s][e].y);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (k < Kh) {
+#pragma unroll
+    for (int s = 0; s < NL_ST; ++s) {
+      const int ii = ii0 + s;
+      if (ii < ConOrder) {
+#pragma unroll
+        for (int e = 0; e < NL_EMAX; ++e)
+          if (e < ne) G[((size_t)ii * E + e0 + e) * Kh + k] = acc[s][e];
+      }
+    }
+  }
+}
+
+// A[ii N^2 + c N + r][e] = g[ii][e][r][c] / N^2 * msk2[r][c]   (NLSA.py:75-79: ifft2(...).real * msk2, img.T.reshape(-1))
+__global__ void __launch_bounds__(256) k_nlsa_pack(const double* __restrict__ g, const double* __restrict__ msk2, int N, int E,
+                                                   double* __restrict__ A) {
+  __shared__ double tile[32][33];
+  const int ii = blockIdx.z / E, e = blockIdx.z - ii * E;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const double* src = g + ((size_t)ii * E + e) * N * N;
+  const double inv = 1.0 / ((double)N * N);
+  for (int y = ty; y < 32; y += 8) {
+    const int r = r0 + y, c = c0 + tx;
+    if (r < N && c < N) tile[y][tx] = src[(size_t)r * N + c] * inv * (msk2 ? msk2[(size_t)r * N + c] : 1.0);
+  }
+  __syncthreads();
+  for (int y = ty; y < 32; y += 8) {
+    const int c = c0 + y, r = r0 + tx;                   // consecutive threads -> consecutive r (rows of A)
+    if (r < N && c < N) A[((size_t)ii * N * N + (size_t)c * N + r) * E + e] = tile[tx][y];
+  }
+}
+
+// partial A^T A: CTA b sums rows [b * rows_per, ...) into part[b][E][E] (fixed order), reduced on the host side of the call
+__global__ void __launch_bounds__(256) k_nlsa_gram_small(const double* __restrict__ A, size_t rows, int E, size_t rows_per,
+                                                         double* __restrict__ part) {
+  __shared__ double red[8];
+  const size_t a = (size_t)blockIdx.x * rows_per, b = min(rows, a + rows_per);
+  for (int pq = 0; pq < E * E; ++pq) {
+    const int p = pq / E, q = pq - p * E;
+    if (q < p) continue;
+    double acc = 0.0;
+    for (size_t r = a + threadIdx.x; r < b; r += 256) acc = fma(A[r * E + p], A[r * E + q], acc);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int w = 0; w < 8; ++w) s += red[w];
+      part[(size_t)blockIdx.x * E * E + pq] = s;
+    }
+  }
+}
+
+// U = A M (svdRF.py:25: U = A (V S^-1)), M [E][E] row-major in constant-sized shared memory
+__global__ void __launch_bounds__(256) k_nlsa_project(const double* __restrict__ A, const double* __restrict__ M, size_t rows,
+                                                      int E, double* __restrict__ U) {
+  __shared__ double sM[32 * 32];
+  for (int t = threadIdx.x; t < E * E; t += 256) sM[t] = M[t];
+  __syncthreads();
+  const size_t r = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (r >= rows) return;
+  double a[32];
+  for (int p = 0; p < E; ++p) a[p] = A[r * E + p];
+  for (int q = 0; q < E; ++q) {
+    double acc = 0.0;
+    for (int p = 0; p < E; ++p) acc = fma(a[p], sM[p * E + q], acc);
+    U[r * E + q] = acc;
+  }
+}
+
+// NLSA.py:95-103: Topo_mean[p][e] = mean_k U[k Npix + p][e]
+__global__ void __launch_bounds__(256) k_nlsa_topo(const double* __restrict__ U, int Npix, int ConOrder, int E,
+                                                   double* __restrict__ topo) {
+  const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (t >= (size_t)Npix * E) return;
+  const size_t p = t / E;
+  const int e = (int)(t - p * E);
+  double acc = 0.0;
+  for (int k = 0; k < ConOrder; ++k) acc += U[((size_t)k * Npix + p) * E + e];
+  topo[t] = acc / ConOrder;
+}
+
+// IMGT[c][p] = sum_i sum_{r<2} U[i Npix + p][r] Q[r][i + c]   (NLSA.py:106-126); CT frames per thread
+constexpr int NL_CT = 8;
+__global__ void __launch_bounds__(128) k_nlsa_reconstruct(const double* __restrict__ U, const double* __restrict__ Q, int Npix,
+                                                          int ConOrder, int E, int nI, int nC, double* __restrict__ IMGT) {
+  extern __shared__ double sQ[];                         // [2][ConOrder + NL_CT]
+  const int c0 = blockIdx.y * NL_CT;
+  const int span = ConOrder + NL_CT;
+  for (int t = threadIdx.x; t < 2 * span; t += 128) {
+    const int r = t / span, m = t - r * span;
+    sQ[t] = (c0 + m < nI) ? Q[(size_t)r * nI + c0 + m] : 0.0;
+  }
+  __syncthreads();
+  const int p = blockIdx.x * 128 + threadIdx.x;
+  if (p >= Npix) return;
+  double acc[NL_CT];
+#pragma unroll
+  for (int c = 0; c < NL_CT; ++c) acc[c] = 0.0;
+  for (int i = 0; i < ConOrder; ++i) {
+    const double u0 = U[((size_t)i * Npix + p) * E], u1 = U[((size_t)i * Npix + p) * E + 1];
+#pragma unroll
+    for (int c = 0; c < NL_CT; ++c) acc[c] = fma(u1, sQ[span + i + c], fma(u0, sQ[i + c], acc[c]));
+  }
+#pragma unroll
+  for (int c = 0; c < NL_CT; ++c)
+    if (c0 + c < nC) IMGT[(size_t)(c0 + c) * Npix + p] = acc[c];
+}
+
+// NLSA.py:129-136: every frame to mean 0, std 1 (population std, two passes); one CTA per frame.  Also aa = sum x^2.
+__global__ void __launch_bounds__(256) k_nlsa_normalize(double* __restrict__ IMGT, int Npix, double* __restrict__ aa) {
+  __shared__ double red[8];
+  __shared__ double bc;
+  double* x = IMGT + (size_t)blockIdx.x * Npix;
+  auto bsum = [&](double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int w = 0; w < 8; ++w) s += red[w];
+      bc = s;
+    }
+    __syncthreads();
+    return bc;
+  };
+  double s = 0.0;
+  for (int p = threadIdx.x; p < Npix; p += 256) s += x[p];
+  const double mean = bsum(s) / Npix;
+  double v = 0.0;
+  for (int p = threadIdx.x; p < Npix; p += 256) {
+    const double d = x[p] - mean;
+    v = fma(d, d, v);
+  }
+  const double sd = sqrt(bsum(v) / Npix);
+  double q = 0.0;
+  for (int p = threadIdx.x; p < Npix; p += 256) {
+    const double y = (x[p] - mean) / sd;
+    x[p] = y;
+    q = fma(y, y, q);
+  }
+  q = bsum(q);
+  if (threadIdx.x == 0) aa[blockIdx.x] = q;
+}
+
+// L2_distance.py:36-41 then **2 (NLSA.py:144): D2[a][b] = sqrt(t)^2, t = aa[a] + aa[b] - 2 <x_a, x_b>, t < 1e-8 -> 0.
+// 64 x 64 tile per CTA (256 threads, 4 x 4 per thread), K chunks of 16 through shared memory; upper-triangle tiles only,
+// mirrored on the way out.
+__global__ void __launch_bounds__(256) k_nlsa_l2(const double* __restrict__ X, const double* __restrict__ aa, int nC, int Npix,
+                                                 double* __restrict__ D2) {
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj < bi) return;
+  __shared__ double sa[16][65], sb[16][65];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  const int lr = threadIdx.x >> 2, lk = (threadIdx.x & 3) * 4;     // loader: 64 rows x 16 k, 4 consecutive k per thread
+  for (int k0 = 0; k0 < Npix; k0 += 16) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = k0 + lk + q;
+      const int ra = bi * 64 + lr, rb = bj * 64 + lr;
+      sa[lk + q][lr] = (ra < nC && k < Npix) ? X[(size_t)ra * Npix + k] : 0.0;
+      sb[lk + q][lr] = (rb < nC && k < Npix) ? X[(size_t)rb * Npix + k] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sa[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sb[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = bi * 64 + ty * 4 + i, c = bj * 64 + tx * 4 + j;
+      if (r < nC && c < nC) {
+        double t = aa[r] + aa[c] - 2 * acc[i][j];
+        if (t < 1e-8) t = 0.0;
+        const double s = sqrt(t);
+        t = s * s;
+        D2[(size_t)r * nC + c] = t;
+        if (bj > bi) D2[(size_t)c * nC + r] = t;
+      }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static int plan_many_d(cufftHandle* h, int N, int batch, cufftType type, cudaStream_t st) {
+  int n[2] = {N, N};
+  NL_CUFFT(cufftPlanMany(h, 2, n, nullptr, 1, 0, nullptr, 1, 0, type, batch));
+  NL_CUFFT(cufftSetStream(*h, st));
+  return 0;
+}
+
+int nlsa_spectra_device(mem_ctx* ctx, const double* img, const double* ctf, int n, int N, double2* H, double* Ch,
+                        cudaStream_t st) {
+  if (n < 1 || N < 2) {
+    set_error("nlsa_spectra: need n >= 1 and N >= 2 (n=%d N=%d)", n, N);
+    return 1;
+  }
+  const int Nh = N / 2 + 1;
+  // batches of at most 512 images bound the cuFFT work area
+  for (int a = 0; a < n; a += 512) {
+    const int nb = std::min(512, n - a);
+    cufftHandle pl;
+    MEM_CHECK(plan_many_d(&pl, N, nb, CUFFT_D2Z, st));
+    cufftResult r = cufftExecD2Z(pl, const_cast<double*>(img) + (size_t)a * N * N,
+                                 reinterpret_cast<cufftDoubleComplex*>(H + (size_t)a * N * Nh));
+    cufftDestroy(pl);
+    if (r != CUFFT_SUCCESS) {
+      set_error("cufftExecD2Z failed (%d)", (int)r);
+      return 1;
+    }
+  }
+  const size_t total = (size_t)n * N * Nh;
+  MEM_LAUNCH(ctx, k_nlsa_weight_spectra, (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16), 256, 0, st, H, ctf, Ch, N, Nh,
+             total);
+  return 0;
+}
+
+int nlsa_cond_device(mem_ctx* ctx, const void* D, int elem_bytes, int nAll, const int* sel, int num, int ConOrder,
+                     double* out, cudaStream_t st) {
+  const int nI = num - ConOrder;
+  if (nI < 1 || ConOrder < 1 || (elem_bytes != 4 && elem_bytes != 8)) {
+    set_error("nlsa_cond: need 1 <= ConOrder < num and float32 / float64 D (num=%d ConOrder=%d)", num, ConOrder);
+    return 1;
+  }
+  const dim3 grid((nI + 255) / 256, nI);
+  if (elem_bytes == 8) MEM_LAUNCH(ctx, k_nlsa_cond<double>, grid, 256, 0, st, (const double*)D, nAll, sel, nI, ConOrder, out);
+  else MEM_LAUNCH(ctx, k_nlsa_cond<float>, grid, 256, 0, st, (const float*)D, nAll, sel, nI, ConOrder, out);
+  return 0;
+}
+
+// A [ConOrder N^2][E] from the weighted spectra; mu_psi [nI][E] float64 on the HOST; msk2 [N][N] float64 device or null
+int nlsa_supervectors_device(mem_ctx* ctx, const double2* H, const double* Ch, const int* sel, const double* mu_psi_host,
+                             int num, int ConOrder, int E, int N, const double* msk2, double* A, cudaStream_t st) {
+  const int nI = num - ConOrder, Nh = N / 2 + 1, Kh = N * Nh;
+  if (nI < 1 || ConOrder < 1 || E < 1 || E > 32) {
+    set_error("nlsa_supervectors: need 1 <= ConOrder < num and 1 <= E <= 32 (num=%d ConOrder=%d E=%d)", num, ConOrder, E);
+    return 1;
+  }
+  const size_t b_iw = ((size_t)nI * Kh * sizeof(double) + 255) & ~(size_t)255;
+  const size_t b_mu = ((size_t)nI * E * sizeof(double) + 255) & ~(size_t)255;
+  const size_t b_G = ((size_t)ConOrder * E * Kh * sizeof(double2) + 255) & ~(size_t)255;
+  const size_t b_g = (size_t)ConOrder * E * N * N * sizeof(double);
+  MEM_CHECK(ctx->scratch.ensure(b_iw + b_mu + b_G + b_g));
+  uint8_t* base = ctx->scratch.as<uint8_t>();
+  double* iw = reinterpret_cast<double*>(base);
+  double* mu = reinterpret_cast<double*>(base + b_iw);
+  double2* G = reinterpret_cast<double2*>(base + b_iw + b_mu);
+  double* g = reinterpret_cast<double*>(base + b_iw + b_mu + b_G);
+  MEM_CUDA(cudaMemcpyAsync(mu, mu_psi_host, (size_t)nI * E * sizeof(double), cudaMemcpyHostToDevice, st));
+  MEM_CUDA(cudaStreamSynchronize(st));                      // mu_psi_host may be a temporary of the caller
+  MEM_LAUNCH(ctx, k_nlsa_wiener, dim3((Kh + 255) / 256, nI), 256, 0, st, Ch, sel, nI, ConOrder, Kh, iw);
+  for (int e0 = 0; e0 < E; e0 += NL_EMAX)
+    MEM_LAUNCH(ctx, k_nlsa_supervector_spectra, dim3((Kh + 127) / 128, (ConOrder + NL_ST - 1) / NL_ST), 128,
+               128 * NL_EMAX * sizeof(double), st, H, sel, iw, mu, nI, ConOrder, E, e0, Kh, G);
+  {
+    cufftHandle pl;
+    MEM_CHECK(plan_many_d(&pl, N, ConOrder * E, CUFFT_Z2D, st));
+    cufftResult r = cufftExecZ2D(pl, reinterpret_cast<cufftDoubleComplex*>(G), g);
+    cufftDestroy(pl);
+    if (r != CUFFT_SUCCESS) {
+      set_error("cufftExecZ2D failed (%d)", (int)r);
+      return 1;
+    }
+  }
+  MEM_LAUNCH(ctx, k_nlsa_pack, dim3((N + 31) / 32, (N + 31) / 32, ConOrder * E), 256, 0, st, g, msk2, N, E, A);
+  return 0;
+}
+
+// AtA [E][E] (HOST) = A^T A
+int nlsa_gram_small_device(mem_ctx* ctx, const double* A, long long rows, int E, double* AtA_host, cudaStream_t st) {
+  if (E < 1 || E > 32 || rows < 1) {
+    set_error("nlsa_gram_small: 1 <= E <= 32, rows >= 1");
+    return 1;
+  }
+  const int nb = (int)std::min<long long>(296, (rows + 1023) / 1024);
+  const size_t rows_per = ((size_t)rows + nb - 1) / nb;
+  MEM_CHECK(ctx->small_out.ensure((size_t)nb * E * E * sizeof(double)));
+  double* part = ctx->small_out.as<double>();
+  MEM_CUDA(cudaMemsetAsync(part, 0, (size_t)nb * E * E * sizeof(double), st));
+  MEM_LAUNCH(ctx, k_nlsa_gram_small, nb, 256, 0, st, A, (size_t)rows, E, rows_per, part);
+  std::vector<double> h((size_t)nb * E * E);
+  MEM_CUDA(cudaMemcpyAsync(h.data(), part, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  MEM_CUDA(cudaStreamSynchronize(st));
+  for (int p = 0; p < E; ++p)
+    for (int q = p; q < E; ++q) {
+      double s = 0.0;
+      for (int b = 0; b < nb; ++b) s += h[(size_t)b * E * E + p * E + q];
+      AtA_host[p * E + q] = AtA_host[q * E + p] = s;
+    }
+  return 0;
+}
+
+// U = A M (M [E][E] HOST), Topo_mean [Npix][E] -> HOST
+int nlsa_project_device(mem_ctx* ctx, const double* A, long long rows, int E, const double* M_host, double* U, int Npix,
+                        int ConOrder, double* topo_host, cudaStream_t st) {
+  if (E < 2 || E > 32 || rows != (long long)Npix * ConOrder) {
+    set_error("nlsa_project: 2 <= E <= 32 and rows == Npix * ConOrder");
+    return 1;
+  }
+  MEM_CHECK(ctx->small_out.ensure((size_t)E * E * sizeof(double) + (size_t)Npix * E * sizeof(double)));
+  double* dM = ctx->small_out.as<double>();
+  double* dT = dM + E * E;
+  MEM_CUDA(cudaMemcpyAsync(dM, M_host, (size_t)E * E * sizeof(double), cudaMemcpyHostToDevice, st));
+  MEM_CUDA(cudaStreamSynchronize(st));
+  MEM_LAUNCH(ctx, k_nlsa_project, (unsigned)((rows + 255) / 256), 256, 0, st, A, dM, (size_t)rows, E, U);
+  MEM_LAUNCH(ctx, k_nlsa_topo, (unsigned)(((size_t)Npix * E + 255) / 256), 256, 0, st, U, Npix, ConOrder, E, dT);
+  MEM_CUDA(cudaMemcpyAsync(topo_host, dT, (size_t)Npix * E * sizeof(double), cudaMemcpyDeviceToHost, st));
+  MEM_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// IMGT [nC][Npix] (device, normalised frames) and D2 [nC][nC] (device) = L2_distance(IMGT, IMGT)^2; Q [2][nI] HOST
+int nlsa_reconstruct_device(mem_ctx* ctx, const double* U, int Npix, int ConOrder, int E, const double* Q_host, int nI, int nC,
+                            double* IMGT, double* D2, cudaStream_t st) {
+  if (nC < 1 || nC + ConOrder > nI + 0 || E < 2) {
+    set_error("nlsa_reconstruct: need 1 <= nC <= nI - ConOrder and E >= 2 (nC=%d nI=%d ConOrder=%d)", nC, nI, ConOrder);
+    return 1;
+  }
+  MEM_CHECK(ctx->small_out.ensure((size_t)(2 * nI + nC) * sizeof(double)));
+  double* dQ = ctx->small_out.as<double>();
+  double* aa = dQ + 2 * nI;
+  MEM_CUDA(cudaMemcpyAsync(dQ, Q_host, (size_t)2 * nI * sizeof(double), cudaMemcpyHostToDevice, st));
+  MEM_CUDA(cudaStreamSynchronize(st));
+  MEM_LAUNCH(ctx, k_nlsa_reconstruct, dim3((Npix + 127) / 128, (nC + NL_CT - 1) / NL_CT), 128,
+             2 * (ConOrder + NL_CT) * sizeof(double), st, U, dQ, Npix, ConOrder, E, nI, nC, IMGT);
+  MEM_LAUNCH(ctx, k_nlsa_normalize, nC, 256, 0, st, IMGT, Npix, aa);
+  if (D2) MEM_LAUNCH(ctx, k_nlsa_l2, dim3((nC + 63) / 64, (nC + 63) / 64), 256, 0, st, IMGT, aa, nC, Npix, D2);
+  return 0;
+}
+
+}  // namespace mem

@@ -13,7 +13,8 @@ def init():
              avg_vol_file='', img_stack_file='', align_param_file='', mask_vol_file='', num_part=0,
              Cs=0.0, EkV=0.0, AmpContrast=0.0, gaussEnv=np.inf, nPix=0, pix_size=0.0,
              PDsizeThL=100, PDsizeThH=2000, numberofJobs=0,
-             num_eigs=15, num_psiTrunc=8, tune=3, rad=5,
+             num_eigs=15, num_psiTrunc=8, num_psis=8, tune=3, rad=5, conOrderRange=50, nClass=50, trajName='1',
+             psi2_dir='', psi2_prog='', psi2_file='', EL_dir='', EL_prog='', EL_file='',
              tess_file='', dist_dir='', dist_prog='', dist_file='', psi_dir='', psi_prog='', psi_file='')
     return None
 

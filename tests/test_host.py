@@ -636,3 +636,26 @@ def test_lanczos_host_selection_against_dense_eigh():
     V, alpha, beta = lanczos(L, 8, v0)
     theta, S, j_eff, done = lanczos_ritz_selection(alpha, beta, k, nS, 1e-12)
     assert done and j_eff == 4 and np.allclose(np.sort(theta), np.sort(lam[:4]), atol=1e-9)
+
+
+def test_vectorised_manifold_fit_equals_the_per_point_restatement(golden_dir):
+    """fit_1D_open_manifold_3D drop-in (one batched eigvals per iteration) vs the oracle's per-point np.roots loop, on
+    the reference's own psirec outputs and on random curves (incl. a degenerate a_3 = 0 start)."""
+    from manifoldem_python_b200 import fit_1D_open_manifold_3D as fit
+    from oracle import nlsa as onl
+    g = np.load(os.path.join(golden_dir, 'nlsa_nS80_N24.npz'))
+    cases = [g['m1_psi0_psirec'], g['md_psi1_psirec']]
+    rng = np.random.default_rng(2)
+    t = rng.uniform(0, 1, 120)
+    cases.append(np.stack([np.cos(np.pi * t), 0.5 * np.cos(2 * np.pi * t), 0.2 * np.cos(3 * np.pi * t)], 1)
+                 + 0.01 * rng.standard_normal((120, 3)))
+    for psi in cases:
+        a, b, tau = fit.op(psi)
+        a0, b0, tau0 = onl.fit_1d_open_manifold_3d(psi)
+        assert np.allclose(a, a0, rtol=1e-12, atol=0) and np.allclose(b, b0, rtol=1e-12, atol=1e-15)
+        assert tau.shape == tau0.shape and np.abs(tau - tau0).max() < 1e-12
+    ref_tau = g['m1_psi0_tau']
+    assert np.abs(fit.op(g['m1_psi0_psirec'])[2] - ref_tau).max() < 1e-9
+    x = np.stack([np.cos(np.pi * t), 0.5 * np.cos(2 * np.pi * t), np.zeros_like(t)], 1)
+    assert np.array_equal(fit._taus(x, np.array([1.0, 0.5, 0.0]), np.zeros(3)),
+                          np.array([onl._tau_of_point(x[p], np.array([1.0, 0.5, 0.0]), np.zeros(3)) for p in range(120)]))
