@@ -49,12 +49,21 @@ class PdState:
         self.D = self.H = self.Ch = None
 
 
-def analyse(state, sel_D, sel_img, NLSAPar, msk2, keep_IMGT_on_device=False):
+def analyse(state, sel_D, sel_img, NLSAPar, msk2, keep_IMGT_on_device=False, timings=None):
     """NLSA.op on a PdState.  sel_D: rows / columns of state.D in snapshot order (DD = D[sel_D][:, sel_D]); sel_img: particle
     index of every snapshot (posPath[posPsi1]).  Returns the reference's 8-tuple; with keep_IMGT_on_device the first entry is
     a `_lib.DeviceArray` [nC][Npix] (frame-major) instead of the (Npix, nC) NumPy array."""
+    import time
     lib = _lib.load()
     ctx = state.ctx
+    clock = [time.perf_counter()]
+
+    def lap(name):
+        if timings is not None:
+            ctx.sync()
+            now = time.perf_counter()
+            timings[name] = timings.get(name, 0.0) + (now - clock[0]) * 1e3
+            clock[0] = now
     num, ConOrder, k, tune = int(NLSAPar['num']), int(NLSAPar['ConOrder']), int(NLSAPar['k']), NLSAPar['tune']
     nS, psiTrunc = int(NLSAPar['nS']), int(NLSAPar['psiTrunc'])
     N, nI = state.N, num - ConOrder
@@ -66,8 +75,10 @@ def analyse(state, sel_D, sel_img, NLSAPar, msk2, keep_IMGT_on_device=False):
     ConD = _lib.DeviceArray(ctx, (nI, nI), np.float64)
     _lib.check(lib.mem_nlsa_cond_device(ctx.handle, state.D.ptr, state.D.dtype.itemsize, state.D.shape[0], selD.ptr, num, ConOrder,
                                         ConD.ptr, None))
+    lap('ConD')
     lambdaC, psiC, sigmaC, mu, logEps, logSumWij, popt, R_squared = DMembeddingII.embed(ConD, k, tune)
     ConD.free()
+    lap('embed_ConD')
     psiC1 = np.copy(psiC)
     ell = psiTrunc - 1
     E = ell + 1
@@ -83,6 +94,7 @@ def analyse(state, sel_D, sel_img, NLSAPar, msk2, keep_IMGT_on_device=False):
         m2 = _lib.DeviceArray(ctx, (N, N), np.float64, np.full((N, N), float(msk2)))
     _lib.check(lib.mem_nlsa_supervectors_device(ctx.handle, state.H.ptr, state.Ch.ptr, selI.ptr, mu_psi.ctypes.data, num, ConOrder,
                                                 E, N, m2.ptr if m2 is not None else None, A.ptr, None))
+    lap('supervectors')
     # ---- svdRF.op :19-26 (D1 > D2 branch): eigh of A^T A on the host, U = A V S^-1 on the device
     AtA = np.empty((E, E))
     _lib.check(lib.mem_nlsa_gram_small_device(ctx.handle, A.ptr, rows, E, AtA.ctypes.data, None))
@@ -98,6 +110,7 @@ def analyse(state, sel_D, sel_img, NLSAPar, msk2, keep_IMGT_on_device=False):
     _lib.check(lib.mem_nlsa_project_device(ctx.handle, A.ptr, rows, E, M.ctypes.data, U.ptr, N * N, ConOrder, Topo_mean.ctypes.data,
                                            None))
     A.free()
+    lap('svd')
     VX = np.matmul(V.T, psiC.T)                                                  # :89
     sdiag = np.diag(S)                                                           # :91 — 1-D: np.diag of svdRF's diagonal matrix
     # ---- :106-144 frames from the first two singular triplets, normalised; squared L2 distances
@@ -107,9 +120,12 @@ def analyse(state, sel_D, sel_img, NLSAPar, msk2, keep_IMGT_on_device=False):
     D2 = _lib.DeviceArray(ctx, (nC, nC), np.float64)
     _lib.check(lib.mem_nlsa_reconstruct_device(ctx.handle, U.ptr, N * N, ConOrder, E, Q.ctypes.data, nI, nC, IMGT_d.ptr, D2.ptr, None))
     U.free()
+    lap('reconstruct_l2')
     lamb, psirec, sigma, mu, logEps, logSumWij, popt, R_squared = DMembeddingII.embed(D2, nC, tune)     # :146
     D2.free()
+    lap('embed_recon')
     a, b, tau = fit_1D_open_manifold_3D.op(psirec)                               # :149
+    lap('manifold_fit')
     for d in (selD, selI, m2):
         if d is not None:
             d.free()

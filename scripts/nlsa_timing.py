@@ -34,10 +34,13 @@ for rep in range(2):
     for psinum in range(npsi):
         sel = np.argsort(psi[:, psinum])
         t2 = time.perf_counter()
-        out = NLSA.analyse(state, sel, sel, par, 1, keep_IMGT_on_device=True)
+        tm = {}
+        out = NLSA.analyse(state, sel, sel, par, 1, keep_IMGT_on_device=True, timings=tm if rep else None)
         state.ctx.sync()
         t3 = time.perf_counter()
         out[0].free()
         print('rep %d psi %d: analyse %.1f ms   (reference: %d fft2/ifft2 pairs of %d^2 + a %d x %d x %d float64 Gram)'
               % (rep, psinum, (t3 - t2) * 1e3, ConOrder * (nS - ConOrder), N, nS - 2 * ConOrder, nS - 2 * ConOrder, N * N))
+        if tm:
+            print('    ', {k: round(v, 1) for k, v in tm.items()})
 state.free()
