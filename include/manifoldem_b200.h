@@ -116,6 +116,15 @@ typedef struct {
 /* all pointers in io are DEVICE pointers; work is enqueued on `stream` (a cudaStream_t, NULL = the
  * context's stream); no host synchronisation. */
 int mem_pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* io, void* stream);
+/* A GROUP of PDs in one call (GetDistancesS2.py:94-120 hands its workers one PD at a time; the tessellation's PDs hold
+ * 117..2,000 particles, too few to fill the GPU one by one).  prm->nS = images of all PDs, io->raw / flip / psi_deg / df
+ * = the PDs' arrays back to back (PD g = images pd_start[g] .. pd_start[g+1]-1, pd_start [n_pd + 1] on the HOST, from 0 to
+ * nS), psi_p_deg [n_pd] on the HOST (prm->psi_p_deg is ignored).  io->D receives the n_pd matrices back to back (PD g at
+ * float offset sum_{h<g} nS_h^2); io->imgAll is optional; every other output, msk2 and the RELION shift are not available
+ * here.  Device pointers; the per-image stages run once over the concatenated stack and one grouped tcgen05 launch
+ * contracts all PDs.  Synchronises twice (two small host tables are uploaded). */
+int mem_pd_distance_batch_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* io, int32_t n_pd,
+                                 const int32_t* pd_start, const double* psi_p_deg, void* stream);
 /* all pointers in io are HOST pointers; stages H2D, runs, copies results back, synchronises. */
 int mem_pd_distance_host(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* io);
 /* the CTF field alone (ctemh_cryoFrank.op, modules/ctemh_cryoFrank.py:24-44, as :339 / :393 store it): uses nS, N,

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'libmanifoldem_b200.so')
 SYMBOLS = [
     'mem_version', 'mem_last_error', 'mem_ctx_create', 'mem_ctx_destroy', 'mem_ctx_sync', 'mem_ctx_set_option', 'mem_ctx_launch_count',
     'mem_ctx_timer_start', 'mem_ctx_timer_stop', 'mem_ctx_kernel_time', 'mem_ctx_kernel_clock', 'mem_host_alloc', 'mem_host_free', 'mem_gather_rows_host', 'mem_dev_alloc', 'mem_dev_free', 'mem_copy_h2d', 'mem_copy_d2h',
-    'mem_pd_distance_device', 'mem_pd_distance_host', 'mem_pd_last_timings', 'mem_contract_device',
+    'mem_pd_distance_device', 'mem_pd_distance_batch_device', 'mem_pd_distance_host', 'mem_pd_last_timings', 'mem_contract_device',
     'mem_contract_knn_device', 'mem_knn_mode',
     'mem_operand_shape', 'mem_knn_device', 'mem_knn_device_f32', 'mem_graph_dense_device', 'mem_graph_compact_device', 'mem_ferguson_device',
     'mem_laplacian_dense_device', 'mem_symv_host', 'mem_nlsa_spectra_device', 'mem_nlsa_cond_device', 'mem_nlsa_supervectors_device', 'mem_nlsa_gram_small_device',
@@ -113,6 +113,7 @@ def load():
         lib.mem_nlsa_gram_small_device.argtypes = [vp, vp, i64, i32, vp, vp]
         lib.mem_nlsa_project_device.argtypes = [vp, vp, i64, i32, vp, vp, i32, i32, vp, vp]
         lib.mem_nlsa_reconstruct_device.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, vp]
+        lib.mem_pd_distance_batch_device.argtypes = [vp, C.POINTER(PdParams), C.POINTER(PdIO), i32, vp, vp, vp]
         lib.mem_s2_pairwise_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         _lib = lib
         return lib

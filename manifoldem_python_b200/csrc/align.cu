@@ -620,4 +620,18 @@ int align_run(mem_ctx* ctx, float* A, float* B, float* imgAll, const double* psi
   return 0;
 }
 
+// Batched PDs (pd_distance_batch_device): the same chain over the concatenated stack; cs2 / pid2 [nS] carry the second
+// rotation's angle per image (its PD's -psi_p).  Boxes that are a multiple of 32 only; no msk2.
+int align_batch_run(mem_ctx* ctx, float* A, float* B, float* imgAll, const double* psi_deg, double2* cs, const double2* cs2,
+                    const uint8_t* pid2, int nS, int N, cudaStream_t st, int rows_done) {
+  MEM_CHECK(ctx->rot_pid.ensure((size_t)nS));
+  uint8_t* pid = ctx->rot_pid.as<uint8_t>();
+  MEM_CHECK(rotate_angles_run(ctx, psi_deg, 0.0, cs, pid, nS, st));
+  MEM_CHECK(prefilter_run(ctx, B, A, nS, N, 1, 0, st, rows_done));
+  MEM_CHECK(rotate_img_run(ctx, A, B, cs, pid, nS, N, st));
+  MEM_CHECK(prefilter_run(ctx, B, A, nS, N, 0, 0, st));
+  MEM_CHECK(rotate_img_run(ctx, A, imgAll, cs2, pid2, nS, N, st));
+  return 0;
+}
+
 }  // namespace mem

@@ -9,6 +9,8 @@
 namespace mem {
 const char* last_error();
 int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* io, cudaStream_t st);
+int pd_distance_batch_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* io, int n_pd, const int* pd_start,
+                             const double* psi_p_deg, cudaStream_t st);
 int knn_device(mem_ctx* ctx, const double* D, int nS, int k, int* idx, double* val, cudaStream_t st);
 int graph_compact_device(mem_ctx* ctx, const double* M, int nS, double* out, long long* count);
 int graph_dense_device(mem_ctx* ctx, const int* idx, const double* val, int nS, int k, double* M, cudaStream_t st);
@@ -73,7 +75,7 @@ int mem_ctx_destroy(mem_ctx* ctx) {
     cufftDestroy(kv.second.r2c);
     cufftDestroy(kv.second.c2r);
   }
-  mem::DevBuf* bufs[] = {&ctx->fft_work, &ctx->raw, &ctx->flip, &ctx->shift, &ctx->psi, &ctx->df, &ctx->msk2, &ctx->rot_cs, &ctx->rot_pid, &ctx->rot_pitch_tab,
+  mem::DevBuf* bufs[] = {&ctx->fft_work, &ctx->raw, &ctx->flip, &ctx->shift, &ctx->psi, &ctx->df, &ctx->msk2, &ctx->rot_cs, &ctx->rot_pid, &ctx->rot_pitch_tab, &ctx->batch_aux,
                          &ctx->imgA, &ctx->imgB, &ctx->imgAll, &ctx->imgFlip, &ctx->spec, &ctx->spec2, &ctx->cbin, &ctx->zhi,
                          &ctx->zlo, &ctx->part_cf, &ctx->part_cfw, &ctx->part_c2, &ctx->part_fl, &ctx->part_int, &ctx->avgspec, &ctx->avgimg,
                          &ctx->stats, &ctx->D, &ctx->ctf64, &ctx->small_out, &ctx->contract_ws, &ctx->contract_items, &ctx->clk_probe, &ctx->scratch,
@@ -215,6 +217,12 @@ int mem_copy_d2h(mem_ctx* ctx, void* dst, const void* src, size_t bytes) {
 int mem_pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* io, void* stream) {
   MEM_CUDA(cudaSetDevice(ctx->device));
   return pd_distance_device(ctx, prm, io, pick(ctx, stream));
+}
+
+int mem_pd_distance_batch_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* io, int32_t n_pd,
+                                 const int32_t* pd_start, const double* psi_p_deg, void* stream) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  return pd_distance_batch_device(ctx, prm, io, n_pd, pd_start, psi_p_deg, pick(ctx, stream));
 }
 
 int mem_pd_distance_host(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* h) {

@@ -97,7 +97,7 @@ struct mem_ctx {
   std::map<long long, mem::FftPlan> plans;   // key = N * 2^20 + batch
   mem::DevBuf fft_work;
   // workspace for one PD
-  mem::DevBuf raw, flip, shift, psi, df, msk2, rot_cs, rot_pid, rot_pitch_tab;
+  mem::DevBuf raw, flip, shift, psi, df, msk2, rot_cs, rot_pid, rot_pitch_tab, batch_aux;
   mem::DevBuf imgA, imgB, imgAll, imgFlip, spec, spec2, cbin, zhi, zlo;
   mem::DevBuf part_cf, part_cfw, part_c2, part_fl, part_int, avgspec, avgimg, stats;
   mem::DevBuf D, ctf64, small_out;
@@ -146,6 +146,10 @@ void knn_set_mode(int mode);
 bool rotate_fast_supported(int N);
 int rotate_angles_run(mem_ctx* ctx, const double* psi_deg, double psi_p_deg, double2* cs, uint8_t* pid, int nS,
                       cudaStream_t st);
+int rotate_angles_batch_run(mem_ctx* ctx, const int* pd_of, const double* psi_p_deg, double2* cs2, uint8_t* pid2, int nS,
+                            cudaStream_t st);
+int contract_tc_grouped(mem_ctx* ctx, const mem_contract_shape* shp, int n_pd, const int* pd_start, const float* Zhi,
+                        const float* Zlo, float* const* D, cudaStream_t st);
 int rotate_img_run(mem_ctx* ctx, const float* coef, float* out, const double2* cs, const uint8_t* pid, int nS, int N,
                    cudaStream_t st);
 int rotate_common_run(mem_ctx* ctx, const float* coef, float* out, const double2* cs_common, double angle_deg, int nS,

@@ -32,7 +32,10 @@ constexpr int STAGE_BYTES = 6 * BOX_BYTES;              // A_hi, A_lo, B_hi(2), 
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int NUM_THREADS = 320;
 
-struct WorkItem { int row0, col0, kb0, kb1, slice, pad0, pad1, pad2; };
+// row0 / col0: tile origin inside its PD; zbase: first row of that PD in the (possibly concatenated) operand matrix;
+// nrows / ldw / ws_off: the PD's size, workspace pitch and workspace offset (floats) — a grouped launch carries the tiles
+// of several PDs in one work list (pd_distance_batch_device); pad0 / pad1: pacing group and its size.
+struct WorkItem { int row0, col0, kb0, kb1, slice, pad0, pad1, zbase, nrows, ldw; long long ws_off; };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -355,7 +358,7 @@ k_contract_tc2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       // ===== TMA producer (both CTAs; each loads its own halves, transaction bytes land on the leader's barrier) =====
       int stage = 0;
       uint32_t phase = 0;
-      const int arow = it.row0 + (int)rank * BOX_ROWS, brow = it.col0 + (int)rank * BOX_ROWS;
+      const int arow = it.zbase + it.row0 + (int)rank * BOX_ROWS, brow = it.zbase + it.col0 + (int)rank * BOX_ROWS;
       // Pacing (multi-wave launches only): the tiles of a super-block share operand panels through the L2 only while
       // they read the same k-blocks at about the same time.  Every PACE_M k-blocks the leader's producer counts
       // itself in at a milestone and does not run more than PACE_W milestones ahead of the slowest tile of its
@@ -459,11 +462,11 @@ k_contract_tc2(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     }
     const int row = it.row0 + (int)rank * BOX_ROWS + q * 32 + lane;
     const int col0 = it.col0 + cg * 64;
-    if (row < nS) {
-      float* dst = ws + ((size_t)it.slice * ldw + row) * ldw + col0;
+    if (row < it.nrows) {
+      float* dst = ws + it.ws_off + ((size_t)it.slice * it.ldw + row) * it.ldw + col0;
 #pragma unroll
       for (int j = 0; j < 64; j += 4) {
-        if (col0 + j < ldw)
+        if (col0 + j < it.ldw)
           *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
       }
     }
@@ -602,7 +605,7 @@ int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, c
   for (int s = 0; s < split; ++s) {
     const int kb0 = (int)((long long)nkb * s / split), kb1 = (int)((long long)nkb * (s + 1) / split);
     for (size_t ti = 0; ti < tiles.size(); ++ti)
-      items.push_back({tiles[ti].first * TM, tiles[ti].second * BN, kb0, kb1, s, 0, 0, 0});
+      items.push_back({tiles[ti].first * TM, tiles[ti].second * BN, kb0, kb1, s, 0, 0, 0, nS, ldw, 0});
   }
   // pacing groups = waves: `units` consecutive work items are resident together (all items have the same length)
   const int n_groups = ((int)items.size() + units - 1) / units;
@@ -671,6 +674,94 @@ int contract_tc(mem_ctx* ctx, const mem_contract_shape* shp, const float* Zhi, c
     MEM_LAUNCH(ctx, k_contract_finalize, fgrid, 256, 0, st, ws, D, nS, ldw, split);
   }
   if (knn && !knn_done) MEM_CHECK(knn_device_f32(ctx, D, nS, knn->k, knn->idx, knn->val, st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Grouped launch: the tiles of SEVERAL PDs in one work list (GetDistancesS2.py:94-120 produces PDs of 117..2,000
+// particles: one such PD is 1-36 tiles, far too few for 74 SM pairs, and a launch + work-table upload per PD costs more
+// than its tiles).  Zhi / Zlo hold the operand rows of all PDs back to back (PD g = rows pd_start[g] .. pd_start[g+1]);
+// one tensor map covers them; a tile that hangs over the end of its PD reads the next PD's rows (finite numbers that
+// land in rows / columns the epilogue never stores), past the last PD the TMA zero-fills.  K is cut into slices of one
+// common length so every work item costs the same and the list fills whole waves of CTA pairs.  D[g] = device pointer
+// of PD g's nS_g x nS_g output.
+int contract_tc_grouped(mem_ctx* ctx, const mem_contract_shape* shp, int n_pd, const int* pd_start, const float* Zhi,
+                        const float* Zlo, float* const* D, cudaStream_t st) {
+  const int n1 = shp->n1_blocks, n3 = shp->n3_blocks, nkb = 2 * n1 + n3;
+  const int units = ctx->sm_count / 2, TM = 2 * BM;
+  const int chunk = 2 | 4 << 8;
+  int total_tiles = 0;
+  for (int g = 0; g < n_pd; ++g) {
+    const int n = pd_start[g + 1] - pd_start[g];
+    if (n < 1) {
+      set_error("contract_tc_grouped: PD %d is empty", g);
+      return 1;
+    }
+    const int tm = (n + TM - 1) / TM;
+    total_tiles += tm * (tm + 1) / 2;
+  }
+  // slices per tile: enough items for >= 4 waves (or as many as the minimum slice length allows), whole waves preferred
+  const int min_kb = 4 * (chunk & 255) * 8;
+  int split = 1;
+  double best = -1;
+  for (int s2 = 1; s2 <= 64; ++s2) {
+    if (s2 > 1 && nkb / s2 < min_kb) break;
+    const long long items = (long long)total_tiles * s2;
+    const long long waves = (items + units - 1) / units;
+    const double eff = (double)items / ((double)waves * units);
+    if (eff > best + 0.02) { best = eff; split = s2; }
+  }
+  std::vector<WorkItem> items;
+  std::vector<long long> ws_off(n_pd);
+  long long ws_total = 0;
+  for (int g = 0; g < n_pd; ++g) {
+    const int n = pd_start[g + 1] - pd_start[g];
+    const int ldw = ((n + 3) / 4) * 4;
+    ws_off[g] = ws_total;
+    ws_total += (long long)split * ldw * ldw;
+  }
+  for (int s2 = 0; s2 < split; ++s2) {
+    const int kb0 = (int)((long long)nkb * s2 / split), kb1 = (int)((long long)nkb * (s2 + 1) / split);
+    for (int g = 0; g < n_pd; ++g) {
+      const int n = pd_start[g + 1] - pd_start[g];
+      const int tm = (n + TM - 1) / TM, ldw = ((n + 3) / 4) * 4;
+      for (int bj = 0; bj < tm; ++bj)
+        for (int bi = 0; bi <= bj; ++bi)
+          items.push_back({bi * TM, bj * BN, kb0, kb1, s2, 0, 1, pd_start[g], n, ldw, ws_off[g]});
+    }
+  }
+  MEM_CHECK(ctx->contract_ws.ensure((size_t)ws_total * sizeof(float)));
+  MEM_CHECK(ctx->clk_probe.ensure(4 * sizeof(unsigned long long)));
+  MEM_CHECK(ctx->contract_items.ensure(items.size() * sizeof(WorkItem)));
+  MEM_CUDA(cudaMemcpyAsync(ctx->contract_items.p, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, st));
+  MEM_CUDA(cudaStreamSynchronize(st));                     // items is a host temporary: one upload per GROUP of PDs
+  ctx->items_key[0] = -1;                                  // the single-PD cache no longer describes the table
+  float* ws = ctx->contract_ws.as<float>();
+  const int rows_all = pd_start[n_pd];
+  CUtensorMap map_hi, map_lo;
+  MEM_CHECK(make_map(ctx, &map_hi, Zhi, rows_all, shp->ldz));
+  MEM_CHECK(make_map(ctx, &map_lo, Zlo, rows_all, shp->ldz));
+  MEM_CUDA(cudaFuncSetAttribute(k_contract_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+  if (ctx->kev_used + 2 > ctx->kev.size()) {
+    for (int i = 0; i < 64; ++i) {
+      cudaEvent_t e;
+      MEM_CUDA(cudaEventCreate(&e));
+      ctx->kev.push_back(e);
+    }
+  }
+  MEM_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used], st));
+  MEM_LAUNCH(ctx, k_contract_tc2, 2 * (int)items.size(), NUM_THREADS2, SMEM2_BYTES, st, map_hi, map_lo,
+             ctx->contract_items.as<WorkItem>(), ws, rows_all, 0, n1, chunk, (int*)nullptr, 0,
+             ctx->clk_probe.as<unsigned long long>());
+  MEM_CUDA(cudaEventRecord(ctx->kev[ctx->kev_used + 1], st));
+  ctx->kev_used += 2;
+  ctx->last_tc_items = 2 * (int)items.size();
+  ctx->last_tc_nkb = (nkb + split - 1) / split;
+  for (int g = 0; g < n_pd; ++g) {
+    const int n = pd_start[g + 1] - pd_start[g], ldw = ((n + 3) / 4) * 4;
+    dim3 fgrid((n + 31) / 32, (n + 31) / 32);
+    MEM_LAUNCH(ctx, k_contract_finalize, fgrid, 256, 0, st, ws + ws_off[g], D[g], n, ldw, split);
+  }
   return 0;
 }
 

@@ -16,6 +16,8 @@ int shift_run(mem_ctx* ctx, const float* raw, const double* shift, float* tmp, f
               cudaStream_t st);
 int align_run(mem_ctx* ctx, float* A, float* B, float* imgAll, const double* psi_deg, double psi_p_deg, double2* cs,
               const uint8_t* msk2, int nS, int N, cudaStream_t st, int rows_done);
+int align_batch_run(mem_ctx* ctx, float* A, float* B, float* imgAll, const double* psi_deg, double2* cs, const double2* cs2,
+                    const uint8_t* pid2, int nS, int N, cudaStream_t st, int rows_done);
 
 // ------------------------------------------------------------------------------------------------
 // error string + arena
@@ -799,6 +801,147 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
     MEM_CHECK(contract_run(ctx, &shp, zhi, zlo, io->D, prm->contraction, prm->k_chunk_blocks, prm->split_k, st,
                            want_knn ? &knn : nullptr));
   }
+  MEM_CUDA(cudaEventRecord(ctx->ev[5], st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A GROUP of PDs in one call (GetDistancesS2.py:94-120 hands the worker one PD at a time; the tessellation's PDs are
+// small — 117..450 particles in the demo, at most 2,000 — so a PD alone cannot fill 148 SMs).  The per-image stages
+// (ingest, low-pass, alignment, FFT, CTF) run ONCE over the concatenated stack of all PDs: an image's second rotation
+// angle is looked up from its PD.  The per-PD reductions (Wiener sums, common component) and the operand writer run per
+// PD on their slice, and ONE grouped tcgen05 launch contracts all PDs (contract_tc_grouped).  Results are those of the
+// one-PD-at-a-time path (same kernels on the same values; the second rotation goes through the per-image kernel).
+//   prm->nS = images of all PDs; io->raw / flip / psi_deg / df concatenated; io->D = the n_pd matrices back to back
+//   (PD g at float offset sum_{h<g} nS_h^2); io->imgAll optional.  No msk2, no RELION shift, no flip / average outputs.
+int pd_distance_batch_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* io, int n_pd, const int* pd_start,
+                             const double* psi_p_deg, cudaStream_t st) {
+  const int nS = prm->nS, N = prm->N;
+  if (n_pd < 1 || pd_start[0] != 0 || pd_start[n_pd] != nS) {
+    set_error("batch: pd_start must run from 0 to nS over n_pd >= 1 PDs");
+    return 1;
+  }
+  if (io->msk2 || prm->relion_shift || io->imgAllFlip || io->CTF || io->imgAvg || io->imgAvgFlip || io->imgAllIntensity ||
+      io->knn_idx || prm->avg_only || !io->D) {
+    set_error("batch: only D (and imgAll) are produced; no msk2 / RELION shift / flip / average / kNN outputs");
+    return 1;
+  }
+  if (!rotate_fast_supported(N)) {
+    set_error("batch: box size %d is not a multiple of 32", N);
+    return 1;
+  }
+  MEM_CHECK(geometry_prepare(ctx, N, prm->filter_type, prm->filter_order, prm->filter_Qc));
+  const Geometry& g = ctx->geom;
+  const size_t NN = (size_t)N * N, Kh = g.Kh;
+  const size_t img_bytes = (size_t)nS * NN * sizeof(float), spec_bytes = (size_t)nS * Kh * sizeof(float2);
+  MEM_CHECK(ctx->imgA.ensure(img_bytes));
+  MEM_CHECK(ctx->imgB.ensure(img_bytes));
+  MEM_CHECK(ctx->spec.ensure(spec_bytes));
+  MEM_CHECK(ctx->rot_cs.ensure((size_t)(nS + 1) * sizeof(double2)));
+  MEM_CHECK(ctx->cbin.ensure((size_t)nS * g.Kr * sizeof(float)));
+  MEM_CHECK(ctx->zhi.ensure((size_t)nS * g.ldz * sizeof(float)));
+  MEM_CHECK(ctx->zlo.ensure((size_t)nS * g.ldz * sizeof(float)));
+  float* imgAll = io->imgAll;
+  if (!imgAll) {
+    MEM_CHECK(ctx->imgAll.ensure(img_bytes));
+    imgAll = ctx->imgAll.as<float>();
+  }
+  int max_n = 0;
+  for (int p = 0; p < n_pd; ++p) max_n = std::max(max_n, pd_start[p + 1] - pd_start[p]);
+  const int per_group = 64;
+  const int Gmax = (max_n + per_group - 1) / per_group;
+  MEM_CHECK(ctx->part_cf.ensure((size_t)Gmax * Kh * sizeof(double2)));
+  MEM_CHECK(ctx->part_c2.ensure((size_t)Gmax * Kh * sizeof(double)));
+  MEM_CHECK(ctx->part_fl.ensure((size_t)Gmax * Kh * sizeof(double2)));
+  MEM_CHECK(ctx->avgspec.ensure(3 * Kh * sizeof(float2)));
+  // per-image PD index, per-PD psi_p, per-image second-rotation angle and pitch id
+  const size_t b_pd = ((size_t)nS * sizeof(int) + 255) & ~(size_t)255, b_pp = ((size_t)n_pd * sizeof(double) + 255) & ~(size_t)255;
+  const size_t b_cs = ((size_t)nS * sizeof(double2) + 255) & ~(size_t)255;
+  MEM_CHECK(ctx->batch_aux.ensure(b_pd + b_pp + b_cs + (size_t)nS));
+  uint8_t* aux = ctx->batch_aux.as<uint8_t>();
+  int* pd_of = reinterpret_cast<int*>(aux);
+  double* d_pp = reinterpret_cast<double*>(aux + b_pd);
+  double2* cs2 = reinterpret_cast<double2*>(aux + b_pd + b_pp);
+  uint8_t* pid2 = aux + b_pd + b_pp + b_cs;
+  {
+    std::vector<int> h(nS);
+    for (int p = 0; p < n_pd; ++p)
+      for (int i = pd_start[p]; i < pd_start[p + 1]; ++i) h[i] = p;
+    MEM_CUDA(cudaMemcpyAsync(pd_of, h.data(), (size_t)nS * sizeof(int), cudaMemcpyHostToDevice, st));
+    MEM_CUDA(cudaMemcpyAsync(d_pp, psi_p_deg, (size_t)n_pd * sizeof(double), cudaMemcpyHostToDevice, st));
+    MEM_CUDA(cudaStreamSynchronize(st));                  // host temporaries
+  }
+  float* A = ctx->imgA.as<float>();
+  float* B = ctx->imgB.as<float>();
+  float2* spec = ctx->spec.as<float2>();
+  double2* cs = ctx->rot_cs.as<double2>();
+  MEM_CUDA(cudaEventRecord(ctx->ev[0], st));
+  int rows_done = 0;
+  if (colfilter_supported(N)) {
+    MEM_CHECK(ctx->stats.ensure((size_t)nS * sizeof(float2)));
+    float2* stats = ctx->stats.as<float2>();
+    MEM_CHECK(ingest_rowfft_run(ctx, io->raw, io->flip, spec, stats, nS, N, prm->transposed, st));
+    MEM_CHECK(colfilter_run(ctx, spec, g.Gtab.as<float>(), stats, nS, N, st));
+    MEM_CHECK(rowifft_prefilter_run(ctx, spec, A, nS, N, st));
+    rows_done = 1;
+  } else {
+    MEM_CHECK(ingest_run(ctx, io->raw, io->flip, A, nS, N, prm->transposed, st));
+    MEM_CHECK(run_fft(ctx, N, nS, true, A, spec, st));
+    const size_t total = (size_t)nS * Kh;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 16);
+    MEM_LAUNCH(ctx, k_specmul, grid, 256, 0, st, spec, g.Gtab.as<float>(), (int)Kh, total);
+    MEM_CHECK(run_fft(ctx, N, nS, false, B, spec, st));
+  }
+  MEM_CUDA(cudaEventRecord(ctx->ev[1], st));
+  MEM_CHECK(rotate_angles_batch_run(ctx, pd_of, d_pp, cs2, pid2, nS, st));
+  MEM_CHECK(align_batch_run(ctx, A, B, imgAll, io->psi_deg, cs, cs2, pid2, nS, N, st, rows_done));
+  MEM_CUDA(cudaEventRecord(ctx->ev[2], st));
+  MEM_CHECK(run_fft(ctx, N, nS, true, imgAll, spec, st));
+  const CtfConst cc = make_ctf_const(prm);
+  MEM_LAUNCH(ctx, k_ctf_bins, dim3((g.Kr + 255) / 256, nS), 256, 0, st, io->df, g.r2_of_bin.as<int>(),
+             ctx->cbin.as<float>(), g.Kr, cc);
+  float* zhi = ctx->zhi.as<float>();
+  float* zlo = ctx->zlo.as<float>();
+  float2* Mspec = ctx->avgspec.as<float2>() + 2 * Kh;
+  const size_t pw_bytes = ((size_t)g.Na * g.Nh + g.Kr) * sizeof(float);
+  const bool radial_sm = pw_bytes <= 200 * 1024;
+  if (radial_sm) MEM_CUDA(cudaFuncSetAttribute(k_operands_radial_sm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pw_bytes));
+  std::vector<float*> Dp(n_pd);
+  size_t doff = 0;
+  for (int p = 0; p < n_pd; ++p) {
+    const int s0 = pd_start[p], n = pd_start[p + 1] - s0;
+    const int G = (n + per_group - 1) / per_group;
+    float2* spec_p = spec + (size_t)s0 * Kh;
+    float* cbin_p = ctx->cbin.as<float>() + (size_t)s0 * g.Kr;
+    float* zhi_p = zhi + (size_t)s0 * g.ldz;
+    float* zlo_p = zlo + (size_t)s0 * g.ldz;
+    MEM_LAUNCH(ctx, k_spec_sums, dim3((g.Kh + 255) / 256, G), 256, 0, st, spec_p, (const float2*)nullptr, cbin_p,
+               g.bin_of_pix.as<int>(), ctx->part_cf.as<double2>(), (double2*)nullptr, ctx->part_c2.as<double>(),
+               ctx->part_fl.as<double2>(), n, g.Kh, g.Kr, per_group);
+    MEM_LAUNCH(ctx, k_avg_spectra, (g.Kh + 255) / 256, 256, 0, st, ctx->part_cf.as<double2>(), (double2*)nullptr,
+               ctx->part_c2.as<double>(), ctx->part_fl.as<double2>(), ctx->avgspec.as<float2>(), Mspec, g.Kh, G);
+    if (radial_sm) {
+      MEM_LAUNCH(ctx, k_operands_radial_sm<false>, n, RADIAL_THREADS, pw_bytes, st, spec_p, Mspec, cbin_p,
+                 g.fold_bin.as<int>(), g.fold_start.as<int>(), g.fold_ent.as<int>(), g.bin_of_pix.as<int>(),
+                 g.special_pix.as<int>(), g.s3_col.as<int>(), zhi_p, zlo_p, N, g.Nh, g.Na, g.Kh, g.Kr, g.n_special,
+                 g.n1_blocks, g.ldz);
+    } else {
+      MEM_LAUNCH(ctx, k_operands_radial, dim3((32 * g.n1_blocks + 255) / 256, n), 256, 0, st, spec_p, Mspec, cbin_p,
+                 g.bin_start.as<int>(), g.bin_pix.as<int>(), g.bin_of_pix.as<int>(), g.special_pix.as<int>(), zhi_p, zlo_p,
+                 N, g.Nh, g.Kh, g.Kr, g.n_special, g.n1_blocks, g.ldz);
+      MEM_LAUNCH(ctx, k_operands_s3, dim3((g.Kh + 255) / 256, G), 256, 0, st, spec_p, Mspec, cbin_p, g.bin_of_pix.as<int>(),
+                 g.s3_col.as<int>(), zhi_p, zlo_p, n, g.Kh, g.Kr, g.ldz, per_group, 1, 0);
+    }
+    Dp[p] = io->D + doff;
+    doff += (size_t)n * n;
+  }
+  const int from = 64 * g.n1_blocks + 2 * g.K3;
+  if (from < g.ldz) MEM_LAUNCH(ctx, k_zero_tail, nS, 64, 0, st, zhi, zlo, nS, g.ldz, from);
+  MEM_CUDA(cudaEventRecord(ctx->ev[3], st));
+  MEM_CUDA(cudaEventRecord(ctx->ev[4], st));
+  mem_contract_shape shp;
+  shp.nS = nS; shp.n1_blocks = g.n1_blocks; shp.n3_blocks = g.n3_blocks; shp.ldz = g.ldz;
+  MEM_CHECK(contract_tc_grouped(ctx, &shp, n_pd, pd_start, zhi, zlo, Dp.data(), st));
   MEM_CUDA(cudaEventRecord(ctx->ev[5], st));
   return 0;
 }

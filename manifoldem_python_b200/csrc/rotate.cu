@@ -58,6 +58,23 @@ __global__ void k_angles2(const double* __restrict__ psi_deg, double psi_p_deg, 
   }
 }
 
+// batched PDs: the second rotation of image i is by -psi_p of ITS PD (pd_of[i]); cs2 / pid2 per image, so the per-image
+// kernel k_rotate_img serves both rotations of a batch
+__global__ void k_angles_batch(const int* __restrict__ pd_of, const double* __restrict__ psi_p_deg, double2* __restrict__ cs2,
+                               uint8_t* __restrict__ pid2, const uint8_t* __restrict__ pitch_of_deg, int nS) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nS) return;
+  const double deg = -psi_p_deg[pd_of[i]];
+  double s, c;
+  sincos(deg * 0.017453292519943295769, &s, &c);
+  cs2[i] = make_double2(c, s);
+  double m = fmod(deg, 360.0);
+  if (m < 0) m += 360.0;
+  int bin = (int)(m + 0.5);
+  if (bin >= 360 || bin < 0) bin = 0;
+  pid2[i] = pitch_of_deg[bin];
+}
+
 // bounding-box origin of the source footprint of the tile at (r0, c0): floor(min over the corners) - 1
 __device__ __forceinline__ void tile_origin(const double2 a, int N, int r0, int c0, int& o0, int& o1) {
   const double ctr = 0.5 * (N - 1);
@@ -320,6 +337,13 @@ int rotate_angles_run(mem_ctx* ctx, const double* psi_deg, double psi_p_deg, dou
   MEM_CHECK(ensure_pitch_table(ctx, st));
   MEM_LAUNCH(ctx, k_angles2, (nS + 1 + 127) / 128, 128, 0, st, psi_deg, psi_p_deg, cs, pid,
              ctx->rot_pitch_tab.as<uint8_t>(), nS);
+  return 0;
+}
+
+int rotate_angles_batch_run(mem_ctx* ctx, const int* pd_of, const double* psi_p_deg, double2* cs2, uint8_t* pid2, int nS,
+                            cudaStream_t st) {
+  MEM_CHECK(ensure_pitch_table(ctx, st));
+  MEM_LAUNCH(ctx, k_angles_batch, (nS + 127) / 128, 128, 0, st, pd_of, psi_p_deg, cs2, pid2, ctx->rot_pitch_tab.as<uint8_t>(), nS);
   return 0;
 }
 

@@ -238,3 +238,62 @@ def run_pd_resident(ind, q, df, stack, nStot, N, pix_size, Cs, EkV, AmpContrast,
     for b in bufs:
         b.free()
     return (D, idx, val) if knn_k else D
+
+
+def run_pd_batch(jobs, stack, nStot, N, pix_size, Cs, EkV, AmpContrast, gaussEnv=np.inf, filterPar=None, ctx=None,
+                 want_imgAll=False):
+    """A GROUP of PDs in one device call (`mem_pd_distance_batch_device`): jobs = [(ind, q, df), ...] — the job tuples
+    GetDistancesS2.divide builds (:37-47), one per PD.  The members of all PDs are gathered into one stack, the per-image
+    stages run once over it, one grouped tcgen05 launch contracts every PD.  SPIDER stacks, msk2 = 1.
+    Returns a list of dicts (D (nS,nS) float32, PD, PDs, Psis, _psi_p[, imgAll]) in job order."""
+    lib = _lib.load()
+    ctx = ctx or _lib.default_context()
+    if filterPar is None:
+        filterPar = dict(type='Butter', Qc=0.5, N=8)
+    raws, flips, psis, dfs, psi_ps, host = [], [], [], [], [], []
+    for ind, q, df in jobs:
+        ind = np.asarray(ind)
+        PDs, PD, psi_p, Psi, s, c = host_angles(np.asarray(q, dtype=np.float64))
+        raw, flip, _base = gather(stack, ind, nStot, N)
+        raws.append(raw)
+        flips.append(flip)
+        psis.append(-(180 / math.pi) * Psi)
+        dfs.append(np.asarray(df, dtype=np.float64))
+        psi_ps.append(float(psi_p))
+        host.append(dict(PD=PD, PDs=PDs, Psis=Psi.reshape(-1, 1), _psi_p=psi_p))
+    sizes = np.array([r.shape[0] for r in raws], dtype=np.int64)
+    start = np.zeros(len(jobs) + 1, dtype=np.int32)
+    start[1:] = np.cumsum(sizes)
+    nS = int(start[-1])
+    d_raw = _lib.DeviceArray(ctx, (nS, N * N), np.float32, np.concatenate(raws))
+    d_flip = _lib.DeviceArray(ctx, (nS,), np.uint8, np.concatenate(flips))
+    d_psi = _lib.DeviceArray(ctx, (nS,), np.float64, np.concatenate(psis))
+    d_df = _lib.DeviceArray(ctx, (nS,), np.float64, np.concatenate(dfs))
+    d_D = _lib.DeviceArray(ctx, (int((sizes ** 2).sum()),), np.float32)
+    d_img = _lib.DeviceArray(ctx, (nS, N, N), np.float32) if want_imgAll else None
+    prm = _lib.PdParams(nS=nS, N=N, transposed=1, relion_shift=0, filter_type=FILTERS[filterPar['type']],
+                        filter_order=int(filterPar['N']), filter_Qc=float(filterPar['Qc']), pix_size=float(pix_size),
+                        Cs=float(Cs), EkV=float(EkV), gaussEnv=float(gaussEnv), AmpContrast=float(AmpContrast), psi_p_deg=0.0,
+                        avg_only=0, contraction=0, k_chunk_blocks=0, split_k=0, knn_k=0)
+    io = _lib.PdIO()
+    io.raw, io.flip, io.psi_deg, io.df, io.D = d_raw.ptr, d_flip.ptr, d_psi.ptr, d_df.ptr, d_D.ptr
+    if d_img is not None:
+        io.imgAll = d_img.ptr
+    pp = np.ascontiguousarray(psi_ps, dtype=np.float64)
+    try:
+        _lib.check(lib.mem_pd_distance_batch_device(ctx.handle, C.byref(prm), C.byref(io), len(jobs), start.ctypes.data,
+                                                    pp.ctypes.data, None))
+        Dall = d_D.download()
+        img = d_img.download() if d_img is not None else None
+    finally:
+        for a in (d_raw, d_flip, d_psi, d_df, d_D, d_img):
+            if a is not None:
+                a.free()
+    off = 0
+    for g, h in enumerate(host):
+        n = int(sizes[g])
+        h['D'] = Dall[off:off + n * n].reshape(n, n)
+        off += n * n
+        if img is not None:
+            h['imgAll'] = img[start[g]:start[g + 1]]
+    return host
