@@ -227,6 +227,14 @@ int mem_nlsa_project_device(mem_ctx* ctx, const double* A, int64_t rows, int32_t
 int mem_nlsa_reconstruct_device(mem_ctx* ctx, const double* U, int32_t Npix, int32_t ConOrder, int32_t E, const double* Q,
                                 int32_t nI, int32_t nC, double* IMGT, double* D2, void* stream);
 
+/* fit_1D_open_manifold_3D.op (modules/fit_1D_open_manifold_3D.py:66-144 with solve_d_R_d_tau_p_3D.py / R_p.py): the alternating
+ * fit x_ij = a_j cos(j pi tau_i) + b_j of the three leading diffusion coordinates x [nS][3], started from ab = (a_1..3, b_1..3)
+ * (get_fit_1D_open_manifold_3D_param.op, computed by the caller), at most max_iter iterations, stopping when the largest relative
+ * change of a and of b (in percent) falls below da_max / db_max.  HOST pointers: ab [6] in / out, tau [nS] out, iters [1] out.
+ * Synchronises. */
+int mem_manifold_fit_host(mem_ctx* ctx, const double* x, int32_t nS, double* ab, double* tau, int32_t max_iter, double da_max,
+                          double db_max, int32_t* iters);
+
 /* ---- upstream of the distance stage: S2 tessellation (modules/S2tessellation.py) ---------- */
 /* classS2 (:59-63): for every particle direction pts[i] (unit 3-vectors, [n][3] float64) the index of the nearest
  * bin centre (centres [nG][3] float64, Euclidean distance in float64, smallest index on a tie) -> idx [n] int32.

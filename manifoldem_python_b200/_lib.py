@@ -18,7 +18,7 @@ SYMBOLS = [
     'mem_contract_knn_device', 'mem_knn_mode',
     'mem_operand_shape', 'mem_knn_device', 'mem_knn_device_f32', 'mem_graph_dense_device', 'mem_graph_compact_device', 'mem_ferguson_device',
     'mem_laplacian_dense_device', 'mem_symv_host', 'mem_nlsa_spectra_device', 'mem_nlsa_cond_device', 'mem_nlsa_supervectors_device', 'mem_nlsa_gram_small_device',
-    'mem_nlsa_project_device', 'mem_nlsa_reconstruct_device', 'mem_lanczos_steps_device', 'mem_lanczos_ritz_device', 'mem_s2_assign_host', 'mem_s2_pairwise_host', 'mem_ctf_host',
+    'mem_nlsa_project_device', 'mem_nlsa_reconstruct_device', 'mem_manifold_fit_host', 'mem_lanczos_steps_device', 'mem_lanczos_ritz_device', 'mem_s2_assign_host', 'mem_s2_pairwise_host', 'mem_ctf_host',
     'mem_gather_square_device',
 ]
 
@@ -113,6 +113,7 @@ def load():
         lib.mem_nlsa_gram_small_device.argtypes = [vp, vp, i64, i32, vp, vp]
         lib.mem_nlsa_project_device.argtypes = [vp, vp, i64, i32, vp, vp, i32, i32, vp, vp]
         lib.mem_nlsa_reconstruct_device.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, vp, vp, vp]
+        lib.mem_manifold_fit_host.argtypes = [vp, vp, i32, vp, vp, i32, C.c_double, C.c_double, vp]
         lib.mem_pd_distance_batch_device.argtypes = [vp, C.POINTER(PdParams), C.POINTER(PdIO), i32, vp, vp, vp]
         lib.mem_s2_pairwise_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         _lib = lib

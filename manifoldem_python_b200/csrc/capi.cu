@@ -33,6 +33,8 @@ int nlsa_project_device(mem_ctx* ctx, const double* A, long long rows, int E, co
                         int ConOrder, double* topo_host, cudaStream_t st);
 int nlsa_reconstruct_device(mem_ctx* ctx, const double* U, int Npix, int ConOrder, int E, const double* Q_host, int nI, int nC,
                             double* IMGT, double* D2, cudaStream_t st);
+int manifold_fit_host(mem_ctx* ctx, const double* x_host, int nS, double* ab_host, double* tau_host, int max_iter,
+                      double da_max, double db_max, int* iters_host, cudaStream_t st);
 int s2_pairwise_host(mem_ctx* ctx, const double* U, int nU, const double* V, int nV, double* dot, double* dist);
 int ctf_host(mem_ctx* ctx, const mem_pd_params* prm, const double* df, double* out);
 int gather_square_device(mem_ctx* ctx, const void* D, int elem_bytes, int nS, const int* sel_host, int m, void* out,
@@ -455,6 +457,12 @@ int mem_nlsa_reconstruct_device(mem_ctx* ctx, const double* U, int32_t Npix, int
                                 int32_t nI, int32_t nC, double* IMGT, double* D2, void* stream) {
   MEM_CUDA(cudaSetDevice(ctx->device));
   return nlsa_reconstruct_device(ctx, U, Npix, ConOrder, E, Q, nI, nC, IMGT, D2, pick(ctx, stream));
+}
+
+int mem_manifold_fit_host(mem_ctx* ctx, const double* x, int32_t nS, double* ab, double* tau, int32_t max_iter, double da_max,
+                          double db_max, int32_t* iters) {
+  MEM_CUDA(cudaSetDevice(ctx->device));
+  return manifold_fit_host(ctx, x, nS, ab, tau, max_iter, da_max, db_max, iters, ctx->stream);
 }
 
 int mem_s2_pairwise_host(mem_ctx* ctx, const double* U, int32_t nU, const double* V, int32_t nV, double* dot, double* dist) {

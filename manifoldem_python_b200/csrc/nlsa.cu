@@ -308,6 +308,186 @@ __global__ void __launch_bounds__(256) k_nlsa_l2(const double* __restrict__ X, c
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fit_1D_open_manifold_3D.op (:60-146) on the device: x_ij = a_j cos(j pi tau_i) + b_j, j = 1..3.  The reference solves
+// one quintic per point and iteration with np.roots (nS x <= 101 companion-matrix eigenproblems in a Python loop); here ONE
+// CTA runs the whole alternating iteration: every thread owns points p, p + 1024, ...; the real roots of
+// d R_p / d beta (beta = cos(pi tau)) inside [-1, 1] are isolated through the derivative chain (between two consecutive
+// critical points a polynomial is monotone: one sign test + safeguarded Newton per interval, no root can be missed), the
+// candidate with the smallest residual wins (tau = 0 and 1 always compete, solve_d_R_d_tau_p_3D.py:48-50), and the
+// 2 x 2 normal equations for (a_j, b_j) are block reductions in a fixed order.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double horner(const double* c, int n, double x) {     // c[0] x^n + ... + c[n]
+  double v = c[0];
+  for (int k = 1; k <= n; ++k) v = fma(v, x, c[k]);
+  return v;
+}
+
+// root of the degree-n polynomial c in [lo, hi] given f(lo) f(hi) <= 0 and monotone f: Newton with bisection safeguard
+__device__ double bracketed_root(const double* c, const double* dc, int n, double lo, double hi, double flo, double fhi) {
+  if (flo == 0.0) return lo;
+  if (fhi == 0.0) return hi;
+  double x = 0.5 * (lo + hi);
+  for (int it = 0; it < 200; ++it) {
+    const double f = horner(c, n, x);
+    if (f == 0.0) return x;
+    if ((f < 0.0) == (flo < 0.0)) { lo = x; flo = f; } else { hi = x; fhi = f; }
+    if (hi - lo <= 4.5e-16 * fmax(1.0, fabs(x))) break;
+    const double d = horner(dc, n - 1, x);
+    double xn = (d != 0.0) ? x - f / d : lo - 1.0;
+    if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+    if (xn == x) break;
+    x = xn;
+  }
+  return x;
+}
+
+// real roots of c (degree n <= 5, leading coefficients may vanish) inside [-1, 1], ascending; crit = the roots of its
+// derivative inside (-1, 1) (ascending, ncrit of them)
+__device__ int roots_between(const double* c, const double* dc, int n, const double* crit, int ncrit, double* out) {
+  int cnt = 0;
+  double lo = -1.0, flo = horner(c, n, lo);
+  for (int k = 0; k <= ncrit; ++k) {
+    const double hi = (k < ncrit) ? crit[k] : 1.0;
+    const double fhi = horner(c, n, hi);
+    if ((flo <= 0.0 && fhi >= 0.0) || (flo >= 0.0 && fhi <= 0.0)) {
+      if (!(flo == 0.0 && fhi == 0.0 && lo != hi && horner(c, n, 0.5 * (lo + hi)) == 0.0)) {   // not identically zero
+        const double r = bracketed_root(c, dc, n, lo, hi, flo, fhi);
+        if (cnt == 0 || r > out[cnt - 1] + 1e-15) out[cnt++] = r;
+      }
+    }
+    lo = hi;
+    flo = fhi;
+  }
+  return cnt;
+}
+
+__device__ double manifold_tau(const double x0, const double x1, const double x2, const double* a, const double* b) {
+  // d R / d beta, solve_d_R_d_tau_p_3D.py:38-43
+  double c5[6] = {48 * a[2] * a[2], 0.0, 8 * a[1] * a[1] - 48 * a[2] * a[2], -12 * a[2] * (x2 - b[2]),
+                  a[0] * a[0] - 4 * a[1] * a[1] + 9 * a[2] * a[2] - 4 * a[1] * (x1 - b[1]),
+                  -a[0] * (x0 - b[0]) + 3 * a[2] * (x2 - b[2])};
+  double c4[5], c3[4], c2[3], c1[2];
+  for (int k = 0; k < 5; ++k) c4[k] = (5 - k) * c5[k];
+  for (int k = 0; k < 4; ++k) c3[k] = (4 - k) * c4[k];
+  for (int k = 0; k < 3; ++k) c2[k] = (3 - k) * c3[k];
+  for (int k = 0; k < 2; ++k) c1[k] = (2 - k) * c2[k];
+  double r1[1], r2[2], r3[3], r4[4], r5[5];
+  int n1 = 0;
+  if (c1[0] != 0.0) {                                     // root of the linear c1 = derivative of the quadratic c2
+    const double r = -c1[1] / c1[0];
+    if (r > -1.0 && r < 1.0) r1[n1++] = r;
+  }
+  const int n2 = roots_between(c2, c1, 2, r1, n1, r2);
+  int m2 = 0;
+  double q2[2];
+  for (int k = 0; k < n2; ++k) if (r2[k] > -1.0 && r2[k] < 1.0) q2[m2++] = r2[k];
+  const int n3 = roots_between(c3, c2, 3, q2, m2, r3);
+  int m3 = 0;
+  double q3[3];
+  for (int k = 0; k < n3; ++k) if (r3[k] > -1.0 && r3[k] < 1.0) q3[m3++] = r3[k];
+  const int n4 = roots_between(c4, c3, 4, q3, m3, r4);
+  int m4 = 0;
+  double q4[4];
+  for (int k = 0; k < n4; ++k) if (r4[k] > -1.0 && r4[k] < 1.0) q4[m4++] = r4[k];
+  const int n5 = roots_between(c5, c4, 5, q4, m4, r5);
+  // candidates: arccos(beta) / pi for every root, then 0 and 1; the smallest R_p wins (first one on a tie)
+  double best_tau = 0.0, best = INFINITY;
+  for (int k = 0; k < n5 + 2; ++k) {
+    const double tau = (k < n5) ? acos(r5[k]) / M_PI : (k == n5 ? 0.0 : 1.0);
+    const double e0 = x0 - b[0] - a[0] * cos(tau * 1 * M_PI);
+    const double e1 = x1 - b[1] - a[1] * cos(tau * 2 * M_PI);
+    const double e2 = x2 - b[2] - a[2] * cos(tau * 3 * M_PI);
+    const double R = e0 * e0 + e1 * e1 + e2 * e2;
+    if (R < best) { best = R; best_tau = tau; }
+  }
+  return best_tau;
+}
+
+// x [nS][3]; ab [6] = initial (a, b) in, final out; tau [nS] out; iters out.  One CTA of 1024 threads.
+__global__ void __launch_bounds__(1024) k_manifold_fit(const double* __restrict__ x, int nS, double* __restrict__ ab,
+                                                       double* __restrict__ tau, int max_iter, double da_max, double db_max,
+                                                       int* __restrict__ iters) {
+  __shared__ double s_ab[6];
+  __shared__ double red[32][12];
+  __shared__ double tot[12];
+  __shared__ int stop;
+  if (threadIdx.x < 6) s_ab[threadIdx.x] = ab[threadIdx.x];
+  if (threadIdx.x == 0) stop = 0;
+  __syncthreads();
+  for (int p = threadIdx.x; p < nS; p += 1024) tau[p] = manifold_tau(x[3 * p], x[3 * p + 1], x[3 * p + 2], s_ab, s_ab + 3);
+  int it = 0;
+  for (it = 1; it <= max_iter; ++it) {
+    // normal equations of x_ij = a_j cos(j pi tau_i) + b_j: sums of cos^2, cos, x cos, x per j
+    double acc[12];
+    for (int k = 0; k < 12; ++k) acc[k] = 0.0;
+    for (int p = threadIdx.x; p < nS; p += 1024) {
+      const double t = tau[p];
+      for (int j = 0; j < 3; ++j) {
+        const double cj = cos(t * (M_PI * (j + 1)));
+        const double xv = x[3 * p + j];
+        acc[j] = fma(cj, cj, acc[j]);
+        acc[3 + j] += cj;
+        acc[6 + j] = fma(xv, cj, acc[6 + j]);
+        acc[9 + j] += xv;
+      }
+    }
+    for (int k = 0; k < 12; ++k) {
+      double v = acc[k];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+      double s2 = 0.0;
+      for (int w = 0; w < 32; ++w) s2 += red[w][threadIdx.x];
+      tot[threadIdx.x] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double da = 0.0, db = 0.0;
+      for (int j = 0; j < 3; ++j) {
+        const double A11 = tot[j], A12 = tot[3 + j], b1 = tot[6 + j], b2 = tot[9 + j], A22 = (double)nS;
+        const double det = A11 * A22 - A12 * A12;
+        const double an = (b1 * A22 - A12 * b2) / det, bn = (A11 * b2 - A12 * b1) / det;
+        da = fmax(da, fabs(an - s_ab[j]) / (fabs(an) + 1e-4));
+        db = fmax(db, fabs(bn - s_ab[3 + j]) / (fabs(bn) + 1e-4));
+        s_ab[j] = an;
+        s_ab[3 + j] = bn;
+      }
+      stop = (da * 100 < da_max && db * 100 < db_max) ? 1 : 0;
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < nS; p += 1024) tau[p] = manifold_tau(x[3 * p], x[3 * p + 1], x[3 * p + 2], s_ab, s_ab + 3);
+    __syncthreads();
+    if (stop) break;
+  }
+  if (threadIdx.x < 6) ab[threadIdx.x] = s_ab[threadIdx.x];
+  if (threadIdx.x == 0) iters[0] = it > max_iter ? max_iter : it;
+}
+
+// x [nS][3] HOST, ab [6] HOST in / out, tau [nS] HOST out.  Synchronises.
+int manifold_fit_host(mem_ctx* ctx, const double* x_host, int nS, double* ab_host, double* tau_host, int max_iter,
+                      double da_max, double db_max, int* iters_host, cudaStream_t st) {
+  if (nS < 1) {
+    set_error("manifold_fit: nS >= 1");
+    return 1;
+  }
+  MEM_CHECK(ctx->small_out.ensure((size_t)(4 * nS + 8) * sizeof(double)));
+  double* dx = ctx->small_out.as<double>();
+  double* dab = dx + 3 * nS;
+  double* dtau = dab + 6;
+  int* dit = reinterpret_cast<int*>(dtau + nS);
+  MEM_CUDA(cudaMemcpyAsync(dx, x_host, (size_t)3 * nS * sizeof(double), cudaMemcpyHostToDevice, st));
+  MEM_CUDA(cudaMemcpyAsync(dab, ab_host, 6 * sizeof(double), cudaMemcpyHostToDevice, st));
+  MEM_LAUNCH(ctx, k_manifold_fit, 1, 1024, 0, st, dx, nS, dab, dtau, max_iter, da_max, db_max, dit);
+  MEM_CUDA(cudaMemcpyAsync(ab_host, dab, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  MEM_CUDA(cudaMemcpyAsync(tau_host, dtau, (size_t)nS * sizeof(double), cudaMemcpyDeviceToHost, st));
+  MEM_CUDA(cudaMemcpyAsync(iters_host, dit, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MEM_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static int plan_many_d(cufftHandle* h, int N, int batch, cufftType type, cudaStream_t st) {
   int n[2] = {N, N};

@@ -88,6 +88,26 @@ def initial_parameters(psi):
 
 
 def op(psi, maxIter=100, delta_a_max=1, delta_b_max=1):
+    """Device path (C ABI mem_manifold_fit_host, nlsa.cu k_manifold_fit): the first (a, b) on the host exactly as the
+    reference computes them, the alternating iteration in one kernel launch."""
+    import ctypes as C
+    from . import _lib
+    from .getDistanceCTF_local_Conj9combinedS2 import _ctx
+    lib = _lib.load()
+    x = np.ascontiguousarray(psi[:, 0:3], dtype=np.float64)
+    nS = x.shape[0]
+    a, b = initial_parameters(psi)
+    ab = np.ascontiguousarray(np.concatenate([a, b]), dtype=np.float64)
+    tau = np.empty(nS)
+    iters = C.c_int32(0)
+    _lib.check(lib.mem_manifold_fit_host(_ctx().handle, x.ctypes.data, nS, ab.ctypes.data, tau.ctypes.data, int(maxIter),
+                                         float(delta_a_max), float(delta_b_max), C.byref(iters)))
+    return ab[:3].copy(), ab[3:].copy(), tau.reshape(-1, 1)
+
+
+def op_host(psi, maxIter=100, delta_a_max=1, delta_b_max=1):
+    """The same fit in NumPy on the host (one batched eigvals per iteration, the LAPACK routine np.roots ends in): the
+    checker of the device kernel in tests/, and a reference for its root isolation."""
     x = psi[:, 0:3]
     nS = x.shape[0]
     a, b = initial_parameters(psi)

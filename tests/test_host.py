@@ -650,12 +650,31 @@ def test_vectorised_manifold_fit_equals_the_per_point_restatement(golden_dir):
     cases.append(np.stack([np.cos(np.pi * t), 0.5 * np.cos(2 * np.pi * t), 0.2 * np.cos(3 * np.pi * t)], 1)
                  + 0.01 * rng.standard_normal((120, 3)))
     for psi in cases:
-        a, b, tau = fit.op(psi)
+        a, b, tau = fit.op_host(psi)
         a0, b0, tau0 = onl.fit_1d_open_manifold_3d(psi)
         assert np.allclose(a, a0, rtol=1e-12, atol=0) and np.allclose(b, b0, rtol=1e-12, atol=1e-15)
         assert tau.shape == tau0.shape and np.abs(tau - tau0).max() < 1e-12
     ref_tau = g['m1_psi0_tau']
-    assert np.abs(fit.op(g['m1_psi0_psirec'])[2] - ref_tau).max() < 1e-9
+    assert np.abs(fit.op_host(g['m1_psi0_psirec'])[2] - ref_tau).max() < 1e-9
     x = np.stack([np.cos(np.pi * t), 0.5 * np.cos(2 * np.pi * t), np.zeros_like(t)], 1)
     assert np.array_equal(fit._taus(x, np.array([1.0, 0.5, 0.0]), np.zeros(3)),
                           np.array([onl._tau_of_point(x[p], np.array([1.0, 0.5, 0.0]), np.zeros(3)) for p in range(120)]))
+
+
+def test_psi_analysis_driver_bookkeeping(tmp_path):
+    """psiAnalysis.divid / fileCheck (modules/psiAnalysis.py:20-50): markers '<prD>_<psi>' under p.psi2_prog mark finished
+    (PD, psi) pairs; a job lists only the psis still to do."""
+    from manifoldem_python_b200 import psiAnalysis, p
+    p.init()
+    p.psi2_prog = str(tmp_path / 'prog')
+    os.makedirs(p.psi2_prog)
+    p.num_psis, p.numberofJobs = 3, 4
+    p.dist_file, p.psi_file, p.psi2_file, p.EL_file = 'D_', 'P_', 'Q_', 'E_'
+    for name in ('0_0', '0_1', '0_2', '2_1', '.hidden'):
+        open(os.path.join(p.psi2_prog, name), 'a').close()
+    fin = psiAnalysis.fileCheck(4)
+    assert fin.shape == (4, 3) and fin.sum() == 4 and fin[0].all() and fin[2, 1] == 1
+    rc = dict(psiNumsAll=np.tile(np.arange(3), (4, 1)), sensesAll=np.ones((4, 3)))
+    jobs = psiAnalysis.divid(4, rc, fin)
+    assert [j[7] for j in jobs] == [[], [0, 1, 2], [0, 2], [0, 1, 2]]
+    assert jobs[2][:4] == ['D_prD_2', 'P_prD_2', 'Q_prD_2', 'E_prD_2'] and jobs[3][6] == 3
