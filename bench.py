@@ -444,6 +444,43 @@ def config1_block(ctx, lib, _lib, local, N):
     return out
 
 
+def nlsa_block(ctx):
+    """One psi of NLSA.op (modules/NLSA.py:23-158) through the device path: a synthetic PD with a 1-D conformational
+    coordinate, 600 snapshots at 128^2, ConOrder = 12, psiTrunc = 8.  Wall clock per step (device sync after each)."""
+    from manifoldem_python_b200 import NLSA, DMembeddingII, synthetic, p
+    p.init()
+    n, Nn = 600, 128
+    rng = np.random.default_rng(0)
+    t = np.sort(rng.uniform(0, 1, n))
+    g = (np.arange(Nn) - Nn / 2) / Nn
+    yy, xx = np.meshgrid(g, g, indexing='ij')
+    img = np.stack([np.exp(-((xx - 0.2 * (ti - 0.5)) ** 2 + yy ** 2) / 0.02) for ti in t]) + 0.3 * rng.standard_normal((n, Nn, Nn))
+    ctf = np.stack([synthetic.ctf_2d(Nn, df) for df in rng.uniform(10000, 30000, n)])
+    flat = img.reshape(n, -1)
+    sq = (flat ** 2).sum(1)
+    D = np.maximum(sq[:, None] + sq[None, :] - 2 * flat @ flat.T, 0)
+    np.random.seed(1)
+    psi = DMembeddingII.embed(D.copy(), n, 3.0)[1]
+    con = n // 50
+    par = dict(num=n, ConOrder=con, k=n - con, tune=3.0, nS=n, save=False, psiTrunc=8)
+    t0 = time.perf_counter()
+    state = NLSA.PdState(D, img, ctf, ctx=ctx)
+    t1 = time.perf_counter()
+    sel = np.argsort(psi[:, 0])
+    tm = {}
+    for rep in range(2):
+        tm = {}
+        t2 = time.perf_counter()
+        out = NLSA.analyse(state, sel, sel, par, 1, keep_IMGT_on_device=True, timings=tm)
+        t3 = time.perf_counter()
+        out[0].free()
+    state.free()
+    return dict(workload='NLSA.op, one psi: %d snapshots x %d^2, ConOrder %d, psiTrunc 8 (the reference: %d fft2 / ifft2 pairs + '
+                         'a %d^2 x %d float64 Gram + up to 101 x %d np.roots calls)' % (n, Nn, con, con * (n - con), n - 2 * con, Nn * Nn, n - 2 * con),
+                upload_and_forward_transforms_ms=(t1 - t0) * 1e3, analyse_ms=(t3 - t2) * 1e3, step_ms={k: round(v, 2) for k, v in tm.items()},
+                tau_range=[float(np.min(out[7])), float(np.max(out[7]))])
+
+
 def config5_block(ctx, lib, _lib, local):
     """BASELINE config 5, one PD: 20,000 particles at 320^2 (73 GB of workspace on one B200), D requested."""
     import torch
@@ -667,15 +704,24 @@ def run_b200(args):
                 L_dev = DMembeddingII.laplacian(M_dev, nS, sig, ctx=ctx, resident=True)
                 ctx.sync()
                 t2 = time.perf_counter()
+                ev, _vecs, einfo = DMembeddingII.eigsh_device(L_dev, nS, 16, ctx=ctx)      # a19 on the device (Lanczos)
+                t3 = time.perf_counter()
                 M_dev.free()
                 L_dev.free()
             details['embedding_front_end'] = dict(
                 workload='kNN (k = nS) + graph + Ferguson sweep on the resident D of one PD, then the Laplacian '
                          '(host wall clock around the device chain, allocations included)',
                 nS=nS, k=nS, knn_graph_sweep_ms=(t1 - t0) * 1e3, laplacian_ms=(t2 - t1) * 1e3,
-                logSumWij_finite=bool(np.isfinite(_ls).all()))
+                eigsh_device_ms=(t3 - t2) * 1e3, lanczos_steps=einfo['steps'], lanczos_converged=bool(einfo['converged']),
+                leading_eigenvalue=float(np.max(ev)), logSumWij_finite=bool(np.isfinite(_ls).all()))
         except Exception as e:                       # the embedding front end is reported beside the headline, never instead of it
             details['embedding_front_end'] = dict(error=repr(e))
+    # ---- one psi of the NLSA / psi-analysis stage on a synthetic PD (600 snapshots at 128^2)
+    if side and (nS, N) == (NS, NPIX):
+        try:
+            details['nlsa_one_psi'] = nlsa_block(ctx)
+        except Exception as e:
+            details['nlsa_one_psi'] = dict(error=repr(e))
     ctx.kernel_time(reset=True)
     if world > 1:
         dist.barrier()
@@ -701,12 +747,24 @@ def run_b200(args):
             [x.join() for x in th]
 
         P_e = max(nthreads, min(P, 48))
+        # static partition of the world x P_e PDs of an e2e step by the measured feed rate of every rank: the box does not
+        # serve its GPUs equally when all copy at once (profiles/r02_h2d_concurrent_8gpu.txt: 23 GB/s on four, 35 GB/s on
+        # the other four), and the e2e leg is bound by exactly that copy
+        from manifoldem_python_b200 import partition
+        rates = [ceil_gbs]
+        if world > 1:
+            tr = torch.zeros(world, dtype=torch.float64, device='cuda:%d' % local)
+            tr[rank] = ceil_gbs
+            dist.all_reduce(tr, op=dist.ReduceOp.SUM)
+            rates = [float(x) for x in tr]
+        counts = partition.counts_by_speed(world * P_e, rates)
+        P_mine = max(1, counts[rank])
         e2e_step(min(P_e, 2 * nthreads))           # warm-up (plans / workspaces of the extra contexts)
         barrier()
         t0 = time.perf_counter()
         e_steps = max(1, min(args.steps, 2))
         for _ in range(e_steps):
-            e2e_step(P_e)
+            e2e_step(P_mine)
         for cx in ctxs:
             cx.sync()
         dt = time.perf_counter() - t0
@@ -714,16 +772,21 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         dt, ceil_min = float(te[0]), -float(te[1])
-        h2d_b, d2h_b = int(P_e * (nS * NN * 4 + nS * 17)), int(P_e * nS * nS * 4)
-        e2e_val = float(nS) * nS * P_e * world * e_steps / dt / 1e9
+        P_all = sum(max(1, c) for c in counts)
+        h2d_b, d2h_b = int(P_mine * (nS * NN * 4 + nS * 17)), int(P_mine * nS * nS * 4)
+        e2e_val = float(nS) * nS * P_all * e_steps / dt / 1e9
         per_gpu_h2d = h2d_b * e_steps / dt / 1e9
+        agg_h2d = float(P_all) * (nS * NN * 4 + nS * 17) * e_steps / dt / 1e9
         e2e = dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=h2d_b, d2h_bytes_per_step=d2h_b,
-                   pds_per_step=P_e, steps=e_steps, in_flight=nthreads,
-                   h2d_gbs_per_gpu=per_gpu_h2d,
-                   h2d_ceiling=dict(gbs_per_gpu_slowest_rank=ceil_min, gbs_this_rank=ceil_gbs, ranks_copying_at_once=world,
+                   pds_per_step=P_mine, pds_per_step_all_ranks=P_all, pds_per_rank=counts, steps=e_steps, in_flight=nthreads,
+                   h2d_gbs_per_gpu=per_gpu_h2d, h2d_gbs_all_ranks=agg_h2d,
+                   h2d_ceiling=dict(gbs_per_rank=rates, gbs_all_ranks=float(sum(rates)), gbs_per_gpu_slowest_rank=ceil_min,
+                                    gbs_this_rank=ceil_gbs, ranks_copying_at_once=world,
                                     how='8 x 512 MB cudaMemcpyAsync from pinned memory, all ranks between the same barriers'),
-                   frac_of_h2d_ceiling=per_gpu_h2d / ceil_min if ceil_min > 0 else None,
-                   note='wall clock bracketed by stream syncs + barrier; H2D of each raw stack from pinned memory and D2H of D inside')
+                   frac_of_h2d_ceiling=agg_h2d / float(sum(rates)) if sum(rates) > 0 else None,
+                   partition='PDs per rank proportional to the rank\'s measured concurrent H2D rate (static)',
+                   note='wall clock bracketed by stream syncs + barrier; H2D of each raw stack from pinned memory and D2H of D inside; '
+                        'h2d / d2h bytes per step are this rank\'s (rank 0)')
         for cx in ctxs[1:]:
             cx.close()
 

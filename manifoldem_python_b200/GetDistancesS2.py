@@ -129,7 +129,11 @@ def op(*argv):
         _run_jobs(input_data, filterPar, p.img_stack_file, sh, size, options, p.nPix, on_done)
     else:
         costs = [partition.pd_cost(len(job[0]), p.nPix) for job in input_data]
-        shards = partition.lpt_partition(costs, n_workers)
+        # MANIFOLDEM_B200_GPU_SPEEDS="1,1,1,1,1.5,1.5,1.5,1.5": relative feed rate of the GPUs when the stage is bound by
+        # the host-to-device copies and the box does not serve its GPUs equally (profiles/r02_h2d_concurrent_8gpu.txt)
+        speeds = os.environ.get('MANIFOLDEM_B200_GPU_SPEEDS')
+        speeds = [float(x) for x in speeds.split(',')][:n_workers] if speeds else None
+        shards = partition.lpt_partition(costs, n_workers, speeds if speeds and len(speeds) == n_workers else None)
         cfg = {k: getattr(p, k) for k in _CFG_KEYS if hasattr(p, k)}
         ctx = multiprocessing.get_context('spawn')
         procs = [ctx.Process(target=_gpu_worker, args=(r, [input_data[i] for i in shards[r]], filterPar,

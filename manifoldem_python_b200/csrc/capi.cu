@@ -107,6 +107,7 @@ int mem_ctx_set_option(mem_ctx* ctx, const char* name, int32_t value) {
     return 1;
   }
   if (!strcmp(name, "legacy_rotate")) ctx->legacy_rotate = value;
+  else if (!strcmp(name, "radial_variant")) ctx->radial_variant = value;
   else {
     set_error("mem_ctx_set_option: unknown option '%s'", name);
     return 1;

@@ -322,12 +322,12 @@ __global__ void k_operands_radial(const float2* __restrict__ spec, const float2*
 // shared memory: (N/2+1) x Nh floats, 66 KB at N = 256, so three blocks share an SM.  Pass 2 gathers every bin's
 // entries from shared memory in a fixed order.  The global gather of the kernel above uses a quarter of every
 // 32-byte sector and one CTF lookup per pixel; this one is bound by the spectrum read.
-constexpr int RADIAL_THREADS = 512;
+constexpr int RADIAL_THREADS = 768;      // measured: 512 -> 768 threads, fft_ctf_operands 1.164 -> 1.127 ms at C4 (2 CTAs / SM either way)
 // The same pass also writes the S3 operands A = C (F - C M) of every pixel it visits (hi/lo split, the job of
 // k_operands_s3 below) and, if FLIP, leaves sign(C) F in place for the C2R of :346-347 — the spectrum is read once
 // for all three operand groups.
-template <bool FLIP>
-__global__ void __launch_bounds__(RADIAL_THREADS, 2)
+template <bool FLIP, int RT = RADIAL_THREADS, int UU = 2>
+__global__ void __launch_bounds__(RT, (RT <= 768 ? 2 : 1))
 k_operands_radial_sm(float2* __restrict__ spec, const float2* __restrict__ Mspec, const float* __restrict__ cbin,
                      const int* __restrict__ fold_bin, const int* __restrict__ fold_start,
                      const int* __restrict__ fold_ent, const int* __restrict__ bin_of_pix,
@@ -342,20 +342,20 @@ k_operands_radial_sm(float2* __restrict__ spec, const float2* __restrict__ Mspec
   float* zl = zlo + (size_t)i * ldz;
   const int Kq = Na * Nh;
   float* cb = pw + Kq;                       // this image's CTF row, staged so the per-entry lookups stay on chip
-  for (int b = threadIdx.x; b < Kr; b += RADIAL_THREADS) cb[b] = cbin[(size_t)i * Kr + b];
+  for (int b = threadIdx.x; b < Kr; b += RT) cb[b] = cbin[(size_t)i * Kr + b];
   __syncthreads();
   const int nyq = (N & 1) ? -1 : N / 2;
-  const int step_x = RADIAL_THREADS % Nh, step_a = RADIAL_THREADS / Nh;
+  const int step_x = RT % Nh, step_a = RT / Nh;
   int a = threadIdx.x / Nh, kx = threadIdx.x % Nh;
   // four entries per thread and trip, every load issued before the first use (the kernel is latency-bound otherwise)
-  constexpr int U = 2;
-  for (int e0 = threadIdx.x; e0 < Kq; e0 += U * RADIAL_THREADS) {
+  constexpr int U = UU;
+  for (int e0 = threadIdx.x; e0 < Kq; e0 += U * RT) {
     float2 f[U], f2[U], mm[U], m2[U];
     int bn[U], sc[U], sc2[U], pe2[U];
     float wself[U], wpart[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int e = e0 + u * RADIAL_THREADS;
+      const int e = e0 + u * RT;
       const bool valid = e < Kq;
       const int ec = valid ? e : 0;
       const bool part = valid && a != 0 && 2 * a != N;
@@ -377,7 +377,7 @@ k_operands_radial_sm(float2* __restrict__ spec, const float2* __restrict__ Mspec
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int e = e0 + u * RADIAL_THREADS;
+      const int e = e0 + u * RT;
       if (e < Kq) {
         const float c = cb[bn[u]];
         const float gx = fmaf(-c, mm[u].x, f[u].x), gy = fmaf(-c, mm[u].y, f[u].y);
@@ -406,7 +406,7 @@ k_operands_radial_sm(float2* __restrict__ spec, const float2* __restrict__ Mspec
     }
   }
   __syncthreads();
-  for (int b = threadIdx.x; b < w1; b += RADIAL_THREADS) {
+  for (int b = threadIdx.x; b < w1; b += RT) {
     float s1 = 0.0f, s2 = 0.0f;
     if (b < Kr) {
       const float c = cb[b];
@@ -758,8 +758,19 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
     const size_t pw_bytes = ((size_t)g.Na * g.Nh + g.Kr) * sizeof(float);
     if (pw_bytes <= 200 * 1024) {
       auto kern = need_flip ? k_operands_radial_sm<true> : k_operands_radial_sm<false>;
+      int rthreads = RADIAL_THREADS;
+      if (!need_flip) {                                  // experiment switch (mem_ctx_set_option "radial_variant")
+        switch (ctx->radial_variant) {
+          case 1: kern = k_operands_radial_sm<false, 640, 2>; rthreads = 640; break;
+          case 2: kern = k_operands_radial_sm<false, 512, 2>; rthreads = 512; break;
+          case 3: kern = k_operands_radial_sm<false, 512, 4>; rthreads = 512; break;
+          case 4: kern = k_operands_radial_sm<false, 1024, 2>; rthreads = 1024; break;
+          case 5: kern = k_operands_radial_sm<false, 512, 1>; rthreads = 512; break;
+          default: break;
+        }
+      }
       MEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pw_bytes));
-      MEM_LAUNCH(ctx, kern, nS, RADIAL_THREADS, pw_bytes, st, spec, Mspec, ctx->cbin.as<float>(),
+      MEM_LAUNCH(ctx, kern, nS, rthreads, pw_bytes, st, spec, Mspec, ctx->cbin.as<float>(),
                  g.fold_bin.as<int>(), g.fold_start.as<int>(), g.fold_ent.as<int>(), g.bin_of_pix.as<int>(),
                  g.special_pix.as<int>(), g.s3_col.as<int>(), zhi, zlo, N, g.Nh, g.Na, g.Kh, g.Kr, g.n_special,
                  g.n1_blocks, g.ldz);

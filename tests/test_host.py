@@ -678,3 +678,20 @@ def test_psi_analysis_driver_bookkeeping(tmp_path):
     jobs = psiAnalysis.divid(4, rc, fin)
     assert [j[7] for j in jobs] == [[], [0, 1, 2], [0, 2], [0, 1, 2]]
     assert jobs[2][:4] == ['D_prD_2', 'P_prD_2', 'Q_prD_2', 'E_prD_2'] and jobs[3][6] == 3
+
+
+def test_partition_with_rank_speeds():
+    """LPT with per-rank speeds: ranks 4-7 one and a half times as fast get one and a half times the PDs; every job once."""
+    from manifoldem_python_b200 import partition
+    costs = [1.0] * 1000
+    speeds = [1.0] * 4 + [1.5] * 4
+    shards = partition.lpt_partition(costs, 8, speeds)
+    assert sorted(i for s in shards for i in s) == list(range(1000))
+    n = [len(s) for s in shards]
+    assert all(abs(x - 100) <= 1 for x in n[:4]) and all(abs(x - 150) <= 1 for x in n[4:])
+    assert partition.imbalance(costs, shards, speeds) < 1.02
+    assert partition.counts_by_speed(384, [23.3] * 4 + [35.5] * 4) == [38] * 4 + [58] * 4
+    assert sum(partition.counts_by_speed(100, [1, 2, 3])) == 100
+    rng = np.random.default_rng(0)
+    costs = list(rng.uniform(1, 5, 57))
+    assert partition.lpt_partition(costs, 3) == partition.lpt_partition(costs, 3, [1, 1, 1])
