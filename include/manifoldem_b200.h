@@ -31,7 +31,11 @@ int         mem_ctx_destroy(mem_ctx* ctx);
 int         mem_ctx_sync(mem_ctx* ctx);
 /* tuning / test switches of a context, by name; unknown names are an error.
  *   "legacy_rotate"  1 = the generic rotation kernel for every box size (default 0: boxes that are a multiple of 32
- *                    take the float4-staged / four-images-per-tap kernels of rotate.cu; results are bit-identical) */
+ *                    take the float4-staged / four-images-per-tap kernels of rotate.cu; results are bit-identical)
+ *   "full_sums"      1 = the per-pixel spectrum sums always run over every image.  Default 0: when only D / the neighbour
+ *                    lists are requested the sums serve nothing but the common component M removed from the contraction
+ *                    operands (D is invariant under any common M), and PDs of >= 1,024 images take every 8th image
+ *   "radial_variant" experiment switch of the operand writer's thread count (0 = default) */
 int         mem_ctx_set_option(mem_ctx* ctx, const char* name, int32_t value);
 /* kernels launched by this library on ctx since the last reset (bench.py gpu_launches) */
 int64_t     mem_ctx_launch_count(mem_ctx* ctx, int reset);

@@ -116,6 +116,7 @@ struct mem_ctx {
   int last_tc_items = 0, last_tc_nkb = 0;   // geometry of the last tcgen05 launch (executed-flop accounting)
   float timings[8] = {};
   void* tmap_encode = nullptr;   // cuTensorMapEncodeTiled entry point
+  int full_sums = 0;             // 1: the spectrum sums always run over every image (tests: M from all images)
   int radial_variant = 0;        // experiments: thread count / unroll of k_operands_radial_sm
   int legacy_rotate = 0;         // tests: 1 = the generic k_rotate for every box (mem_ctx_set_option)
 };

@@ -441,7 +441,10 @@ __global__ void __launch_bounds__(256) k_spec_sums(const float2* __restrict__ sp
                                                    const float* __restrict__ cbin, const int* __restrict__ bin_of_pix,
                                                    double2* __restrict__ part_cf, double2* __restrict__ part_cfw,
                                                    double* __restrict__ part_c2, double2* __restrict__ part_fl,
-                                                   int nS, int Kh, int Kr, int per_group) {
+                                                   int nS, int Kh, int Kr, int per_group, int img_stride) {
+  // img_stride > 1: the sums run over every img_stride-th image only (nS = number of images visited).  Used when the sums
+  // serve nothing but the common component M of the contraction operands: D is invariant under F_i -> F_i - C_i M for ANY
+  // common M, so M only has to remove the bulk of the shared signal, which a subset estimates as well.
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= Kh) return;
   const int g = blockIdx.y;
@@ -455,10 +458,10 @@ __global__ void __launch_bounds__(256) k_spec_sums(const float2* __restrict__ sp
     float2 fu[U], fwu[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int i = min(ib + u, i1 - 1);
-      cu[u] = cbin[(size_t)i * Kr + b];
-      fu[u] = spec[(size_t)i * Kh + p];
-      if (specw) fwu[u] = specw[(size_t)i * Kh + p];
+      const size_t i = (size_t)min(ib + u, i1 - 1) * img_stride;
+      cu[u] = cbin[i * Kr + b];
+      fu[u] = spec[i * Kh + p];
+      if (specw) fwu[u] = specw[i * Kh + p];
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -748,11 +751,17 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
   float* zlo = ctx->zlo.as<float>();
   double2* part_cfw = specw ? ctx->part_cfw.as<double2>() : (double2*)nullptr;
   float2* Mspec = ctx->avgspec.as<float2>() + 2 * Kh;
-  MEM_LAUNCH(ctx, k_spec_sums, dim3((g.Kh + 255) / 256, G), 256, 0, st, spec, specw, ctx->cbin.as<float>(),
+  // the Wiener / flip averages need the sums over every image; when only D (or the neighbour lists) is asked for, the sums
+  // feed nothing but M, and every 8th image of a large PD estimates the shared signal as well (>= 128 images)
+  const bool sums_for_M_only = !(io->imgAvg || io->imgAvgFlip || io->imgAllIntensity) && !ctx->full_sums;
+  const int sum_stride = (sums_for_M_only && nS >= 1024) ? 8 : 1;
+  const int nSum = (nS + sum_stride - 1) / sum_stride;
+  const int Gs = (nSum + per_group - 1) / per_group;
+  MEM_LAUNCH(ctx, k_spec_sums, dim3((g.Kh + 255) / 256, Gs), 256, 0, st, spec, specw, ctx->cbin.as<float>(),
              g.bin_of_pix.as<int>(), ctx->part_cf.as<double2>(), part_cfw, ctx->part_c2.as<double>(),
-             ctx->part_fl.as<double2>(), nS, g.Kh, g.Kr, per_group);
+             ctx->part_fl.as<double2>(), nSum, g.Kh, g.Kr, per_group, sum_stride);
   MEM_LAUNCH(ctx, k_avg_spectra, (g.Kh + 255) / 256, 256, 0, st, ctx->part_cf.as<double2>(), part_cfw,
-             ctx->part_c2.as<double>(), ctx->part_fl.as<double2>(), ctx->avgspec.as<float2>(), Mspec, g.Kh, G);
+             ctx->part_c2.as<double>(), ctx->part_fl.as<double2>(), ctx->avgspec.as<float2>(), Mspec, g.Kh, Gs);
   bool s3_done = false;      // the shared-memory radial kernel also writes S3 and the flipped spectra
   if (want_D) {
     const size_t pw_bytes = ((size_t)g.Na * g.Nh + g.Kr) * sizeof(float);
@@ -928,7 +937,7 @@ int pd_distance_batch_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_p
     float* zlo_p = zlo + (size_t)s0 * g.ldz;
     MEM_LAUNCH(ctx, k_spec_sums, dim3((g.Kh + 255) / 256, G), 256, 0, st, spec_p, (const float2*)nullptr, cbin_p,
                g.bin_of_pix.as<int>(), ctx->part_cf.as<double2>(), (double2*)nullptr, ctx->part_c2.as<double>(),
-               ctx->part_fl.as<double2>(), n, g.Kh, g.Kr, per_group);
+               ctx->part_fl.as<double2>(), n, g.Kh, g.Kr, per_group, 1);
     MEM_LAUNCH(ctx, k_avg_spectra, (g.Kh + 255) / 256, 256, 0, st, ctx->part_cf.as<double2>(), (double2*)nullptr,
                ctx->part_c2.as<double>(), ctx->part_fl.as<double2>(), ctx->avgspec.as<float2>(), Mspec, g.Kh, G);
     if (radial_sm) {
