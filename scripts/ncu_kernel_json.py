@@ -29,7 +29,9 @@ d = dict(kernel=r[h.index('Kernel Name')][:80], ncu_file=rep.split('/')[-1],
          dram_bytes_read=get('dram__bytes_read.sum'), dram_bytes_write=get('dram__bytes_write.sum'),
          duration_ms=get('gpu__time_duration.sum', 1e3), sm_mhz=get('smsp__cycles_elapsed.avg.per_second', 1e-6),
          tensor_pipe_active_pct_of_elapsed=get('sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_elapsed')
-         or get('sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_elapsed'),
+         or get('sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_elapsed')
+         or get('sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed'),
+         tensor_pipe_cycles_active_realtime_pct=get('TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed'),
          issue_active_pct=get('smsp__issue_active.avg.pct_of_peak_sustained_elapsed'),
          lsu_data_pipe_pct=get('l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed'),
          l2_hit_pct=get('lts__t_sector_hit_rate.pct'))
