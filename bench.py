@@ -902,7 +902,7 @@ def dropin_block(h_raw, pds, nS, N):
         q = np.concatenate([q, q], axis=1)                      # augmented set (conjugates appended); only first halves used
         df = np.tile(rng.uniform(10000.0, 30000.0, n_half), 2)
         CG = [np.arange(k * nS, (k + 1) * nS) for k in range(n_pd)]
-        for layout in ('sidecar', 'pickle'):
+        for layout in ('sidecar', 'sidecar_recipe', 'pickle'):
             p.init()
             p.nPix, p.pix_size, p.Cs, p.EkV, p.AmpContrast = N, EM['pix_size'], EM['Cs'], EM['EkV'], EM['AmpContrast']
             p.mask_vol_file, p.relion_data, p.num_part, p.ncpu = '', False, n_half, 1
@@ -913,7 +913,8 @@ def dropin_block(h_raw, pds, nS, N):
             p.dist_file = os.path.join(p.dist_dir, 'IMGs_')
             p.tess_file = os.path.join(base, 'tess_' + layout)
             p.numberofJobs = n_pd
-            p.record_layout = layout
+            p.record_layout = layout.split('_')[0]
+            p.record_virtual_images = (layout == 'sidecar_recipe')    # imgAll / imgAllFlip kept as a recipe, rebuilt on read
             myio.fout1(p.tess_file, ['CG', 'q', 'df', 'sh'], [CG, q, df, (np.zeros(n_half), np.zeros(n_half))], layout='pickle')
             t0 = time.perf_counter()
             with contextlib.redirect_stdout(sys.stderr):        # the stage driver prints like the reference's; stdout = ONE JSON line
@@ -924,9 +925,18 @@ def dropin_block(h_raw, pds, nS, N):
                        if os.path.isfile(os.path.join(p.dist_dir, f)))
             out[layout] = dict(s_per_pd=dt / n_pd, pds_done=done, record_gb_per_pd=size / n_pd / 1e9,
                                gpairs_s=n_pd * float(nS) * nS / dt / 1e9)
+            if layout == 'sidecar_recipe':                 # what a consumer pays to get the image arrays back
+                t1 = time.perf_counter()
+                rec0 = myio.fin1(p.dist_file + 'prD_0')
+                img0 = rec0['imgAll']
+                out[layout]['read_back_imgAll_and_imgAllFlip_s'] = time.perf_counter() - t1
+                out[layout]['note'] = ('imgAll / imgAllFlip are kept as a recipe (stack path + the ind / q / df already in the record) and '
+                                       'rebuilt by the same kernels when read: bit-identical values, shape %s' % (img0.shape,))
+                del rec0, img0
             shutil.rmtree(p.dist_dir, ignore_errors=True)
-            if hasattr(p, 'record_layout'):
-                del p.record_layout
+            for attr in ('record_layout', 'record_virtual_images'):
+                if hasattr(p, attr):
+                    delattr(p, attr)
     finally:
         shutil.rmtree(base, ignore_errors=True)
     return out

@@ -118,11 +118,26 @@ def op(input_data, filterPar, imgFileName, sh, nStot, options, fields=None):
                                   AmpContrast=float(p.AmpContrast),
                                   shape=(nS_, N, N) if options.get('parallel') else (nS_, N * N))
             want = tuple(f for f in want if f != 'CTF')
+        # p.record_virtual_images (opt-in): keep the recipe instead of imgAll / imgAllFlip — the stack's path; ind, q, df are in
+        # the record anyway — and let myio rebuild them with the same kernels when a consumer reads the key (myio._image_fields)
+        if getattr(p, 'record_virtual_images', False) and not options.get('avgOnly', False):
+            sh_pd = None
+            if relion:                                  # the shifts of this PD's members only (sh is indexed by particle)
+                base_idx = np.where(np.asarray(ind) >= nStot // 2, np.asarray(ind) - nStot // 2, np.asarray(ind))
+                sh_pd = (np.asarray(sh[0])[base_idx].copy(), np.asarray(sh[1])[base_idx].copy())
+            for name in ('imgAll', 'imgAllFlip'):
+                if name in want:
+                    virtual[name] = dict(virtual='images', stack=os.path.abspath(imgFileName), relion=relion, nStot=int(nStot), N=N,
+                                         pix_size=float(p.pix_size), Cs=float(p.Cs), EkV=float(p.EkV),
+                                         gaussEnv=float(getattr(p, 'gaussEnv', np.inf)), AmpContrast=float(p.AmpContrast),
+                                         filterPar=dict(filterPar), sh_members=sh_pd, shape=(len(np.asarray(ind)), N, N))
+            want = tuple(f for f in want if f not in virtual)
     with _checkout() as slot:      # the arrays of `res` live in the slot's pinned arena until the record is on disk
         res = pd_stage.run_pd(ind, q, df, stack, nStot, N, p.pix_size, p.Cs, p.EkV, p.AmpContrast,
                               gaussEnv=getattr(p, 'gaussEnv', np.inf), filterPar=filterPar, msk2=msk2, relion=relion,
                               sh=sh, avg_only=bool(options.get('avgOnly', False)), ctx=slot.ctx, angles=angles,
-                              fields=want, float64=(layout != 'sidecar'), arena=slot.arena)
+                              fields=want, float64=(layout != 'sidecar'), arena=slot.arena,
+                              intensity=True if virtual else None)
         if (options.get('parallel') or options.get('avgOnly')) and res['CTF'] is not None:
             res['CTF'] = res['CTF'].reshape(-1, N, N)     # only the default non-avgOnly branch flattens CTF (:392-393)
         res['options'] = options

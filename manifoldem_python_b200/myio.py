@@ -65,6 +65,14 @@ class Record(dict):
             a = _ctf_field(self[spec['df_key']], spec)
             super().__setitem__(k, a)
             return a
+        if spec.get('virtual') == 'images':
+            # one pass of the distance stage's own kernels rebuilds every image array of the record that is still virtual
+            names = [k] + [o for o, sp in self._lazy.items() if sp.get('virtual') == 'images']
+            out = _image_fields(self, spec, names)
+            for o in names:
+                self._lazy.pop(o, None)
+                super().__setitem__(o, out[o])
+            return out[k]
         a = np.load(os.path.join(os.path.dirname(self._base), spec['file']), mmap_mode='r')
         if tuple(a.shape) != tuple(spec['shape']):
             raise IOError('sidecar %s has shape %s, manifest says %s' % (spec['file'], a.shape, spec['shape']))
@@ -165,6 +173,32 @@ def _ctf_field(df, spec):
     out = np.empty((nS, N * N), dtype=np.float64)
     _lib.check(lib.mem_ctf_host(_ctx().handle, C.byref(prm), df.ctypes.data, out.ctypes.data))
     return out.reshape(spec['shape'])
+
+
+def _image_fields(rec, spec, names):
+    """A record written with virtual={'imgAll': ..., 'imgAllFlip': ...} does not store the aligned / phase-flipped image
+    stacks (2 x 4 N^2 bytes per particle — 1 GB of a C4-sized record, and what bounds the distance stage from disk to disk:
+    the box writes 2.3 GB/s) but the recipe: the particle stack's path and the PD's ind / q / df are in the record already.
+    The arrays are produced when a key is read, by the kernels that produced them inside the distance stage
+    (pd_stage.run_pd on the same inputs: deterministic, bit-identical values, ~0.1 s for a C4-sized PD — about what reading
+    1 GB back from disk costs).  The stack file must still be where it was."""
+    from . import pd_stage
+    from .getDistanceCTF_local_Conj9combinedS2 import _ctx
+    N = int(spec['N'])
+    stack = pd_stage.open_stack(spec['stack'], N, bool(spec['relion']))
+    msk2 = rec['msk2']
+    msk2 = None if np.ndim(msk2) == 0 else np.asarray(msk2)
+    sh = None
+    if spec.get('sh_members') is not None:              # back to arrays indexed by particle, as run_pd takes them
+        ind = np.asarray(rec['ind'])
+        half = int(spec['nStot']) // 2
+        base = np.where(ind >= half, ind - half, ind)
+        sh = (np.zeros(half), np.zeros(half))
+        sh[0][base], sh[1][base] = spec['sh_members'][0], spec['sh_members'][1]
+    res = pd_stage.run_pd(rec['ind'], rec['q'], rec['df'], stack, int(spec['nStot']), N, spec['pix_size'], spec['Cs'], spec['EkV'],
+                          spec['AmpContrast'], gaussEnv=spec['gaussEnv'], filterPar=spec['filterPar'], msk2=msk2,
+                          relion=bool(spec['relion']), sh=sh, fields=tuple(names), float64=True, ctx=_ctx(), intensity=False)
+    return {o: res[o] for o in names}
 
 
 def _sidecars_ok(arrays, filename):

@@ -413,3 +413,54 @@ def test_both_eigen_solvers_give_the_same_embedding(golden_dir):
     assert np.allclose(a[3], b[3], rtol=1e-7, atol=1e-12)                 # mu
     for j in range(8):
         assert abs(np.corrcoef(a[1][:, j], b[1][:, j])[0, 1]) > 0.999999, j
+
+
+@pytest.mark.parametrize('relion', [False, True])
+def test_virtual_image_arrays_in_sidecar_records(tmp_path, relion):
+    """p.record_virtual_images: the record keeps the recipe (stack path; ind, q, df are in it anyway) instead of imgAll /
+    imgAllFlip; reading the keys rebuilds them with the distance stage's own kernels — bit for bit what the default
+    record stores — and every other key is unchanged.  SPIDER and RELION (per-member shifts) stacks."""
+    from manifoldem_python_b200 import getDistanceCTF_local_Conj9combinedS2 as worker
+    from manifoldem_python_b200 import myio, p, synthetic
+    N, nS = 64, 40
+    pd = synthetic.make_pd(nS, N, seed=63, snr=2.0)
+    p.init()
+    p.user_dir, p.proj_name = str(tmp_path), 'virt'
+    p.create_dir()
+    em = pd['em']
+    p.nPix, p.pix_size, p.Cs, p.EkV, p.AmpContrast = N, em['pix_size'], em['Cs'], em['EkV'], em['AmpContrast']
+    stack_file = str(tmp_path / ('stack.mrcs' if relion else 'stack.dat'))
+    sh = pd['sh']
+    if relion:
+        rng = np.random.default_rng(1)
+        n_half = pd['nStot'] // 2
+        sh = (rng.uniform(-2, 2, n_half), rng.uniform(-2, 2, n_half))
+        hdr = np.zeros(256, dtype='<i4')
+        hdr[0], hdr[1], hdr[2], hdr[3] = N, N, n_half, 2
+        with open(stack_file, 'wb') as f:
+            f.write(hdr.tobytes())
+            f.write(pd['stack'].astype('<f4').tobytes())
+    else:
+        pd['stack'].tofile(stack_file)
+    opts = dict(verbose=False, avgOnly=False, visual=False, parallel=False, relion_data=relion, thres=2000)
+    recs = {}
+    try:
+        for prD, virt in enumerate((False, True)):
+            p.record_layout, p.record_virtual_images = 'sidecar', virt
+            f = '{}prD_{}'.format(p.dist_file, prD)
+            worker.op([pd['ind'], pd['q'], pd['df'], f, prD], dict(type='Butter', Qc=0.5, N=8), stack_file, sh, pd['nStot'], opts)
+            recs[virt] = myio.fin1(f)
+    finally:
+        del p.record_layout, p.record_virtual_images
+    a, b = recs[True], recs[False]
+    assert a._lazy['imgAll']['virtual'] == 'images' and a._lazy['imgAllFlip']['virtual'] == 'images'
+    assert not os.path.exists('{}prD_1.imgAll.npy'.format(p.dist_file)) and os.path.exists('{}prD_0.imgAll.npy'.format(p.dist_file))
+    assert list(a.keys()) == list(b.keys())
+    img = a['imgAll']                                   # one recomputation fills both virtual image arrays
+    assert 'imgAllFlip' not in a._lazy
+    for k in b:
+        if isinstance(b[k], np.ndarray):
+            assert a[k].dtype == b[k].dtype and a[k].shape == b[k].shape and np.array_equal(a[k], b[k]), k
+        else:
+            assert a[k] == b[k], k
+    assert img.dtype == np.float64 and img.shape == (nS, N, N)
