@@ -195,14 +195,17 @@ __global__ void __launch_bounds__(CF_THREADS, 2) k_colfilter256(float2* __restri
 // to k_colfilter256, which applies the normalisation in Fourier space.
 // ------------------------------------------------------------------------------------------------
 constexpr int IR_BP = 257;      // band pitch (floats): odd, so the transposing stores are conflict-free
-constexpr int IR_EP = 272;      // exchange floats2 per row pair: [16][17]
-__global__ void __launch_bounds__(256, 3) k_ingest_rowfft256(const float* __restrict__ raw, const uint8_t* __restrict__ flip,
+constexpr int IR_EP = 272;      // (k_colfilter-era constant; the row kernels keep their exchange inside the band, see below)
+// Shared memory = the band alone (32.9 KB): the FFT exchange of a row pair — 256 float2 — lives in the two band rows the
+// pair has just loaded into registers (2 x 257 floats = 2,056 B), element (a, b) at a * 16 + (b ^ a): unit-stride across the
+// 16 lanes of a transform both ways (an XOR swizzle instead of the [16][17] padding, which would not fit).  With 64
+// registers that is four CTAs per SM instead of three (the kernel is latency-bound: 24 -> 32 warps).
+__global__ void __launch_bounds__(256, 4) k_ingest_rowfft256(const float* __restrict__ raw, const uint8_t* __restrict__ flip,
                                                            float2* __restrict__ spec, float2* __restrict__ stats,
                                                            int transposed) {
   constexpr int N = 256, Nh = 129;
   extern __shared__ float2 ir_smem[];
-  float2* ex = ir_smem;                                             // [16 row pairs][16][17]
-  float* band = reinterpret_cast<float*>(ir_smem + 16 * IR_EP);     // [32][IR_BP]
+  float* band = reinterpret_cast<float*>(ir_smem);                  // [32][IR_BP]
   __shared__ double red[24];
   __shared__ float2 tws[256];                     // tws[k1][t] = W256^(t k1): the constant bank would serialise the 16
   tws[threadIdx.x] = c_tw256[((threadIdx.x >> 4) * (threadIdx.x & 15)) & 255];   // distinct t of a warp on every lookup
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(256, 3) k_ingest_rowfft256(const float* __rest
   const float off = src[0];
   double s = 0, s2 = 0;
   int cnt = 0;                                     // pixels outside the disc (the only ones that enter the sums)
-  float2* e = ex + p * IR_EP;
+  float2* e = reinterpret_cast<float2*>(band + (2 * p) * IR_BP);    // exchange of this row pair = its own two band rows
   const int partner = (lane & 16) + ((16 - t) & 15);
   for (int b0 = 0; b0 < N; b0 += 32) {
     float rs = 0.0f, rs2 = 0.0f;
@@ -262,11 +265,12 @@ __global__ void __launch_bounds__(256, 3) k_ingest_rowfft256(const float* __rest
 #pragma unroll
     for (int m = 0; m < 16; ++m) v[m] = make_float2(b1[16 * m], b1[IR_BP + 16 * m]);
     fft16<-1>(v);
+    __syncwarp();                                   // every lane of the pair has its rows in registers: they become the exchange
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) e[k1 * 17 + t] = cmul(v[k1], tws[k1 * 16 + t]);
+    for (int k1 = 0; k1 < 16; ++k1) e[k1 * 16 + (t ^ k1)] = cmul(v[k1], tws[k1 * 16 + t]);
     __syncwarp();
 #pragma unroll
-    for (int n2 = 0; n2 < 16; ++n2) v[n2] = e[t * 17 + n2];
+    for (int n2 = 0; n2 < 16; ++n2) v[n2] = e[t * 16 + (n2 ^ t)];
     fft16<-1>(v);                                   // v[k2] = Z[t + 16 k2]
     float2* o1 = out + (b0 + 2 * p) * Nh + t;
     float2* o2 = o1 + Nh;
@@ -316,17 +320,16 @@ __global__ void __launch_bounds__(256, 3) k_ingest_rowfft256(const float* __rest
 // owning samples [8 l, 8 l + 8), and stores them row-coalesced.  The low-passed image itself never reaches HBM.
 // ------------------------------------------------------------------------------------------------
 constexpr int RP_BP = 264;      // band pitch: 256 samples + one pad float per 32 (conflict-free for both access patterns)
-__global__ void __launch_bounds__(256, 3) k_rowifft_prefilter256(const float2* __restrict__ spec, float* __restrict__ outimg) {
+__global__ void __launch_bounds__(256, 4) k_rowifft_prefilter256(const float2* __restrict__ spec, float* __restrict__ outimg) {
   constexpr int N = 256, Nh = 129, E = 8;
   extern __shared__ float2 ir_smem[];
-  float2* ex = ir_smem;
-  float* band = reinterpret_cast<float*>(ir_smem + 16 * IR_EP);     // [32][RP_BP]
+  float* band = reinterpret_cast<float*>(ir_smem);                  // [32][RP_BP]; the exchange of a row pair lives in its rows
   const int i = blockIdx.x;
   const float2* in = spec + (size_t)i * N * Nh;
   float* dst = outimg + (size_t)i * N * N;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p = threadIdx.x >> 4, t = threadIdx.x & 15;
-  float2* e = ex + p * IR_EP;
+  float2* e = reinterpret_cast<float2*>(band + (2 * p) * RP_BP);    // 2 x 264 floats >= 256 float2, swizzled as in the forward kernel
   constexpr float half = 0.5f * N, r2lim = half * half;
   const float zE = 2.6571717e-05f;                  // z^8, z = sqrt(3) - 2
   __shared__ float2 tws[256];                       // tws[n1][t] = conj W256^(t n1), see k_ingest_rowfft256
@@ -354,11 +357,12 @@ __global__ void __launch_bounds__(256, 3) k_rowifft_prefilter256(const float2* _
     }
     fft16<1>(v);
 #pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) e[n1 * 17 + t] = cmul(v[n1], tws[n1 * 16 + t]);
+    for (int n1 = 0; n1 < 16; ++n1) e[n1 * 16 + (t ^ n1)] = cmul(v[n1], tws[n1 * 16 + t]);
     __syncwarp();
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) v[k1] = e[t * 17 + k1];
+    for (int k1 = 0; k1 < 16; ++k1) v[k1] = e[t * 16 + (k1 ^ t)];
     fft16<1>(v);                                    // v[m] = z[t + 16 m]: row 2p in .x, row 2p + 1 in .y
+    __syncwarp();                                   // the exchange has been read by every lane: its memory becomes the two rows
     float* r1 = band + (2 * p) * RP_BP;
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
@@ -415,7 +419,7 @@ int ingest_rowfft_run(mem_ctx* ctx, const float* raw, const uint8_t* flip, float
     return 1;
   }
   MEM_CHECK(ensure_twiddles(ctx, st));
-  const size_t smem = 16 * IR_EP * sizeof(float2) + 32 * IR_BP * sizeof(float);
+  const size_t smem = 32 * IR_BP * sizeof(float);
   MEM_CUDA(cudaFuncSetAttribute(k_ingest_rowfft256, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   MEM_LAUNCH(ctx, k_ingest_rowfft256, nS, 256, smem, st, raw, flip, spec, stats, transposed);
   return 0;
@@ -427,7 +431,7 @@ int rowifft_prefilter_run(mem_ctx* ctx, const float2* spec, float* out, int nS, 
     return 1;
   }
   MEM_CHECK(ensure_twiddles(ctx, st));
-  const size_t smem = 16 * IR_EP * sizeof(float2) + 32 * RP_BP * sizeof(float);
+  const size_t smem = 32 * RP_BP * sizeof(float);
   MEM_CUDA(cudaFuncSetAttribute(k_rowifft_prefilter256, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   MEM_LAUNCH(ctx, k_rowifft_prefilter256, nS, 256, smem, st, spec, out);
   return 0;
