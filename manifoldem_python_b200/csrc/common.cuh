@@ -117,6 +117,7 @@ struct mem_ctx {
   float timings[8] = {};
   void* tmap_encode = nullptr;   // cuTensorMapEncodeTiled entry point
   int full_sums = 0;             // 1: the spectrum sums always run over every image (tests: M from all images)
+  int rowfft_blocks = 0;         // experiments: CTAs per SM the row FFT kernels are compiled for (0 = default 4)
   int radial_variant = 0;        // experiments: thread count / unroll of k_operands_radial_sm
   int legacy_rotate = 0;         // tests: 1 = the generic k_rotate for every box (mem_ctx_set_option)
 };

@@ -200,7 +200,8 @@ constexpr int IR_EP = 272;      // (k_colfilter-era constant; the row kernels ke
 // pair has just loaded into registers (2 x 257 floats = 2,056 B), element (a, b) at a * 16 + (b ^ a): unit-stride across the
 // 16 lanes of a transform both ways (an XOR swizzle instead of the [16][17] padding, which would not fit).  With 64
 // registers that is four CTAs per SM instead of three (the kernel is latency-bound: 24 -> 32 warps).
-__global__ void __launch_bounds__(256, 4) k_ingest_rowfft256(const float* __restrict__ raw, const uint8_t* __restrict__ flip,
+template <int MB>
+__global__ void __launch_bounds__(256, MB) k_ingest_rowfft256(const float* __restrict__ raw, const uint8_t* __restrict__ flip,
                                                            float2* __restrict__ spec, float2* __restrict__ stats,
                                                            int transposed) {
   constexpr int N = 256, Nh = 129;
@@ -320,7 +321,8 @@ __global__ void __launch_bounds__(256, 4) k_ingest_rowfft256(const float* __rest
 // owning samples [8 l, 8 l + 8), and stores them row-coalesced.  The low-passed image itself never reaches HBM.
 // ------------------------------------------------------------------------------------------------
 constexpr int RP_BP = 264;      // band pitch: 256 samples + one pad float per 32 (conflict-free for both access patterns)
-__global__ void __launch_bounds__(256, 4) k_rowifft_prefilter256(const float2* __restrict__ spec, float* __restrict__ outimg) {
+template <int MB>
+__global__ void __launch_bounds__(256, MB) k_rowifft_prefilter256(const float2* __restrict__ spec, float* __restrict__ outimg) {
   constexpr int N = 256, Nh = 129, E = 8;
   extern __shared__ float2 ir_smem[];
   float* band = reinterpret_cast<float*>(ir_smem);                  // [32][RP_BP]; the exchange of a row pair lives in its rows
@@ -420,8 +422,12 @@ int ingest_rowfft_run(mem_ctx* ctx, const float* raw, const uint8_t* flip, float
   }
   MEM_CHECK(ensure_twiddles(ctx, st));
   const size_t smem = 32 * IR_BP * sizeof(float);
-  MEM_CUDA(cudaFuncSetAttribute(k_ingest_rowfft256, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  MEM_LAUNCH(ctx, k_ingest_rowfft256, nS, 256, smem, st, raw, flip, spec, stats, transposed);
+  auto kern = k_ingest_rowfft256<4>;
+  if (ctx->rowfft_blocks == 5) kern = k_ingest_rowfft256<5>;
+  else if (ctx->rowfft_blocks == 6) kern = k_ingest_rowfft256<6>;
+  else if (ctx->rowfft_blocks == 3) kern = k_ingest_rowfft256<3>;
+  MEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MEM_LAUNCH(ctx, kern, nS, 256, smem, st, raw, flip, spec, stats, transposed);
   return 0;
 }
 
@@ -432,8 +438,12 @@ int rowifft_prefilter_run(mem_ctx* ctx, const float2* spec, float* out, int nS, 
   }
   MEM_CHECK(ensure_twiddles(ctx, st));
   const size_t smem = 32 * RP_BP * sizeof(float);
-  MEM_CUDA(cudaFuncSetAttribute(k_rowifft_prefilter256, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  MEM_LAUNCH(ctx, k_rowifft_prefilter256, nS, 256, smem, st, spec, out);
+  auto kern = k_rowifft_prefilter256<4>;
+  if (ctx->rowfft_blocks == 5) kern = k_rowifft_prefilter256<5>;
+  else if (ctx->rowfft_blocks == 6) kern = k_rowifft_prefilter256<6>;
+  else if (ctx->rowfft_blocks == 3) kern = k_rowifft_prefilter256<3>;
+  MEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MEM_LAUNCH(ctx, kern, nS, 256, smem, st, spec, out);
   return 0;
 }
 
