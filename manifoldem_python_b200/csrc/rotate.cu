@@ -22,6 +22,7 @@
 
 #include <math.h>
 #include <algorithm>
+#include <stdlib.h>
 
 namespace mem {
 
@@ -169,7 +170,8 @@ __global__ void __launch_bounds__(256) k_rotate_img(const float* __restrict__ co
 template <int P4>   // tile pitch in float4 units
 __global__ void __launch_bounds__(256) k_rotate_common(const float* __restrict__ coef, float* __restrict__ out,
                                                        const double2* __restrict__ cs_common, int N, int nS,
-                                                       const uint8_t* __restrict__ msk2, float* __restrict__ out_masked) {
+                                                       const uint8_t* __restrict__ msk2, float* __restrict__ out_masked,
+                                                       int rrows, int rcols) {
   extern __shared__ __align__(16) float4 tile4[];
   const double2 a = cs_common[0];
   const int img0 = blockIdx.z * 4;
@@ -191,12 +193,14 @@ __global__ void __launch_bounds__(256) k_rotate_common(const float* __restrict__
     int gxb = w1 + ln + 32;
     gxb -= (gxb >= N) ? N : 0;
     gxb -= (gxb >= N) ? N : 0;
-    const bool second = ln + 32 < 4 * RG;
+    const bool second = ln + 32 < rcols;                 // rcols <= 4 RG: the columns this launch's angle can reach
     int gy = w0 + wp;
     gy -= (gy >= N) ? N : 0;
+    // rrows <= RROWS: the rows this launch's angle can reach (31 (|cos| + |sin|) + 6) — the shared-memory tile is sized by
+    // it, so small angles fit more CTAs per SM (the kernel is bound by shared-memory latency at 4 CTAs)
 #pragma unroll
     for (int it = 0; it < (RROWS + 7) / 8; ++it) {
-      if (it * 8 + wp < RROWS) {                          // warp-uniform
+      if (it * 8 + wp < rrows) {                          // warp-uniform
         const float* rowp = s0 + gy * N;
         float4* t = tile4 + (it * 8 + wp) * P4;
         t[ln] = make_float4(__ldg(rowp + gxa), __ldg(rowp + d1 + gxa), __ldg(rowp + d2 + gxa), __ldg(rowp + d3 + gxa));
@@ -293,20 +297,24 @@ static double sim_img(double c, double s, int P) {
   return tot / 6;
 }
 
-// mean wavefronts per quarter-warp phase of an LDS.128: 8 lanes = 8 consecutive pixels of a row, float4 pitch P4
+// mean wavefronts per quarter-warp phase of an LDS.128: 8 lanes = 8 consecutive pixels of a row, float4 pitch P4; averaged over
+// a 12 x 12 grid of sub-pixel offsets of the first lane (the measured kernel time follows this figure closely: at -40 degrees
+// the pitches 55 and 63 take 2.34 ms where 58 takes 1.57)
 static double sim_common(double c, double s, int P4) {
-  static const double offs[8][2] = {{0.13, 0.71}, {0.52, 0.08}, {0.91, 0.44}, {0.27, 0.95},
-                                    {0.66, 0.31}, {0.40, 0.58}, {0.05, 0.23}, {0.78, 0.86}};
   double tot = 0;
-  for (auto& o : offs) {
-    int addr[8];
-    for (int l = 0; l < 8; ++l) {
-      const int i = (int)floor(30.0 + o[0] + l * s), j = (int)floor(30.0 + o[1] + l * c);
-      addr[l] = i * P4 + j;
+  int n = 0;
+  for (int a = 0; a < 12; ++a)
+    for (int b = 0; b < 12; ++b) {
+      const double o0 = (a + 0.37) / 12.0, o1 = (b + 0.61) / 12.0;
+      int addr[8];
+      for (int l = 0; l < 8; ++l) {
+        const int i = (int)floor(30.0 + o0 + l * s), j = (int)floor(30.0 + o1 + l * c);
+        addr[l] = i * P4 + j;
+      }
+      tot += wavefronts(addr, 8, 8);
+      ++n;
     }
-    tot += wavefronts(addr, 8, 8);
-  }
-  return tot / 8;
+  return tot / n;
 }
 
 static int ensure_pitch_table(mem_ctx* ctx, cudaStream_t st) {
@@ -357,30 +365,39 @@ int rotate_img_run(mem_ctx* ctx, const float* coef, float* out, const double2* c
 int rotate_common_run(mem_ctx* ctx, const float* coef, float* out, const double2* cs_common, double angle_deg, int nS,
                       int N, const uint8_t* msk2, float* out_masked, cudaStream_t st) {
   const double a = angle_deg * M_PI / 180.0;
-  // the quarter-warp of an LDS.128 walks along an output row: source step (sin, cos) per lane
-  const int P4s[8] = {57, 58, 59, 60, 61, 62, 63, 64};
+  // the quarter-warp of an LDS.128 walks along an output row: source step (sin, cos) per lane.  The tile holds only the rows and
+  // columns this angle can reach (31 (|cos| + |sin|) + taps + alignment); the float4 pitch is the best of the candidates
+  // from that width up to 64, by simulating the bank pattern — small tiles mean more CTAs per SM (4 at 45 degrees with the old fixed
+  // 50 x 58 tile, 5 now; 8 near the axes)
+  const double ext = (RT - 1) * (fabs(cos(a)) + fabs(sin(a)));
+  const int rrows = std::min(RROWS, (int)floor(ext + 1e-9) + 6);
+  const int rcols = std::min(4 * RG, (int)floor(ext + 1e-9) + 6 + 3);
   double best = 1e9;
-  int bi = 0;
-  for (int k = 0; k < 8; ++k) {
-    const double w = sim_common(cos(a), sin(a), P4s[k]);
-    if (w < best - 1e-9) { best = w; bi = k; }
+  int P4 = 64;
+  for (int cand = std::max(40, rcols); cand <= 64; ++cand) {
+    const double w = sim_common(cos(a), sin(a), cand);
+    if (w < best - 1e-9) { best = w; P4 = cand; }
+  }
+  if (const char* ov = getenv("MANIFOLDEM_B200_ROT_P4")) {              // experiments: force the pitch
+    const int v = atoi(ov);
+    if (v >= rcols && v <= 64) P4 = v;
   }
   const dim3 grid(N / RT, N / RT, (nS + 3) / 4);
-  const size_t smem = (size_t)RROWS * P4s[bi] * sizeof(float4);
-#define LAUNCH_COMMON(P4)                                                                                   \
-  do {                                                                                                      \
-    MEM_CUDA(cudaFuncSetAttribute(k_rotate_common<P4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    MEM_LAUNCH(ctx, k_rotate_common<P4>, grid, 256, smem, st, coef, out, cs_common, N, nS, msk2, out_masked);  \
-  } while (0)
-  switch (P4s[bi]) {
-    case 57: LAUNCH_COMMON(57); break;
-    case 58: LAUNCH_COMMON(58); break;
-    case 59: LAUNCH_COMMON(59); break;
-    case 60: LAUNCH_COMMON(60); break;
-    case 61: LAUNCH_COMMON(61); break;
-    case 62: LAUNCH_COMMON(62); break;
-    case 63: LAUNCH_COMMON(63); break;
-    default: LAUNCH_COMMON(64); break;
+  const size_t smem = (size_t)rrows * P4 * sizeof(float4);
+#define LAUNCH_COMMON(PP)                                                                                   \
+  case PP:                                                                                                  \
+    MEM_CUDA(cudaFuncSetAttribute(k_rotate_common<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    MEM_LAUNCH(ctx, k_rotate_common<PP>, grid, 256, smem, st, coef, out, cs_common, N, nS, msk2, out_masked, rrows, rcols);  \
+    break;
+  switch (P4) {
+    LAUNCH_COMMON(40) LAUNCH_COMMON(41) LAUNCH_COMMON(42) LAUNCH_COMMON(43) LAUNCH_COMMON(44) LAUNCH_COMMON(45)
+    LAUNCH_COMMON(46) LAUNCH_COMMON(47) LAUNCH_COMMON(48) LAUNCH_COMMON(49) LAUNCH_COMMON(50) LAUNCH_COMMON(51)
+    LAUNCH_COMMON(52) LAUNCH_COMMON(53) LAUNCH_COMMON(54) LAUNCH_COMMON(55) LAUNCH_COMMON(56) LAUNCH_COMMON(57)
+    LAUNCH_COMMON(58) LAUNCH_COMMON(59) LAUNCH_COMMON(60) LAUNCH_COMMON(61) LAUNCH_COMMON(62) LAUNCH_COMMON(63)
+    default:
+      MEM_CUDA(cudaFuncSetAttribute(k_rotate_common<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      MEM_LAUNCH(ctx, k_rotate_common<64>, grid, 256, smem, st, coef, out, cs_common, N, nS, msk2, out_masked, rrows, rcols);
+      break;
   }
 #undef LAUNCH_COMMON
   return 0;

@@ -23,7 +23,8 @@ flip = _lib.DeviceArray(ctx, (nS,), np.uint8, pd['flip'])
 psi = _lib.DeviceArray(ctx, (nS,), np.float64, pd['psi_deg'])
 df = _lib.DeviceArray(ctx, (nS,), np.float64, pd['df'])
 D = _lib.DeviceArray(ctx, (nS, nS), np.float32)
-prm = bench.pd_params(_lib, nS, N, pd['psi_p'])
+prm = bench.pd_params(_lib, nS, N, float(os.environ.get('PSI_P', pd['psi_p'])))
+print('psi_p', prm.psi_p_deg)
 io = _lib.PdIO()
 io.raw, io.flip, io.psi_deg, io.df, io.D = raw.ptr, flip.ptr, psi.ptr, df.ptr, D.ptr
 ref = None
