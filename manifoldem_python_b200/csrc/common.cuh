@@ -117,6 +117,7 @@ struct mem_ctx {
   float timings[8] = {};
   void* tmap_encode = nullptr;   // cuTensorMapEncodeTiled entry point
   int full_sums = 0;             // 1: the spectrum sums always run over every image (tests: M from all images)
+  int cufft_a10 = 0;             // 1: the a10 transform through cuFFT's 2-D plan even for N = 256 (tests / comparison)
   int rowfft_blocks = 0;         // experiments: CTAs per SM the row FFT kernels are compiled for (0 = default 4)
   int radial_variant = 0;        // experiments: thread count / unroll of k_operands_radial_sm
   int legacy_rotate = 0;         // tests: 1 = the generic k_rotate for every box (mem_ctx_set_option)
@@ -132,6 +133,8 @@ int colfilter_run(mem_ctx* ctx, float2* spec, const float* G, const float2* stat
 // a2 + a3 + row R2C in one pass for the same box sizes: raw particles -> row-transformed half spectra + (mean, 1/std)
 int ingest_rowfft_run(mem_ctx* ctx, const float* raw, const uint8_t* flip, float2* spec, float2* stats, int nS, int N,
                       int transposed, cudaStream_t st);
+// a10 forward transform for the same box sizes with the library's own FFT kernels (rows R2C, then columns)
+int fft2_forward_run(mem_ctx* ctx, const float* img, float2* spec, int nS, int N, cudaStream_t st);
 // inverse row pass (C2R) + annular mask + row pass of the periodic spline prefilter: half spectra -> out [nS][N][N]
 int rowifft_prefilter_run(mem_ctx* ctx, const float2* spec, float* out, int nS, int N, cudaStream_t st);
 // kNN lists wanted from the contraction (a15 fused behind a12): idx [nS][k] int32, val [nS][k] float64, device.

@@ -108,6 +108,8 @@ constexpr int CF_SLABS = 6;
 // stats != NULL: the rows came from k_ingest_rowfft256, i.e. from images that are only shifted by a per-image offset,
 // not yet normalised; (x - mean) / std is linear, so it is applied here: subtract mean * N^2 at (ky, kx) = (0, 0) and
 // scale the filter by 1 / std.
+// FWD: the column pass of the a10 transform — forward FFT along ky only, no filter, no way back.
+template <bool FWD = false>
 __global__ void __launch_bounds__(CF_THREADS, 2) k_colfilter256(float2* __restrict__ spec, const float* __restrict__ G,
                                                              const float2* __restrict__ stats, int Nh, int nS,
                                                              int img_stride) {
@@ -120,8 +122,10 @@ __global__ void __launch_bounds__(CF_THREADS, 2) k_colfilter256(float2* __restri
   const bool live = kx < Nh;
   const int kxc = live ? kx : 0;
   float gk[16];
+  if (!FWD) {
 #pragma unroll
-  for (int k2 = 0; k2 < 16; ++k2) gk[k2] = live ? G[(t + 16 * k2) * Nh + kxc] : 0.0f;
+    for (int k2 = 0; k2 < 16; ++k2) gk[k2] = live ? G[(t + 16 * k2) * Nh + kxc] : 0.0f;
+  }
   __shared__ float2 tws[256];                     // tws[k1][t] = W256^(t k1)
   if (threadIdx.x < 256) tws[threadIdx.x] = c_tw256[((threadIdx.x >> 4) * (threadIdx.x & 15)) & 255];
   __syncthreads();
@@ -154,6 +158,14 @@ __global__ void __launch_bounds__(CF_THREADS, 2) k_colfilter256(float2* __restri
 #pragma unroll
     for (int n2 = 0; n2 < 16; ++n2) v[n2] = ex[(t * 16 + n2) * CF_COLS + col];
     fft16<-1>(v);                                   // v[k2] = X[t + 16 k2]
+    if (FWD) {
+      if (live) {
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) base[(t + 16 * k2) * Nh] = v[k2];
+      }
+      __syncthreads();                              // `ex` is rewritten by the next image
+      continue;
+    }
     float scale = 1.0f;
     if (stats) {
       const float2 ms = stats[img];                 // (mean - offset, 1 / std): what is left to subtract from the offset image
@@ -200,7 +212,8 @@ constexpr int IR_EP = 272;      // (k_colfilter-era constant; the row kernels ke
 // pair has just loaded into registers (2 x 257 floats = 2,056 B), element (a, b) at a * 16 + (b ^ a): unit-stride across the
 // 16 lanes of a transform both ways (an XOR swizzle instead of the [16][17] padding, which would not fit).  With 64
 // registers that is four CTAs per SM instead of three (the kernel is latency-bound: 24 -> 32 warps).
-template <int MB>
+// PLAIN: the a10 transform of the aligned images (:344): picture-orientation rows, no flip, no offset, no moments.
+template <int MB, bool PLAIN = false>
 __global__ void __launch_bounds__(256, MB) k_ingest_rowfft256(const float* __restrict__ raw, const uint8_t* __restrict__ flip,
                                                            float2* __restrict__ spec, float2* __restrict__ stats,
                                                            int transposed) {
@@ -213,18 +226,25 @@ __global__ void __launch_bounds__(256, MB) k_ingest_rowfft256(const float* __res
   const int i = blockIdx.x;
   const float* src = raw + (size_t)i * N * N;
   float2* out = spec + (size_t)i * N * Nh;
-  const bool fl = flip[i] != 0;
+  const bool fl = PLAIN ? false : flip[i] != 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p = threadIdx.x >> 4, t = threadIdx.x & 15;
   const float half = 0.5f * N, r2lim = half * half;
-  const float off = src[0];
+  const float off = PLAIN ? 0.0f : src[0];
   double s = 0, s2 = 0;
   int cnt = 0;                                     // pixels outside the disc (the only ones that enter the sums)
   float2* e = reinterpret_cast<float2*>(band + (2 * p) * IR_BP);    // exchange of this row pair = its own two band rows
   const int partner = (lane & 16) + ((16 - t) & 15);
   for (int b0 = 0; b0 < N; b0 += 32) {
     float rs = 0.0f, rs2 = 0.0f;
-    if (transposed) {                               // picture[rp][c] = raw[c][rp]; lanes run along rp (contiguous in raw)
+    if (PLAIN) {
+#pragma unroll
+      for (int k = warp; k < 32; k += 8) {
+        const float* rowp = src + (b0 + k) * N;
+#pragma unroll
+        for (int c = lane; c < N; c += 32) band[k * IR_BP + c] = rowp[c];
+      }
+    } else if (transposed) {                        // picture[rp][c] = raw[c][rp]; lanes run along rp (contiguous in raw)
       const int rp = b0 + lane;
       const int r = fl ? N - 1 - rp : rp;
       const float x = (float)rp - half + 1.0f, x2 = x * x;     // annularMask.py:24-30, centre (N/2-1, N/2)
@@ -291,6 +311,7 @@ __global__ void __launch_bounds__(256, MB) k_ingest_rowfft256(const float* __res
     }
     __syncthreads();                                // the band and the exchange rows are rewritten by the next band
   }
+  if (PLAIN) return;
   double dc = (double)cnt;
   for (int o = 16; o > 0; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -457,8 +478,28 @@ int colfilter_run(mem_ctx* ctx, float2* spec, const float* G, const float2* stat
   static_assert(CF_SLABS * CF_COLS >= 129, "slabs must cover the half spectrum");
   const int per_slab = std::max(1, std::min(nS, (2 * ctx->sm_count) / CF_SLABS));   // CTAs per slab, two CTAs per SM
   const size_t smem = 2 * 256 * CF_COLS * sizeof(float2);
-  MEM_CUDA(cudaFuncSetAttribute(k_colfilter256, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  MEM_LAUNCH(ctx, k_colfilter256, per_slab * CF_SLABS, CF_THREADS, smem, st, spec, G, stats, Nh, nS, per_slab);
+  MEM_CUDA(cudaFuncSetAttribute(k_colfilter256<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MEM_LAUNCH(ctx, k_colfilter256<false>, per_slab * CF_SLABS, CF_THREADS, smem, st, spec, G, stats, Nh, nS, per_slab);
+  return 0;
+}
+
+// a10 (:344) for N = 256 with our own kernels: real rows -> half spectra (k_ingest_rowfft256 PLAIN), then the forward column pass
+int fft2_forward_run(mem_ctx* ctx, const float* img, float2* spec, int nS, int N, cudaStream_t st) {
+  if (N != 256) {
+    set_error("fft2_forward: no kernel for N = %d", N);
+    return 1;
+  }
+  MEM_CHECK(ensure_twiddles(ctx, st));
+  const size_t smem_r = 32 * IR_BP * sizeof(float);
+  auto kr = k_ingest_rowfft256<4, true>;
+  MEM_CUDA(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+  MEM_LAUNCH(ctx, kr, nS, 256, smem_r, st, img, (const uint8_t*)nullptr, spec, (float2*)nullptr, 0);
+  const int Nh = N / 2 + 1;
+  const int per_slab = std::max(1, std::min(nS, (2 * ctx->sm_count) / CF_SLABS));
+  const size_t smem_c = 2 * 256 * CF_COLS * sizeof(float2);
+  MEM_CUDA(cudaFuncSetAttribute(k_colfilter256<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+  MEM_LAUNCH(ctx, k_colfilter256<true>, per_slab * CF_SLABS, CF_THREADS, smem_c, st, spec, (const float*)nullptr,
+             (const float2*)nullptr, Nh, nS, per_slab);
   return 0;
 }
 

@@ -740,6 +740,8 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
     MEM_CHECK(run_fft(ctx, N, nS, true, B, spec, st));
     specw = ctx->spec2.as<float2>();
     MEM_CHECK(run_fft(ctx, N, nS, true, imgAll, specw, st));
+  } else if (colfilter_supported(N) && !ctx->cufft_a10) {
+    MEM_CHECK(fft2_forward_run(ctx, imgAll, spec, nS, N, st));
   } else {
     MEM_CHECK(run_fft(ctx, N, nS, true, imgAll, spec, st));
   }
@@ -916,7 +918,8 @@ int pd_distance_batch_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_p
   MEM_CHECK(rotate_angles_batch_run(ctx, pd_of, d_pp, cs2, pid2, nS, st));
   MEM_CHECK(align_batch_run(ctx, A, B, imgAll, io->psi_deg, cs, cs2, pid2, nS, N, st, rows_done));
   MEM_CUDA(cudaEventRecord(ctx->ev[2], st));
-  MEM_CHECK(run_fft(ctx, N, nS, true, imgAll, spec, st));
+  if (colfilter_supported(N) && !ctx->cufft_a10) MEM_CHECK(fft2_forward_run(ctx, imgAll, spec, nS, N, st));
+  else MEM_CHECK(run_fft(ctx, N, nS, true, imgAll, spec, st));
   const CtfConst cc = make_ctf_const(prm);
   MEM_LAUNCH(ctx, k_ctf_bins, dim3((g.Kr + 255) / 256, nS), 256, 0, st, io->df, g.r2_of_bin.as<int>(),
              ctx->cbin.as<float>(), g.Kr, cc);
