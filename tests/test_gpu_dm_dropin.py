@@ -464,3 +464,20 @@ def test_virtual_image_arrays_in_sidecar_records(tmp_path, relion):
         else:
             assert a[k] == b[k], k
     assert img.dtype == np.float64 and img.shape == (nS, N, N)
+
+
+def test_device_lanczos_edge_cases():
+    """k close to nS (the recurrence runs to j = nS and becomes exact), a matrix with an invariant start subspace
+    (block-diagonal: the solver still returns k pairs of the reachable block or reports non-convergence), tiny nS."""
+    from manifoldem_python_b200 import DMembeddingII, _lib
+    from manifoldem_python_b200.getDistanceCTF_local_Conj9combinedS2 import _ctx
+    L = _diffusion_like_matrix(24, 3)
+    w = np.linalg.eigvalsh(L)
+    Ld = _lib.DeviceArray(_ctx(), (24, 24), np.float64, L)
+    vals, vecs, info = DMembeddingII.eigsh_device(Ld, 24, 20)
+    Ld.free()
+    assert info['converged'] and info['steps'] <= 24
+    assert np.allclose(np.sort(np.abs(vals)), np.sort(np.abs(w))[-20:], atol=1e-10)
+    assert np.abs(L @ vecs - vecs * vals).max() < 1e-9
+    vals2, vecs2, info2 = DMembeddingII.eigsh_device(_lib.DeviceArray(_ctx(), (3, 3), np.float64, np.diag([3.0, 2.0, 1.0])), 3, 5)
+    assert vals2.shape[0] <= 2 and abs(vals2[0]) >= abs(vals2[-1])
