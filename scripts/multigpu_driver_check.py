@@ -60,6 +60,26 @@ def main():
             assert rec['D'].shape == (nS, nS) and np.array_equal(rec['D'], rec['D'].T) and np.isfinite(rec['D']).all()
         print('GetDistancesS2.op with p.ncpu=%d on %d visible GPUs: %d PDs in %.1f s (incl. worker spawn + CUDA init), '
               'all markers present, progress %s' % (n_gpus, GetDistancesS2._n_gpus(), len(CG), dt, Sig.vals[-3:]))
+        # the next two stages through their drivers: embedding per PD (single process), psi analysis sharded over the GPUs
+        from manifoldem_python_b200 import manifoldTrimmingAuto, psiAnalysis
+        np.random.seed(1)
+        for prD in range(len(CG)):
+            manifoldTrimmingAuto.op(['{}prD_{}'.format(p.dist_file, prD), '{}prD_{}'.format(p.psi_file, prD),
+                                     os.path.join(tmp, 'eig_%d.txt' % prD), prD], 0, 3.0, 5.0, False, dict(outputFile='', Is=True))
+        out = os.path.join(tmp, 'outputs_multi')
+        p.psi2_dir, p.EL_dir = os.path.join(out, 'psi_analysis/'), os.path.join(out, 'ELConc10/')
+        p.psi2_prog, p.EL_prog = os.path.join(p.psi2_dir, 'progress/'), os.path.join(p.EL_dir, 'progress/')
+        for d in (p.psi2_prog, p.EL_prog):
+            os.makedirs(d)
+        p.psi2_file, p.EL_file = os.path.join(p.psi2_dir, 'S2_'), os.path.join(p.EL_dir, 'S2_')
+        p.num_psis, p.conOrderRange, p.num_psiTrunc, p.nClass, p.trajName, p.tune = 2, 10, 5, 50, '1', 3
+        Sig.vals = []
+        t0 = time.time()
+        psiAnalysis.op(Sig())
+        dt = time.time() - t0
+        done = sorted(os.listdir(p.psi2_prog))
+        assert len(done) == 2 * len(CG) and Sig.vals[-1] == 100, (done, Sig.vals[-3:])
+        print('psiAnalysis.op on %d visible GPUs: %d (PD, psi) pairs in %.1f s, all markers present' % (GetDistancesS2._n_gpus(), len(done), dt))
 
 
 if __name__ == '__main__':
