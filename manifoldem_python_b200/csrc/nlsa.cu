@@ -161,6 +161,46 @@ __global__ void __launch_bounds__(256) k_nlsa_gram_small(const double* __restric
   }
 }
 
+// the same for E <= 8 (psiTrunc's default): every thread walks its rows once, the E (E + 1) / 2 products of a row accumulate in
+// registers (A is read ONCE, 64 contiguous bytes per row, instead of once per (p, q) pair with a stride of E doubles)
+__global__ void __launch_bounds__(256) k_nlsa_gram_small8(const double* __restrict__ A, size_t rows, int E, size_t rows_per,
+                                                          double* __restrict__ part) {
+  __shared__ double red[8];
+  const size_t a = (size_t)blockIdx.x * rows_per, b = min(rows, a + rows_per);
+  double acc[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+  for (size_t r = a + threadIdx.x; r < b; r += 256) {
+    double x[8];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) x[p] = p < E ? A[r * E + p] : 0.0;
+    int k = 0;
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+#pragma unroll
+      for (int q = p; q < 8; ++q) {
+        acc[k] = fma(x[p], x[q], acc[k]);
+        ++k;
+      }
+  }
+  int k = 0;
+#pragma unroll
+  for (int p = 0; p < 8; ++p)
+#pragma unroll
+    for (int q = p; q < 8; ++q, ++k) {
+      double v = acc[k];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+      __syncthreads();
+      if (threadIdx.x == 0 && p < E && q < E) {
+        double s2 = 0.0;
+        for (int w = 0; w < 8; ++w) s2 += red[w];
+        part[(size_t)blockIdx.x * E * E + p * E + q] = s2;
+      }
+    }
+}
+
 // U = A M (svdRF.py:25: U = A (V S^-1)), M [E][E] row-major in constant-sized shared memory
 __global__ void __launch_bounds__(256) k_nlsa_project(const double* __restrict__ A, const double* __restrict__ M, size_t rows,
                                                       int E, double* __restrict__ U) {
@@ -584,7 +624,8 @@ int nlsa_gram_small_device(mem_ctx* ctx, const double* A, long long rows, int E,
   MEM_CHECK(ctx->small_out.ensure((size_t)nb * E * E * sizeof(double)));
   double* part = ctx->small_out.as<double>();
   MEM_CUDA(cudaMemsetAsync(part, 0, (size_t)nb * E * E * sizeof(double), st));
-  MEM_LAUNCH(ctx, k_nlsa_gram_small, nb, 256, 0, st, A, (size_t)rows, E, rows_per, part);
+  if (E <= 8) MEM_LAUNCH(ctx, k_nlsa_gram_small8, nb, 256, 0, st, A, (size_t)rows, E, rows_per, part);
+  else MEM_LAUNCH(ctx, k_nlsa_gram_small, nb, 256, 0, st, A, (size_t)rows, E, rows_per, part);
   std::vector<double> h((size_t)nb * E * E);
   MEM_CUDA(cudaMemcpyAsync(h.data(), part, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
   MEM_CUDA(cudaStreamSynchronize(st));
