@@ -179,7 +179,8 @@ class DeviceArray:
 
     def free(self):
         if self.ptr:
-            self.lib.mem_dev_free(self.ctx.handle, self.ptr)
+            # a context that was closed before its arrays: plain cudaFree (handle None), never a dangling context pointer
+            self.lib.mem_dev_free(self.ctx.handle if self.ctx.handle else None, self.ptr)
             self.ptr = None
 
     def __del__(self):

@@ -1,5 +1,6 @@
 // capi.cu — extern "C" surface declared in include/manifoldem_b200.h.
 #include "common.cuh"
+#include <stdlib.h>
 
 #include <math.h>
 #include <algorithm>
@@ -197,14 +198,39 @@ int mem_host_free(void* p) {
   MEM_CUDA(cudaFreeHost(p));
   return 0;
 }
+// Device arrays of the Python layer come from CUDA's stream-ordered allocator on the context's stream (the default memory
+// pool keeps what is freed: a cudaMalloc / cudaFree pair per temporary — each free synchronising the device — was 40 % of a
+// 10 ms DMembeddingII.embed call at nS = 2,000).  MANIFOLDEM_B200_ALLOC=sync selects plain cudaMalloc / cudaFree.
+static bool alloc_async() {
+  static const bool v = [] {
+    const char* e = getenv("MANIFOLDEM_B200_ALLOC");
+    return !(e && !strcmp(e, "sync"));
+  }();
+  return v;
+}
 int mem_dev_alloc(mem_ctx* ctx, void** out, size_t bytes) {
   MEM_CUDA(cudaSetDevice(ctx->device));
+  if (alloc_async()) {
+    if (!ctx->pool_ready) {
+      cudaMemPool_t pool;
+      MEM_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+      uint64_t keep = 8ull << 30;                         // hold up to 8 GB of freed blocks for reuse
+      MEM_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+      ctx->pool_ready = 1;
+    }
+    MEM_CUDA(cudaMallocAsync(out, bytes ? bytes : 1, ctx->stream));
+    return 0;
+  }
   MEM_CUDA(cudaMalloc(out, bytes ? bytes : 1));
   return 0;
 }
 int mem_dev_free(mem_ctx* ctx, void* p) {
   if (ctx) MEM_CUDA(cudaSetDevice(ctx->device));
-  MEM_CUDA(cudaFree(p));
+  if (ctx && alloc_async()) {
+    MEM_CUDA(cudaFreeAsync(p, ctx->stream));              // ordered behind the work already enqueued on the context's stream
+    return 0;
+  }
+  MEM_CUDA(cudaFree(p));                                  // also frees stream-ordered allocations (synchronises)
   return 0;
 }
 int mem_copy_h2d(mem_ctx* ctx, void* dst, const void* src, size_t bytes) {

@@ -116,6 +116,7 @@ struct mem_ctx {
   int last_tc_items = 0, last_tc_nkb = 0;   // geometry of the last tcgen05 launch (executed-flop accounting)
   float timings[8] = {};
   void* tmap_encode = nullptr;   // cuTensorMapEncodeTiled entry point
+  int pool_ready = 0;            // the device's default memory pool has its release threshold set
   int full_sums = 0;             // 1: the spectrum sums always run over every image (tests: M from all images)
   int cufft_a10 = 0;             // 1: the a10 transform through cuFFT's 2-D plan even for N = 256 (tests / comparison)
   int rowfft_blocks = 0;         // experiments: CTAs per SM the row FFT kernels are compiled for (0 = default 4)
