@@ -15,7 +15,7 @@ def init():
              PDsizeThL=100, PDsizeThH=2000, numberofJobs=0,
              num_eigs=15, num_psiTrunc=8, num_psis=8, tune=3, rad=5, conOrderRange=50, nClass=50, trajName='1',
              psi2_dir='', psi2_prog='', psi2_file='', EL_dir='', EL_prog='', EL_file='',
-             tess_file='', dist_dir='', dist_prog='', dist_file='', psi_dir='', psi_prog='', psi_file='')
+             out_dir='', tess_file='', dist_dir='', dist_prog='', dist_file='', psi_dir='', psi_prog='', psi_file='')
     return None
 
 
@@ -23,6 +23,7 @@ def create_dir():
     """distances/ and diff_maps/ trees with their progress/ marker directories (p.py:125-133, :205-208)."""
     g = globals()
     out = os.path.join(g['user_dir'], 'outputs_{}'.format(g['proj_name']))
+    g['out_dir'] = out
     g['dist_dir'] = os.path.join(out, 'distances/')
     g['dist_prog'] = os.path.join(g['dist_dir'], 'progress/')
     g['psi_dir'] = os.path.join(out, 'diff_maps/')

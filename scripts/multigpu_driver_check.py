@@ -60,12 +60,15 @@ def main():
             assert rec['D'].shape == (nS, nS) and np.array_equal(rec['D'], rec['D'].T) and np.isfinite(rec['D']).all()
         print('GetDistancesS2.op with p.ncpu=%d on %d visible GPUs: %d PDs in %.1f s (incl. worker spawn + CUDA init), '
               'all markers present, progress %s' % (n_gpus, GetDistancesS2._n_gpus(), len(CG), dt, Sig.vals[-3:]))
-        # the next two stages through their drivers: embedding per PD (single process), psi analysis sharded over the GPUs
-        from manifoldem_python_b200 import manifoldTrimmingAuto, psiAnalysis
-        np.random.seed(1)
-        for prD in range(len(CG)):
-            manifoldTrimmingAuto.op(['{}prD_{}'.format(p.dist_file, prD), '{}prD_{}'.format(p.psi_file, prD),
-                                     os.path.join(tmp, 'eig_%d.txt' % prD), prD], 0, 3.0, 5.0, False, dict(outputFile='', Is=True))
+        # the next two stages through their drivers, both sharded over the GPUs
+        from manifoldem_python_b200 import manifoldAnalysis, psiAnalysis
+        p.tune, p.rad = 3.0, 5.0
+        Sig.vals = []
+        t0 = time.time()
+        manifoldAnalysis.op(Sig())
+        dt = time.time() - t0
+        assert sorted(int(f) for f in os.listdir(p.psi_prog)) == list(range(len(CG))) and Sig.vals[-1] == 100
+        print('manifoldAnalysis.op on %d visible GPUs: %d PDs in %.1f s, all markers present' % (GetDistancesS2._n_gpus(), len(CG), dt))
         out = os.path.join(tmp, 'outputs_multi')
         p.psi2_dir, p.EL_dir = os.path.join(out, 'psi_analysis/'), os.path.join(out, 'ELConc10/')
         p.psi2_prog, p.EL_prog = os.path.join(p.psi2_dir, 'progress/'), os.path.join(p.EL_dir, 'progress/')

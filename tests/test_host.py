@@ -695,3 +695,20 @@ def test_partition_with_rank_speeds():
     rng = np.random.default_rng(0)
     costs = list(rng.uniform(1, 5, 57))
     assert partition.lpt_partition(costs, 3) == partition.lpt_partition(costs, 3, [1, 1, 1])
+
+
+def test_manifold_analysis_driver_bookkeeping(tmp_path):
+    """manifoldAnalysis.divide / fileCheck / count (modules/manifoldAnalysis.py:30-54): one job per PD without a marker under
+    p.psi_prog, the eigenvalue file under out_dir/topos/PrD_<prD + 1>/."""
+    from manifoldem_python_b200 import manifoldAnalysis, p
+    p.init()
+    p.user_dir, p.proj_name = str(tmp_path), 'ma'
+    p.create_dir()
+    p.numberofJobs = 5
+    for name in ('1', '3', '.hidden'):
+        open(os.path.join(p.psi_prog, name), 'a').close()
+    assert manifoldAnalysis.fileCheck() == [1, 3] and manifoldAnalysis.count(5) == 3
+    jobs = manifoldAnalysis.divide(5)
+    assert [j[3] for j in jobs] == [0, 2, 4]
+    assert jobs[1][0] == p.dist_file + 'prD_2' and jobs[1][1] == p.psi_file + 'prD_2'
+    assert jobs[2][2] == '{}/topos/PrD_5/eig_spec.txt'.format(p.out_dir)
