@@ -730,7 +730,7 @@ def run_b200(args):
     e2e = None
     if not args.no_e2e:
         ceil_gbs = h2d_ceiling(ctx, _lib, lib, local, barrier)
-        nthreads = 3
+        nthreads = max(1, int(os.environ.get('MANIFOLDEM_B200_BENCH_INFLIGHT', '3')))
         ctxs = [ctx] + [_lib.Context(local) for _ in range(nthreads - 1)]
         h_D = [_lib.PinnedArray((nS, nS), np.float32) for _ in range(nthreads)]
 
