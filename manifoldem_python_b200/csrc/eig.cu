@@ -68,16 +68,32 @@ __global__ void __launch_bounds__(256) k_lz_dots(const double* __restrict__ V, c
   if (threadIdx.x == 0) h[blockIdx.x] = acc;
 }
 
-// w -= sum_b h[b] V[b];  alpha[j] (+)= h[j]
+// w -= sum_b h[b] V[b];  alpha[j] (+)= h[j].  CTA = 32 elements x 8 groups of basis vectors (group g sums b = g, g + 8, ...):
+// at nS ~ 1,000 a thread per element alone is four CTAs walking 150 dependent loads each (22 us per launch, 62 % of the solver).
 __global__ void __launch_bounds__(256) k_lz_update(double* __restrict__ w, const double* __restrict__ V,
                                                    const double* __restrict__ h, int nb, int nS,
                                                    double* __restrict__ alpha_j, int accumulate) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i == 0) alpha_j[0] = (accumulate ? alpha_j[0] : 0.0) + h[nb - 1];
-  if (i >= nS) return;
-  double acc = w[i];
-  for (int b = 0; b < nb; ++b) acc = fma(-h[b], V[(size_t)b * nS + i], acc);
-  w[i] = acc;
+  __shared__ double part[8][33];
+  const int lx = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lx;
+  if (blockIdx.x == 0 && threadIdx.x == 0) alpha_j[0] = (accumulate ? alpha_j[0] : 0.0) + h[nb - 1];
+  double a0 = 0.0, a1 = 0.0;
+  if (i < nS) {
+    int b = g;
+    for (; b + 8 < nb; b += 16) {
+      a0 = fma(h[b], V[(size_t)b * nS + i], a0);
+      a1 = fma(h[b + 8], V[(size_t)(b + 8) * nS + i], a1);
+    }
+    if (b < nb) a0 = fma(h[b], V[(size_t)b * nS + i], a0);
+  }
+  part[g][lx] = a0 + a1;
+  __syncthreads();
+  if (g == 0 && i < nS) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += part[k][lx];
+    w[i] -= s;
+  }
 }
 
 // beta = ||w||, vnext = w / beta (one CTA)
@@ -155,7 +171,7 @@ int lanczos_steps_device(mem_ctx* ctx, const double* L, int nS, double* V, doubl
     MEM_LAUNCH(ctx, k_lz_symv, (nS + 7) / 8, 256, 0, st, L, vj, w, nS);
     for (int pass = 0; pass < 2; ++pass) {
       MEM_LAUNCH(ctx, k_lz_dots, j + 1, 256, 0, st, V, w, h, nS);
-      MEM_LAUNCH(ctx, k_lz_update, gN, 256, 0, st, w, V, h, j + 1, nS, alpha + j, pass);
+      MEM_LAUNCH(ctx, k_lz_update, (nS + 31) / 32, 256, 0, st, w, V, h, j + 1, nS, alpha + j, pass);
     }
     MEM_LAUNCH(ctx, k_lz_normalize, 1, 1024, 0, st, w, V + (size_t)(j + 1) * nS, beta + j + 1, nS);
   }
