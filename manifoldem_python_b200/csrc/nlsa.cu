@@ -16,6 +16,7 @@
 // Layouts: spectra H [n][N][Nh] complex128 (cuFFT D2Z), A / U [ConOrder N^2][E] row-major with the reference's
 // transposed pixel order (row = ii N^2 + c N + r for picture pixel (r, c), NLSA.py:79), IMGT [nC][Npix] (frame-major).
 #include "common.cuh"
+#include <algorithm>
 
 namespace mem {
 
@@ -295,53 +296,62 @@ __global__ void __launch_bounds__(256) k_nlsa_normalize(double* __restrict__ IMG
 }
 
 // L2_distance.py:36-41 then **2 (NLSA.py:144): D2[a][b] = sqrt(t)^2, t = aa[a] + aa[b] - 2 <x_a, x_b>, t < 1e-8 -> 0.
-// 64 x 64 tile per CTA (256 threads, 4 x 4 per thread), K chunks of 16 through shared memory; upper-triangle tiles only,
-// mirrored on the way out.
+// 128 x 128 tile per CTA (256 threads, 8 x 8 per thread with rows ty + 16 i / columns tx + 16 j: the operand reads from shared
+// memory are broadcasts or unit-stride), K chunks of 8; upper-triangle tiles only, mirrored on the way out.  64 FMA per 16
+// shared-memory loads: the first version (4 x 4 per thread) ran at 10 % of the float64 pipe.
 __global__ void __launch_bounds__(256) k_nlsa_l2(const double* __restrict__ X, const double* __restrict__ aa, int nC, int Npix,
                                                  double* __restrict__ D2) {
   const int bi = blockIdx.y, bj = blockIdx.x;
   if (bj < bi) return;
-  __shared__ double sa[16][65], sb[16][65];
+  __shared__ double sa[8][128], sb[8][128];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  double acc[4][4];
+  double acc[8][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  const int lr = threadIdx.x >> 2, lk = (threadIdx.x & 3) * 4;     // loader: 64 rows x 16 k, 4 consecutive k per thread
-  for (int k0 = 0; k0 < Npix; k0 += 16) {
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+  const int lr = threadIdx.x >> 1, lk = (threadIdx.x & 1) * 4;     // loader: row lr of the tile, 4 consecutive k
+  const int ra = bi * 128 + lr, rb = bj * 128 + lr;
+  const double* pa = X + (size_t)min(ra, nC - 1) * Npix + lk;
+  const double* pb = X + (size_t)min(rb, nC - 1) * Npix + lk;
+  for (int k0 = 0; k0 < Npix; k0 += 8) {
+    double va[4], vb[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int k = k0 + lk + q;
-      const int ra = bi * 64 + lr, rb = bj * 64 + lr;
-      sa[lk + q][lr] = (ra < nC && k < Npix) ? X[(size_t)ra * Npix + k] : 0.0;
-      sb[lk + q][lr] = (rb < nC && k < Npix) ? X[(size_t)rb * Npix + k] : 0.0;
+      const bool ok = k0 + lk + q < Npix;
+      va[q] = (ok && ra < nC) ? pa[k0 + q] : 0.0;
+      vb[q] = (ok && rb < nC) ? pb[k0 + q] : 0.0;
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      double a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = sa[k][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = sb[k][tx * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    for (int q = 0; q < 4; ++q) {
+      sa[lk + q][lr] = va[q];
+      sb[lk + q][lr] = vb[q];
     }
     __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      double a[8], b[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = sa[k][ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] = sb[k][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int r = bi * 64 + ty * 4 + i, c = bj * 64 + tx * 4 + j;
+    for (int j = 0; j < 8; ++j) {
+      const int r = bi * 128 + ty + 16 * i, c = bj * 128 + tx + 16 * j;
       if (r < nC && c < nC) {
         double t = aa[r] + aa[c] - 2 * acc[i][j];
         if (t < 1e-8) t = 0.0;
-        const double s = sqrt(t);
-        t = s * s;
+        const double sq = sqrt(t);
+        t = sq * sq;
         D2[(size_t)r * nC + c] = t;
         if (bj > bi) D2[(size_t)c * nC + r] = t;
       }
@@ -350,12 +360,12 @@ __global__ void __launch_bounds__(256) k_nlsa_l2(const double* __restrict__ X, c
 
 // ------------------------------------------------------------------------------------------------
 // fit_1D_open_manifold_3D.op (:60-146) on the device: x_ij = a_j cos(j pi tau_i) + b_j, j = 1..3.  The reference solves
-// one quintic per point and iteration with np.roots (nS x <= 101 companion-matrix eigenproblems in a Python loop); here ONE
-// CTA runs the whole alternating iteration: every thread owns points p, p + 1024, ...; the real roots of
+// one quintic per point and iteration with np.roots (nS x <= 101 companion-matrix eigenproblems in a Python loop); here a thread
+// owns a point: the real roots of
 // d R_p / d beta (beta = cos(pi tau)) inside [-1, 1] are isolated through the derivative chain (between two consecutive
 // critical points a polynomial is monotone: one sign test + safeguarded Newton per interval, no root can be missed), the
 // candidate with the smallest residual wins (tau = 0 and 1 always compete, solve_d_R_d_tau_p_3D.py:48-50), and the
-// 2 x 2 normal equations for (a_j, b_j) are block reductions in a fixed order.
+// 2 x 2 normal equations for (a_j, b_j) are block reductions in a fixed order (k_manifold_tau / k_manifold_update below).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double horner(const double* c, int n, double x) {     // c[0] x^n + ... + c[n]
   double v = c[0];
@@ -444,66 +454,70 @@ __device__ double manifold_tau(const double x0, const double x1, const double x2
   return best_tau;
 }
 
-// x [nS][3]; ab [6] = initial (a, b) in, final out; tau [nS] out; iters out.  One CTA of 1024 threads.
-__global__ void __launch_bounds__(1024) k_manifold_fit(const double* __restrict__ x, int nS, double* __restrict__ ab,
-                                                       double* __restrict__ tau, int max_iter, double da_max, double db_max,
-                                                       int* __restrict__ iters) {
-  __shared__ double s_ab[6];
+// The alternating iteration as two kernels per step — every point's tau over the whole grid, then one CTA for the 2 x 2 normal
+// equations — chained through a small device state {stop, converged, iterations}: the host enqueues ten steps at a time and
+// reads `stop` in between (a single CTA doing everything left 147 SMs idle: 4.4 ms for 960 points, now ~1 ms).
+//   k_manifold_tau     skipped once stop is set; otherwise tau_p for every point from the current (a, b)
+//   k_manifold_update  stop set -> return; converged set -> the taus just computed belong to the final (a, b): set stop;
+//                      else new (a, b) from the taus, iteration count + 1, converged if both relative changes are small
+__global__ void __launch_bounds__(128) k_manifold_tau(const double* __restrict__ x, int nS, const double* __restrict__ ab,
+                                                      double* __restrict__ tau, const int* __restrict__ state) {
+  if (state[0]) return;
+  const int p = blockIdx.x * 128 + threadIdx.x;
+  if (p >= nS) return;
+  double a[3] = {ab[0], ab[1], ab[2]}, b[3] = {ab[3], ab[4], ab[5]};
+  tau[p] = manifold_tau(x[3 * p], x[3 * p + 1], x[3 * p + 2], a, b);
+}
+
+__global__ void __launch_bounds__(1024) k_manifold_update(const double* __restrict__ x, int nS, double* __restrict__ ab,
+                                                          const double* __restrict__ tau, double da_max, double db_max,
+                                                          int* __restrict__ state) {
   __shared__ double red[32][12];
   __shared__ double tot[12];
-  __shared__ int stop;
-  if (threadIdx.x < 6) s_ab[threadIdx.x] = ab[threadIdx.x];
-  if (threadIdx.x == 0) stop = 0;
-  __syncthreads();
-  for (int p = threadIdx.x; p < nS; p += 1024) tau[p] = manifold_tau(x[3 * p], x[3 * p + 1], x[3 * p + 2], s_ab, s_ab + 3);
-  int it = 0;
-  for (it = 1; it <= max_iter; ++it) {
-    // normal equations of x_ij = a_j cos(j pi tau_i) + b_j: sums of cos^2, cos, x cos, x per j
-    double acc[12];
-    for (int k = 0; k < 12; ++k) acc[k] = 0.0;
-    for (int p = threadIdx.x; p < nS; p += 1024) {
-      const double t = tau[p];
-      for (int j = 0; j < 3; ++j) {
-        const double cj = cos(t * (M_PI * (j + 1)));
-        const double xv = x[3 * p + j];
-        acc[j] = fma(cj, cj, acc[j]);
-        acc[3 + j] += cj;
-        acc[6 + j] = fma(xv, cj, acc[6 + j]);
-        acc[9 + j] += xv;
-      }
-    }
-    for (int k = 0; k < 12; ++k) {
-      double v = acc[k];
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < 12) {
-      double s2 = 0.0;
-      for (int w = 0; w < 32; ++w) s2 += red[w][threadIdx.x];
-      tot[threadIdx.x] = s2;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double da = 0.0, db = 0.0;
-      for (int j = 0; j < 3; ++j) {
-        const double A11 = tot[j], A12 = tot[3 + j], b1 = tot[6 + j], b2 = tot[9 + j], A22 = (double)nS;
-        const double det = A11 * A22 - A12 * A12;
-        const double an = (b1 * A22 - A12 * b2) / det, bn = (A11 * b2 - A12 * b1) / det;
-        da = fmax(da, fabs(an - s_ab[j]) / (fabs(an) + 1e-4));
-        db = fmax(db, fabs(bn - s_ab[3 + j]) / (fabs(bn) + 1e-4));
-        s_ab[j] = an;
-        s_ab[3 + j] = bn;
-      }
-      stop = (da * 100 < da_max && db * 100 < db_max) ? 1 : 0;
-    }
-    __syncthreads();
-    for (int p = threadIdx.x; p < nS; p += 1024) tau[p] = manifold_tau(x[3 * p], x[3 * p + 1], x[3 * p + 2], s_ab, s_ab + 3);
-    __syncthreads();
-    if (stop) break;
+  if (state[0]) return;
+  if (state[1]) {
+    if (threadIdx.x == 0) state[0] = 1;
+    return;
   }
-  if (threadIdx.x < 6) ab[threadIdx.x] = s_ab[threadIdx.x];
-  if (threadIdx.x == 0) iters[0] = it > max_iter ? max_iter : it;
+  double acc[12];
+  for (int k = 0; k < 12; ++k) acc[k] = 0.0;
+  for (int p = threadIdx.x; p < nS; p += 1024) {
+    const double t = tau[p];
+    for (int j = 0; j < 3; ++j) {
+      const double cj = cos(t * (M_PI * (j + 1)));
+      const double xv = x[3 * p + j];
+      acc[j] = fma(cj, cj, acc[j]);
+      acc[3 + j] += cj;
+      acc[6 + j] = fma(xv, cj, acc[6 + j]);
+      acc[9 + j] += xv;
+    }
+  }
+  for (int k = 0; k < 12; ++k) {
+    double v = acc[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 12) {
+    double s2 = 0.0;
+    for (int w = 0; w < 32; ++w) s2 += red[w][threadIdx.x];
+    tot[threadIdx.x] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double da = 0.0, db = 0.0;
+    for (int j = 0; j < 3; ++j) {
+      const double A11 = tot[j], A12 = tot[3 + j], b1 = tot[6 + j], b2 = tot[9 + j], A22 = (double)nS;
+      const double det = A11 * A22 - A12 * A12;
+      const double an = (b1 * A22 - A12 * b2) / det, bn = (A11 * b2 - A12 * b1) / det;
+      da = fmax(da, fabs(an - ab[j]) / (fabs(an) + 1e-4));
+      db = fmax(db, fabs(bn - ab[3 + j]) / (fabs(bn) + 1e-4));
+      ab[j] = an;
+      ab[3 + j] = bn;
+    }
+    state[2] += 1;
+    if (da * 100 < da_max && db * 100 < db_max) state[1] = 1;
+  }
 }
 
 // x [nS][3] HOST, ab [6] HOST in / out, tau [nS] HOST out.  Synchronises.
@@ -517,14 +531,28 @@ int manifold_fit_host(mem_ctx* ctx, const double* x_host, int nS, double* ab_hos
   double* dx = ctx->small_out.as<double>();
   double* dab = dx + 3 * nS;
   double* dtau = dab + 6;
-  int* dit = reinterpret_cast<int*>(dtau + nS);
+  int* dstate = reinterpret_cast<int*>(dtau + nS);          // {stop, converged, iterations}
   MEM_CUDA(cudaMemcpyAsync(dx, x_host, (size_t)3 * nS * sizeof(double), cudaMemcpyHostToDevice, st));
   MEM_CUDA(cudaMemcpyAsync(dab, ab_host, 6 * sizeof(double), cudaMemcpyHostToDevice, st));
-  MEM_LAUNCH(ctx, k_manifold_fit, 1, 1024, 0, st, dx, nS, dab, dtau, max_iter, da_max, db_max, dit);
+  MEM_CUDA(cudaMemsetAsync(dstate, 0, 4 * sizeof(int), st));
+  const int grid = (nS + 127) / 128;
+  MEM_LAUNCH(ctx, k_manifold_tau, grid, 128, 0, st, dx, nS, dab, dtau, dstate);
+  int state[4] = {0, 0, 0, 0};
+  for (int done = 0; done < max_iter && !state[0];) {
+    const int n = std::min(10, max_iter - done);
+    for (int k = 0; k < n; ++k) {
+      MEM_LAUNCH(ctx, k_manifold_update, 1, 1024, 0, st, dx, nS, dab, dtau, da_max, db_max, dstate);
+      MEM_LAUNCH(ctx, k_manifold_tau, grid, 128, 0, st, dx, nS, dab, dtau, dstate);
+    }
+    done += n;
+    MEM_CUDA(cudaMemcpyAsync(state, dstate, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    MEM_CUDA(cudaStreamSynchronize(st));
+    if (state[1]) break;                                   // converged: the tau kernel behind that update has run
+  }
   MEM_CUDA(cudaMemcpyAsync(ab_host, dab, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
   MEM_CUDA(cudaMemcpyAsync(tau_host, dtau, (size_t)nS * sizeof(double), cudaMemcpyDeviceToHost, st));
-  MEM_CUDA(cudaMemcpyAsync(iters_host, dit, sizeof(int), cudaMemcpyDeviceToHost, st));
   MEM_CUDA(cudaStreamSynchronize(st));
+  iters_host[0] = state[2];
   return 0;
 }
 
@@ -672,7 +700,7 @@ int nlsa_reconstruct_device(mem_ctx* ctx, const double* U, int Npix, int ConOrde
   MEM_LAUNCH(ctx, k_nlsa_reconstruct, dim3((Npix + 127) / 128, (nC + NL_CT - 1) / NL_CT), 128,
              2 * (ConOrder + NL_CT) * sizeof(double), st, U, dQ, Npix, ConOrder, E, nI, nC, IMGT);
   MEM_LAUNCH(ctx, k_nlsa_normalize, nC, 256, 0, st, IMGT, Npix, aa);
-  if (D2) MEM_LAUNCH(ctx, k_nlsa_l2, dim3((nC + 63) / 64, (nC + 63) / 64), 256, 0, st, IMGT, aa, nC, Npix, D2);
+  if (D2) MEM_LAUNCH(ctx, k_nlsa_l2, dim3((nC + 127) / 128, (nC + 127) / 128), 256, 0, st, IMGT, aa, nC, Npix, D2);
   return 0;
 }
 
