@@ -78,6 +78,7 @@ int mem_ctx_destroy(mem_ctx* ctx) {
     cufftDestroy(kv.second.r2c);
     cufftDestroy(kv.second.c2r);
   }
+  for (auto& kv : ctx->plans_d) cufftDestroy(kv.second);
   mem::DevBuf* bufs[] = {&ctx->fft_work, &ctx->raw, &ctx->flip, &ctx->shift, &ctx->psi, &ctx->df, &ctx->msk2, &ctx->rot_cs, &ctx->rot_pid, &ctx->rot_pitch_tab, &ctx->batch_aux,
                          &ctx->imgA, &ctx->imgB, &ctx->imgAll, &ctx->imgFlip, &ctx->spec, &ctx->spec2, &ctx->cbin, &ctx->zhi,
                          &ctx->zlo, &ctx->part_cf, &ctx->part_cfw, &ctx->part_c2, &ctx->part_fl, &ctx->part_int, &ctx->avgspec, &ctx->avgimg,

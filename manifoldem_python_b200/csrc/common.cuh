@@ -95,6 +95,7 @@ struct mem_ctx {
   int sm_count = 148;
   mem::Geometry geom;
   std::map<long long, mem::FftPlan> plans;   // key = N * 2^20 + batch
+  std::map<long long, cufftHandle> plans_d;  // float64 2-D plans of the NLSA stage: key = (type, N, batch)
   mem::DevBuf fft_work;
   // workspace for one PD
   mem::DevBuf raw, flip, shift, psi, df, msk2, rot_cs, rot_pid, rot_pitch_tab, batch_aux;

@@ -557,9 +557,21 @@ int manifold_fit_host(mem_ctx* ctx, const double* x_host, int nS, double* ab_hos
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-static int plan_many_d(cufftHandle* h, int N, int batch, cufftType type, cudaStream_t st) {
-  int n[2] = {N, N};
-  NL_CUFFT(cufftPlanMany(h, 2, n, nullptr, 1, 0, nullptr, 1, 0, type, batch));
+// float64 2-D plans, cached per context (creating one costs 1 - 15 ms; a PD asks for the same two shapes once per psi)
+static int plan_many_d(mem_ctx* ctx, cufftHandle* h, int N, int batch, cufftType type, cudaStream_t st) {
+  const long long key = ((long long)type << 48) + ((long long)N << 28) + batch;
+  auto it = ctx->plans_d.find(key);
+  if (it == ctx->plans_d.end()) {
+    if (ctx->plans_d.size() >= 16) {                      // a few shapes per PD size: keep the cache small
+      for (auto& kv : ctx->plans_d) cufftDestroy(kv.second);
+      ctx->plans_d.clear();
+    }
+    int n[2] = {N, N};
+    cufftHandle pl;
+    NL_CUFFT(cufftPlanMany(&pl, 2, n, nullptr, 1, 0, nullptr, 1, 0, type, batch));
+    it = ctx->plans_d.emplace(key, pl).first;
+  }
+  *h = it->second;
   NL_CUFFT(cufftSetStream(*h, st));
   return 0;
 }
@@ -575,10 +587,9 @@ int nlsa_spectra_device(mem_ctx* ctx, const double* img, const double* ctf, int 
   for (int a = 0; a < n; a += 512) {
     const int nb = std::min(512, n - a);
     cufftHandle pl;
-    MEM_CHECK(plan_many_d(&pl, N, nb, CUFFT_D2Z, st));
+    MEM_CHECK(plan_many_d(ctx, &pl, N, nb, CUFFT_D2Z, st));
     cufftResult r = cufftExecD2Z(pl, const_cast<double*>(img) + (size_t)a * N * N,
                                  reinterpret_cast<cufftDoubleComplex*>(H + (size_t)a * N * Nh));
-    cufftDestroy(pl);
     if (r != CUFFT_SUCCESS) {
       set_error("cufftExecD2Z failed (%d)", (int)r);
       return 1;
@@ -629,9 +640,8 @@ int nlsa_supervectors_device(mem_ctx* ctx, const double2* H, const double* Ch, c
                128 * NL_EMAX * sizeof(double), st, H, sel, iw, mu, nI, ConOrder, E, e0, Kh, G);
   {
     cufftHandle pl;
-    MEM_CHECK(plan_many_d(&pl, N, ConOrder * E, CUFFT_Z2D, st));
+    MEM_CHECK(plan_many_d(ctx, &pl, N, ConOrder * E, CUFFT_Z2D, st));
     cufftResult r = cufftExecZ2D(pl, reinterpret_cast<cufftDoubleComplex*>(G), g);
-    cufftDestroy(pl);
     if (r != CUFFT_SUCCESS) {
       set_error("cufftExecZ2D failed (%d)", (int)r);
       return 1;
