@@ -87,23 +87,33 @@ __global__ void __launch_bounds__(128) k_nlsa_supervector_spectra(const double2*
     }
     __syncthreads();
     if (k < Kh) {
+      // shift s of the tile reads snapshot row (i + ConOrder - ii0 - 1) - s: from one i to the next the window of NL_ST rows
+      // slides by one, so only the leading row is loaded (hw[0]); the others move down a register
+      const int lead = ConOrder - ii0 - 1;
+      double2 hw[NL_ST];
+#pragma unroll
+      for (int s = 1; s < NL_ST; ++s) {
+        const int row = i0 + lead - s;                    // rows of iteration i0 behind the leading one (row >= 0 iff ii0 + s < ConOrder)
+        hw[s] = row >= 0 ? H[(size_t)sel[row] * Kh + k] : make_double2(0.0, 0.0);
+      }
       for (int i = 0; i < ni; ++i) {
+        hw[0] = H[(size_t)sel[i0 + i + lead] * Kh + k];
         const double w = iw[(size_t)(i0 + i) * Kh + k];
         double wm[NL_EMAX];
 #pragma unroll
         for (int e = 0; e < NL_EMAX; ++e) wm[e] = s_mu[i * NL_EMAX + e] * w;
 #pragma unroll
         for (int s = 0; s < NL_ST; ++s) {
-          const int ii = ii0 + s;
-          if (ii < ConOrder) {
-            const double2 h = H[(size_t)sel[i0 + i + ConOrder - ii - 1] * Kh + k];
+          if (ii0 + s < ConOrder) {
 #pragma unroll
             for (int e = 0; e < NL_EMAX; ++e) {
-              acc[s][e].x = fma(h.x, wm[e], acc[s][e].x);
-              acc[s][e].y = fma(h.y, wm[e], acc[s][e].y);
+              acc[s][e].x = fma(hw[s].x, wm[e], acc[s][e].x);
+              acc[s][e].y = fma(hw[s].y, wm[e], acc[s][e].y);
             }
           }
         }
+#pragma unroll
+        for (int s = NL_ST - 1; s > 0; --s) hw[s] = hw[s - 1];
       }
     }
   }
