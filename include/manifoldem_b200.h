@@ -35,8 +35,9 @@ int         mem_ctx_sync(mem_ctx* ctx);
  *   "full_sums"      1 = the per-pixel spectrum sums always run over every image.  Default 0: when only D / the neighbour
  *                    lists are requested the sums serve nothing but the common component M removed from the contraction
  *                    operands (D is invariant under any common M), and PDs of >= 1,024 images take every 8th image
- *   "cufft_a10"      1 = the a10 forward transform through cuFFT's 2-D plan also at N = 256 (default 0: the library's own row /
- *                    column FFT kernels; other boxes always take cuFFT)
+ *   "cufft_a10"      1 = the a10 forward transform through cuFFT's 2-D plan also at N = 128 / 256 (default 0: the library's own
+ *                    row / column FFT kernels; other boxes always take cuFFT)
+ *   "cufft_lowpass"  1 = ingest, low-pass and a10 through the generic kernels + cuFFT also at N = 128 / 256 (comparison / tests)
  *   "radial_variant", "rowfft_blocks"   experiment switches (thread count of the operand writer, CTAs per SM the row FFT kernels
  *                    are compiled for); 0 = the measured defaults */
 int         mem_ctx_set_option(mem_ctx* ctx, const char* name, int32_t value);

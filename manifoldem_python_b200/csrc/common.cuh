@@ -119,6 +119,7 @@ struct mem_ctx {
   void* tmap_encode = nullptr;   // cuTensorMapEncodeTiled entry point
   int pool_ready = 0;            // the device's default memory pool has its release threshold set
   int full_sums = 0;             // 1: the spectrum sums always run over every image (tests: M from all images)
+  int cufft_lowpass = 0;         // 1: ingest / low-pass / a10 through the generic kernels + cuFFT even where own FFT kernels exist (tests)
   int cufft_a10 = 0;             // 1: the a10 transform through cuFFT's 2-D plan even for N = 256 (tests / comparison)
   int rowfft_blocks = 0;         // experiments: CTAs per SM the row FFT kernels are compiled for (0 = default 4)
   int radial_variant = 0;        // experiments: thread count / unroll of k_operands_radial_sm

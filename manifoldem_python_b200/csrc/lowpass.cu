@@ -13,6 +13,8 @@
 //   inverse:  X[k1 + 16 k2] is again a "residue + 16 m" set, so the inverse starts from the registers:
 //             inverse FFT-16 over k2, conjugate twiddle, exchange, inverse FFT-16, store rows t + 16 m.
 // Shared memory is touched only by the two exchanges; all its accesses are unit-stride across lanes.
+// N = 128 = 16 x 8 has the same three kernels with eight threads per transform (second half of the file); other boxes take
+// the generic ingest + cuFFT path of preprocess.cu.
 #include "common.cuh"
 #include "spline.cuh"
 
@@ -418,7 +420,352 @@ __global__ void __launch_bounds__(256, MB) k_rowifft_prefilter256(const float2* 
   }
 }
 
-bool colfilter_supported(int N) { return N == 256; }
+// ================================================================================================
+// N = 128 = 16 x 8 (BASELINE config 2).  The same three passes with EIGHT threads per transform: thread t holds
+// z[t + 8 m], m < 16; FFT-16 over m in registers, twiddle W128^(t k1), exchange, and two FFT-8 over t for
+// k1 = t and t + 8 leave X[t + 8 j], j = g + 2 k2 — the same "residue + 8 j" set the transform started from, so
+// forward, filter and inverse chain in registers exactly as at 256.
+// ================================================================================================
+// 8-point DFT in registers, natural order in and out: n = 2 n1 + n2, k = k1 + 4 k2
+template <int S>
+__device__ __forceinline__ void fft8(float2 (&x)[8]) {
+  constexpr float R = 0.70710678118654752f;
+  fft4<S>(x[0], x[2], x[4], x[6]);                 // x[2 k1]     = A[0][k1]
+  fft4<S>(x[1], x[3], x[5], x[7]);                 // x[2 k1 + 1] = A[1][k1]
+  x[3] = cmul(x[3], make_float2(R, (float)S * R));
+  x[5] = (S < 0) ? make_float2(x[5].y, -x[5].x) : make_float2(-x[5].y, x[5].x);
+  x[7] = cmul(x[7], make_float2(-R, (float)S * R));
+  float2 y[8];
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) {
+    y[k1] = cadd(x[2 * k1], x[2 * k1 + 1]);
+    y[k1 + 4] = csub(x[2 * k1], x[2 * k1 + 1]);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x[k] = y[k];
+}
+
+// second half of the 128-point transform of a ROW kernel: e = the transform's 128 float2 of exchange space, element
+// (k1, t) at k1 * 8 + (t ^ (k1 & 7)) — unit-stride across the 8 lanes both ways; the two transforms of a half-warp sit
+// 136 float2 apart, so they use complementary halves of the 16 eight-byte banks.  tw[k1 * 8 + t] = W128^(+-t k1).
+template <int S>
+__device__ __forceinline__ void fft128_finish(float2 (&v)[16], float2* e, const float2* tw, int t) {
+#pragma unroll
+  for (int k1 = 0; k1 < 16; ++k1) e[k1 * 8 + (t ^ (k1 & 7))] = cmul(v[k1], tw[k1 * 8 + t]);
+  __syncwarp();
+  float2 u0[8], u1[8];
+#pragma unroll
+  for (int tt = 0; tt < 8; ++tt) {
+    u0[tt] = e[t * 8 + (tt ^ t)];
+    u1[tt] = e[(t + 8) * 8 + (tt ^ t)];
+  }
+  fft8<S>(u0);
+  fft8<S>(u1);
+#pragma unroll
+  for (int k2 = 0; k2 < 8; ++k2) {
+    v[2 * k2] = u0[k2];                              // X[t + 16 k2]
+    v[2 * k2 + 1] = u1[k2];                          // X[t + 8 + 16 k2]
+  }
+}
+
+constexpr int CF8_COLS = 22;                  // 3 slabs cover Nh = 65 (one idle column)
+constexpr int CF8_SLABS = 3;
+constexpr int CF8_THREADS = 8 * CF8_COLS;
+
+template <bool FWD = false>
+__global__ void __launch_bounds__(CF8_THREADS, 4) k_colfilter128(float2* __restrict__ spec, const float* __restrict__ G,
+                                                               const float2* __restrict__ stats, int Nh, int nS,
+                                                               int img_stride) {
+  extern __shared__ float2 cf_smem[];
+  float2* ex = cf_smem;                           // [128][CF8_COLS]
+  float2* stage = cf_smem + 128 * CF8_COLS;       // next image's slab
+  const int t = threadIdx.x / CF8_COLS, col = threadIdx.x - t * CF8_COLS;
+  const int slab = blockIdx.x % CF8_SLABS;
+  const int kx = slab * CF8_COLS + col;
+  const bool live = kx < Nh;
+  const int kxc = live ? kx : 0;
+  float gk[16];
+  if (!FWD) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) gk[j] = live ? G[(t + 8 * j) * Nh + kxc] : 0.0f;
+  }
+  __shared__ float2 tws[128];                     // tws[k1][t] = W128^(t k1)
+  if (threadIdx.x < 128) tws[threadIdx.x] = c_tw256[(2 * (threadIdx.x >> 3) * (threadIdx.x & 7)) & 255];
+  __syncthreads();
+  int img = blockIdx.x / CF8_SLABS;
+  if (img < nS) {
+    const float2* src = spec + (size_t)img * 128 * Nh + kxc;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) cp_async8(stage + (t + 8 * m) * CF8_COLS + col, src + (t + 8 * m) * Nh);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (; img < nS; img += img_stride) {
+    float2* base = spec + (size_t)img * 128 * Nh + kxc;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    float2 v[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) v[m] = stage[(t + 8 * m) * CF8_COLS + col];
+    const int nxt = img + img_stride;
+    if (nxt < nS) {
+      const float2* src = spec + (size_t)nxt * 128 * Nh + kxc;
+#pragma unroll
+      for (int m = 0; m < 16; ++m) cp_async8(stage + (t + 8 * m) * CF8_COLS + col, src + (t + 8 * m) * Nh);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    float2 u0[8], u1[8];
+    fft16<-1>(v);
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) ex[(k1 * 8 + t) * CF8_COLS + col] = cmul(v[k1], tws[k1 * 8 + t]);
+    __syncthreads();
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt) {
+      u0[tt] = ex[(t * 8 + tt) * CF8_COLS + col];
+      u1[tt] = ex[((t + 8) * 8 + tt) * CF8_COLS + col];
+    }
+    fft8<-1>(u0);
+    fft8<-1>(u1);
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) {
+      v[2 * k2] = u0[k2];
+      v[2 * k2 + 1] = u1[k2];                       // v[j] = X[t + 8 j]
+    }
+    if (FWD) {
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) base[(t + 8 * j) * Nh] = v[j];
+      }
+      __syncthreads();
+      continue;
+    }
+    float scale = 1.0f;
+    if (stats) {
+      const float2 ms = stats[img];
+      scale = ms.y;
+      if (t == 0 && kx == 0) v[0].x -= ms.x * 16384.0f;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float g = gk[j] * scale;
+      v[j].x *= g;
+      v[j].y *= g;
+    }
+    fft16<1>(v);                                    // inverse over j
+    __syncthreads();                                // every thread is done reading the forward exchange
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) {
+      const float2 w = tws[n1 * 8 + t];
+      ex[(n1 * 8 + t) * CF8_COLS + col] = cmul(v[n1], make_float2(w.x, -w.y));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt) {
+      u0[tt] = ex[(t * 8 + tt) * CF8_COLS + col];
+      u1[tt] = ex[((t + 8) * 8 + tt) * CF8_COLS + col];
+    }
+    fft8<1>(u0);
+    fft8<1>(u1);
+    if (live) {
+#pragma unroll
+      for (int k2 = 0; k2 < 8; ++k2) {
+        base[(t + 16 * k2) * Nh] = u0[k2];
+        base[(t + 8 + 16 * k2) * Nh] = u1[k2];
+      }
+    }
+    __syncthreads();                                // `ex` is rewritten by the next image
+  }
+}
+
+// a2 + a3 + row pass of a5 at N = 128: one CTA per image, two bands of 64 picture rows; a warp owns 8 band rows = 4 row
+// pairs, 8 threads per pair.  The exchange of the warp's four transforms lives in those 8 rows once every lane has its
+// values in registers (8 x 133 floats = 532 float2 >= 528).
+constexpr int IR8_BP = 133;
+template <bool PLAIN = false>
+__global__ void __launch_bounds__(256, 4) k_ingest_rowfft128(const float* __restrict__ raw, const uint8_t* __restrict__ flip,
+                                                          float2* __restrict__ spec, float2* __restrict__ stats,
+                                                          int transposed) {
+  constexpr int N = 128, Nh = 65;
+  extern __shared__ float2 ir_smem[];
+  float* band = reinterpret_cast<float*>(ir_smem);                  // [64][IR8_BP]
+  __shared__ double red[24];
+  __shared__ float2 tws[128];
+  if (threadIdx.x < 128) tws[threadIdx.x] = c_tw256[(2 * (threadIdx.x >> 3) * (threadIdx.x & 7)) & 255];
+  const int i = blockIdx.x;
+  const float* src = raw + (size_t)i * N * N;
+  float2* out = spec + (size_t)i * N * Nh;
+  const bool fl = PLAIN ? false : flip[i] != 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = threadIdx.x >> 3, t = threadIdx.x & 7, q = lane >> 3;
+  const float half = 0.5f * N, r2lim = half * half;
+  const float off = PLAIN ? 0.0f : src[0];
+  double s = 0, s2 = 0;
+  int cnt = 0;
+  float2* e = reinterpret_cast<float2*>(band + (8 * warp) * IR8_BP) + q * 128 + 8 * ((q + 1) >> 1);
+  const int partner = (lane & 24) + ((8 - t) & 7);
+  for (int b0 = 0; b0 < N; b0 += 64) {
+    float rs = 0.0f, rs2 = 0.0f;
+    if (PLAIN) {
+#pragma unroll
+      for (int k = warp; k < 64; k += 8) {
+        const float* rowp = src + (b0 + k) * N;
+#pragma unroll
+        for (int c = lane; c < N; c += 32) band[k * IR8_BP + c] = rowp[c];
+      }
+    } else if (transposed) {                        // picture[rp][c] = raw[c][rp]; lanes run along rp
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int rp = b0 + 32 * h + lane;
+        const int r = fl ? N - 1 - rp : rp;
+        const float x = (float)rp - half + 1.0f, x2 = x * x;
+#pragma unroll
+        for (int c = warp; c < N; c += 8) {
+          const float v = src[c * N + r] - off;
+          const float y = (float)c - half;
+          const bool in = x2 + y * y < r2lim;
+          const float m = in ? 0.0f : v;
+          cnt += in ? 0 : 1;
+          rs += m;
+          rs2 = fmaf(m, m, rs2);
+          band[(32 * h + lane) * IR8_BP + c] = v;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = warp; k < 64; k += 8) {
+        const int rp = b0 + k;
+        const int r = fl ? N - 1 - rp : rp;
+        const float x = (float)rp - half + 1.0f, x2 = x * x;
+#pragma unroll
+        for (int c = lane; c < N; c += 32) {
+          const float v = src[r * N + c] - off;
+          const float y = (float)c - half;
+          const bool in = x2 + y * y < r2lim;
+          const float m = in ? 0.0f : v;
+          cnt += in ? 0 : 1;
+          rs += m;
+          rs2 = fmaf(m, m, rs2);
+          band[k * IR8_BP + c] = v;
+        }
+      }
+    }
+    s += (double)rs;
+    s2 += (double)rs2;
+    __syncthreads();
+    float2 v[16];
+    const float* b1 = band + (2 * p) * IR8_BP + t;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) v[m] = make_float2(b1[8 * m], b1[IR8_BP + 8 * m]);
+    fft16<-1>(v);
+    __syncwarp();                                   // every lane of the warp has its rows in registers: they become the exchange
+    fft128_finish<-1>(v, e, tws, t);                // v[j] = Z[t + 8 j]
+    float2* o1 = out + (b0 + 2 * p) * Nh + t;
+    float2* o2 = o1 + Nh;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {                   // k = t + 8 j <= 63; partner N - k lives in thread 8 - t, slot 15 - j
+      float2 zn;
+      zn.x = __shfl_sync(0xffffffffu, v[15 - j].x, partner);
+      zn.y = __shfl_sync(0xffffffffu, v[15 - j].y, partner);
+      if (t == 0) zn = v[(16 - j) & 15];            // k = 8 j: the partner 8 (16 - j) is the thread's own
+      const float2 zk = v[j];
+      o1[8 * j] = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+      o2[8 * j] = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
+    }
+    if (t == 0) {                                   // k = 64 (Nyquist): real for both rows
+      o1[64] = make_float2(v[8].x, 0.0f);
+      o2[64] = make_float2(v[8].y, 0.0f);
+    }
+    __syncthreads();
+  }
+  if (PLAIN) return;
+  double dc = (double)cnt;
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    dc += __shfl_xor_sync(0xffffffffu, dc, o);
+  }
+  if (lane == 0) { red[warp] = s; red[8 + warp] = s2; red[16 + warp] = dc; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s = 0; s2 = 0; dc = 0;
+    for (int w = 0; w < 8; ++w) { s += red[w]; s2 += red[8 + w]; dc += red[16 + w]; }
+    const double o = (double)off, n = (double)N * N;
+    const double S1 = s + o * dc, S2 = s2 + 2.0 * o * s + o * o * dc;
+    const double mean = S1 / n;
+    const double var = S2 / n - mean * mean;
+    stats[i] = make_float2((float)(mean - o), (float)(1.0 / sqrt(var)));
+  }
+}
+
+// the way back at N = 128: inverse row transform + annular mask + row pass of the first spline prefilter; bands of 64
+// rows, pitch 132 (128 samples + one pad float per 32); lane l of the filtering warp owns samples [4 l, 4 l + 4)
+constexpr int RP8_BP = 132;
+__global__ void __launch_bounds__(256, 4) k_rowifft_prefilter128(const float2* __restrict__ spec, float* __restrict__ outimg) {
+  constexpr int N = 128, Nh = 65, E = 4;
+  extern __shared__ float2 ir_smem[];
+  float* band = reinterpret_cast<float*>(ir_smem);                  // [64][RP8_BP]
+  const int i = blockIdx.x;
+  const float2* in = spec + (size_t)i * N * Nh;
+  float* dst = outimg + (size_t)i * N * N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = threadIdx.x >> 3, t = threadIdx.x & 7, q = lane >> 3;
+  float2* e = reinterpret_cast<float2*>(band + (8 * warp) * RP8_BP) + q * 128 + 8 * ((q + 1) >> 1);   // 8 x 132 floats = 528 float2
+  constexpr float half = 0.5f * N, r2lim = half * half;
+  const float zE = 5.1547761e-03f;                  // z^4, z = sqrt(3) - 2
+  __shared__ float2 tws[128];                       // conj W128^(t n1)
+  if (threadIdx.x < 128) {
+    const float2 w = c_tw256[(2 * (threadIdx.x >> 3) * (threadIdx.x & 7)) & 255];
+    tws[threadIdx.x] = make_float2(w.x, -w.y);
+  }
+  __syncthreads();
+  for (int b0 = 0; b0 < N; b0 += 64) {
+    const float2* x1 = in + (b0 + 2 * p) * Nh;
+    const float2* x2 = x1 + Nh;
+    float2 v[16];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {                   // k = t + 8 m <= 63
+      float2 a = x1[t + 8 * m], b = x2[t + 8 * m];
+      if (m == 0 && t == 0) { a.y = 0.0f; b.y = 0.0f; }
+      v[m] = make_float2(a.x - b.y, a.y + b.x);
+    }
+#pragma unroll
+    for (int m = 8; m < 16; ++m) {                  // k = t + 8 m >= 64: conjugate of entry N - k
+      const int kk = N - t - 8 * m;
+      float2 a = x1[kk], b = x2[kk];
+      if (m == 8 && t == 0) { a.y = 0.0f; b.y = 0.0f; }
+      v[m] = make_float2(a.x + b.y, b.x - a.y);
+    }
+    fft16<1>(v);
+    fft128_finish<1>(v, e, tws, t);                 // v[j] = z[t + 8 j]: row 2p in .x, row 2p + 1 in .y
+    __syncwarp();                                   // the exchange has been read by every lane of the warp: its memory becomes rows
+    float* r1 = band + (2 * p) * RP8_BP;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = t + 8 * j;
+      r1[c + (c >> 5)] = v[j].x;
+      r1[RP8_BP + c + (c >> 5)] = v[j].y;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int qq = 0; qq < 8; ++qq) {
+      const int row = warp + 8 * qq;
+      float* ln = band + row * RP8_BP;
+      const float xm = (float)(b0 + row) - half + 1.0f;
+      const float lim = r2lim - xm * xm;
+      const int c0 = lane * E;
+      float sv[E];
+#pragma unroll
+      for (int j = 0; j < E; ++j) {
+        const float y = (float)(c0 + j) - half;
+        const float val = ln[c0 + j + ((c0 + j) >> 5)];
+        sv[j] = (y * y < lim) ? 6.0f * val : 0.0f;
+      }
+      spline_line_warp<E>(sv, zE, lane);
+      *reinterpret_cast<float4*>(dst + (b0 + row) * N + c0) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+    }
+    __syncthreads();
+  }
+}
+
+bool colfilter_supported(int N) { return N == 256 || N == 128; }
 
 static int ensure_twiddles(mem_ctx* ctx, cudaStream_t st) {
   static thread_local int tw_device = -1;
@@ -437,11 +784,16 @@ static int ensure_twiddles(mem_ctx* ctx, cudaStream_t st) {
 
 int ingest_rowfft_run(mem_ctx* ctx, const float* raw, const uint8_t* flip, float2* spec, float2* stats, int nS, int N,
                       int transposed, cudaStream_t st) {
-  if (N != 256) {
+  if (!colfilter_supported(N)) {
     set_error("ingest_rowfft: no kernel for N = %d", N);
     return 1;
   }
   MEM_CHECK(ensure_twiddles(ctx, st));
+  if (N == 128) {
+    const size_t smem = 64 * IR8_BP * sizeof(float);
+    MEM_LAUNCH(ctx, k_ingest_rowfft128<false>, nS, 256, smem, st, raw, flip, spec, stats, transposed);
+    return 0;
+  }
   const size_t smem = 32 * IR_BP * sizeof(float);
   auto kern = k_ingest_rowfft256<4>;
   if (ctx->rowfft_blocks == 5) kern = k_ingest_rowfft256<5>;
@@ -453,11 +805,16 @@ int ingest_rowfft_run(mem_ctx* ctx, const float* raw, const uint8_t* flip, float
 }
 
 int rowifft_prefilter_run(mem_ctx* ctx, const float2* spec, float* out, int nS, int N, cudaStream_t st) {
-  if (N != 256) {
+  if (!colfilter_supported(N)) {
     set_error("rowifft_prefilter: no kernel for N = %d", N);
     return 1;
   }
   MEM_CHECK(ensure_twiddles(ctx, st));
+  if (N == 128) {
+    const size_t smem = 64 * RP8_BP * sizeof(float);
+    MEM_LAUNCH(ctx, k_rowifft_prefilter128, nS, 256, smem, st, spec, out);
+    return 0;
+  }
   const size_t smem = 32 * RP_BP * sizeof(float);
   auto kern = k_rowifft_prefilter256<4>;
   if (ctx->rowfft_blocks == 5) kern = k_rowifft_prefilter256<5>;
@@ -468,12 +825,22 @@ int rowifft_prefilter_run(mem_ctx* ctx, const float2* spec, float* out, int nS, 
   return 0;
 }
 
+template <bool FWD>
+static int colpass128(mem_ctx* ctx, float2* spec, const float* G, const float2* stats, int nS, cudaStream_t st) {
+  static_assert(CF8_SLABS * CF8_COLS >= 65, "slabs must cover the half spectrum");
+  const int per_slab = std::max(1, std::min(nS, (4 * ctx->sm_count) / CF8_SLABS));   // four CTAs per SM
+  const size_t smem = 2 * 128 * CF8_COLS * sizeof(float2);
+  MEM_LAUNCH(ctx, k_colfilter128<FWD>, per_slab * CF8_SLABS, CF8_THREADS, smem, st, spec, G, stats, 65, nS, per_slab);
+  return 0;
+}
+
 int colfilter_run(mem_ctx* ctx, float2* spec, const float* G, const float2* stats, int nS, int N, cudaStream_t st) {
-  if (N != 256) {
+  if (!colfilter_supported(N)) {
     set_error("colfilter: no kernel for N = %d", N);
     return 1;
   }
   MEM_CHECK(ensure_twiddles(ctx, st));
+  if (N == 128) return colpass128<false>(ctx, spec, G, stats, nS, st);
   const int Nh = N / 2 + 1;
   static_assert(CF_SLABS * CF_COLS >= 129, "slabs must cover the half spectrum");
   const int per_slab = std::max(1, std::min(nS, (2 * ctx->sm_count) / CF_SLABS));   // CTAs per slab, two CTAs per SM
@@ -483,13 +850,18 @@ int colfilter_run(mem_ctx* ctx, float2* spec, const float* G, const float2* stat
   return 0;
 }
 
-// a10 (:344) for N = 256 with our own kernels: real rows -> half spectra (k_ingest_rowfft256 PLAIN), then the forward column pass
+// a10 (:344) with our own kernels: real rows -> half spectra (the PLAIN row kernel), then the forward column pass
 int fft2_forward_run(mem_ctx* ctx, const float* img, float2* spec, int nS, int N, cudaStream_t st) {
-  if (N != 256) {
+  if (!colfilter_supported(N)) {
     set_error("fft2_forward: no kernel for N = %d", N);
     return 1;
   }
   MEM_CHECK(ensure_twiddles(ctx, st));
+  if (N == 128) {
+    const size_t smem = 64 * IR8_BP * sizeof(float);
+    MEM_LAUNCH(ctx, k_ingest_rowfft128<true>, nS, 256, smem, st, img, (const uint8_t*)nullptr, spec, (float2*)nullptr, 0);
+    return colpass128<true>(ctx, spec, nullptr, nullptr, nS, st);
+  }
   const size_t smem_r = 32 * IR_BP * sizeof(float);
   auto kr = k_ingest_rowfft256<4, true>;
   MEM_CUDA(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));

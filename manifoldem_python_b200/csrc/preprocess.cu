@@ -10,6 +10,10 @@
 
 namespace mem {
 
+// own FFT kernels (lowpass.cu) exist for this box and are not switched off
+static inline bool own_fft(const mem_ctx* ctx, int N) { return colfilter_supported(N) && !ctx->cufft_lowpass; }
+
+
 int ingest_run(mem_ctx* ctx, const float* raw, const uint8_t* flip, float* out, int nS, int N, int transposed,
                cudaStream_t st);
 int shift_run(mem_ctx* ctx, const float* raw, const double* shift, float* tmp, float* out, int nS, int N,
@@ -711,7 +715,7 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
     picture = B;
     transposed = 0;
   }
-  if (colfilter_supported(N)) {
+  if (own_fft(ctx, N)) {
     // One pass of ours turns the raw particles into row-transformed half spectra (ingest, moments and the R2C row pass
     // fused), one more does the whole column pass — FFT, normalisation, * G, inverse FFT — and cuFFT's 1-D C2R
     // brings the rows back: the data crosses HBM three times instead of seven.
@@ -740,7 +744,7 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
     MEM_CHECK(run_fft(ctx, N, nS, true, B, spec, st));
     specw = ctx->spec2.as<float2>();
     MEM_CHECK(run_fft(ctx, N, nS, true, imgAll, specw, st));
-  } else if (colfilter_supported(N) && !ctx->cufft_a10) {
+  } else if (own_fft(ctx, N) && !ctx->cufft_a10) {
     MEM_CHECK(fft2_forward_run(ctx, imgAll, spec, nS, N, st));
   } else {
     MEM_CHECK(run_fft(ctx, N, nS, true, imgAll, spec, st));
@@ -899,7 +903,7 @@ int pd_distance_batch_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_p
   double2* cs = ctx->rot_cs.as<double2>();
   MEM_CUDA(cudaEventRecord(ctx->ev[0], st));
   int rows_done = 0;
-  if (colfilter_supported(N)) {
+  if (own_fft(ctx, N)) {
     MEM_CHECK(ctx->stats.ensure((size_t)nS * sizeof(float2)));
     float2* stats = ctx->stats.as<float2>();
     MEM_CHECK(ingest_rowfft_run(ctx, io->raw, io->flip, spec, stats, nS, N, prm->transposed, st));
@@ -918,7 +922,7 @@ int pd_distance_batch_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_p
   MEM_CHECK(rotate_angles_batch_run(ctx, pd_of, d_pp, cs2, pid2, nS, st));
   MEM_CHECK(align_batch_run(ctx, A, B, imgAll, io->psi_deg, cs, cs2, pid2, nS, N, st, rows_done));
   MEM_CUDA(cudaEventRecord(ctx->ev[2], st));
-  if (colfilter_supported(N) && !ctx->cufft_a10) MEM_CHECK(fft2_forward_run(ctx, imgAll, spec, nS, N, st));
+  if (own_fft(ctx, N) && !ctx->cufft_a10) MEM_CHECK(fft2_forward_run(ctx, imgAll, spec, nS, N, st));
   else MEM_CHECK(run_fft(ctx, N, nS, true, imgAll, spec, st));
   const CtfConst cc = make_ctf_const(prm);
   MEM_LAUNCH(ctx, k_ctf_bins, dim3((g.Kr + 255) / 256, nS), 256, 0, st, io->df, g.r2_of_bin.as<int>(),

@@ -1,5 +1,5 @@
-"""Stage timings of one C4-shaped PD under a context option's values (kernel-variant experiments).
-    python scripts/variant_check.py <option> <v0> <v1> ..."""
+"""Stage timings of one PD (C4 shape unless NS / NPIX are set in the environment) under a context option's values
+(kernel-variant experiments).    [NS=1000 NPIX=128] python scripts/variant_check.py <option> <v0> <v1> ..."""
 import ctypes as C
 import os
 import sys
@@ -13,7 +13,7 @@ import bench                              # noqa: E402
 
 opt = sys.argv[1]
 vals = [int(a) for a in sys.argv[2:]]
-nS, N = 2000, 256
+nS, N = int(os.environ.get('NS', 2000)), int(os.environ.get('NPIX', 256))
 lib = _lib.load()
 ctx = _lib.Context(0)
 pds, rng = bench.make_inputs(nS, N, 1, seed=0)

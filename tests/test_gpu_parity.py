@@ -119,7 +119,7 @@ def test_golden_relion(env, golden_dir):
     _check_fields(res, ref)
 
 
-@pytest.mark.parametrize('N', [100, 256, 300])
+@pytest.mark.parametrize('N', [100, 128, 256, 300])
 def test_relion_shift_large_boxes(env, N):
     """RELION branch at box sizes whose mirror extension (2N-2) takes the long-line prefilter kernels."""
     _lib, pd_stage, synthetic = env
@@ -146,6 +146,37 @@ def test_oracle_parity_tc(env, nS, N, snr, seed):
     ref = _oracle(pd, N, rotate_impl='periodic')
     _check_D(res['D'], ref['D'])
     _check_fields(res, ref)
+
+
+@pytest.mark.parametrize('N', [128, 256])
+@pytest.mark.parametrize('relion', [False, True])
+def test_own_fft_kernels_match_cufft_path(env, N, relion):
+    """The fused ingest / low-pass / a10 kernels of lowpass.cu (N = 128: 16 x 8, N = 256: 16 x 16) against the generic
+    kernels + cuFFT (context option cufft_lowpass): the same images to fp32 FFT round-off, the same D to 1e-5.
+    SPIDER stacks take the transposing ingest, RELION stacks the row-major one behind the sub-pixel shift."""
+    _lib, pd_stage, synthetic = env
+    nS = 70
+    pd = synthetic.make_pd(nS, N, seed=300 + N, snr=0.5)
+    em = pd['em']
+    kw = {}
+    stack = pd['stack']
+    if relion:
+        rng = np.random.default_rng(N)
+        kw = dict(relion=True, sh=(rng.uniform(-3, 3, nS), rng.uniform(-3, 3, nS)))
+        stack = stack.reshape(nS, N, N)
+    ctx = _lib.Context(0)
+    try:
+        out = []
+        for generic in (0, 1):
+            ctx.set_option('cufft_lowpass', generic)
+            out.append(pd_stage.run_pd(pd['ind'], pd['q'], pd['df'], stack, pd['nStot'], N, em['pix_size'], em['Cs'],
+                                       em['EkV'], em['AmpContrast'], ctx=ctx, **kw))
+    finally:
+        ctx.close()
+    own, gen = out
+    _check_D(own['D'], gen['D'])
+    for k in ('imgAll', 'imgAllFlip', 'imgAvg', 'imgAvgFlip', 'imgAllIntensity'):
+        assert np.abs(own[k] - gen[k]).max() <= IMG_TOL * np.abs(gen[k]).max(), k
 
 
 def test_oracle_parity_single_cta_tiles(env):
