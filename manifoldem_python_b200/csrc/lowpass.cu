@@ -1,9 +1,11 @@
-// lowpass.cu — column pass of the a5 low-pass (getDistanceCTF_local_Conj9combinedS2.py:286-293),
-//   img <- Re ifft2( fft2(img) * ifftshift(G) ).
-// The transform is separable, the filter is not: rows go through cuFFT (1-D R2C / C2R), and everything that
-// happens along ky — forward FFT, multiplication by G(ky,kx)/N^2, inverse FFT — is done here in ONE kernel, so
-// the half spectrum crosses HBM once (read + write) instead of three times (2-D plan column pass, scale kernel,
-// 2-D plan column pass).  HBM-bound: 16 * N * Nh bytes per image.
+// lowpass.cu — ingest, a5 low-pass (getDistanceCTF_local_Conj9combinedS2.py:286-293),
+//   img <- Re ifft2( fft2(img) * ifftshift(G) ),
+// and the a10 forward transform (:344) with the library's own FFT kernels for N = 256 and N = 128.
+// The transform is separable, the filter is not: the row passes are fused into their neighbours (k_ingest_rowfft*: ingest +
+// moments + R2C rows; k_rowifft_prefilter*: C2R rows + annular mask + row pass of the first spline prefilter), and everything
+// that happens along ky — forward FFT, normalisation, multiplication by G(ky,kx)/N^2, inverse FFT — is ONE kernel
+// (k_colfilter*), so the half spectrum crosses HBM once (read + write) in the column pass instead of three times (2-D plan
+// column pass, scale kernel, 2-D plan column pass).  HBM-bound: 16 * N * Nh bytes per image and pass.
 //
 // N = 256 = 16 x 16.  A CTA owns COLS adjacent kx columns of one image, 16 threads per column.
 //   forward:  thread t loads rows t + 16 m (m = 0..15) of its column straight from global memory (lanes run along kx:
