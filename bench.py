@@ -509,9 +509,11 @@ def config5_block(ctx, lib, _lib, local):
     return out
 
 
-def h2d_ceiling(ctx, _lib, lib, local, barrier):
+def h2d_ceiling(ctx, _lib, lib, local, barrier, sources=None):
     """Concurrent pinned-host -> device copy rate of this rank while every other rank does the same (the roofline of the
-    e2e leg: 524 MB of raw particles per PD).  8 copies of 512 MB from one pinned buffer."""
+    e2e leg: 524 MB of raw particles per PD).  Returns (rate over the e2e leg's own pinned source buffers, each copied
+    once in turn — what the leg streams from host DRAM —, rate of 8 copies of ONE 512 MB pinned buffer — the figure a bare
+    copy loop reports, part of which a large host cache can serve)."""
     n = 512 << 20
     h = _lib.PinnedArray((n,), np.uint8)
     h.array[::4096] = 1
@@ -523,9 +525,20 @@ def h2d_ceiling(ctx, _lib, lib, local, barrier):
         _lib.check(lib.mem_copy_h2d(ctx.handle, d.ptr, h.ptr, n))
     dt = time.perf_counter() - t0
     barrier()
+    single = 8 * n / dt / 1e9
+    pool = single
+    if sources:
+        m = min(n, min(int(a.array.nbytes) for a in sources))
+        barrier()
+        t0 = time.perf_counter()
+        for a in sources:
+            _lib.check(lib.mem_copy_h2d(ctx.handle, d.ptr, a.ptr, m))
+        dt = time.perf_counter() - t0
+        barrier()
+        pool = len(sources) * m / dt / 1e9
     d.free()
     h.free()
-    return 8 * n / dt / 1e9
+    return pool, single
 
 
 def contraction_ncu():
@@ -729,7 +742,7 @@ def run_b200(args):
     # ---- e2e: host buffers through mem_pd_distance_host, 3 PDs in flight; and the bare concurrent H2D ceiling
     e2e = None
     if not args.no_e2e:
-        ceil_gbs = h2d_ceiling(ctx, _lib, lib, local, barrier)
+        ceil_gbs, ceil_single = h2d_ceiling(ctx, _lib, lib, local, barrier, sources=h_raw)
         nthreads = max(1, int(os.environ.get('MANIFOLDEM_B200_BENCH_INFLIGHT', '3')))
         ctxs = [ctx] + [_lib.Context(local) for _ in range(nthreads - 1)]
         h_D = [_lib.PinnedArray((nS, nS), np.float32) for _ in range(nthreads)]
@@ -760,33 +773,87 @@ def run_b200(args):
         counts = partition.counts_by_speed(world * P_e, rates)
         P_mine = max(1, counts[rank])
         e2e_step(min(P_e, 2 * nthreads))           # warm-up (plans / workspaces of the extra contexts)
+        e_steps = max(1, min(args.steps, 2))
+        P_all = sum(max(1, c) for c in counts)
+        pd_h2d = nS * NN * 4 + nS * 17
+
+        def all_ranks(x):                            # one float per rank -> list over ranks
+            if world == 1:
+                return [float(x)]
+            tv = torch.zeros(world, dtype=torch.float64, device='cuda:%d' % local)
+            tv[rank] = x
+            dist.all_reduce(tv, op=dist.ReduceOp.SUM)
+            return [float(v) for v in tv]
+
+        # (a) static partition: rank r runs counts[r] PDs per step
         barrier()
         t0 = time.perf_counter()
-        e_steps = max(1, min(args.steps, 2))
         for _ in range(e_steps):
             e2e_step(P_mine)
         for cx in ctxs:
             cx.sync()
-        dt = time.perf_counter() - t0
-        te = torch.tensor([dt, -ceil_gbs], dtype=torch.float64, device='cuda:%d' % local)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        dt, ceil_min = float(te[0]), -float(te[1])
-        P_all = sum(max(1, c) for c in counts)
-        h2d_b, d2h_b = int(P_mine * (nS * NN * 4 + nS * 17)), int(P_mine * nS * nS * 4)
-        e2e_val = float(nS) * nS * P_all * e_steps / dt / 1e9
-        per_gpu_h2d = h2d_b * e_steps / dt / 1e9
-        agg_h2d = float(P_all) * (nS * NN * 4 + nS * 17) * e_steps / dt / 1e9
+        dt_mine = time.perf_counter() - t0
+        sec_static = all_ranks(dt_mine)
+        dt = max(sec_static)
+        sched = dict(static=dict(value=float(nS) * nS * P_all * e_steps / dt / 1e9, seconds_per_rank=sec_static,
+                                 pds_per_rank_per_step=counts))
+        done_mine = P_mine * e_steps
+        done_all = [max(1, c) * e_steps for c in counts]
+        chosen = 'static'
+        # (b) one job queue for the box, as the reference's Pool.imap_unordered (GetDistancesS2.py:110-113) and the drop-in
+        # driver's job queue hand PDs out: a shared counter in the rendezvous store; a rank takes the next PD when one of its
+        # in-flight slots frees up, so every GPU is fed at the rate its host link delivers at that moment
+        if world > 1 and os.environ.get('MANIFOLDEM_B200_BENCH_E2E_SCHED', 'queue') != 'static':
+            store = dist.distributed_c10d._get_default_store()
+            total = P_all * e_steps
+            taken = [0] * nthreads
+
+            def qworker(w):
+                while True:
+                    k = int(store.add('e2e_queue', 1)) - 1
+                    if k >= total:
+                        return
+                    j = k % POOL
+                    io = _lib.PdIO()
+                    io.raw, io.flip = h_raw[j].ptr, pds[j]['flip'].ctypes.data
+                    io.psi_deg, io.df, io.D = pds[j]['psi_deg'].ctypes.data, pds[j]['df'].ctypes.data, h_D[w].ptr
+                    _lib.check(lib.mem_pd_distance_host(ctxs[w].handle, C.byref(prms[j]), C.byref(io)))
+                    taken[w] += 1
+            barrier()
+            t0 = time.perf_counter()
+            th = [threading.Thread(target=qworker, args=(w,)) for w in range(nthreads)]
+            [x.start() for x in th]
+            [x.join() for x in th]
+            for cx in ctxs:
+                cx.sync()
+            dq_mine = time.perf_counter() - t0
+            sec_q = all_ranks(dq_mine)
+            took = [int(round(v)) for v in all_ranks(float(sum(taken)))]
+            sched['queue'] = dict(value=float(nS) * nS * total / max(sec_q) / 1e9, seconds_per_rank=sec_q, pds_per_rank=took)
+            if sched['queue']['value'] > sched['static']['value']:
+                dt, done_mine, done_all, chosen = max(sec_q), sum(taken), took, 'queue'
+        ceil_min = min(rates)
+        n_done = sum(done_all)
+        h2d_b, d2h_b = int(done_mine * pd_h2d / e_steps), int(done_mine * nS * nS * 4 / e_steps)
+        e2e_val = float(nS) * nS * n_done / dt / 1e9
+        per_gpu_h2d = done_mine * pd_h2d / dt / 1e9
+        agg_h2d = float(n_done) * pd_h2d / dt / 1e9
         e2e = dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=h2d_b, d2h_bytes_per_step=d2h_b,
-                   pds_per_step=P_mine, pds_per_step_all_ranks=P_all, pds_per_rank=counts, steps=e_steps, in_flight=nthreads,
+                   pds_per_step=done_mine // e_steps, pds_per_step_all_ranks=n_done // e_steps,
+                   pds_per_rank=[c // e_steps for c in done_all], steps=e_steps, in_flight=nthreads,
                    h2d_gbs_per_gpu=per_gpu_h2d, h2d_gbs_all_ranks=agg_h2d,
                    h2d_ceiling=dict(gbs_per_rank=rates, gbs_all_ranks=float(sum(rates)), gbs_per_gpu_slowest_rank=ceil_min,
-                                    gbs_this_rank=ceil_gbs, ranks_copying_at_once=world,
-                                    how='8 x 512 MB cudaMemcpyAsync from pinned memory, all ranks between the same barriers'),
+                                    gbs_this_rank=ceil_gbs, gbs_this_rank_one_buffer_repeated=ceil_single,
+                                    ranks_copying_at_once=world,
+                                    how='one 512 MB cudaMemcpyAsync from each of the leg\'s %d pinned source stacks in turn, all ranks '
+                                        'between the same barriers (one_buffer_repeated: 8 copies of a single 512 MB buffer)' % len(h_raw)),
                    frac_of_h2d_ceiling=agg_h2d / float(sum(rates)) if sum(rates) > 0 else None,
-                   partition='PDs per rank proportional to the rank\'s measured concurrent H2D rate (static)',
-                   note='wall clock bracketed by stream syncs + barrier; H2D of each raw stack from pinned memory and D2H of D inside; '
-                        'h2d / d2h bytes per step are this rank\'s (rank 0)')
+                   schedule=chosen, schedules=sched,
+                   partition=('one PD queue for the box (shared counter in the rendezvous store): a rank takes the next PD when an '
+                              'in-flight slot frees up' if chosen == 'queue' else
+                              'PDs per rank proportional to the rank\'s measured concurrent H2D rate (static)'),
+                   note='wall clock bracketed by stream syncs + barrier, max over ranks; H2D of each raw stack from pinned memory and '
+                        'D2H of D inside; h2d / d2h bytes per step are this rank\'s (rank 0)')
         for cx in ctxs[1:]:
             cx.close()
 

@@ -712,3 +712,38 @@ def test_manifold_analysis_driver_bookkeeping(tmp_path):
     assert [j[3] for j in jobs] == [0, 2, 4]
     assert jobs[1][0] == p.dist_file + 'prD_2' and jobs[1][1] == p.psi_file + 'prD_2'
     assert jobs[2][2] == '{}/topos/PrD_5/eig_spec.txt'.format(p.out_dir)
+
+
+def _queue_consumer(queue, out, tag):
+    """Spawned stand-in for a GPU worker: the queue loop of the driver with a recording job function."""
+    from manifoldem_python_b200 import GetDistancesS2
+    import time as _t
+
+    def rec(job, *a):
+        _t.sleep(0.002)
+        out.put((tag, job[4]))
+    n = GetDistancesS2._run_queue(queue, None, None, None, 0, {}, 1e9, op=rec)
+    out.put((tag, -1 - n))
+
+
+def test_job_queue_hands_every_pd_out_once():
+    """The box-wide job queue of GetDistancesS2 (the reference's imap_unordered, :110-113): two consumer processes with two
+    slots each drain it, every PD runs exactly once and every slot sees an end marker (both processes exit)."""
+    import multiprocessing
+    from manifoldem_python_b200 import GetDistancesS2
+    ctx = multiprocessing.get_context('spawn')
+    queue, out = ctx.Queue(), ctx.Queue()
+    n_jobs, n_proc = 60, 2
+    for prD in range(n_jobs):
+        queue.put([np.arange(3), None, None, 'f%d' % prD, prD])
+    for _ in range(n_proc * GetDistancesS2._inflight(1e9)):
+        queue.put(None)
+    procs = [ctx.Process(target=_queue_consumer, args=(queue, out, t)) for t in range(n_proc)]
+    [pr.start() for pr in procs]
+    got = [out.get(timeout=120) for _ in range(n_jobs + n_proc)]
+    [pr.join() for pr in procs]
+    assert all(pr.exitcode == 0 for pr in procs)
+    ran = sorted(j for _, j in got if j >= 0)
+    assert ran == list(range(n_jobs))
+    counts = {t: -1 - j for t, j in got if j < 0}
+    assert sum(counts.values()) == n_jobs and sorted(counts) == [0, 1]
