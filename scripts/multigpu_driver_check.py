@@ -1,5 +1,5 @@
 """GetDistancesS2.op on a box with several GPUs: p.ncpu caps the worker count, one spawned process per GPU,
-static LPT partition, markers as the only gather.  python scripts/multigpu_driver_check.py [n_gpus]"""
+one job queue for the box (distance stage) / static LPT partition (embedding, psi analysis), markers as the only gather.  python scripts/multigpu_driver_check.py [n_gpus]"""
 import os
 import pickle
 import sys
