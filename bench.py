@@ -803,8 +803,17 @@ def run_b200(args):
         # (b) one job queue for the box, as the reference's Pool.imap_unordered (GetDistancesS2.py:110-113) and the drop-in
         # driver's job queue hand PDs out: a shared counter in the rendezvous store; a rank takes the next PD when one of its
         # in-flight slots frees up, so every GPU is fed at the rate its host link delivers at that moment
+        store = None
         if world > 1 and os.environ.get('MANIFOLDEM_B200_BENCH_E2E_SCHED', 'queue') != 'static':
-            store = dist.distributed_c10d._get_default_store()
+            try:
+                store = dist.distributed_c10d._get_default_store()
+                store.add('e2e_queue_probe', 1)
+            except Exception as e:                   # no usable store: the static shares stand
+                sched['queue'] = dict(error=repr(e))
+                store = None
+        if world > 1 and min(all_ranks(1.0 if store is not None else 0.0)) < 1.0:
+            store = None                             # every rank or none
+        if store is not None:
             total = P_all * e_steps
             taken = [0] * nthreads
 
