@@ -717,8 +717,8 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
   }
   if (own_fft(ctx, N)) {
     // One pass of ours turns the raw particles into row-transformed half spectra (ingest, moments and the R2C row pass
-    // fused), one more does the whole column pass — FFT, normalisation, * G, inverse FFT — and cuFFT's 1-D C2R
-    // brings the rows back: the data crosses HBM three times instead of seven.
+    // fused), one more does the whole column pass — FFT, normalisation, * G, inverse FFT — and a third brings the rows
+    // back (C2R, annular mask, row pass of the first spline prefilter): three crossings of HBM instead of nine.
     MEM_CHECK(ctx->stats.ensure((size_t)nS * sizeof(float2)));
     float2* stats = ctx->stats.as<float2>();
     MEM_CHECK(ingest_rowfft_run(ctx, picture, io->flip, spec, stats, nS, N, transposed, st));
