@@ -132,6 +132,8 @@ int fft_get(mem_ctx* ctx, int N, int batch, FftPlan* out, bool rows_only = false
 // column pass of the low-pass on the row-transformed half spectra: FFT along ky, * G, inverse FFT, in place.
 // Returns false when the box size has no specialised kernel (the caller keeps the 2-D cuFFT path).
 bool colfilter_supported(int N);
+bool colpass_supported(int N);   // own column pass only (rows through cuFFT 1-D plans)
+int colpass_run(mem_ctx* ctx, float2* spec, const float* G, int nS, int N, int fwd_only, cudaStream_t st);
 int colfilter_run(mem_ctx* ctx, float2* spec, const float* G, const float2* stats, int nS, int N, cudaStream_t st);
 // a2 + a3 + row R2C in one pass for the same box sizes: raw particles -> row-transformed half spectra + (mean, 1/std)
 int ingest_rowfft_run(mem_ctx* ctx, const float* raw, const uint8_t* flip, float2* spec, float2* stats, int nS, int N,

@@ -15,8 +15,9 @@
 //   inverse:  X[k1 + 16 k2] is again a "residue + 16 m" set, so the inverse starts from the registers:
 //             inverse FFT-16 over k2, conjugate twiddle, exchange, inverse FFT-16, store rows t + 16 m.
 // Shared memory is touched only by the two exchanges; all its accesses are unit-stride across lanes.
-// N = 128 = 16 x 8 has the same three kernels with eight threads per transform (second half of the file); other boxes take
-// the generic ingest + cuFFT path of preprocess.cu.
+// N = 128 = 16 x 8 has the same three kernels with eight threads per transform (second half of the file); N = 320 = 20 x 16 has
+// the column pass only (rows through cuFFT's batched 1-D plans); other boxes take the generic ingest + 2-D cuFFT path of
+// preprocess.cu.
 #include "common.cuh"
 #include "spline.cuh"
 
@@ -767,7 +768,152 @@ __global__ void __launch_bounds__(256, 4) k_rowifft_prefilter128(const float2* _
   }
 }
 
+// ================================================================================================
+// N = 320 = 20 x 16 (BASELINE config 5): the COLUMN pass only — the rows go through cuFFT's batched 1-D plans (a warp-sized
+// thread group cannot hold a 320-point transform with uniform work).  20 threads per column, thread t holds x[t + 20 m],
+// m < 16: FFT-16 in registers, twiddle W320^(t k1), exchange, then threads k1 < 16 run an FFT-20 (4 x 5) over t and hold
+// X[k1 + 16 k2], k2 < 20; filter; inverse FFT-20 over k2, conjugate twiddle, exchange, inverse FFT-16 on all 20 threads:
+// x[t + 20 n2] again.  The four thread rows t >= 16 idle in the FFT-20 stages as whole warps.
+// ================================================================================================
+__constant__ float2 c_tw320[320];           // exp(-2 pi i j / 320)
+
+// 5-point DFT in registers, natural order in and out
+template <int S>
+__device__ __forceinline__ void fft5(float2& x0, float2& x1, float2& x2, float2& x3, float2& x4) {
+  constexpr float C1 = 0.30901699437494745f, C2 = -0.80901699437494745f, S1 = 0.95105651629515353f, S2 = 0.58778525229247314f;
+  const float2 t1 = cadd(x1, x4), t2 = cadd(x2, x3), t3 = csub(x1, x4), t4 = csub(x2, x3);
+  const float2 a1 = make_float2(x0.x + C1 * t1.x + C2 * t2.x, x0.y + C1 * t1.y + C2 * t2.y);
+  const float2 a2 = make_float2(x0.x + C2 * t1.x + C1 * t2.x, x0.y + C2 * t1.y + C1 * t2.y);
+  const float2 b1 = make_float2(S1 * t3.x + S2 * t4.x, S1 * t3.y + S2 * t4.y);
+  const float2 b2 = make_float2(S2 * t3.x - S1 * t4.x, S2 * t3.y - S1 * t4.y);
+  x0 = make_float2(x0.x + t1.x + t2.x, x0.y + t1.y + t2.y);
+  // forward (S < 0): X1 = a1 - i b1, X4 = a1 + i b1, X2 = a2 - i b2, X3 = a2 + i b2;  -i (p, q) = (q, -p)
+  const float sg = (S < 0) ? 1.0f : -1.0f;
+  x1 = make_float2(a1.x + sg * b1.y, a1.y - sg * b1.x);
+  x4 = make_float2(a1.x - sg * b1.y, a1.y + sg * b1.x);
+  x2 = make_float2(a2.x + sg * b2.y, a2.y - sg * b2.x);
+  x3 = make_float2(a2.x - sg * b2.y, a2.y + sg * b2.x);
+}
+
+// 20-point DFT in registers, natural order in and out: n = 5 n1 + n2, k = k1 + 4 k2
+template <int S>
+__device__ __forceinline__ void fft20(float2 (&x)[20]) {
+  // cos / sin of 2 pi j / 20, j = n2 k1 <= 12
+  constexpr float C[13] = {1.0f, 0.95105651629515353f, 0.80901699437494745f, 0.58778525229247314f, 0.30901699437494745f, 0.0f,
+                           -0.30901699437494745f, -0.58778525229247314f, -0.80901699437494745f, -0.95105651629515353f, -1.0f,
+                           -0.95105651629515353f, -0.80901699437494745f};
+  constexpr float Sn[13] = {0.0f, 0.30901699437494745f, 0.58778525229247314f, 0.80901699437494745f, 0.95105651629515353f, 1.0f,
+                            0.95105651629515353f, 0.80901699437494745f, 0.58778525229247314f, 0.30901699437494745f, 0.0f,
+                            -0.30901699437494745f, -0.58778525229247314f};
+#pragma unroll
+  for (int n2 = 0; n2 < 5; ++n2) {
+    fft4<S>(x[n2], x[5 + n2], x[10 + n2], x[15 + n2]);      // x[n2 + 5 k1] = A[n2][k1]
+#pragma unroll
+    for (int k1 = 1; k1 < 4; ++k1)
+      if (n2 != 0) x[n2 + 5 * k1] = cmul(x[n2 + 5 * k1], make_float2(C[n2 * k1], (float)S * Sn[n2 * k1]));
+  }
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) fft5<S>(x[5 * k1], x[5 * k1 + 1], x[5 * k1 + 2], x[5 * k1 + 3], x[5 * k1 + 4]);   // x[5 k1 + k2] = X[k1 + 4 k2]
+  float2 y[20];
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1)
+#pragma unroll
+    for (int k2 = 0; k2 < 5; ++k2) y[k1 + 4 * k2] = x[5 * k1 + k2];
+#pragma unroll
+  for (int k = 0; k < 20; ++k) x[k] = y[k];
+}
+
+constexpr int CF20_COLS = 16;                 // 11 slabs cover Nh = 161 (15 idle columns in the last slab)
+constexpr int CF20_SLABS = 11;
+constexpr int CF20_THREADS = 20 * CF20_COLS;
+
+template <bool FWD = false>
+__global__ void __launch_bounds__(CF20_THREADS, 2) k_colfilter320(float2* __restrict__ spec, const float* __restrict__ G, int nS,
+                                                               int img_stride) {
+  constexpr int N = 320, Nh = 161;
+  extern __shared__ float2 cf_smem[];
+  float2* ex = cf_smem;                           // [320][CF20_COLS]
+  float2* stage = cf_smem + N * CF20_COLS;        // next image's slab
+  const int t = threadIdx.x / CF20_COLS, col = threadIdx.x - t * CF20_COLS;
+  const int slab = blockIdx.x % CF20_SLABS;
+  const int kx = slab * CF20_COLS + col;
+  const bool live = kx < Nh;
+  const int kxc = live ? kx : 0;
+  const bool second = t < 16;                     // the threads that run the FFT-20 stages (as k1 = t)
+  float gk[20];
+  if (!FWD) {
+#pragma unroll
+    for (int k2 = 0; k2 < 20; ++k2) gk[k2] = (live && second) ? G[(t + 16 * k2) * Nh + kxc] : 0.0f;
+  }
+  __shared__ float2 tws[320];                     // tws[k1 * 20 + t] = W320^(t k1), k1 < 16, t < 20
+  tws[threadIdx.x] = c_tw320[((threadIdx.x / 20) * (threadIdx.x % 20)) % 320];
+  __syncthreads();
+  int img = blockIdx.x / CF20_SLABS;
+  if (img < nS) {
+    const float2* src = spec + (size_t)img * N * Nh + kxc;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) cp_async8(stage + (t + 20 * m) * CF20_COLS + col, src + (t + 20 * m) * Nh);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (; img < nS; img += img_stride) {
+    float2* base = spec + (size_t)img * N * Nh + kxc;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    float2 v[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) v[m] = stage[(t + 20 * m) * CF20_COLS + col];
+    const int nxt = img + img_stride;
+    if (nxt < nS) {
+      const float2* src = spec + (size_t)nxt * N * Nh + kxc;
+#pragma unroll
+      for (int m = 0; m < 16; ++m) cp_async8(stage + (t + 20 * m) * CF20_COLS + col, src + (t + 20 * m) * Nh);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    fft16<-1>(v);                                   // v[k1] = A_t[k1]
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) ex[(k1 * 20 + t) * CF20_COLS + col] = cmul(v[k1], tws[k1 * 20 + t]);
+    __syncthreads();
+    float2 u[20];
+    if (second) {
+#pragma unroll
+      for (int tt = 0; tt < 20; ++tt) u[tt] = ex[(t * 20 + tt) * CF20_COLS + col];
+      fft20<-1>(u);                                 // u[k2] = X[t + 16 k2]
+      if (FWD) {
+        if (live) {
+#pragma unroll
+          for (int k2 = 0; k2 < 20; ++k2) base[(t + 16 * k2) * Nh] = u[k2];
+        }
+      } else {
+#pragma unroll
+        for (int k2 = 0; k2 < 20; ++k2) {
+          u[k2].x *= gk[k2];
+          u[k2].y *= gk[k2];
+        }
+        fft20<1>(u);                                // inverse over k2: u[n1] = C_t[n1]
+      }
+    }
+    __syncthreads();                                // every thread is done reading the forward exchange
+    if (FWD) continue;
+    if (second) {
+#pragma unroll
+      for (int n1 = 0; n1 < 20; ++n1) {
+        const float2 w = tws[t * 20 + n1];          // W320^(n1 k1), k1 = t
+        ex[(n1 * 16 + t) * CF20_COLS + col] = cmul(u[n1], make_float2(w.x, -w.y));
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) v[k1] = ex[(t * 16 + k1) * CF20_COLS + col];
+    fft16<1>(v);                                    // v[n2] = x[t + 20 n2]
+    if (live) {
+#pragma unroll
+      for (int n2 = 0; n2 < 16; ++n2) base[(t + 20 * n2) * Nh] = v[n2];
+    }
+    __syncthreads();                                // `ex` is rewritten by the next image
+  }
+}
+
 bool colfilter_supported(int N) { return N == 256 || N == 128; }
+bool colpass_supported(int N) { return N == 320; }
 
 static int ensure_twiddles(mem_ctx* ctx, cudaStream_t st) {
   static thread_local int tw_device = -1;
@@ -780,6 +926,40 @@ static int ensure_twiddles(mem_ctx* ctx, cudaStream_t st) {
     MEM_CUDA(cudaMemcpyToSymbolAsync(c_tw256, tw, sizeof(tw), 0, cudaMemcpyHostToDevice, st));
     MEM_CUDA(cudaStreamSynchronize(st));
     tw_device = ctx->device;
+  }
+  return 0;
+}
+
+static int ensure_twiddles320(mem_ctx* ctx, cudaStream_t st) {
+  static thread_local int tw_device = -1;
+  if (tw_device != ctx->device) {
+    float2 tw[320];
+    for (int j = 0; j < 320; ++j) {
+      const double a = -2.0 * M_PI * j / 320.0;
+      tw[j] = make_float2((float)cos(a), (float)sin(a));
+    }
+    MEM_CUDA(cudaMemcpyToSymbolAsync(c_tw320, tw, sizeof(tw), 0, cudaMemcpyHostToDevice, st));
+    MEM_CUDA(cudaStreamSynchronize(st));
+    tw_device = ctx->device;
+  }
+  return 0;
+}
+
+// column pass alone (N = 320): spec holds row-transformed half spectra (cuFFT 1-D R2C); fwd_only = the a10 transform
+int colpass_run(mem_ctx* ctx, float2* spec, const float* G, int nS, int N, int fwd_only, cudaStream_t st) {
+  if (!colpass_supported(N)) {
+    set_error("colpass: no kernel for N = %d", N);
+    return 1;
+  }
+  MEM_CHECK(ensure_twiddles320(ctx, st));
+  const int per_slab = std::max(1, std::min(nS, (2 * ctx->sm_count) / CF20_SLABS));
+  const size_t smem = 2 * 320 * CF20_COLS * sizeof(float2);
+  if (fwd_only) {
+    MEM_CUDA(cudaFuncSetAttribute(k_colfilter320<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MEM_LAUNCH(ctx, k_colfilter320<true>, per_slab * CF20_SLABS, CF20_THREADS, smem, st, spec, G, nS, per_slab);
+  } else {
+    MEM_CUDA(cudaFuncSetAttribute(k_colfilter320<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MEM_LAUNCH(ctx, k_colfilter320<false>, per_slab * CF20_SLABS, CF20_THREADS, smem, st, spec, G, nS, per_slab);
   }
   return 0;
 }

@@ -726,6 +726,12 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
     // inverse row transform fused with the annular mask and the row pass of the first spline prefilter -> A
     MEM_CHECK(rowifft_prefilter_run(ctx, spec, A, nS, N, st));
     rows_done = 1;
+  } else if (colpass_supported(N) && !ctx->cufft_lowpass) {
+    // N = 320: rows through cuFFT's batched 1-D plans, the whole column pass (FFT, * G, inverse FFT) in one kernel of ours
+    MEM_CHECK(ingest_run(ctx, picture, io->flip, A, nS, N, transposed, st));
+    MEM_CHECK(run_fft(ctx, N, nS, true, A, spec, st, true));
+    MEM_CHECK(colpass_run(ctx, spec, g.Gtab.as<float>(), nS, N, 0, st));
+    MEM_CHECK(run_fft(ctx, N, nS, false, B, spec, st, true));
   } else {
     MEM_CHECK(ingest_run(ctx, picture, io->flip, A, nS, N, transposed, st));
     MEM_CHECK(run_fft(ctx, N, nS, true, A, spec, st));
@@ -746,6 +752,9 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
     MEM_CHECK(run_fft(ctx, N, nS, true, imgAll, specw, st));
   } else if (own_fft(ctx, N) && !ctx->cufft_a10) {
     MEM_CHECK(fft2_forward_run(ctx, imgAll, spec, nS, N, st));
+  } else if (colpass_supported(N) && !ctx->cufft_lowpass && !ctx->cufft_a10) {
+    MEM_CHECK(run_fft(ctx, N, nS, true, imgAll, spec, st, true));
+    MEM_CHECK(colpass_run(ctx, spec, nullptr, nS, N, 1, st));
   } else {
     MEM_CHECK(run_fft(ctx, N, nS, true, imgAll, spec, st));
   }
@@ -910,6 +919,11 @@ int pd_distance_batch_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_p
     MEM_CHECK(colfilter_run(ctx, spec, g.Gtab.as<float>(), stats, nS, N, st));
     MEM_CHECK(rowifft_prefilter_run(ctx, spec, A, nS, N, st));
     rows_done = 1;
+  } else if (colpass_supported(N) && !ctx->cufft_lowpass) {
+    MEM_CHECK(ingest_run(ctx, io->raw, io->flip, A, nS, N, prm->transposed, st));
+    MEM_CHECK(run_fft(ctx, N, nS, true, A, spec, st, true));
+    MEM_CHECK(colpass_run(ctx, spec, g.Gtab.as<float>(), nS, N, 0, st));
+    MEM_CHECK(run_fft(ctx, N, nS, false, B, spec, st, true));
   } else {
     MEM_CHECK(ingest_run(ctx, io->raw, io->flip, A, nS, N, prm->transposed, st));
     MEM_CHECK(run_fft(ctx, N, nS, true, A, spec, st));
@@ -922,8 +936,14 @@ int pd_distance_batch_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_p
   MEM_CHECK(rotate_angles_batch_run(ctx, pd_of, d_pp, cs2, pid2, nS, st));
   MEM_CHECK(align_batch_run(ctx, A, B, imgAll, io->psi_deg, cs, cs2, pid2, nS, N, st, rows_done));
   MEM_CUDA(cudaEventRecord(ctx->ev[2], st));
-  if (own_fft(ctx, N) && !ctx->cufft_a10) MEM_CHECK(fft2_forward_run(ctx, imgAll, spec, nS, N, st));
-  else MEM_CHECK(run_fft(ctx, N, nS, true, imgAll, spec, st));
+  if (own_fft(ctx, N) && !ctx->cufft_a10) {
+    MEM_CHECK(fft2_forward_run(ctx, imgAll, spec, nS, N, st));
+  } else if (colpass_supported(N) && !ctx->cufft_lowpass && !ctx->cufft_a10) {
+    MEM_CHECK(run_fft(ctx, N, nS, true, imgAll, spec, st, true));
+    MEM_CHECK(colpass_run(ctx, spec, nullptr, nS, N, 1, st));
+  } else {
+    MEM_CHECK(run_fft(ctx, N, nS, true, imgAll, spec, st));
+  }
   const CtfConst cc = make_ctf_const(prm);
   MEM_LAUNCH(ctx, k_ctf_bins, dim3((g.Kr + 255) / 256, nS), 256, 0, st, io->df, g.r2_of_bin.as<int>(),
              ctx->cbin.as<float>(), g.Kr, cc);

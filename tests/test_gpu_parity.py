@@ -148,10 +148,10 @@ def test_oracle_parity_tc(env, nS, N, snr, seed):
     _check_fields(res, ref)
 
 
-@pytest.mark.parametrize('N,nS', [(128, 70), (256, 70), (128, 2), (256, 3), (128, 301)])
+@pytest.mark.parametrize('N,nS', [(128, 70), (256, 70), (128, 2), (256, 3), (128, 301), (320, 24), (320, 3)])
 @pytest.mark.parametrize('relion', [False, True])
 def test_own_fft_kernels_match_cufft_path(env, N, nS, relion):
-    """The fused ingest / low-pass / a10 kernels of lowpass.cu (N = 128: 16 x 8, N = 256: 16 x 16) against the generic
+    """The fused ingest / low-pass / a10 kernels of lowpass.cu (N = 128: 16 x 8, N = 256: 16 x 16; N = 320: column pass 20 x 16) against the generic
     kernels + cuFFT (context option cufft_lowpass): the same images to fp32 FFT round-off, the same D to 1e-5.
     SPIDER stacks take the transposing ingest, RELION stacks the row-major one behind the sub-pixel shift."""
     _lib, pd_stage, synthetic = env
