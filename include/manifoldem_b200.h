@@ -38,7 +38,8 @@ int         mem_ctx_sync(mem_ctx* ctx);
  *   "cufft_a10"      1 = the a10 forward transform through cuFFT's 2-D plan also at N = 128 / 256 (default 0: the library's own
  *                    row / column FFT kernels; other boxes always take cuFFT)
  *   "cufft_lowpass"  1 = ingest, low-pass and a10 through the generic kernels + cuFFT's 2-D plans also at N = 128 / 256 / 320
- *                    (comparison / tests; default 0: own row and column kernels at 128 / 256, own column pass at 320)
+ *                    (comparison / tests; default 0: own row and column kernels at 128 / 256 / 320)
+ *   "cufft_rows320"  1 = at N = 320 only the column pass is the library's own, rows through cuFFT's batched 1-D plans (comparison)
  *   "radial_variant", "rowfft_blocks"   experiment switches (thread count of the operand writer, CTAs per SM the row FFT kernels
  *                    are compiled for); 0 = the measured defaults */
 int         mem_ctx_set_option(mem_ctx* ctx, const char* name, int32_t value);

@@ -114,6 +114,7 @@ int mem_ctx_set_option(mem_ctx* ctx, const char* name, int32_t value) {
   else if (!strcmp(name, "rowfft_blocks")) ctx->rowfft_blocks = value;
   else if (!strcmp(name, "cufft_a10")) ctx->cufft_a10 = value;
   else if (!strcmp(name, "cufft_lowpass")) ctx->cufft_lowpass = value;
+  else if (!strcmp(name, "cufft_rows320")) ctx->cufft_rows320 = value;
   else {
     set_error("mem_ctx_set_option: unknown option '%s'", name);
     return 1;

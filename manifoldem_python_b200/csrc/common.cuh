@@ -119,6 +119,7 @@ struct mem_ctx {
   void* tmap_encode = nullptr;   // cuTensorMapEncodeTiled entry point
   int pool_ready = 0;            // the device's default memory pool has its release threshold set
   int full_sums = 0;             // 1: the spectrum sums always run over every image (tests: M from all images)
+  int cufft_rows320 = 0;         // 1: the row passes at N = 320 through cuFFT's 1-D plans + generic ingest / prefilter (comparison)
   int cufft_lowpass = 0;         // 1: ingest / low-pass / a10 through the generic kernels + cuFFT even where own FFT kernels exist (tests)
   int cufft_a10 = 0;             // 1: the a10 transform through cuFFT's 2-D plan even for N = 256 (tests / comparison)
   int rowfft_blocks = 0;         // experiments: CTAs per SM the row FFT kernels are compiled for (0 = default 4)
@@ -133,7 +134,10 @@ int fft_get(mem_ctx* ctx, int N, int batch, FftPlan* out, bool rows_only = false
 // Returns false when the box size has no specialised kernel (the caller keeps the 2-D cuFFT path).
 bool colfilter_supported(int N);
 bool colpass_supported(int N);   // own column pass only (rows through cuFFT 1-D plans)
-int colpass_run(mem_ctx* ctx, float2* spec, const float* G, int nS, int N, int fwd_only, cudaStream_t st);
+int colpass_run(mem_ctx* ctx, float2* spec, const float* G, const float2* stats, int nS, int N, int fwd_only, cudaStream_t st);
+int rows320_forward_run(mem_ctx* ctx, const float* raw, const uint8_t* flip, float2* spec, float2* stats, int nS, int transposed,
+                        int plain, cudaStream_t st);
+int rows320_inverse_run(mem_ctx* ctx, const float2* spec, float* out, int nS, cudaStream_t st);
 int colfilter_run(mem_ctx* ctx, float2* spec, const float* G, const float2* stats, int nS, int N, cudaStream_t st);
 // a2 + a3 + row R2C in one pass for the same box sizes: raw particles -> row-transformed half spectra + (mean, 1/std)
 int ingest_rowfft_run(mem_ctx* ctx, const float* raw, const uint8_t* flip, float2* spec, float2* stats, int nS, int N,

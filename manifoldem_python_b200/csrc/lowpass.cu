@@ -15,8 +15,8 @@
 //   inverse:  X[k1 + 16 k2] is again a "residue + 16 m" set, so the inverse starts from the registers:
 //             inverse FFT-16 over k2, conjugate twiddle, exchange, inverse FFT-16, store rows t + 16 m.
 // Shared memory is touched only by the two exchanges; all its accesses are unit-stride across lanes.
-// N = 128 = 16 x 8 has the same three kernels with eight threads per transform (second half of the file); N = 320 = 20 x 16 has
-// the column pass only (rows through cuFFT's batched 1-D plans); other boxes take the generic ingest + 2-D cuFFT path of
+// N = 128 = 16 x 8 has the same three kernels with eight threads per transform, N = 320 = 20 x 16 with twenty threads per
+// transform and CTA-level exchanges (second half of the file); other boxes take the generic ingest + 2-D cuFFT path of
 // preprocess.cu.
 #include "common.cuh"
 #include "spline.cuh"
@@ -769,8 +769,8 @@ __global__ void __launch_bounds__(256, 4) k_rowifft_prefilter128(const float2* _
 }
 
 // ================================================================================================
-// N = 320 = 20 x 16 (BASELINE config 5): the COLUMN pass only — the rows go through cuFFT's batched 1-D plans (a warp-sized
-// thread group cannot hold a 320-point transform with uniform work).  20 threads per column, thread t holds x[t + 20 m],
+// N = 320 = 20 x 16 (BASELINE config 5).  A warp-sized thread group cannot hold a 320-point transform with uniform work, so the
+// split lives on CTA level.  Column pass: 20 threads per column, thread t holds x[t + 20 m],
 // m < 16: FFT-16 in registers, twiddle W320^(t k1), exchange, then threads k1 < 16 run an FFT-20 (4 x 5) over t and hold
 // X[k1 + 16 k2], k2 < 20; filter; inverse FFT-20 over k2, conjugate twiddle, exchange, inverse FFT-16 on all 20 threads:
 // x[t + 20 n2] again.  The four thread rows t >= 16 idle in the FFT-20 stages as whole warps.
@@ -828,8 +828,8 @@ constexpr int CF20_SLABS = 11;
 constexpr int CF20_THREADS = 20 * CF20_COLS;
 
 template <bool FWD = false>
-__global__ void __launch_bounds__(CF20_THREADS, 2) k_colfilter320(float2* __restrict__ spec, const float* __restrict__ G, int nS,
-                                                               int img_stride) {
+__global__ void __launch_bounds__(CF20_THREADS, 2) k_colfilter320(float2* __restrict__ spec, const float* __restrict__ G,
+                                                               const float2* __restrict__ stats, int nS, int img_stride) {
   constexpr int N = 320, Nh = 161;
   extern __shared__ float2 cf_smem[];
   float2* ex = cf_smem;                           // [320][CF20_COLS]
@@ -883,10 +883,17 @@ __global__ void __launch_bounds__(CF20_THREADS, 2) k_colfilter320(float2* __rest
           for (int k2 = 0; k2 < 20; ++k2) base[(t + 16 * k2) * Nh] = u[k2];
         }
       } else {
+        float scale = 1.0f;
+        if (stats) {                                // rows from k_ingest_rowfft320: normalise here, (x - mean) / std is linear
+          const float2 ms = stats[img];
+          scale = ms.y;
+          if (t == 0 && kx == 0) u[0].x -= ms.x * 102400.0f;
+        }
 #pragma unroll
         for (int k2 = 0; k2 < 20; ++k2) {
-          u[k2].x *= gk[k2];
-          u[k2].y *= gk[k2];
+          const float g = gk[k2] * scale;
+          u[k2].x *= g;
+          u[k2].y *= g;
         }
         fft20<1>(u);                                // inverse over k2: u[n1] = C_t[n1]
       }
@@ -909,6 +916,221 @@ __global__ void __launch_bounds__(CF20_THREADS, 2) k_colfilter320(float2* __rest
       for (int n2 = 0; n2 < 16; ++n2) base[(t + 20 * n2) * Nh] = v[n2];
     }
     __syncthreads();                                // `ex` is rewritten by the next image
+  }
+}
+
+// Row passes at N = 320 with the same 20 x 16 split on CTA level: a band of 32 picture rows = 16 row pairs, thread (t, pair)
+// with the pair index fastest, exchanges through the band's own shared memory behind block barriers (the band is in registers
+// by then).  The two half spectra of a pair are separated from a natural-order copy of Z in shared memory by the store loop
+// (lanes along kx: coalesced).
+constexpr int R20_PR = 16;                    // row pairs per band
+constexpr int R20_THREADS = 20 * R20_PR;      // 320
+constexpr int R20_BP = 321;                   // band pitch (floats) of the forward kernel; also the pitch (float2) of the Z copy
+constexpr int R20_RBP = 331;                  // band pitch of the inverse kernel: 320 samples + one pad per 32, odd multiple mod 16
+constexpr int R20_SMEM = 32 * R20_RBP * 4;    // 42,368 B >= every view of the buffer
+
+// first half of the forward transform of one row pair: v[m] = z[t + 20 m] -> Z[t + 16 k2] in u (threads t < 16)
+__device__ __forceinline__ void fwd320_pair(float2 (&v)[16], float2 (&u)[20], float2* ex, const float2* tws, int t, int pr) {
+  fft16<-1>(v);
+  __syncthreads();                                  // every thread has its band values in registers: the band becomes the exchange
+#pragma unroll
+  for (int k1 = 0; k1 < 16; ++k1) ex[(k1 * 20 + t) * R20_PR + pr] = cmul(v[k1], tws[k1 * 20 + t]);
+  __syncthreads();
+  if (t < 16) {
+#pragma unroll
+    for (int tt = 0; tt < 20; ++tt) u[tt] = ex[(t * 20 + tt) * R20_PR + pr];
+    fft20<-1>(u);
+  }
+  __syncthreads();                                  // the exchange has been read: its memory becomes the natural-order copy of Z
+}
+
+template <bool PLAIN = false>
+__global__ void __launch_bounds__(R20_THREADS, 2) k_ingest_rowfft320(const float* __restrict__ raw, const uint8_t* __restrict__ flip,
+                                                                  float2* __restrict__ spec, float2* __restrict__ stats,
+                                                                  int transposed) {
+  constexpr int N = 320, Nh = 161, NW = R20_THREADS / 32;
+  extern __shared__ float2 ir_smem[];
+  float* band = reinterpret_cast<float*>(ir_smem);                  // [32][R20_BP]
+  float2* ex = ir_smem;                                             // [320][R20_PR]
+  float2* zb = ir_smem;                                             // [R20_PR][R20_BP] natural-order Z of every pair
+  __shared__ double red[3 * NW];
+  __shared__ float2 tws[320];
+  tws[threadIdx.x] = c_tw320[((threadIdx.x / 20) * (threadIdx.x % 20)) % 320];
+  const int i = blockIdx.x;
+  const float* src = raw + (size_t)i * N * N;
+  float2* out = spec + (size_t)i * N * Nh;
+  const bool fl = PLAIN ? false : flip[i] != 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = threadIdx.x / R20_PR, pr = threadIdx.x % R20_PR;
+  const float half = 0.5f * N, r2lim = half * half;
+  const float off = PLAIN ? 0.0f : src[0];
+  double s = 0, s2 = 0;
+  int cnt = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < N; b0 += 32) {
+    float rs = 0.0f, rs2 = 0.0f;
+    if (PLAIN) {
+      for (int k = warp; k < 32; k += NW) {
+        const float* rowp = src + (b0 + k) * N;
+#pragma unroll
+        for (int c = lane; c < N; c += 32) band[k * R20_BP + c] = rowp[c];
+      }
+    } else if (transposed) {                        // picture[rp][c] = raw[c][rp]; lanes run along rp
+      const int rp = b0 + lane;
+      const int r = fl ? N - 1 - rp : rp;
+      const float x = (float)rp - half + 1.0f, x2 = x * x;
+#pragma unroll 8
+      for (int c = warp; c < N; c += NW) {
+        const float v = src[c * N + r] - off;
+        const float y = (float)c - half;
+        const bool in = x2 + y * y < r2lim;
+        const float m = in ? 0.0f : v;
+        cnt += in ? 0 : 1;
+        rs += m;
+        rs2 = fmaf(m, m, rs2);
+        band[lane * R20_BP + c] = v;
+      }
+    } else {
+      for (int k = warp; k < 32; k += NW) {
+        const int rp = b0 + k;
+        const int r = fl ? N - 1 - rp : rp;
+        const float x = (float)rp - half + 1.0f, x2 = x * x;
+#pragma unroll
+        for (int c = lane; c < N; c += 32) {
+          const float v = src[r * N + c] - off;
+          const float y = (float)c - half;
+          const bool in = x2 + y * y < r2lim;
+          const float m = in ? 0.0f : v;
+          cnt += in ? 0 : 1;
+          rs += m;
+          rs2 = fmaf(m, m, rs2);
+          band[k * R20_BP + c] = v;
+        }
+      }
+    }
+    s += (double)rs;
+    s2 += (double)rs2;
+    __syncthreads();
+    float2 v[16], u[20];
+    const float* b1 = band + (2 * pr) * R20_BP + t;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) v[m] = make_float2(b1[20 * m], b1[R20_BP + 20 * m]);
+    fwd320_pair(v, u, ex, tws, t, pr);
+    if (t < 16) {
+#pragma unroll
+      for (int k2 = 0; k2 < 20; ++k2) zb[pr * R20_BP + t + 16 * k2] = u[k2];
+    }
+    __syncthreads();
+    for (int q = warp; q < R20_PR; q += NW) {       // X1[k] = (Z[k] + conj Z[N-k]) / 2, X2[k] = (Z[k] - conj Z[N-k]) / 2i
+      const float2* z = zb + q * R20_BP;
+      float2* o1 = out + (b0 + 2 * q) * Nh;
+      float2* o2 = o1 + Nh;
+      for (int k = lane; k < Nh; k += 32) {
+        const float2 zk = z[k];
+        const float2 zn = z[k == 0 ? 0 : N - k];
+        o1[k] = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+        o2[k] = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
+      }
+    }
+    __syncthreads();                                // the buffer is the next band
+  }
+  if (PLAIN) return;
+  double dc = (double)cnt;
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    dc += __shfl_xor_sync(0xffffffffu, dc, o);
+  }
+  if (lane == 0) { red[warp] = s; red[NW + warp] = s2; red[2 * NW + warp] = dc; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s = 0; s2 = 0; dc = 0;
+    for (int w = 0; w < NW; ++w) { s += red[w]; s2 += red[NW + w]; dc += red[2 * NW + w]; }
+    const double o = (double)off, n = (double)N * N;
+    const double S1 = s + o * dc, S2 = s2 + 2.0 * o * s + o * o * dc;
+    const double mean = S1 / n;
+    const double var = S2 / n - mean * mean;
+    stats[i] = make_float2((float)(mean - o), (float)(1.0 / sqrt(var)));
+  }
+}
+
+// the way back at N = 320: half spectra of a row pair -> Z in natural order -> inverse FFT-320 (FFT-20 on threads t < 16,
+// conjugate twiddle, exchange, FFT-16 on all) -> the two real rows in shared memory -> annular mask + row pass of the first
+// spline prefilter (lane l owns samples [10 l, 10 l + 10)), row-contiguous stores
+__global__ void __launch_bounds__(R20_THREADS, 2) k_rowifft_prefilter320(const float2* __restrict__ spec, float* __restrict__ outimg) {
+  constexpr int N = 320, Nh = 161, E = 10, NW = R20_THREADS / 32;
+  extern __shared__ float2 ir_smem[];
+  float* band = reinterpret_cast<float*>(ir_smem);                  // [32][R20_RBP]
+  float2* ex = ir_smem;                                             // [320][R20_PR]
+  float2* zb = ir_smem;                                             // [R20_PR][R20_BP]
+  const int i = blockIdx.x;
+  const float2* in = spec + (size_t)i * N * Nh;
+  float* dst = outimg + (size_t)i * N * N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = threadIdx.x / R20_PR, pr = threadIdx.x % R20_PR;
+  constexpr float half = 0.5f * N, r2lim = half * half;
+  const float zE = 1.9077634e-06f;                  // z^10, z = sqrt(3) - 2
+  __shared__ float2 tws[320];                       // conj W320^(t k1)
+  {
+    const float2 w = c_tw320[((threadIdx.x / 20) * (threadIdx.x % 20)) % 320];
+    tws[threadIdx.x] = make_float2(w.x, -w.y);
+  }
+  __syncthreads();
+  for (int b0 = 0; b0 < N; b0 += 32) {
+    for (int q = warp; q < R20_PR; q += NW) {       // Z[k] = X1[k] + i X2[k], Z[N-k] = conj X1[k] + i conj X2[k]
+      const float2* x1 = in + (b0 + 2 * q) * Nh;
+      const float2* x2 = x1 + Nh;
+      float2* z = zb + q * R20_BP;
+      for (int k = lane; k < Nh; k += 32) {
+        float2 a = x1[k], b = x2[k];
+        if (k == 0 || k == N / 2) { a.y = 0.0f; b.y = 0.0f; }      // a C2R ignores the imaginary parts of the DC and Nyquist terms
+        z[k] = make_float2(a.x - b.y, a.y + b.x);
+        if (k != 0 && k != N / 2) z[N - k] = make_float2(a.x + b.y, b.x - a.y);
+      }
+    }
+    __syncthreads();
+    float2 u[20], v[16];
+    if (t < 16) {
+#pragma unroll
+      for (int k2 = 0; k2 < 20; ++k2) u[k2] = zb[pr * R20_BP + t + 16 * k2];
+      fft20<1>(u);                                  // u[n1] = C_t[n1]
+    }
+    __syncthreads();                                // Z has been read: its memory becomes the exchange
+    if (t < 16) {
+#pragma unroll
+      for (int n1 = 0; n1 < 20; ++n1) ex[(n1 * 16 + t) * R20_PR + pr] = cmul(u[n1], tws[t * 20 + n1]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) v[k1] = ex[(t * 16 + k1) * R20_PR + pr];
+    fft16<1>(v);                                    // v[n2] = z[t + 20 n2]: row 2 pr in .x, row 2 pr + 1 in .y
+    __syncthreads();                                // the exchange has been read: its memory becomes the 32 rows
+    float* r1 = band + (2 * pr) * R20_RBP;
+#pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) {
+      const int c = t + 20 * n2;
+      r1[c + (c >> 5)] = v[n2].x;
+      r1[R20_RBP + c + (c >> 5)] = v[n2].y;
+    }
+    __syncthreads();
+    for (int row = warp; row < 32; row += NW) {
+      const float* ln = band + row * R20_RBP;
+      const float xm = (float)(b0 + row) - half + 1.0f;
+      const float lim = r2lim - xm * xm;            // keep the pixel iff y * y < lim
+      const int c0 = lane * E;
+      float sv[E];
+#pragma unroll
+      for (int j = 0; j < E; ++j) {
+        const float y = (float)(c0 + j) - half;
+        const float val = ln[c0 + j + ((c0 + j) >> 5)];
+        sv[j] = (y * y < lim) ? 6.0f * val : 0.0f;
+      }
+      spline_line_warp<E>(sv, zE, lane);
+      float2* orow = reinterpret_cast<float2*>(dst + (b0 + row) * N + c0);
+#pragma unroll
+      for (int j = 0; j < E / 2; ++j) orow[j] = make_float2(sv[2 * j], sv[2 * j + 1]);
+    }
+    __syncthreads();                                // the rows are overwritten by the next band's Z
   }
 }
 
@@ -945,8 +1167,9 @@ static int ensure_twiddles320(mem_ctx* ctx, cudaStream_t st) {
   return 0;
 }
 
-// column pass alone (N = 320): spec holds row-transformed half spectra (cuFFT 1-D R2C); fwd_only = the a10 transform
-int colpass_run(mem_ctx* ctx, float2* spec, const float* G, int nS, int N, int fwd_only, cudaStream_t st) {
+// column pass alone (N = 320): spec holds row-transformed half spectra; fwd_only = the a10 transform; stats != NULL: the rows
+// came from k_ingest_rowfft320 (not yet normalised)
+int colpass_run(mem_ctx* ctx, float2* spec, const float* G, const float2* stats, int nS, int N, int fwd_only, cudaStream_t st) {
   if (!colpass_supported(N)) {
     set_error("colpass: no kernel for N = %d", N);
     return 1;
@@ -956,11 +1179,26 @@ int colpass_run(mem_ctx* ctx, float2* spec, const float* G, int nS, int N, int f
   const size_t smem = 2 * 320 * CF20_COLS * sizeof(float2);
   if (fwd_only) {
     MEM_CUDA(cudaFuncSetAttribute(k_colfilter320<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MEM_LAUNCH(ctx, k_colfilter320<true>, per_slab * CF20_SLABS, CF20_THREADS, smem, st, spec, G, nS, per_slab);
+    MEM_LAUNCH(ctx, k_colfilter320<true>, per_slab * CF20_SLABS, CF20_THREADS, smem, st, spec, G, stats, nS, per_slab);
   } else {
     MEM_CUDA(cudaFuncSetAttribute(k_colfilter320<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MEM_LAUNCH(ctx, k_colfilter320<false>, per_slab * CF20_SLABS, CF20_THREADS, smem, st, spec, G, nS, per_slab);
+    MEM_LAUNCH(ctx, k_colfilter320<false>, per_slab * CF20_SLABS, CF20_THREADS, smem, st, spec, G, stats, nS, per_slab);
   }
+  return 0;
+}
+
+// row passes at N = 320 (see k_ingest_rowfft320 / k_rowifft_prefilter320)
+int rows320_forward_run(mem_ctx* ctx, const float* raw, const uint8_t* flip, float2* spec, float2* stats, int nS, int transposed,
+                        int plain, cudaStream_t st) {
+  MEM_CHECK(ensure_twiddles320(ctx, st));
+  if (plain) MEM_LAUNCH(ctx, k_ingest_rowfft320<true>, nS, R20_THREADS, R20_SMEM, st, raw, flip, spec, stats, transposed);
+  else MEM_LAUNCH(ctx, k_ingest_rowfft320<false>, nS, R20_THREADS, R20_SMEM, st, raw, flip, spec, stats, transposed);
+  return 0;
+}
+
+int rows320_inverse_run(mem_ctx* ctx, const float2* spec, float* out, int nS, cudaStream_t st) {
+  MEM_CHECK(ensure_twiddles320(ctx, st));
+  MEM_LAUNCH(ctx, k_rowifft_prefilter320, nS, R20_THREADS, R20_SMEM, st, spec, out);
   return 0;
 }
 

@@ -728,10 +728,19 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
     rows_done = 1;
   } else if (colpass_supported(N) && !ctx->cufft_lowpass) {
     // N = 320: rows through cuFFT's batched 1-D plans, the whole column pass (FFT, * G, inverse FFT) in one kernel of ours
-    MEM_CHECK(ingest_run(ctx, picture, io->flip, A, nS, N, transposed, st));
-    MEM_CHECK(run_fft(ctx, N, nS, true, A, spec, st, true));
-    MEM_CHECK(colpass_run(ctx, spec, g.Gtab.as<float>(), nS, N, 0, st));
-    MEM_CHECK(run_fft(ctx, N, nS, false, B, spec, st, true));
+    if (!ctx->cufft_rows320) {                       // own row passes as well: three crossings, as at 256
+      MEM_CHECK(ctx->stats.ensure((size_t)nS * sizeof(float2)));
+      float2* stats = ctx->stats.as<float2>();
+      MEM_CHECK(rows320_forward_run(ctx, picture, io->flip, spec, stats, nS, transposed, 0, st));
+      MEM_CHECK(colpass_run(ctx, spec, g.Gtab.as<float>(), stats, nS, N, 0, st));
+      MEM_CHECK(rows320_inverse_run(ctx, spec, A, nS, st));
+      rows_done = 1;
+    } else {
+      MEM_CHECK(ingest_run(ctx, picture, io->flip, A, nS, N, transposed, st));
+      MEM_CHECK(run_fft(ctx, N, nS, true, A, spec, st, true));
+      MEM_CHECK(colpass_run(ctx, spec, g.Gtab.as<float>(), nullptr, nS, N, 0, st));
+      MEM_CHECK(run_fft(ctx, N, nS, false, B, spec, st, true));
+    }
   } else {
     MEM_CHECK(ingest_run(ctx, picture, io->flip, A, nS, N, transposed, st));
     MEM_CHECK(run_fft(ctx, N, nS, true, A, spec, st));
@@ -753,8 +762,9 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
   } else if (own_fft(ctx, N) && !ctx->cufft_a10) {
     MEM_CHECK(fft2_forward_run(ctx, imgAll, spec, nS, N, st));
   } else if (colpass_supported(N) && !ctx->cufft_lowpass && !ctx->cufft_a10) {
-    MEM_CHECK(run_fft(ctx, N, nS, true, imgAll, spec, st, true));
-    MEM_CHECK(colpass_run(ctx, spec, nullptr, nS, N, 1, st));
+    if (!ctx->cufft_rows320) MEM_CHECK(rows320_forward_run(ctx, imgAll, nullptr, spec, nullptr, nS, 0, 1, st));
+    else MEM_CHECK(run_fft(ctx, N, nS, true, imgAll, spec, st, true));
+    MEM_CHECK(colpass_run(ctx, spec, nullptr, nullptr, nS, N, 1, st));
   } else {
     MEM_CHECK(run_fft(ctx, N, nS, true, imgAll, spec, st));
   }
@@ -920,10 +930,19 @@ int pd_distance_batch_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_p
     MEM_CHECK(rowifft_prefilter_run(ctx, spec, A, nS, N, st));
     rows_done = 1;
   } else if (colpass_supported(N) && !ctx->cufft_lowpass) {
-    MEM_CHECK(ingest_run(ctx, io->raw, io->flip, A, nS, N, prm->transposed, st));
-    MEM_CHECK(run_fft(ctx, N, nS, true, A, spec, st, true));
-    MEM_CHECK(colpass_run(ctx, spec, g.Gtab.as<float>(), nS, N, 0, st));
-    MEM_CHECK(run_fft(ctx, N, nS, false, B, spec, st, true));
+    if (!ctx->cufft_rows320) {
+      MEM_CHECK(ctx->stats.ensure((size_t)nS * sizeof(float2)));
+      float2* stats = ctx->stats.as<float2>();
+      MEM_CHECK(rows320_forward_run(ctx, io->raw, io->flip, spec, stats, nS, prm->transposed, 0, st));
+      MEM_CHECK(colpass_run(ctx, spec, g.Gtab.as<float>(), stats, nS, N, 0, st));
+      MEM_CHECK(rows320_inverse_run(ctx, spec, A, nS, st));
+      rows_done = 1;
+    } else {
+      MEM_CHECK(ingest_run(ctx, io->raw, io->flip, A, nS, N, prm->transposed, st));
+      MEM_CHECK(run_fft(ctx, N, nS, true, A, spec, st, true));
+      MEM_CHECK(colpass_run(ctx, spec, g.Gtab.as<float>(), nullptr, nS, N, 0, st));
+      MEM_CHECK(run_fft(ctx, N, nS, false, B, spec, st, true));
+    }
   } else {
     MEM_CHECK(ingest_run(ctx, io->raw, io->flip, A, nS, N, prm->transposed, st));
     MEM_CHECK(run_fft(ctx, N, nS, true, A, spec, st));
@@ -939,8 +958,9 @@ int pd_distance_batch_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_p
   if (own_fft(ctx, N) && !ctx->cufft_a10) {
     MEM_CHECK(fft2_forward_run(ctx, imgAll, spec, nS, N, st));
   } else if (colpass_supported(N) && !ctx->cufft_lowpass && !ctx->cufft_a10) {
-    MEM_CHECK(run_fft(ctx, N, nS, true, imgAll, spec, st, true));
-    MEM_CHECK(colpass_run(ctx, spec, nullptr, nS, N, 1, st));
+    if (!ctx->cufft_rows320) MEM_CHECK(rows320_forward_run(ctx, imgAll, nullptr, spec, nullptr, nS, 0, 1, st));
+    else MEM_CHECK(run_fft(ctx, N, nS, true, imgAll, spec, st, true));
+    MEM_CHECK(colpass_run(ctx, spec, nullptr, nullptr, nS, N, 1, st));
   } else {
     MEM_CHECK(run_fft(ctx, N, nS, true, imgAll, spec, st));
   }
