@@ -324,3 +324,14 @@ def test_bad_inputs_fail_loudly(env):
     assert lib.mem_contract_device(ctx.handle, C.byref(shp), None, None, None, 0, 0, 0, None) != 0
     shp = _lib.ContractShape(nS=4, n1_blocks=1, n3_blocks=1, ldz=96)
     assert lib.mem_contract_device(ctx.handle, C.byref(shp), None, None, None, 7, 0, 0, None) != 0   # unknown kind
+
+
+@pytest.mark.parametrize('N', [128, 256, 320])
+def test_reference_vectors_at_baseline_box_sizes(env, golden_dir, N):
+    """The CUDA path against outputs of the unmodified reference at the box sizes that take size-specific kernels (FFT-128 /
+    256 / 320, rotation kernels for multiples of 32): tests/golden/pd_box_N*.npz (make_golden_boxes.py)."""
+    from _box_golden import _box_case, check_box_outputs
+    _lib, pd_stage, synthetic = env
+    g, pd = _box_case(golden_dir, N)
+    res = _gpu(pd_stage, pd, N, fields=('D', 'imgAll'))
+    check_box_outputs(res, g, d_rtol=D_RTOL, img_tol=IMG_TOL)

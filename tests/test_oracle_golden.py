@@ -162,3 +162,17 @@ def test_psi_analysis_class_representatives_vs_reference(golden_dir):
         assert np.array_equal(tauinds, g['pa_psi%d_tauinds' % psinum]) and np.array_equal(tau, g['pa_psi%d_tau' % psinum])
         # sigma of the Ferguson fit depends on curve_fit's random start at the 1e-6 level, and IMGT with it
         assert np.allclose(IMG1, g['pa_psi%d_IMG1' % psinum], rtol=0, atol=1e-4)
+
+
+from _box_golden import _box_case, check_box_outputs   # noqa: E402
+
+
+@pytest.mark.parametrize('N', [128, 256, 320])
+def test_pd_at_baseline_box_sizes(golden_dir, N):
+    """The oracle (reference's tile + rotate, and the periodic closed form) at the box sizes BASELINE names."""
+    g, pd = _box_case(golden_dir, N)
+    em = pd['em']
+    for impl in ('tile', 'periodic'):
+        out = opd.pd_distance(pd['ind'], pd['q'], pd['df'], pd['stack'], pd['nStot'], N, em['pix_size'], em['Cs'], em['EkV'],
+                              em['AmpContrast'], rotate_impl=impl)
+        check_box_outputs(out, g, d_rtol=1e-8, img_tol=2e-7)
