@@ -98,7 +98,7 @@ struct mem_ctx {
   std::map<long long, cufftHandle> plans_d;  // float64 2-D plans of the NLSA stage: key = (type, N, batch)
   mem::DevBuf fft_work;
   // workspace for one PD
-  mem::DevBuf raw, flip, shift, psi, df, msk2, rot_cs, rot_pid, rot_pitch_tab, batch_aux;
+  mem::DevBuf raw, flip, shift, psi, df, msk2, rot_cs, rot_pid, rot_pitch_tab, batch_aux, mspec_all;
   mem::DevBuf imgA, imgB, imgAll, imgFlip, spec, spec2, cbin, zhi, zlo;
   mem::DevBuf part_cf, part_cfw, part_c2, part_fl, part_int, avgspec, avgimg, stats;
   mem::DevBuf D, ctf64, small_out;

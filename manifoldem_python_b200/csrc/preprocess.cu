@@ -337,9 +337,10 @@ k_operands_radial_sm(float2* __restrict__ spec, const float2* __restrict__ Mspec
                      const int* __restrict__ fold_ent, const int* __restrict__ bin_of_pix,
                      const int* __restrict__ special_pix, const int* __restrict__ s3_col, float* __restrict__ zhi,
                      float* __restrict__ zlo, int N, int Nh, int Na, int Kh, int Kr, int n_special, int n1_blocks,
-                     int64_t ldz) {
+                     int64_t ldz, const int* __restrict__ pd_of) {
   extern __shared__ float pw[];
   const int i = blockIdx.x;
+  if (pd_of) Mspec += (size_t)pd_of[i] * Kh;       // batched PDs: one common component per PD
   const int w1 = 32 * n1_blocks;
   float2* F = spec + (size_t)i * Kh;
   float* zh = zhi + (size_t)i * ldz;
@@ -489,6 +490,40 @@ __global__ void __launch_bounds__(256) k_spec_sums(const float2* __restrict__ sp
   if (specw) part_cfw[(size_t)g * Kh + p] = scw;
   part_c2[(size_t)g * Kh + p] = sc2;
   part_fl[(size_t)g * Kh + p] = sfl;
+}
+
+// The common component of EVERY PD of a batch in one launch: M_p = sum_i C_i F_i / sum_i C_i^2 over the images of PD p
+// (grid.y = PD; the per-PD k_spec_sums + k_avg_spectra pair of the single-PD path costs two launches per PD, which is what a
+// batch of reference-sized PDs spends its time on).  fp64 sums, four loads in flight per thread.
+__global__ void __launch_bounds__(256) k_mspec_batch(const float2* __restrict__ spec, const float* __restrict__ cbin,
+                                                     const int* __restrict__ bin_of_pix, const int* __restrict__ pd_start,
+                                                     float2* __restrict__ Mspec, int Kh, int Kr) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Kh) return;
+  const int i0 = pd_start[blockIdx.y], i1 = pd_start[blockIdx.y + 1];
+  const int b = bin_of_pix[p];
+  double2 scf = make_double2(0, 0);
+  double sc2 = 0;
+  constexpr int U = 4;
+  for (int ib = i0; ib < i1; ib += U) {
+    float cu[U];
+    float2 fu[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t i = (size_t)min(ib + u, i1 - 1);
+      cu[u] = cbin[i * Kr + b];
+      fu[u] = spec[i * Kh + p];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (ib + u < i1) {
+        scf.x += (double)(cu[u] * fu[u].x);
+        scf.y += (double)(cu[u] * fu[u].y);
+        sc2 += (double)(cu[u] * cu[u]);
+      }
+    }
+  }
+  Mspec[(size_t)blockIdx.y * Kh + p] = (sc2 > 1e-30) ? make_float2((float)(scf.x / sc2), (float)(scf.y / sc2)) : make_float2(0.0f, 0.0f);
 }
 
 // a12 operands, S3 part (pass 2) + a10 phase flip.  The distance is invariant under F_i -> F_i - C_i M for
@@ -807,7 +842,7 @@ int pd_distance_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_pd_io* 
       MEM_LAUNCH(ctx, kern, nS, rthreads, pw_bytes, st, spec, Mspec, ctx->cbin.as<float>(),
                  g.fold_bin.as<int>(), g.fold_start.as<int>(), g.fold_ent.as<int>(), g.bin_of_pix.as<int>(),
                  g.special_pix.as<int>(), g.s3_col.as<int>(), zhi, zlo, N, g.Nh, g.Na, g.Kh, g.Kr, g.n_special,
-                 g.n1_blocks, g.ldz);
+                 g.n1_blocks, g.ldz, (const int*)nullptr);
       s3_done = true;
     } else {   // boxes above ~ 450 px: the folded power map does not fit shared memory
       MEM_LAUNCH(ctx, k_operands_radial, dim3((32 * g.n1_blocks + 255) / 256, nS), 256, 0, st, spec, Mspec,
@@ -902,18 +937,21 @@ int pd_distance_batch_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_p
   // per-image PD index, per-PD psi_p, per-image second-rotation angle and pitch id
   const size_t b_pd = ((size_t)nS * sizeof(int) + 255) & ~(size_t)255, b_pp = ((size_t)n_pd * sizeof(double) + 255) & ~(size_t)255;
   const size_t b_cs = ((size_t)nS * sizeof(double2) + 255) & ~(size_t)255;
-  MEM_CHECK(ctx->batch_aux.ensure(b_pd + b_pp + b_cs + (size_t)nS));
+  const size_t b_id = ((size_t)nS + 255) & ~(size_t)255;
+  MEM_CHECK(ctx->batch_aux.ensure(b_pd + b_pp + b_cs + b_id + (size_t)(n_pd + 1) * sizeof(int)));
   uint8_t* aux = ctx->batch_aux.as<uint8_t>();
   int* pd_of = reinterpret_cast<int*>(aux);
   double* d_pp = reinterpret_cast<double*>(aux + b_pd);
   double2* cs2 = reinterpret_cast<double2*>(aux + b_pd + b_pp);
   uint8_t* pid2 = aux + b_pd + b_pp + b_cs;
+  int* d_start = reinterpret_cast<int*>(aux + b_pd + b_pp + b_cs + b_id);
   {
     std::vector<int> h(nS);
     for (int p = 0; p < n_pd; ++p)
       for (int i = pd_start[p]; i < pd_start[p + 1]; ++i) h[i] = p;
     MEM_CUDA(cudaMemcpyAsync(pd_of, h.data(), (size_t)nS * sizeof(int), cudaMemcpyHostToDevice, st));
     MEM_CUDA(cudaMemcpyAsync(d_pp, psi_p_deg, (size_t)n_pd * sizeof(double), cudaMemcpyHostToDevice, st));
+    MEM_CUDA(cudaMemcpyAsync(d_start, pd_start, (size_t)(n_pd + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
     MEM_CUDA(cudaStreamSynchronize(st));                  // host temporaries
   }
   float* A = ctx->imgA.as<float>();
@@ -976,31 +1014,38 @@ int pd_distance_batch_device(mem_ctx* ctx, const mem_pd_params* prm, const mem_p
   std::vector<float*> Dp(n_pd);
   size_t doff = 0;
   for (int p = 0; p < n_pd; ++p) {
-    const int s0 = pd_start[p], n = pd_start[p + 1] - s0;
-    const int G = (n + per_group - 1) / per_group;
-    float2* spec_p = spec + (size_t)s0 * Kh;
-    float* cbin_p = ctx->cbin.as<float>() + (size_t)s0 * g.Kr;
-    float* zhi_p = zhi + (size_t)s0 * g.ldz;
-    float* zlo_p = zlo + (size_t)s0 * g.ldz;
-    MEM_LAUNCH(ctx, k_spec_sums, dim3((g.Kh + 255) / 256, G), 256, 0, st, spec_p, (const float2*)nullptr, cbin_p,
-               g.bin_of_pix.as<int>(), ctx->part_cf.as<double2>(), (double2*)nullptr, ctx->part_c2.as<double>(),
-               ctx->part_fl.as<double2>(), n, g.Kh, g.Kr, per_group, 1);
-    MEM_LAUNCH(ctx, k_avg_spectra, (g.Kh + 255) / 256, 256, 0, st, ctx->part_cf.as<double2>(), (double2*)nullptr,
-               ctx->part_c2.as<double>(), ctx->part_fl.as<double2>(), ctx->avgspec.as<float2>(), Mspec, g.Kh, G);
-    if (radial_sm) {
-      MEM_LAUNCH(ctx, k_operands_radial_sm<false>, n, RADIAL_THREADS, pw_bytes, st, spec_p, Mspec, cbin_p,
-                 g.fold_bin.as<int>(), g.fold_start.as<int>(), g.fold_ent.as<int>(), g.bin_of_pix.as<int>(),
-                 g.special_pix.as<int>(), g.s3_col.as<int>(), zhi_p, zlo_p, N, g.Nh, g.Na, g.Kh, g.Kr, g.n_special,
-                 g.n1_blocks, g.ldz);
-    } else {
+    Dp[p] = io->D + doff;
+    doff += (size_t)(pd_start[p + 1] - pd_start[p]) * (pd_start[p + 1] - pd_start[p]);
+  }
+  if (radial_sm) {
+    // one launch for the common components of all PDs, one for the operands of all images (M looked up by the image's PD)
+    MEM_CHECK(ctx->mspec_all.ensure((size_t)n_pd * Kh * sizeof(float2)));
+    float2* M_all = ctx->mspec_all.as<float2>();
+    MEM_LAUNCH(ctx, k_mspec_batch, dim3((g.Kh + 255) / 256, n_pd), 256, 0, st, spec, ctx->cbin.as<float>(), g.bin_of_pix.as<int>(),
+               d_start, M_all, g.Kh, g.Kr);
+    MEM_LAUNCH(ctx, k_operands_radial_sm<false>, nS, RADIAL_THREADS, pw_bytes, st, spec, M_all, ctx->cbin.as<float>(),
+               g.fold_bin.as<int>(), g.fold_start.as<int>(), g.fold_ent.as<int>(), g.bin_of_pix.as<int>(),
+               g.special_pix.as<int>(), g.s3_col.as<int>(), zhi, zlo, N, g.Nh, g.Na, g.Kh, g.Kr, g.n_special, g.n1_blocks, g.ldz,
+               (const int*)pd_of);
+  } else {
+    for (int p = 0; p < n_pd; ++p) {
+      const int s0 = pd_start[p], n = pd_start[p + 1] - s0;
+      const int G = (n + per_group - 1) / per_group;
+      float2* spec_p = spec + (size_t)s0 * Kh;
+      float* cbin_p = ctx->cbin.as<float>() + (size_t)s0 * g.Kr;
+      float* zhi_p = zhi + (size_t)s0 * g.ldz;
+      float* zlo_p = zlo + (size_t)s0 * g.ldz;
+      MEM_LAUNCH(ctx, k_spec_sums, dim3((g.Kh + 255) / 256, G), 256, 0, st, spec_p, (const float2*)nullptr, cbin_p,
+                 g.bin_of_pix.as<int>(), ctx->part_cf.as<double2>(), (double2*)nullptr, ctx->part_c2.as<double>(),
+                 ctx->part_fl.as<double2>(), n, g.Kh, g.Kr, per_group, 1);
+      MEM_LAUNCH(ctx, k_avg_spectra, (g.Kh + 255) / 256, 256, 0, st, ctx->part_cf.as<double2>(), (double2*)nullptr,
+                 ctx->part_c2.as<double>(), ctx->part_fl.as<double2>(), ctx->avgspec.as<float2>(), Mspec, g.Kh, G);
       MEM_LAUNCH(ctx, k_operands_radial, dim3((32 * g.n1_blocks + 255) / 256, n), 256, 0, st, spec_p, Mspec, cbin_p,
                  g.bin_start.as<int>(), g.bin_pix.as<int>(), g.bin_of_pix.as<int>(), g.special_pix.as<int>(), zhi_p, zlo_p,
                  N, g.Nh, g.Kh, g.Kr, g.n_special, g.n1_blocks, g.ldz);
       MEM_LAUNCH(ctx, k_operands_s3, dim3((g.Kh + 255) / 256, G), 256, 0, st, spec_p, Mspec, cbin_p, g.bin_of_pix.as<int>(),
                  g.s3_col.as<int>(), zhi_p, zlo_p, n, g.Kh, g.Kr, g.ldz, per_group, 1, 0);
     }
-    Dp[p] = io->D + doff;
-    doff += (size_t)n * n;
   }
   const int from = 64 * g.n1_blocks + 2 * g.K3;
   if (from < g.ldz) MEM_LAUNCH(ctx, k_zero_tail, nS, 64, 0, st, zhi, zlo, nS, g.ldz, from);
